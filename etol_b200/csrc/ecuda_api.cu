@@ -1,0 +1,615 @@
+// ecuda_api.cu -- __global__ kernels for sm_100a and the extern "C" entry points of include/ecuda.h.
+//
+// Kernel layout: one CTA per (VGP instance, phase). The instance's obstacle/track records are
+// fetched into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier, SASS: UBLKCP) while
+// the threads un-scale the decision vector into shared memory; then the barrier-free phases of
+// ecuda_phases.cuh run. Results are written with streaming stores straight into the caller's
+// f / g / Jacobian-triplet arrays (IPOPT layout), so the only HBM traffic is the algorithmic one:
+// 8*(nvars + 1 + ncons + nnz) bytes per instance plus its obstacle records.
+//
+// There is no CPU fallback in this file: without a usable sm_100 device every compute entry point
+// returns ECUDA_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "ecuda_phases.cuh"
+
+namespace ecuda {
+
+constexpr int kThreads = 256;
+
+// ---- TMA bulk copy helpers (PTX) -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ ProbDev pb,
+                                                   const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    stage_vars(pb, ph, io, m, b, tid, nthr, io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    phase_b<M>(pb, ph, p, io, m, b, tid, nthr);
+    __syncthreads();
+    phase_c<M>(pb, ph, p, io, m, b, tid, nthr);
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads) k_grad(const __grid_constant__ ProbDev pb,
+                                                   const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, false);
+    __syncthreads();
+    cost_nodes<M>(pb, ph, m, tid, nthr);
+    __syncthreads();
+    gradient_phase<M>(pb, ph, io, m, b, tid, nthr);
+}
+
+// multi-phase objective: f = sf * (((f_0 + f_1) + f_2) + ...)
+__global__ void k_sum_phases(const double* fpart, double* f, int batch, int nphases, double sf) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double tot = fpart[static_cast<size_t>(b) * nphases];
+    for (int p = 1; p < nphases; ++p) tot = tot + fpart[static_cast<size_t>(b) * nphases + p];
+    f[b] = sf * tot;
+}
+
+// per-instance summary {f, max bound violation}; one warp per instance, shuffle max-reduce
+__global__ void k_summary(const double* f, const double* g, const double* gl, const double* gu, double* out,
+                          int batch, int ncons) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= batch) return;
+    const double* gb = g + static_cast<size_t>(warp) * ncons;
+    const double* lb = gl + static_cast<size_t>(warp) * ncons;
+    const double* ub = gu + static_cast<size_t>(warp) * ncons;
+    double v = 0.0;
+    for (int r = lane; r < ncons; r += 32) {
+        double gv = gb[r];
+        v = fmax(v, fmax(lb[r] - gv, gv - ub[r]));
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) {
+        out[2 * warp] = f[warp];
+        out[2 * warp + 1] = v;
+    }
+}
+
+// ---- context ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace ecuda
+
+using namespace ecuda;
+
+struct ecuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool have_problem = false, have_inst = false, have_bounds = false;
+    HostProblem hp;
+    ProbDev pd{};
+    DevBuf colptr, isz, sg, inst, gl, gu, fpart;
+    DevBuf coll[ECUDA_MAX_PHASES];  // D | Dt | tau | w per phase
+    DevBuf sx, sf_, sgv, sjac, sgrad, ssum;  // staging for host-memory calls
+    size_t smem_bytes = 0;
+    int64_t launches = 0;
+    int ipopt_jac_mode = ECUDA_JAC_EXACT;
+    std::vector<double> h_sz, h_sg;
+};
+
+static std::string g_create_err;
+
+static int fail(ecuda_ctx* h, int code, const std::string& msg) {
+    if (h)
+        h->err = msg;
+    else
+        g_create_err = msg;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(h, ECUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+static int ensure(ecuda_ctx* h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return ECUDA_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(h, ECUDA_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    b.bytes = bytes;
+    return ECUDA_OK;
+}
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+static int upload_scaling(ecuda_ctx* h) {
+    const int nv = h->hp.dims.nvars, ng = h->hp.dims.ncons;
+    std::vector<double> isz(nv);
+    for (int c = 0; c < nv; ++c) isz[c] = 1.0 / h->h_sz[c];  // reciprocal rounded once, on the host
+    int rc;
+    if ((rc = ensure(h, h->isz, sizeof(double) * nv))) return rc;
+    if ((rc = ensure(h, h->sg, sizeof(double) * ng))) return rc;
+    CU(cudaMemcpy(h->isz.p, isz.data(), sizeof(double) * nv, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->sg.p, h->h_sg.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
+    h->pd.isz = static_cast<const double*>(h->isz.p);
+    h->pd.sg = static_cast<const double*>(h->sg.p);
+    return ECUDA_OK;
+}
+
+static int upload_collocation(ecuda_ctx* h, int p) {
+    const Collocation& c = h->hp.col[p];
+    const size_t N = c.N;
+    std::vector<double> pack(2 * N * N + 2 * N);
+    for (size_t k = 0; k < N; ++k)
+        for (size_t l = 0; l < N; ++l) {
+            pack[k * N + l] = c.D[k * N + l];
+            pack[N * N + l * N + k] = c.D[k * N + l];
+        }
+    std::memcpy(&pack[2 * N * N], c.tau.data(), sizeof(double) * N);
+    std::memcpy(&pack[2 * N * N + N], c.w.data(), sizeof(double) * N);
+    int rc;
+    if ((rc = ensure(h, h->coll[p], sizeof(double) * pack.size()))) return rc;
+    CU(cudaMemcpy(h->coll[p].p, pack.data(), sizeof(double) * pack.size(), cudaMemcpyHostToDevice));
+    const double* base = static_cast<const double*>(h->coll[p].p);
+    h->pd.ph[p].D = base;
+    h->pd.ph[p].Dt = base + N * N;
+    h->pd.ph[p].tau = base + 2 * N * N;
+    h->pd.ph[p].w = base + 2 * N * N + N;
+    return ECUDA_OK;
+}
+
+template <int M>
+static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
+    // opt in to the full 227 KB of dynamic shared memory (per function and device; it only permits)
+    CU(cudaFuncSetAttribute(k_eval<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_grad<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int grid = io.batch * h->pd.nphases;
+    if (io.grad) {
+        k_grad<M><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
+        ++h->launches;
+    }
+    if (io.f || io.g || io.jac) {
+        k_eval<M><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
+        ++h->launches;
+        if (io.f && h->pd.nphases > 1) {
+            k_sum_phases<<<(io.batch + 127) / 128, 128, 0, st>>>(io.fpart, io.f, io.batch, h->pd.nphases, h->pd.sf);
+            ++h->launches;
+        }
+    }
+    CU(cudaGetLastError());
+    return ECUDA_OK;
+}
+
+static int launch_eval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
+    switch (h->pd.model) {
+        case ECUDA_MODEL_SI2D: return launch_eval_t<ECUDA_MODEL_SI2D>(h, io, st);
+        case ECUDA_MODEL_PM3D: return launch_eval_t<ECUDA_MODEL_PM3D>(h, io, st);
+        case ECUDA_MODEL_FW6: return launch_eval_t<ECUDA_MODEL_FW6>(h, io, st);
+    }
+    return fail(h, ECUDA_ERR_ARG, "unknown model");
+}
+
+extern "C" {
+
+const char* ecuda_last_error(ecuda_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ecuda_create(int device, ecuda_handle* out) {
+    ecuda_ctx* h = nullptr;
+    if (!out) return fail(nullptr, ECUDA_ERR_ARG, "null output handle");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ECUDA_ERR_CUDA,
+                    std::string("eCUDA needs an NVIDIA sm_100 GPU and has no CPU fallback: ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device present"));
+    if (device < 0 || device >= n) return fail(nullptr, ECUDA_ERR_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, ECUDA_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, ECUDA_ERR_CUDA,
+                    "eCUDA kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor));
+    h = new (std::nothrow) ecuda_ctx;
+    if (!h) return fail(nullptr, ECUDA_ERR_ALLOC, "out of host memory");
+    h->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e);
+        delete h;
+        return fail(nullptr, ECUDA_ERR_CUDA, msg);
+    }
+    *out = h;
+    return ECUDA_OK;
+}
+
+int ecuda_destroy(ecuda_handle h) {
+    if (!h) return ECUDA_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->sx, &h->sf_, &h->sgv,
+                      &h->sjac, &h->sgrad, &h->ssum})
+        release(*b);
+    for (auto& b : h->coll) release(b);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return ECUDA_OK;
+}
+
+int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!desc) return fail(h, ECUDA_ERR_ARG, "null problem description");
+    CU(cudaSetDevice(h->device));
+    std::string err;
+    HostProblem hp;
+    if (!build_layout(*desc, &hp, &err)) return fail(h, ECUDA_ERR_ARG, err);
+    build_structure(&hp);
+    hp.col.resize(hp.nphases);
+    for (int p = 0; p < hp.nphases; ++p)
+        if (!build_collocation(desc->collocation, hp.N[p], &hp.col[p], &err)) return fail(h, ECUDA_ERR_ARG, err);
+    h->hp = hp;
+    h->have_problem = false;
+    h->have_inst = false;
+    h->have_bounds = false;
+    ProbDev& pd = h->pd;
+    std::memset(&pd, 0, sizeof(pd));
+    pd.model = desc->model;
+    pd.ns = hp.ns;
+    pd.nc = hp.nc;
+    pd.ne = hp.ne;
+    pd.nphases = hp.nphases;
+    pd.nvars = hp.dims.nvars;
+    pd.ncons = hp.dims.ncons;
+    pd.nnz = hp.dims.nnz;
+    pd.nlink = hp.dims.nlinkages;
+    pd.linkoff = hp.linkoff;
+    pd.ntracks = desc->ntracks;
+    pd.nway = desc->nwaypoints;
+    pd.track_off = hp.track_off;
+    pd.track_size = hp.dims.track_size;
+    pd.rec_size = hp.dims.rec_size;
+    pd.inst_stride = hp.dims.inst_stride;
+    pd.maximize = desc->maximize ? 1 : 0;
+    pd.dense = desc->pattern_mode == ECUDA_PATTERN_DENSE_NODE;
+    pd.sf = 1.0;
+    std::memcpy(pd.xrank, hp.xrank, sizeof(pd.xrank));
+    std::memcpy(pd.urank, hp.urank, sizeof(pd.urank));
+    std::memcpy(pd.xcnt, hp.xcnt, sizeof(pd.xcnt));
+    std::memcpy(pd.ucnt, hp.ucnt, sizeof(pd.ucnt));
+    size_t smem = 0;
+    for (int p = 0; p < hp.nphases; ++p) {
+        PhaseDev& ph = pd.ph[p];
+        ph.N = hp.N[p];
+        ph.npath = hp.npath[p];
+        ph.nstat = hp.nstat[p];
+        ph.nb = (hp.N[p] + ECUDA_DOT_BLOCK - 1) / ECUDA_DOT_BLOCK;
+        ph.zoff = hp.zoff[p];
+        ph.goff = hp.goff[p];
+        ph.nvars = hp.nvars_p[p];
+        ph.inst_off = hp.inst_off[p];
+        int rc = upload_collocation(h, p);
+        if (rc) return rc;
+        size_t s = cta_doubles(pd, ph, kThreads) * sizeof(double);
+        smem = s > smem ? s : smem;
+    }
+    if (smem > 227 * 1024)
+        return fail(h, ECUDA_ERR_ARG, "phase too large for one CTA's shared memory (" + std::to_string(smem) + " B)");
+    h->smem_bytes = smem;
+    int rc;
+    if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
+    CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));
+    pd.colptr = static_cast<const int*>(h->colptr.p);
+    h->h_sz.assign(pd.nvars, 1.0);
+    h->h_sg.assign(pd.ncons, 1.0);
+    if ((rc = upload_scaling(h))) return rc;
+    if ((rc = ensure(h, h->fpart, sizeof(double) * desc->batch * hp.nphases))) return rc;
+    if ((rc = ensure(h, h->inst, sizeof(double) * desc->batch * pd.inst_stride))) return rc;
+    CU(cudaMemset(h->inst.p, 0, sizeof(double) * desc->batch * pd.inst_stride));
+    h->have_problem = true;
+    // a problem with no obstacle data needs no upload
+    bool any = desc->ntracks > 0;
+    for (int p = 0; p < hp.nphases; ++p) any = any || hp.nstat[p] > 0;
+    h->have_inst = !any;
+    return ECUDA_OK;
+}
+
+int ecuda_get_dims(ecuda_handle h, ecuda_dims* out) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!out) return fail(h, ECUDA_ERR_ARG, "null output");
+    *out = h->hp.dims;
+    return ECUDA_OK;
+}
+
+int ecuda_get_structure(ecuda_handle h, int32_t* iRow, int32_t* jCol, int32_t* group_of_col) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    const int base = h->hp.desc.index_base;
+    for (int e = 0; e < h->hp.dims.nnz; ++e) {
+        if (iRow) iRow[e] = h->hp.irow[e] + base;
+        if (jCol) jCol[e] = h->hp.jcol[e] + base;
+    }
+    if (group_of_col) std::memcpy(group_of_col, h->hp.group_of_col.data(), sizeof(int32_t) * h->hp.dims.nvars);
+    return ECUDA_OK;
+}
+
+int ecuda_get_collocation(ecuda_handle h, int phase, double* tau, double* w, double* D) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (phase < 0 || phase >= h->hp.nphases) return fail(h, ECUDA_ERR_ARG, "phase out of range");
+    const Collocation& c = h->hp.col[phase];
+    if (tau) std::memcpy(tau, c.tau.data(), sizeof(double) * c.N);
+    if (w) std::memcpy(w, c.w.data(), sizeof(double) * c.N);
+    if (D) std::memcpy(D, c.D.data(), sizeof(double) * c.N * c.N);
+    return ECUDA_OK;
+}
+
+int ecuda_set_collocation(ecuda_handle h, int phase, const double* tau, const double* w, const double* D) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (phase < 0 || phase >= h->hp.nphases || !tau || !w || !D) return fail(h, ECUDA_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    Collocation& c = h->hp.col[phase];
+    std::memcpy(c.tau.data(), tau, sizeof(double) * c.N);
+    std::memcpy(c.w.data(), w, sizeof(double) * c.N);
+    std::memcpy(c.D.data(), D, sizeof(double) * c.N * c.N);
+    return upload_collocation(h, phase);
+}
+
+int ecuda_set_scaling(ecuda_handle h, const double* sz, const double* sg, double sf) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < h->pd.nvars; ++c) {
+        h->h_sz[c] = sz ? sz[c] : 1.0;
+        if (!(h->h_sz[c] > 0.0)) return fail(h, ECUDA_ERR_ARG, "variable scale factors must be positive");
+    }
+    for (int r = 0; r < h->pd.ncons; ++r) h->h_sg[r] = sg ? sg[r] : 1.0;
+    h->pd.sf = sf;
+    return upload_scaling(h);
+}
+
+int ecuda_upload_instances(ecuda_handle h, const double* inst, int memkind) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!inst) return fail(h, ECUDA_ERR_ARG, "null instance data");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * h->hp.desc.batch * h->pd.inst_stride;
+    CU(cudaMemcpyAsync(h->inst.p, inst, bytes,
+                       memkind == ECUDA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_inst = true;
+    return ECUDA_OK;
+}
+
+int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int memkind) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!gl || !gu) return fail(h, ECUDA_ERR_ARG, "null bounds");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * h->hp.desc.batch * h->pd.ncons;
+    int rc;
+    if ((rc = ensure(h, h->gl, bytes))) return rc;
+    if ((rc = ensure(h, h->gu, bytes))) return rc;
+    auto kind = memkind == ECUDA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(h->gl.p, gl, bytes, kind, h->stream));
+    CU(cudaMemcpyAsync(h->gu.p, gu, bytes, kind, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_bounds = true;
+    return ECUDA_OK;
+}
+
+static int eval_common(ecuda_handle h, const double* x, double* f, double* g, double* jac, double* grad,
+                       int jac_mode, int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
+    if (!x) return fail(h, ECUDA_ERR_ARG, "null decision vector");
+    if (jac_mode != ECUDA_JAC_EXACT && jac_mode != ECUDA_JAC_FD_INDEXSET) return fail(h, ECUDA_ERR_ARG, "bad jac_mode");
+    if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const size_t B = h->hp.desc.batch, nv = h->pd.nvars, ng = h->pd.ncons, nz = h->pd.nnz;
+    EvalIO io{};
+    io.inst = static_cast<const double*>(h->inst.p);
+    io.fpart = static_cast<double*>(h->fpart.p);
+    io.jac_mode = jac_mode;
+    io.batch = static_cast<int>(B);
+    if (memkind == ECUDA_MEM_DEVICE) {
+        io.x = x;
+        io.f = f;
+        io.g = g;
+        io.jac = jac;
+        io.grad = grad;
+        return launch_eval(h, io, st);
+    }
+    int rc;
+    if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
+    if (f && (rc = ensure(h, h->sf_, sizeof(double) * B))) return rc;
+    if (g && (rc = ensure(h, h->sgv, sizeof(double) * B * ng))) return rc;
+    if (jac && (rc = ensure(h, h->sjac, sizeof(double) * B * nz))) return rc;
+    if (grad && (rc = ensure(h, h->sgrad, sizeof(double) * B * nv))) return rc;
+    CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * nv, cudaMemcpyHostToDevice, st));
+    io.x = static_cast<const double*>(h->sx.p);
+    io.f = f ? static_cast<double*>(h->sf_.p) : nullptr;
+    io.g = g ? static_cast<double*>(h->sgv.p) : nullptr;
+    io.jac = jac ? static_cast<double*>(h->sjac.p) : nullptr;
+    io.grad = grad ? static_cast<double*>(h->sgrad.p) : nullptr;
+    if ((rc = launch_eval(h, io, st))) return rc;
+    if (f) CU(cudaMemcpyAsync(f, io.f, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (g) CU(cudaMemcpyAsync(g, io.g, sizeof(double) * B * ng, cudaMemcpyDeviceToHost, st));
+    if (jac) CU(cudaMemcpyAsync(jac, io.jac, sizeof(double) * B * nz, cudaMemcpyDeviceToHost, st));
+    if (grad) CU(cudaMemcpyAsync(grad, io.grad, sizeof(double) * B * nv, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ECUDA_OK;
+}
+
+int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode, int memkind,
+               void* stream) {
+    return eval_common(h, x, f, g, jac, nullptr, jac_mode, memkind, stream);
+}
+
+int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream) {
+    if (h && !grad) return fail(h, ECUDA_ERR_ARG, "null gradient output");
+    return eval_common(h, x, nullptr, nullptr, nullptr, grad, ECUDA_JAC_EXACT, memkind, stream);
+}
+
+int ecuda_summary(ecuda_handle h, const double* x, double* out, int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_bounds) return fail(h, ECUDA_ERR_STATE, "upload_bounds has not been called");
+    if (!out) return fail(h, ECUDA_ERR_ARG, "null output");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const size_t B = h->hp.desc.batch, ng = h->pd.ncons;
+    int rc;
+    if ((rc = ensure(h, h->sf_, sizeof(double) * B))) return rc;
+    if ((rc = ensure(h, h->sgv, sizeof(double) * B * ng))) return rc;
+    const double* xd = x;
+    if (memkind == ECUDA_MEM_HOST) {
+        if ((rc = ensure(h, h->sx, sizeof(double) * B * h->pd.nvars))) return rc;
+        CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * h->pd.nvars, cudaMemcpyHostToDevice, st));
+        xd = static_cast<const double*>(h->sx.p);
+    }
+    rc = eval_common(h, xd, static_cast<double*>(h->sf_.p), static_cast<double*>(h->sgv.p), nullptr, nullptr,
+                     ECUDA_JAC_EXACT, ECUDA_MEM_DEVICE, st);
+    if (rc) return rc;
+    double* od = out;
+    if (memkind == ECUDA_MEM_HOST) {
+        if ((rc = ensure(h, h->ssum, sizeof(double) * 2 * B))) return rc;
+        od = static_cast<double*>(h->ssum.p);
+    }
+    const int warps_per_block = 4;
+    k_summary<<<(unsigned)((B + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, st>>>(
+        static_cast<const double*>(h->sf_.p), static_cast<const double*>(h->sgv.p),
+        static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), od, (int)B, (int)ng);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (memkind == ECUDA_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, od, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_sync(ecuda_handle h) {
+    if (!h) return ECUDA_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return ECUDA_OK;
+}
+
+int64_t ecuda_launch_count(ecuda_handle h) { return h ? h->launches : 0; }
+
+// ---- IPOPT TNLP-shaped shims (single instance) -----------------------------------------------------------
+static int ipopt_guard(ecuda_handle h, int n) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (h->hp.desc.batch != 1) return fail(h, ECUDA_ERR_STATE, "IPOPT shims need batch == 1");
+    if (n != h->pd.nvars) return fail(h, ECUDA_ERR_ARG, "n does not match nvars");
+    return ECUDA_OK;
+}
+int ecuda_set_ipopt_jac_mode(ecuda_handle h, int jac_mode) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (jac_mode != ECUDA_JAC_EXACT && jac_mode != ECUDA_JAC_FD_INDEXSET) return fail(h, ECUDA_ERR_ARG, "bad jac_mode");
+    h->ipopt_jac_mode = jac_mode;
+    return ECUDA_OK;
+}
+int ecuda_ipopt_eval_f(ecuda_handle h, int n, const double* x, int new_x, double* obj) {
+    (void)new_x;
+    int rc = ipopt_guard(h, n);
+    if (rc) return rc;
+    return eval_common(h, x, obj, nullptr, nullptr, nullptr, ECUDA_JAC_EXACT, ECUDA_MEM_HOST, nullptr);
+}
+int ecuda_ipopt_eval_grad_f(ecuda_handle h, int n, const double* x, int new_x, double* grad) {
+    (void)new_x;
+    int rc = ipopt_guard(h, n);
+    if (rc) return rc;
+    return eval_common(h, x, nullptr, nullptr, nullptr, grad, ECUDA_JAC_EXACT, ECUDA_MEM_HOST, nullptr);
+}
+int ecuda_ipopt_eval_g(ecuda_handle h, int n, const double* x, int new_x, int m, double* g) {
+    (void)new_x;
+    int rc = ipopt_guard(h, n);
+    if (rc) return rc;
+    if (m != h->pd.ncons) return fail(h, ECUDA_ERR_ARG, "m does not match ncons");
+    return eval_common(h, x, nullptr, g, nullptr, nullptr, ECUDA_JAC_EXACT, ECUDA_MEM_HOST, nullptr);
+}
+int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, int m, int nele_jac, int32_t* iRow,
+                           int32_t* jCol, double* values) {
+    (void)new_x;
+    int rc = ipopt_guard(h, n);
+    if (rc) return rc;
+    if (m != h->pd.ncons || nele_jac != h->pd.nnz) return fail(h, ECUDA_ERR_ARG, "m / nele_jac mismatch");
+    if (!values) return ecuda_get_structure(h, iRow, jCol, nullptr);
+    return eval_common(h, x, nullptr, nullptr, values, nullptr, h->ipopt_jac_mode, ECUDA_MEM_HOST, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// ecuda_internal.hpp -- data structures shared by the host side of libecuda.so and the kernels.
+// Product code. Never includes anything from oracle/.
+#ifndef ECUDA_INTERNAL_HPP_
+#define ECUDA_INTERNAL_HPP_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/ecuda.h"
+
+#if defined(__CUDACC__)
+#define ECUDA_HD __host__ __device__ __forceinline__
+#else
+#define ECUDA_HD inline
+#endif
+
+namespace ecuda {
+
+// ---- what the kernels see (passed by value as a __grid_constant__ kernel parameter) -------------
+struct PhaseDev {
+    int N;          // collocation nodes
+    int npath;      // path rows per node = nstat + ntracks
+    int nstat;      // static obstacle records of this phase
+    int nb;         // ceil(N / ECUDA_DOT_BLOCK)
+    int zoff;       // first decision variable of the phase
+    int goff;       // first constraint row of the phase
+    int nvars;      // (ns+nc)*N + 2
+    int inst_off;   // offset (doubles) of this phase's static records inside the instance block
+    const double* D;    // [N][N] row-major
+    const double* Dt;   // [N][N] transposed (Dt[l*N+k] = D[k][l]) : coalesced over rows k
+    const double* tau;  // [N]
+    const double* w;    // [N]
+};
+
+struct ProbDev {
+    int model, ns, nc, ne, nphases;
+    int nvars, ncons, nnz, nlink, linkoff;
+    int ntracks, nway, track_off, track_size, rec_size, inst_stride;
+    int maximize, dense;
+    double sf;
+    const int* colptr;    // [nvars+1]
+    const double* isz;    // [nvars]  1/sz
+    const double* sg;     // [ncons]
+    // position of defect row (k,i) inside the node-local part of column X(k,j) / U(k,j); -1 = absent
+    signed char xrank[ECUDA_MAX_STATES][ECUDA_MAX_STATES];
+    signed char urank[ECUDA_MAX_CONTROLS][ECUDA_MAX_STATES];
+    int xcnt[ECUDA_MAX_STATES];
+    int ucnt[ECUDA_MAX_CONTROLS];
+    PhaseDev ph[ECUDA_MAX_PHASES];
+};
+
+// per-call pointers (device memory)
+struct EvalIO {
+    const double* x;     // [B][nvars] scaled decision vectors
+    const double* inst;  // [B][inst_stride]
+    double* f;           // [B] or null
+    double* fpart;       // [B][nphases] scratch for multi-phase objective
+    double* g;           // [B][ncons] or null
+    double* jac;         // [B][nnz] or null
+    double* grad;        // [B][nvars] or null
+    int jac_mode;
+    int batch;
+};
+
+// ---- host-side problem description ------------------------------------------------------------------
+struct ModelInfo {
+    int ns, nc_default, nc_used, rec_size;
+    unsigned fx[ECUDA_MAX_STATES];  // states read by f_i   (MODEL_DEPS)
+    unsigned fu[ECUDA_MAX_STATES];  // controls read by f_i
+    unsigned path_x;                // states read by every path row
+};
+bool model_info(int model, ModelInfo* out);
+
+struct Collocation {
+    int N = 0;
+    std::vector<double> tau, w, D;
+};
+bool build_collocation(int kind, int N, Collocation* out, std::string* err);
+
+struct HostProblem {
+    ecuda_problem_desc desc{};
+    ecuda_dims dims{};
+    ModelInfo mi{};
+    int ns = 0, nc = 0, ne = 0, nphases = 0, linkoff = 0;
+    std::vector<int> N, npath, nstat, zoff, goff, nvars_p, inst_off;
+    int track_off = 0;
+    std::vector<int32_t> irow, jcol, colptr, group_of_col;
+    std::vector<Collocation> col;
+    signed char xrank[ECUDA_MAX_STATES][ECUDA_MAX_STATES];
+    signed char urank[ECUDA_MAX_CONTROLS][ECUDA_MAX_STATES];
+    int xcnt[ECUDA_MAX_STATES];
+    int ucnt[ECUDA_MAX_CONTROLS];
+};
+// validates desc, fills dims/layout (no pattern). Returns false + err on bad input.
+bool build_layout(const ecuda_problem_desc& d, HostProblem* hp, std::string* err);
+// pattern (CSC, rows ascending per column) + CPR grouping
+void build_structure(HostProblem* hp);
+
+}  // namespace ecuda
+#endif

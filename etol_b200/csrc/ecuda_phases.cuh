@@ -1,0 +1,608 @@
+// ecuda_phases.cuh -- the per-instance evaluation of the collocation NLP, written as barrier-free
+// "phases" over the threads of one CTA. One CTA evaluates one (instance, phase) pair:
+//
+//   stage     z~ -> unscaled z in shared memory; per-column FD data (z+-delta, 1/(2 delta));
+//             the instance's obstacle/track records (bulk-copied by the kernel)
+//   phase B   per node: state derivatives f, h*f, running cost, path rows (K1 + K3);
+//             per (row k, state j): the blocked dot product  sum_l D[k][l] X[l][j]  (K2);
+//             event / duration / linkage rows
+//   phase C   objective quadrature (K0); defect rows; Jacobian values written straight into the
+//             (col,row)-sorted triplet array (K4), either exact or by index-set central differences
+//
+// Reference counterparts: PSOPT's defect assembly and quadrature entered through ePSOPT::solve
+// (src/ePSOPT/ePSOPT.cpp:84) with the callbacks of src/ePSOPT/ePSOPT.cpp:186-306, and its
+// derivatives="automatic"/"numerical" Jacobian drivers (mode chosen at ePSOPT.cpp:64).
+//
+// Finite differences are evaluated *row-restricted*: perturbing column c only changes the rows in
+// c's sparsity pattern, and each of those rows is recomputed with exactly the operation sequence a
+// full re-evaluation of g(z +- delta e_c) would use, so the values equal the column-grouped
+// (Curtis-Powell-Reid) scheme bit for bit while doing O(nnz) instead of O(groups * ncons) work.
+// The blocked summation of D*X (ECUDA_DOT_BLOCK) is what makes the re-evaluation of a defect row
+// after a one-element change cost one block instead of the whole dot product.
+//
+// All functions are __host__ __device__: tests/emu steps the same source on the CPU so that index
+// logic can be checked where there is no GPU. The product only ever runs the __global__ kernels.
+#ifndef ECUDA_PHASES_CUH_
+#define ECUDA_PHASES_CUH_
+
+#include <math.h>
+
+#include "ecuda_models.cuh"
+
+namespace ecuda {
+
+#if defined(__CUDA_ARCH__)
+#define ECUDA_LDG(p) __ldg(p)
+#define ECUDA_STREAM_STORE(p, v) __stcs((p), (v))
+#else
+#define ECUDA_LDG(p) (*(p))
+#define ECUDA_STREAM_STORE(p, v) (*(p) = (v))
+#endif
+
+#define ECUDA_SQRT_EPS 1.4901161193847656e-08 /* 2^-26 */
+
+struct CtaMem {
+    double* z;     // [nvars_p] unscaled variables of this phase
+    double* xp;    // [nvars_p] (z~ + delta) * isz
+    double* xm;    // [nvars_p] (z~ - delta) * isz
+    double* rinv;  // [nvars_p] 1 / (2 delta)
+    double* hf;    // [N*ns]    h * f_i(node k)
+    double* dotv;  // [N*ns]    (D X)[k][i]
+    double* Lk;    // [N]       running cost per node
+    double* inst;  // [inst_stride] obstacle + track records of the instance
+    double* P;     // [nb][nthr] thread-private block sums
+};
+
+// shared-memory footprint in doubles for one CTA working on phase `ph`
+ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr) {
+    size_t n = 0;
+    n += 4 * static_cast<size_t>(ph.nvars + (ph.nvars & 1));
+    n += 2 * static_cast<size_t>(ph.N) * pb.ns;
+    n += static_cast<size_t>(ph.N + (ph.N & 1));
+    n += static_cast<size_t>(pb.inst_stride);
+    n += static_cast<size_t>(ph.nb) * nthr;
+    return n;
+}
+
+ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& ph, int nthr) {
+    size_t nv = static_cast<size_t>(ph.nvars + (ph.nvars & 1));
+    m.inst = base;  // first: 16-byte aligned destination of the bulk copy
+    base += pb.inst_stride;
+    m.z = base;     base += nv;
+    m.xp = base;    base += nv;
+    m.xm = base;    base += nv;
+    m.rinv = base;  base += nv;
+    m.hf = base;    base += static_cast<size_t>(ph.N) * pb.ns;
+    m.dotv = base;  base += static_cast<size_t>(ph.N) * pb.ns;
+    m.Lk = base;    base += static_cast<size_t>(ph.N + (ph.N & 1));
+    m.P = base;
+}
+
+struct PhaseTimes {
+    double t0, tf, h, m;
+};
+ECUDA_HD PhaseTimes phase_times(const ProbDev& pb, const PhaseDev& ph, const double* z) {
+    PhaseTimes pt;
+    pt.t0 = z[(pb.ns + pb.nc) * ph.N];
+    pt.tf = z[(pb.ns + pb.nc) * ph.N + 1];
+    pt.h = 0.5 * (pt.tf - pt.t0);
+    pt.m = 0.5 * (pt.tf + pt.t0);
+    return pt;
+}
+
+// ---- stage ------------------------------------------------------------------------------------------
+ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, CtaMem& m, int b, int tid,
+                         int nthr, bool fd) {
+    const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
+    const double* is = pb.isz + ph.zoff;
+    for (int c = tid; c < ph.nvars; c += nthr) {
+        double zt = ECUDA_LDG(xs + c);
+        double s = ECUDA_LDG(is + c);
+        m.z[c] = zt * s;
+        if (fd) {
+            double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt));
+            m.xp[c] = (zt + delta) * s;
+            m.xm[c] = (zt - delta) * s;
+            m.rinv[c] = 1.0 / (2.0 * delta);
+        }
+    }
+}
+
+// ---- small helpers ----------------------------------------------------------------------------------
+template <int M>
+ECUDA_HD double path_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int q, double x, double y,
+                         double t) {
+    if (q < ph.nstat) return Model<M>::static_row(m.inst + ph.inst_off + q * Model<M>::REC, x, y);
+    return track_row(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x, y, t);
+}
+
+// blocked dot of row k of D with state j of X, optionally with X[lsub][j] replaced by xsub
+ECUDA_HD double dot_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int k, int j, int lsub,
+                        double xsub) {
+    const double* X = m.z + pb.nc * ph.N + j;
+    const double* Dt = ph.Dt + k;
+    const int N = ph.N, ns = pb.ns;
+    double total = 0.0;
+    for (int l0 = 0; l0 < N; l0 += ECUDA_DOT_BLOCK) {
+        int l1 = l0 + ECUDA_DOT_BLOCK < N ? l0 + ECUDA_DOT_BLOCK : N;
+        double p = 0.0;
+        for (int l = l0; l < l1; ++l) {
+            double xv = (l == lsub) ? xsub : X[l * ns];
+            p = fma(ECUDA_LDG(Dt + static_cast<size_t>(l) * N), xv, p);
+        }
+        total = (l0 == 0) ? p : total + p;
+    }
+    return total;
+}
+
+// unscaled value of a variable of another phase of the same instance (linkage rows)
+ECUDA_HD double other_phase_value(const ProbDev& pb, const EvalIO& io, int b, int gcol) {
+    return ECUDA_LDG(io.x + static_cast<size_t>(b) * pb.nvars + gcol) * ECUDA_LDG(pb.isz + gcol);
+}
+
+// ---- phase B: node evaluations, dots, event/duration/linkage rows --------------------------------------
+template <int M>
+ECUDA_HD void phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
+                      int nthr) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
+    const double* sg = pb.sg;
+    for (int k = tid; k < N; k += nthr) {
+        const double* x = m.z + nc * N + k * ns;
+        const double* u = m.z + k * nc;
+        double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+        double f[NS];
+        Model<M>::f(x, u, t, f);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) m.hf[k * ns + i] = pt.h * f[i];
+        double L = Model<M>::cost(x, u, t);
+        m.Lk[k] = pb.maximize ? -1.0 * L : L;
+        if (g) {
+            const int r0 = ph.goff + ns * N + pb.ne + k * ph.npath;
+            for (int q = 0; q < ph.npath; ++q)
+                ECUDA_STREAM_STORE(g + r0 + q, ECUDA_LDG(sg + r0 + q) * path_row<M>(pb, ph, m, q, x[0], x[1], t));
+        }
+        (void)NCU;
+    }
+    for (int it = tid; it < ns * N; it += nthr) {
+        int j = it / N, k = it - j * N;
+        m.dotv[k * ns + j] = dot_row(pb, ph, m, k, j, -1, 0.0);
+    }
+    if (g) {
+        for (int e = tid; e < pb.ne; e += nthr) {
+            int r = ph.goff + ns * N + e;
+            int node = (e < ns) ? 0 : N - 1;
+            int i = (e < ns) ? e : e - ns;
+            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * m.z[nc * N + node * ns + i]);
+        }
+        if (tid == 0) {
+            int r = ph.goff + ns * N + pb.ne + ph.npath * N;
+            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * (pt.tf - pt.t0));
+        }
+        if (p + 1 < pb.nphases) {
+            const PhaseDev& nx = pb.ph[p + 1];
+            for (int i = tid; i <= ns; i += nthr) {
+                int r = pb.linkoff + p * (ns + 1) + i;
+                double mine = (i < ns) ? m.z[nc * N + (N - 1) * ns + i] : pt.tf;
+                int ocol = (i < ns) ? nx.zoff + nc * nx.N + i : nx.zoff + (ns + nc) * nx.N;
+                double other = other_phase_value(pb, io, b, ocol);
+                ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * (mine - other));
+            }
+        }
+    }
+}
+
+// ---- phase C ------------------------------------------------------------------------------------------
+// objective of this phase: h * sum_k w_k L_k, serial ascending fma chain
+ECUDA_HD void objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                              int b) {
+    if (!io.f) return;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    double acc = 0.0;
+    for (int k = 0; k < ph.N; ++k) acc = fma(ECUDA_LDG(ph.w + k), m.Lk[k], acc);
+    double fp = pt.h * acc;
+    if (pb.nphases == 1)
+        io.f[b] = pb.sf * fp;
+    else
+        io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
+}
+
+// position of defect row (k, state j) inside column X(l, j), k != l
+ECUDA_HD int dot_entry_pos(const ProbDev& pb, int j, int k, int l) { return k < l ? k : k - 1 + pb.xcnt[j]; }
+
+// defect rows of g and the D-coupled Jacobian entries (row (k,j), columns X(l,j), l != k)
+ECUDA_HD void defect_item(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, CtaMem& m, int b, int j, int k,
+                          int tid, int nthr) {
+    const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    const int r = ph.goff + k * ns + j;
+    const double sgr = ECUDA_LDG(pb.sg + r);
+    const double hfv = m.hf[k * ns + j];
+    if (io.g) ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, sgr * (m.dotv[k * ns + j] - hfv));
+    if (!io.jac) return;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    const int col0 = ph.zoff + nc * N + j;  // global column of X(0, j); X(l, j) = col0 + l*ns
+    const double* Dt = ph.Dt + k;
+    if (io.jac_mode == ECUDA_JAC_EXACT) {
+        for (int l = 0; l < N; ++l) {
+            if (l == k) continue;
+            int col = col0 + l * ns;
+            double v = (sgr * ECUDA_LDG(Dt + static_cast<size_t>(l) * N)) * ECUDA_LDG(pb.isz + col);
+            ECUDA_STREAM_STORE(jac + ECUDA_LDG(pb.colptr + col) + dot_entry_pos(pb, j, k, l), v);
+        }
+        return;
+    }
+    // index-set central differences, row-restricted
+    const double* X = m.z + nc * N + j;
+    double* P = m.P + tid;  // P[b*nthr]
+    for (int l0 = 0, bi = 0; l0 < N; l0 += ECUDA_DOT_BLOCK, ++bi) {
+        int l1 = l0 + ECUDA_DOT_BLOCK < N ? l0 + ECUDA_DOT_BLOCK : N;
+        double s = 0.0;
+        for (int l = l0; l < l1; ++l) s = fma(ECUDA_LDG(Dt + static_cast<size_t>(l) * N), X[l * ns], s);
+        P[bi * nthr] = s;
+    }
+    double pre = 0.0;  // P[0] + ... + P[bi-1], serial
+    for (int l0 = 0, bi = 0; l0 < N; l0 += ECUDA_DOT_BLOCK, ++bi) {
+        double d[ECUDA_DOT_BLOCK], xv[ECUDA_DOT_BLOCK];
+#pragma unroll
+        for (int i = 0; i < ECUDA_DOT_BLOCK; ++i) {
+            bool in = l0 + i < N;
+            d[i] = in ? ECUDA_LDG(Dt + static_cast<size_t>(l0 + i) * N) : 0.0;
+            xv[i] = in ? X[(l0 + i) * ns] : 0.0;
+        }
+        const int nin = (N - l0) < ECUDA_DOT_BLOCK ? (N - l0) : ECUDA_DOT_BLOCK;
+#pragma unroll
+        for (int a = 0; a < ECUDA_DOT_BLOCK; ++a) {
+            const int ls = l0 + a;
+            if (a < nin && ls != k) {
+                const int lcol = nc * N + ls * ns + j;  // phase-local column
+                double sp = 0.0, sm = 0.0;
+                const double xpv = m.xp[lcol], xmv = m.xm[lcol];
+#pragma unroll
+                for (int i = 0; i < ECUDA_DOT_BLOCK; ++i) {
+                    if (i < nin) {
+                        sp = fma(d[i], (i == a) ? xpv : xv[i], sp);
+                        sm = fma(d[i], (i == a) ? xmv : xv[i], sm);
+                    }
+                }
+                double tp = (bi == 0) ? sp : pre + sp;
+                double tm = (bi == 0) ? sm : pre + sm;
+                for (int b2 = bi + 1; b2 < ph.nb; ++b2) {
+                    double pv = P[b2 * nthr];
+                    tp = tp + pv;
+                    tm = tm + pv;
+                }
+                double gp = sgr * (tp - hfv);
+                double gm = sgr * (tm - hfv);
+                int col = ph.zoff + lcol;
+                ECUDA_STREAM_STORE(jac + ECUDA_LDG(pb.colptr + col) + dot_entry_pos(pb, j, k, ls),
+                                   (gp - gm) * m.rinv[lcol]);
+            }
+        }
+        double own = P[bi * nthr];
+        pre = (bi == 0) ? own : pre + own;
+    }
+}
+
+// node-local Jacobian entries of column c at node k: c in [0,nc) control, [nc,nc+ns) state,
+// nc+ns -> t0, nc+ns+1 -> tf
+template <int M>
+ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m, int b,
+                        int k, int c) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
+    const bool fd = io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    const double tau = ECUDA_LDG(ph.tau + k);
+    const double t = pt.h * tau + pt.m;
+    const double* sg = pb.sg;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    double x[NS], u[NCU];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = m.z[nc * N + k * ns + i];
+#pragma unroll
+    for (int i = 0; i < NCU; ++i) u[i] = m.z[k * nc + i];
+    const int rdef0 = ph.goff + k * ns;
+    const int rpath0 = ph.goff + ns * N + pb.ne + k * np;
+
+    if (c < nc) {  // ---- control column U(k, j)
+        const int j = c, lcol = k * nc + j, col = ph.zoff + lcol;
+        const int base = ECUDA_LDG(pb.colptr + col);
+        if (fd) {
+            double up[NCU], um[NCU], fp[NS], fm[NS];
+#pragma unroll
+            for (int i = 0; i < NCU; ++i) {
+                up[i] = (i == j) ? m.xp[lcol] : u[i];
+                um[i] = (i == j) ? m.xm[lcol] : u[i];
+            }
+            Model<M>::f(x, up, t, fp);
+            Model<M>::f(x, um, t, fm);
+            const double ri = m.rinv[lcol];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                int rk = pb.urank[j][i];
+                if (rk >= 0) {
+                    double s = ECUDA_LDG(sg + rdef0 + i), dv = m.dotv[k * ns + i];
+                    double gp = s * (dv - pt.h * fp[i]);
+                    double gm = s * (dv - pt.h * fm[i]);
+                    ECUDA_STREAM_STORE(jac + base + rk, (gp - gm) * ri);
+                }
+            }
+        } else {
+            double dfdx[NS][NS], dfdu[NS][NCU];
+            Model<M>::jac(x, u, dfdx, dfdu);
+            const double is = ECUDA_LDG(pb.isz + col);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                int rk = pb.urank[j][i];
+                if (rk >= 0) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < NCU; ++jj)
+                        if (jj == j) d = dfdu[i][jj];
+                    double v = -(pt.h * d);
+                    ECUDA_STREAM_STORE(jac + base + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+                }
+            }
+        }
+        return;
+    }
+    if (c < nc + ns) {  // ---- state column X(k, j)
+        const int j = c - nc, lcol = nc * N + k * ns + j, col = ph.zoff + lcol;
+        const int base = ECUDA_LDG(pb.colptr + col);
+        const bool reads_path = (j < 2);  // every obstacle row reads the two horizontal positions
+        int pos = N - 1 + pb.xcnt[j];
+        if (fd) {
+            const double xpv = m.xp[lcol], xmv = m.xm[lcol], ri = m.rinv[lcol];
+            double xq[NS], xr[NS], fp[NS], fm[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                xq[i] = (i == j) ? xpv : x[i];
+                xr[i] = (i == j) ? xmv : x[i];
+            }
+            Model<M>::f(xq, u, t, fp);
+            Model<M>::f(xr, u, t, fm);
+            const double dp = dot_row(pb, ph, m, k, j, k, xpv);
+            const double dm = dot_row(pb, ph, m, k, j, k, xmv);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                int rk = pb.xrank[j][i];
+                if (rk >= 0) {
+                    double s = ECUDA_LDG(sg + rdef0 + i);
+                    double dvp = (i == j) ? dp : m.dotv[k * ns + i];
+                    double dvm = (i == j) ? dm : m.dotv[k * ns + i];
+                    double gp = s * (dvp - pt.h * fp[i]);
+                    double gm = s * (dvm - pt.h * fm[i]);
+                    ECUDA_STREAM_STORE(jac + base + k + rk, (gp - gm) * ri);
+                }
+            }
+            if (k == 0 || k == N - 1) {
+                int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
+                double s = ECUDA_LDG(sg + r);
+                ECUDA_STREAM_STORE(jac + base + pos, (s * xpv - s * xmv) * ri);
+                ++pos;
+            }
+            if (reads_path) {
+                for (int q = 0; q < np; ++q) {
+                    double s = ECUDA_LDG(sg + rpath0 + q);
+                    double vp = path_row<M>(pb, ph, m, q, xq[0], xq[1], t);
+                    double vm = path_row<M>(pb, ph, m, q, xr[0], xr[1], t);
+                    ECUDA_STREAM_STORE(jac + base + pos + q, (s * vp - s * vm) * ri);
+                }
+                pos += np;
+            }
+            if (k == N - 1 && p + 1 < pb.nphases) {
+                const PhaseDev& nx = pb.ph[p + 1];
+                int r = pb.linkoff + p * (ns + 1) + j;
+                double s = ECUDA_LDG(sg + r);
+                double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + j);
+                ECUDA_STREAM_STORE(jac + base + pos, (s * (xpv - o) - s * (xmv - o)) * ri);
+            }
+            if (k == 0 && p > 0) {
+                const PhaseDev& pv = pb.ph[p - 1];
+                int r = pb.linkoff + (p - 1) * (ns + 1) + j;
+                double s = ECUDA_LDG(sg + r);
+                double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * ns + j);
+                ECUDA_STREAM_STORE(jac + base + pos, (s * (o - xpv) - s * (o - xmv)) * ri);
+            }
+        } else {
+            double dfdx[NS][NS], dfdu[NS][NCU];
+            Model<M>::jac(x, u, dfdx, dfdu);
+            const double is = ECUDA_LDG(pb.isz + col);
+            const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                int rk = pb.xrank[j][i];
+                if (rk >= 0) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < NS; ++jj)
+                        if (jj == j) d = dfdx[i][jj];
+                    double v = ((i == j) ? dkk : 0.0) - pt.h * d;
+                    ECUDA_STREAM_STORE(jac + base + k + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+                }
+            }
+            if (k == 0 || k == N - 1) {
+                int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
+                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+                ++pos;
+            }
+            if (reads_path) {
+                for (int q = 0; q < np; ++q) {
+                    double ddx, ddy, ddt = 0.0;
+                    if (q < ph.nstat)
+                        Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x[0], x[1], &ddx, &ddy);
+                    else
+                        track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0],
+                                           x[1], t, &ddx, &ddy, &ddt);
+                    double v = (j == 0) ? ddx : ddy;
+                    ECUDA_STREAM_STORE(jac + base + pos + q, (ECUDA_LDG(sg + rpath0 + q) * v) * is);
+                }
+                pos += np;
+            }
+            if (k == N - 1 && p + 1 < pb.nphases) {
+                int r = pb.linkoff + p * (ns + 1) + j;
+                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+            }
+            if (k == 0 && p > 0) {
+                int r = pb.linkoff + (p - 1) * (ns + 1) + j;
+                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
+            }
+        }
+        return;
+    }
+    // ---- time columns t0 / tf
+    const int which = c - nc - ns;  // 0: t0, 1: tf
+    const int lcol = (ns + nc) * N + which, col = ph.zoff + lcol;
+    const int base = ECUDA_LDG(pb.colptr + col);
+    const int ntr = np - ph.nstat;
+    if (fd) {
+        const double ri = m.rinv[lcol];
+        const double t0p = which == 0 ? m.xp[lcol] : pt.t0, tfp = which == 1 ? m.xp[lcol] : pt.tf;
+        const double t0m = which == 0 ? m.xm[lcol] : pt.t0, tfm = which == 1 ? m.xm[lcol] : pt.tf;
+        const double hp = 0.5 * (tfp - t0p), mp = 0.5 * (tfp + t0p);
+        const double hm = 0.5 * (tfm - t0m), mm = 0.5 * (tfm + t0m);
+        const double tp = hp * tau + mp, tm = hm * tau + mm;
+        double fp[NS], fm[NS];
+        Model<M>::f(x, u, tp, fp);
+        Model<M>::f(x, u, tm, fm);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double s = ECUDA_LDG(sg + rdef0 + i), dv = m.dotv[k * ns + i];
+            double gp = s * (dv - hp * fp[i]);
+            double gm = s * (dv - hm * fm[i]);
+            ECUDA_STREAM_STORE(jac + base + k * ns + i, (gp - gm) * ri);
+        }
+        for (int q = ph.nstat; q < np; ++q) {
+            double s = ECUDA_LDG(sg + rpath0 + q);
+            double vp = path_row<M>(pb, ph, m, q, x[0], x[1], tp);
+            double vm = path_row<M>(pb, ph, m, q, x[0], x[1], tm);
+            ECUDA_STREAM_STORE(jac + base + ns * N + k * ntr + (q - ph.nstat), (s * vp - s * vm) * ri);
+        }
+        if (k == 0) {
+            int r = ph.goff + ns * N + pb.ne + np * N;
+            double s = ECUDA_LDG(sg + r);
+            ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
+            if (which == 0 && p > 0) {
+                const PhaseDev& pv = pb.ph[p - 1];
+                int rl = pb.linkoff + (p - 1) * (ns + 1) + ns;
+                double sl = ECUDA_LDG(sg + rl);
+                double o = other_phase_value(pb, io, b, pv.zoff + (ns + nc) * pv.N + 1);
+                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
+            }
+            if (which == 1 && p + 1 < pb.nphases) {
+                const PhaseDev& nx = pb.ph[p + 1];
+                int rl = pb.linkoff + p * (ns + 1) + ns;
+                double sl = ECUDA_LDG(sg + rl);
+                double o = other_phase_value(pb, io, b, nx.zoff + (ns + nc) * nx.N);
+                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
+            }
+        }
+    } else {
+        const double is = ECUDA_LDG(pb.isz + col);
+        const double dtk = which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau);  // d t_k / d t0|tf
+        double f[NS];
+        Model<M>::f(x, u, t, f);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            // d zeta / d t0 = +f/2 ; d zeta / d tf = -f/2   (the models have no explicit time dependence)
+            double v = which == 0 ? 0.5 * f[i] : -0.5 * f[i];
+            ECUDA_STREAM_STORE(jac + base + k * ns + i, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+        }
+        for (int q = ph.nstat; q < np; ++q) {
+            double ddx, ddy, ddt;
+            track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0], x[1], t, &ddx,
+                               &ddy, &ddt);
+            ECUDA_STREAM_STORE(jac + base + ns * N + k * ntr + (q - ph.nstat),
+                               (ECUDA_LDG(sg + rpath0 + q) * (ddt * dtk)) * is);
+        }
+        if (k == 0) {
+            int r = ph.goff + ns * N + pb.ne + np * N;
+            ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr, (ECUDA_LDG(sg + r) * (which == 0 ? -1.0 : 1.0)) * is);
+            if (which == 0 && p > 0) {
+                int rl = pb.linkoff + (p - 1) * (ns + 1) + ns;
+                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * -1.0) * is);
+            }
+            if (which == 1 && p + 1 < pb.nphases) {
+                int rl = pb.linkoff + p * (ns + 1) + ns;
+                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * 1.0) * is);
+            }
+        }
+    }
+}
+
+template <int M>
+ECUDA_HD void phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
+                      int nthr) {
+    const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
+    if (io.g || io.jac)
+        for (int it = tid; it < ns * N; it += nthr) {
+            int j = it / N, k = it - j * N;
+            defect_item(pb, ph, io, m, b, j, k, tid, nthr);
+        }
+    if (io.jac) {
+        // handed out from the top of the thread range downwards: the threads that had no defect
+        // item above start on these first
+        const int nitems = (nc + ns + 2) * N;
+        for (int it = nthr - 1 - tid; it < nitems; it += nthr) {
+            int c = it / N, k = it - c * N;
+            node_item<M>(pb, ph, p, io, m, b, k, c);
+        }
+    }
+}
+
+// running cost per node only (the gradient kernel needs Lk but none of the rest of phase B)
+template <int M>
+ECUDA_HD void cost_nodes(const ProbDev& pb, const PhaseDev& ph, CtaMem& m, int tid, int nthr) {
+    const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    for (int k = tid; k < N; k += nthr) {
+        double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+        double L = Model<M>::cost(m.z + nc * N + k * ns, m.z + k * nc, t);
+        m.Lk[k] = pb.maximize ? -1.0 * L : L;
+    }
+}
+
+// gradient of the objective (exact), one thread per node
+template <int M>
+ECUDA_HD void gradient_phase(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const CtaMem& m, int b,
+                             int tid, int nthr) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    double* grad = io.grad + static_cast<size_t>(b) * pb.nvars + ph.zoff;
+    const double* is = pb.isz + ph.zoff;
+    for (int k = tid; k < N; k += nthr) {
+        const double* x = m.z + nc * N + k * ns;
+        const double* u = m.z + k * nc;
+        double dx[NS], du[NCU];
+        Model<M>::dcost(x, u, dx, du);
+        const double w = ECUDA_LDG(ph.w + k);
+        const double sgn = pb.maximize ? -1.0 : 1.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            int c = nc * N + k * ns + i;
+            grad[c] = (pb.sf * (pt.h * (w * (sgn * dx[i])))) * ECUDA_LDG(is + c);
+        }
+        for (int j = 0; j < nc; ++j) {
+            int c = k * nc + j;
+            double d = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < NCU; ++jj)
+                if (jj == j) d = du[jj];
+            grad[c] = (pb.sf * (pt.h * (w * (sgn * d)))) * ECUDA_LDG(is + c);
+        }
+    }
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) acc = fma(ECUDA_LDG(ph.w + k), m.Lk[k], acc);
+        int c0 = (ns + nc) * N;
+        grad[c0] = (pb.sf * (-0.5 * acc)) * ECUDA_LDG(is + c0);
+        grad[c0 + 1] = (pb.sf * (0.5 * acc)) * ECUDA_LDG(is + c0 + 1);
+    }
+}
+
+}  // namespace ecuda
+#endif

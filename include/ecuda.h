@@ -1,0 +1,176 @@
+/*
+ * ecuda.h -- extern "C" boundary of the eCUDA collocation-NLP evaluator (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the hot path that ETOL's ePSOPT plugin hands to IPOPT:
+ * objective, constraint vector and sparse constraint Jacobian of the pseudospectral NLP, evaluated
+ * for a batch of independent vehicle guidance problems (VGPs) per call.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the ETOL tree):
+ *   - ecuda_set_problem            <- ePSOPT::setup()                 src/ePSOPT/ePSOPT.cpp:40-81
+ *                                     (nstates/ncontrols/nevents/nodes/npath, collocation method)
+ *   - ecuda_upload_instances       <- the VGP data the example lambdas capture:
+ *                                     obstacles  src/Examples/PSOPT/etol_psopt_example1.cpp:140-151
+ *                                     tracks     src/Examples/PSOPT/etol_psopt_example1.cpp:199-223
+ *   - ecuda_eval (f)               <- ePSOPT::integrand_cost + endpoint_cost
+ *                                     src/ePSOPT/ePSOPT.cpp:186-216,302-306   (PSOPT quadrature)
+ *   - ecuda_eval (g)               <- ePSOPT::dae + ePSOPT::events + ePSOPT::linkages
+ *                                     src/ePSOPT/ePSOPT.cpp:218-297           (PSOPT defect assembly)
+ *   - ecuda_eval (jac)             <- PSOPT/ADOL-C sparse Jacobian selected at
+ *                                     src/ePSOPT/ePSOPT.cpp:64 ("automatic" = exact,
+ *                                     "numerical" = column-grouped finite differences)
+ *   - ecuda_get_structure          <- the (iRow,jCol) triplet pattern PSOPT hands IPOPT, plus the
+ *                                     column grouping ("index sets") of the perturbation scheme
+ *   - ecuda_si2d_edge_records      <- edge -> ellipse geometry,
+ *                                     src/Examples/PSOPT/etol_psopt_example1.cpp:164-179
+ *
+ * Conventions: opaque handle, int status (0 = ok, <0 = error, text via ecuda_last_error), no C++
+ * types, no exceptions, caller-owned buffers, one handle per (host thread, device). There is NO
+ * CPU fallback: every compute entry point fails with ECUDA_ERR_CUDA when no sm_100 device can be
+ * used. All floating point is IEEE binary64; all indices are 32-bit.
+ *
+ * NLP layout (normative). Per phase p with ns states, nc controls, N nodes:
+ *   z_p = [ U (node-major, z[k*nc+j]) | X (node-major, z[nc*N + k*ns + i]) | t0 | tf ]
+ *   g_p = [ defects (g[k*ns+i]) | events (2*ns) | path (g[ns*N+2*ns + k*npath + q]) | tf - t0 ]
+ * Phases are concatenated; linkage rows (state + time continuity between consecutive phases)
+ * follow the last phase block. Jacobian triplets are sorted by (column, row).
+ */
+#ifndef ECUDA_H_
+#define ECUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECUDA_ABI_VERSION 1
+#define ECUDA_MAX_PHASES 8
+#define ECUDA_MAX_STATES 8
+#define ECUDA_MAX_CONTROLS 8
+#define ECUDA_DOT_BLOCK 8 /* block length of the canonical blocked summation used for D*X */
+
+/* status codes */
+#define ECUDA_OK 0
+#define ECUDA_ERR_ARG (-1)     /* bad argument / unsupported configuration */
+#define ECUDA_ERR_STATE (-2)   /* call order violated (e.g. eval before set_problem) */
+#define ECUDA_ERR_CUDA (-3)    /* CUDA runtime failure or no usable device */
+#define ECUDA_ERR_ALLOC (-4)   /* host or device allocation failed */
+
+/* device models of the VGP callbacks (dynamics, running cost, path constraints) */
+enum ecuda_model {
+    ECUDA_MODEL_SI2D = 0, /* 2-D single integrator + ellipse-per-edge + moving circles (reference VGP) */
+    ECUDA_MODEL_PM3D = 1, /* 3-D point mass (6 states, 3 controls) + vertical cylinders */
+    ECUDA_MODEL_FW6 = 2   /* 6-state fixed-wing kinematics + vertical cylinders */
+};
+
+enum ecuda_collocation { ECUDA_LEGENDRE = 0, ECUDA_CHEBYSHEV = 1 };
+
+/* DENSE_NODE: every defect row depends on all states/controls of its node (PSOPT's assumption);
+ * MODEL_DEPS: only the variables the model's dynamics actually read. */
+enum ecuda_pattern { ECUDA_PATTERN_DENSE_NODE = 0, ECUDA_PATTERN_MODEL_DEPS = 1 };
+
+/* EXACT       ~ PSOPT derivatives="automatic" (the reference default, ePSOPT.cpp:64)
+ * FD_INDEXSET ~ PSOPT derivatives="numerical": central differences, step 2^-26*(1+|z|), all
+ *               columns of a Curtis-Powell-Reid group perturbed together. */
+enum ecuda_jac_mode { ECUDA_JAC_EXACT = 0, ECUDA_JAC_FD_INDEXSET = 1 };
+
+enum ecuda_mem { ECUDA_MEM_HOST = 0, ECUDA_MEM_DEVICE = 1 };
+
+typedef struct ecuda_ctx* ecuda_handle;
+
+typedef struct {
+    int32_t model;                      /* enum ecuda_model */
+    int32_t nphases;                    /* 1..ECUDA_MAX_PHASES (ePSOPT itself uses 1) */
+    int32_t nnodes[ECUDA_MAX_PHASES];   /* collocation nodes per phase (= nsteps+1) */
+    int32_t nstatic[ECUDA_MAX_PHASES];  /* static obstacle records per phase (edges / cylinders) */
+    int32_t ncontrols;                  /* 0 = model default; si2d accepts >= 2 (extra controls unused) */
+    int32_t ntracks;                    /* moving-obstacle tracks per instance (si2d only) */
+    int32_t nwaypoints;                 /* waypoints per track (>= 2 when ntracks > 0) */
+    int32_t collocation;                /* enum ecuda_collocation */
+    int32_t pattern_mode;               /* enum ecuda_pattern */
+    int32_t maximize;                   /* 1: running cost is negated (ePSOPT.cpp:212-213) */
+    int32_t batch;                      /* number of independent VGP instances B */
+    int32_t index_base;                 /* 0 (C) or 1 (Fortran) for ecuda_get_structure */
+} ecuda_problem_desc;
+
+typedef struct {
+    int32_t nvars;        /* decision variables per instance */
+    int32_t ncons;        /* constraint rows per instance */
+    int32_t nnz;          /* structural Jacobian non-zeros per instance */
+    int32_t ngroups;      /* CPR column groups */
+    int32_t nstates;
+    int32_t ncontrols;
+    int32_t nlinkages;    /* linkage rows */
+    int32_t inst_stride;  /* doubles per instance in the instance-data block */
+    int32_t rec_size;     /* doubles per static obstacle record */
+    int32_t track_size;   /* doubles per track record (1 + 3*nwaypoints) */
+} ecuda_dims;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int ecuda_abi_version(void);
+int ecuda_create(int device, ecuda_handle* out);
+int ecuda_destroy(ecuda_handle h);
+const char* ecuda_last_error(ecuda_handle h); /* h may be NULL: error of the last failed create */
+
+/* ---- problem structure (host work, done once per structure) ----------------------------------- */
+int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc);
+int ecuda_get_dims(ecuda_handle h, ecuda_dims* out);
+/* iRow/jCol: nnz entries sorted by (col,row); group_of_col: nvars entries. Any pointer may be NULL. */
+int ecuda_get_structure(ecuda_handle h, int32_t* iRow, int32_t* jCol, int32_t* group_of_col);
+/* nodes tau[N], quadrature weights w[N], differentiation matrix D[N*N] (row-major) of one phase */
+int ecuda_get_collocation(ecuda_handle h, int phase, double* tau, double* w, double* D);
+/* override the collocation data of one phase (e.g. to inject an externally computed D) */
+int ecuda_set_collocation(ecuda_handle h, int phase, const double* tau, const double* w,
+                          const double* D);
+/* PSOPT-style scaling: solver sees z~ = z*sz, g~ = g*sg, f~ = f*sf. NULL = all ones. Shared by
+ * the whole batch. Host pointers. */
+int ecuda_set_scaling(ecuda_handle h, const double* sz, const double* sg, double sf);
+
+/* ---- per-instance problem data --------------------------------------------------------------- */
+/* inst: [B][inst_stride] doubles. Per instance: for each phase p, nstatic[p] static records of
+ * rec_size doubles (si2d edge: xc,yc,cos,sin,asq,bsq; cylinder: cx,cy,r^2,0), then ntracks track
+ * records (radius, then nwaypoints x (t,x,y)), zero-padded to inst_stride. */
+int ecuda_upload_instances(ecuda_handle h, const double* inst, int memkind);
+/* optional constraint bounds [B][ncons] used only by ecuda_summary (violation measure) */
+int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int memkind);
+
+/* ---- evaluation (the hot path) --------------------------------------------------------------- */
+/* x: [B][nvars] scaled decision vectors. Outputs (each may be NULL = not requested):
+ * f [B], g [B][ncons], jac [B][nnz] in the triplet order of ecuda_get_structure.
+ * memkind says where x/f/g/jac live (all the same kind). HOST buffers are staged through device
+ * buffers owned by the handle (pinned host memory makes the copies asynchronous). The work is
+ * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream) and is
+ * asynchronous with respect to the host for DEVICE buffers; HOST calls return after the results
+ * have landed. */
+int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,
+               int memkind, void* stream);
+/* gradient of the (scaled) objective, [B][nvars]; exact. */
+int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream);
+/* per-instance summary [B][2] = { f, max bound violation of g } (needs ecuda_upload_bounds) */
+int ecuda_summary(ecuda_handle h, const double* x, double* out, int memkind, void* stream);
+int ecuda_sync(ecuda_handle h);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
+int64_t ecuda_launch_count(ecuda_handle h);
+
+/* IPOPT TNLP-shaped single-instance shims (B must be 1; host pointers). values==NULL in
+ * eval_jac_g returns the structure, as IPOPT's convention requires. */
+int ecuda_ipopt_eval_f(ecuda_handle h, int n, const double* x, int new_x, double* obj);
+int ecuda_ipopt_eval_grad_f(ecuda_handle h, int n, const double* x, int new_x, double* grad);
+int ecuda_ipopt_eval_g(ecuda_handle h, int n, const double* x, int new_x, int m, double* g);
+int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, int m, int nele_jac,
+                           int32_t* iRow, int32_t* jCol, double* values);
+int ecuda_set_ipopt_jac_mode(ecuda_handle h, int jac_mode);
+
+/* ---- host-side helpers (no GPU needed) ------------------------------------------------------- */
+/* polygon (ncorners x,y pairs, closed implicitly) -> ncorners edge records of 6 doubles each */
+int ecuda_si2d_edge_records(const double* corners_xy, int ncorners, double* rec6);
+/* dims/structure without a device: same results as set_problem + get_dims/get_structure */
+int ecuda_host_dims(const ecuda_problem_desc* desc, ecuda_dims* out);
+int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t* jCol,
+                         int32_t* group_of_col);
+int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double* D);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECUDA_H_ */

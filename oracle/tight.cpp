@@ -1,0 +1,212 @@
+// tight.cpp (oracle) -- the same arithmetic as evaluate.cpp without the type erasure: plain double
+// loops, obstacle geometry hoisted out of the node loop. TEST INFRASTRUCTURE (see oracle.hpp).
+//
+// Purpose: (1) a second, independently written CPU implementation that must agree BIT FOR BIT with
+// the reference-style one (tests/test_oracle_styles.py); (2) the "CPU-tight" baseline of
+// BASELINE.md section 2, reported next to the reference-style number for honesty.
+// Model math: src/Examples/PSOPT/etol_psopt_example1.cpp:101-258; driver semantics:
+// src/ePSOPT/ePSOPT.cpp:186-306; transcription: SURVEY.md Appendix A.
+#include <cmath>
+#include <stdexcept>
+
+#include "../include/ecuda_detmath.h"
+#include "oracle.hpp"
+
+namespace oracle {
+
+namespace {
+
+struct EdgeRec {
+    double xc, yc, ct, st, asq, bsq;
+};
+struct PhasePre {
+    std::vector<EdgeRec> edges;
+    std::vector<double> cyl;  // cx, cy, r2
+};
+
+std::vector<PhasePre> precompute(const Problem& P, const Instance& I) {
+    std::vector<PhasePre> out(P.L.nphases);
+    for (int p = 0; p < P.L.nphases; ++p) {
+        for (const Border& bd : I.phases[p].borders) {
+            size_t n = bd.size();
+            for (size_t i = 0; i < n; ++i) {
+                EdgeGeom g = edge_geometry(bd[i], bd[(i + 1) % n]);
+                out[p].edges.push_back({g.xc, g.yc, std::cos(g.tt), std::sin(g.tt), g.asq, g.bsq});
+            }
+        }
+        for (const Cylinder& c : I.phases[p].cylinders) {
+            out[p].cyl.push_back(c.cx);
+            out[p].cyl.push_back(c.cy);
+            out[p].cyl.push_back(c.r * c.r);
+        }
+    }
+    return out;
+}
+
+double interp(double t, const std::vector<double>& tv, const std::vector<double>& ref) {
+    size_t j = 0;
+    if (t > tv.back()) {
+        j = tv.size() - 2;
+    } else if (t >= tv.front()) {
+        for (size_t c = 0; c + 1 < tv.size(); ++c)
+            if (t >= tv[c] && t <= tv[c + 1]) j = c;
+    }
+    return (t - tv[j]) * (ref[j + 1] - ref[j]) / (tv[j + 1] - tv[j]) + ref[j];
+}
+
+void dynamics(int model, const double* x, const double* u, double* f) {
+    if (model == SI2D) {
+        f[0] = u[0];
+        f[1] = u[1];
+    } else if (model == PM3D) {
+        f[0] = x[3];
+        f[1] = x[4];
+        f[2] = x[5];
+        f[3] = u[0];
+        f[4] = u[1];
+        f[5] = u[2];
+    } else {
+        double sg, cg, sp, cp;
+        ecuda_sincos(x[4], &sg, &cg);
+        ecuda_sincos(x[5], &sp, &cp);
+        f[0] = (x[3] * cg) * cp;
+        f[1] = (x[3] * cg) * sp;
+        f[2] = x[3] * sg;
+        f[3] = u[0] - 9.80665 * sg;
+        f[4] = u[1];
+        f[5] = u[2];
+    }
+}
+
+void path_rows(const Problem& P, const PhasePre& pre, const Instance& I, const double* x, double t,
+               double* out) {
+    int q = 0;
+    if (P.spec.model == SI2D) {
+        for (const EdgeRec& e : pre.edges) {
+            double dx = x[0] - e.xc, dy = x[1] - e.yc;
+            double delx = e.ct * dx - e.st * dy;
+            double dely = e.st * dx + e.ct * dy;
+            out[q++] = e.asq * e.bsq - (e.bsq * (delx * delx) + e.asq * (dely * dely));
+        }
+        for (const Track& tr : I.tracks) {
+            double xc = interp(t, tr.t, tr.x), yc = interp(t, tr.t, tr.y);
+            double dx = x[0] - xc, dy = x[1] - yc;
+            double dist = dx * dx + dy * dy;
+            out[q++] = dist * (-1.) + tr.radius * tr.radius;
+        }
+    } else {
+        for (size_t c = 0; c < pre.cyl.size(); c += 3) {
+            double dx = x[0] - pre.cyl[c], dy = x[1] - pre.cyl[c + 1];
+            out[q++] = pre.cyl[c + 2] - (dx * dx + dy * dy);
+        }
+    }
+}
+
+double running_cost(int model, const double* u, bool maximize) {
+    double l = (model == SI2D) ? u[0] * u[0] + u[1] * u[1] : (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
+    return maximize ? -1.0 * l : l;
+}
+
+void g_tight(const Problem& P, const std::vector<PhasePre>& pre, const Instance& I, const double* zs,
+             double* g, std::vector<double>& z, std::vector<double>& F) {
+    const Layout& L = P.L;
+    const int ns = L.ns;
+    for (int c = 0; c < L.nvars; ++c) z[c] = zs[c] * P.sc.isz[c];
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p], np = L.npath[p];
+        const Collocation& C = P.col[p];
+        double t0 = z[L.it0(p)], tf = z[L.itf(p)];
+        double h = 0.5 * (tf - t0), m = 0.5 * (tf + t0);
+        double pathv[256];
+        if (np > 256) throw std::invalid_argument("tight oracle supports <= 256 path rows per node");
+        for (int k = 0; k < N; ++k) {
+            double t = h * C.tau[k] + m;
+            dynamics(P.spec.model, &z[L.ix(p, k, 0)], &z[L.iu(p, k, 0)], &F[static_cast<size_t>(k) * ns]);
+            path_rows(P, pre[p], I, &z[L.ix(p, k, 0)], t, pathv);
+            for (int q = 0; q < np; ++q) g[L.rpath(p, k, q)] = P.sc.sg[L.rpath(p, k, q)] * pathv[q];
+        }
+        const double* X = &z[L.ix(p, 0, 0)];
+        for (int k = 0; k < N; ++k) {
+            const double* Dr = &C.D[static_cast<size_t>(k) * N];
+            for (int i = 0; i < ns; ++i) {
+                double total = 0.0;
+                for (int b0 = 0; b0 < N; b0 += DOT_BLOCK) {
+                    int b1 = b0 + DOT_BLOCK < N ? b0 + DOT_BLOCK : N;
+                    double s = 0.0;
+                    for (int l = b0; l < b1; ++l) s = std::fma(Dr[l], X[static_cast<size_t>(l) * ns + i], s);
+                    total = (b0 == 0) ? s : total + s;
+                }
+                double zeta = total - h * F[static_cast<size_t>(k) * ns + i];
+                g[L.rdef(p, k, i)] = P.sc.sg[L.rdef(p, k, i)] * zeta;
+            }
+        }
+        for (int i = 0; i < ns; ++i) {
+            g[L.rev(p, i)] = P.sc.sg[L.rev(p, i)] * z[L.ix(p, 0, i)];
+            g[L.rev(p, ns + i)] = P.sc.sg[L.rev(p, ns + i)] * z[L.ix(p, N - 1, i)];
+        }
+        g[L.rlast(p)] = P.sc.sg[L.rlast(p)] * (tf - t0);
+    }
+    for (int a = 0; a + 1 < L.nphases; ++a) {
+        for (int i = 0; i < ns; ++i)
+            g[L.rlink(a, i)] = P.sc.sg[L.rlink(a, i)] * (z[L.ix(a, L.N[a] - 1, i)] - z[L.ix(a + 1, 0, i)]);
+        g[L.rlink(a, ns)] = P.sc.sg[L.rlink(a, ns)] * (z[L.itf(a)] - z[L.it0(a + 1)]);
+    }
+}
+
+}  // namespace
+
+void Problem::eval_g_tight(const Instance& I, const double* zs, double* g) const {
+    auto pre = precompute(*this, I);
+    std::vector<double> z(L.nvars), F;
+    int maxN = 0;
+    for (int n : L.N) maxN = n > maxN ? n : maxN;
+    F.resize(static_cast<size_t>(maxN) * L.ns);
+    g_tight(*this, pre, I, zs, g, z, F);
+}
+
+void Problem::eval_f_tight(const Instance& I, const double* zs, double* f) const {
+    double total = 0.0;
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p];
+        double t0 = zs[L.it0(p)] * sc.isz[L.it0(p)], tf = zs[L.itf(p)] * sc.isz[L.itf(p)];
+        double h = 0.5 * (tf - t0);
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) {
+            double u[8];
+            for (int j = 0; j < L.nc; ++j) u[j] = zs[L.iu(p, k, j)] * sc.isz[L.iu(p, k, j)];
+            acc = std::fma(col[p].w[k], running_cost(spec.model, u, spec.maximize), acc);
+        }
+        double fp = h * acc;
+        total = (p == 0) ? fp : total + fp;
+    }
+    *f = sc.sf * total;
+}
+
+void Problem::eval_jac_fd_tight(const Instance& I, const double* zs, double* vals) const {
+    auto pre = precompute(*this, I);
+    const double sqrt_eps = 1.4901161193847656e-08;
+    std::vector<double> zp(L.nvars), zm(L.nvars), gp(L.ncons), gm(L.ncons), rinv(L.nvars), z(L.nvars), F;
+    int maxN = 0;
+    for (int n : L.N) maxN = n > maxN ? n : maxN;
+    F.resize(static_cast<size_t>(maxN) * L.ns);
+    // columns of each group, built once
+    std::vector<std::vector<int>> members(S.ngroups);
+    for (int c = 0; c < L.nvars; ++c) members[S.group_of_col[c]].push_back(c);
+    for (int c = 0; c < L.nvars; ++c) zp[c] = zm[c] = zs[c];
+    for (int grp = 0; grp < S.ngroups; ++grp) {
+        for (int c : members[grp]) {
+            double delta = sqrt_eps * (1.0 + std::fabs(zs[c]));
+            zp[c] = zs[c] + delta;
+            zm[c] = zs[c] - delta;
+            rinv[c] = 1.0 / (2.0 * delta);
+        }
+        g_tight(*this, pre, I, zp.data(), gp.data(), z, F);
+        g_tight(*this, pre, I, zm.data(), gm.data(), z, F);
+        for (int c : members[grp]) {
+            for (int e = S.colptr[c]; e < S.colptr[c + 1]; ++e) vals[e] = (gp[S.irow[e]] - gm[S.irow[e]]) * rinv[c];
+            zp[c] = zm[c] = zs[c];
+        }
+    }
+}
+
+}  // namespace oracle
