@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- NLP constraint+Jacobian evaluations per second over batched VGPs (BASELINE.json).
+
+One "step" = one pass of the hot path over one batch: for every instance of the batch the
+objective f, the constraint vector g[ncons] and the sparse Jacobian values J[nnz] (index-set
+finite differences, triplet layout) at one fixed decision vector.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path (this repo)
+  python bench.py --impl reference [...]                       the CPU path on the host cores
+
+Workload at N=1: BASELINE.json configs[1] -- the 3-D point-mass UAS VGP (8 cylinders, 40 LGL nodes)
+batched to 4096 random instances. N>1 (torchrun, one process per GPU): every rank evaluates its own
+4096 instances (weak scaling) and the ranks exchange per-instance summaries {f, max violation}
+with one NCCL all-gather per step.
+
+The `--impl reference` arm times the reference's CPU algorithm for the same path. The reference's
+own binaries (PSOPT 5.0.0 + ADOL-C + IPOPT) cannot be built in this image,
+so it runs the oracle port: per-node std::function/std::any callbacks like ePSOPT::dae and the
+column-grouped finite-difference Jacobian, on all host threads (cpu_baseline.kind = "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "nlp_constraint_jacobian_evals_per_sec"
+UNIT = "evals/s"
+BATCH_PER_GPU = 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ecuda", choices=["ecuda", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
+    ap.add_argument("--jac", default="fd", choices=["fd", "exact"])
+    ap.add_argument("--gather", default="summary", choices=["summary", "full", "none"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(wl, args, n_gpus):
+    return {"workload": "C2: pm3d UAS VGP (6 states, 3 controls, 8 cylinders, 40 Legendre nodes), "
+                        f"{wl.batch} random instances per GPU, evaluation only at fixed decision vectors",
+            "instances_per_gpu": wl.batch, "n_instances": wl.batch * n_gpus, "nvars": wl.nvars, "ncons": wl.ncons,
+            "jacobian": "fd_indexset" if args.jac == "fd" else "exact", "pattern": "dense_node",
+            "l2": "flushed between timed steps (256 MiB write); outputs per step (446 MB) exceed L2",
+            "parallelism": f"instances sharded over {n_gpus} GPU(s), gather={args.gather if n_gpus > 1 else 'n/a'}"}
+
+
+# ---- clocks sampler (B200_PROFILING.md recipe) -----------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t_begin - 0.05 <= ts <= t_end + 0.15:
+                sm.append(clk)
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample taken
+            for ts, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the CPU arm ---------------------------------------------------------------------------------------------
+def cpu_sample(wl, seconds_budget, jac_mode, style=0):
+    """times the oracle on a bounded sample of the workload, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    nthr = ob.max_threads()
+    probe_n = min(wl.batch, nthr)
+    sub = wl.slice_batch(0, min(wl.batch, 64 * nthr))
+    orc = ob.Oracle(sub)
+    r = orc.eval(sub.x[:probe_n], want=("f", "g", "jac"), jac_mode=jac_mode, style=style, nthreads=nthr,
+                 count=probe_n)
+    per_round = max(r["seconds"], 1e-6)
+    rounds = int(max(1, min(seconds_budget / per_round, sub.batch // probe_n)))
+    n = probe_n * rounds
+    r = orc.eval(sub.x[:n], want=("f", "g", "jac"), jac_mode=jac_mode, style=style, nthreads=nthr, count=n)
+    return {"value": n / r["seconds"], "unit": UNIT, "cores": nthr, "kind": "port",
+            "sample": f"{n} of {wl.batch} instances, f+g+J({'fd_indexset' if jac_mode == 1 else 'exact'}), "
+                      f"{'reference-style std::function/std::any callbacks' if style == 0 else 'tight loops'}, "
+                      f"OpenMP over instances, {r['seconds']:.2f} s",
+            "seconds": r["seconds"], "n": n}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from etol_b200 import workloads as W
+    wl = W.pm3d(batch=args.batch)
+    jac_mode = 1 if args.jac == "fd" else 0
+    per_step_budget = max(0.5, min(8.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(wl, per_step_budget / 4, jac_mode)
+    tot_n, tot_s, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_sample(wl, per_step_budget, jac_mode)
+        tot_n += last["n"]
+        tot_s += last["seconds"]
+    value = tot_n / tot_s
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(wl, args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
+                             "sample": f"each step: {last['sample']}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "oracle port of the reference CPU path (PSOPT/ADOL-C cannot be built here); host cores only"}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- the CUDA arm ----------------------------------------------------------------------------------------------
+def run_ecuda(args):
+    import torch
+    import torch.distributed as dist
+    from etol_b200 import capi, workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the eCUDA path has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    jac_mode = capi.JAC_FD if args.jac == "fd" else capi.JAC_EXACT
+    # every rank draws its own 4096 instances (weak scaling): seed offset by rank
+    wl = W.pm3d(batch=args.batch, seed=W.SEED + rank)
+    ev = capi.Evaluator(wl, device=local)
+    B, nv, ng, nz = wl.batch, ev.nvars, ev.ncons, ev.nnz
+    x = torch.from_numpy(wl.x).to(dev)
+    f = torch.empty(B, dtype=torch.float64, device=dev)
+    g = torch.empty((B, ng), dtype=torch.float64, device=dev)
+    jac = torch.empty((B, nz), dtype=torch.float64, device=dev)
+    summ = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
+    full_gather = None
+    if world > 1 and args.gather == "full":
+        full_gather = torch.empty((world * B, nz), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step():
+        ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, capi.MEM_DEVICE, sp)
+        if world > 1 and args.gather != "none":
+            # per-instance {f, max violation} from the f, g just computed, then one all-gather
+            ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), sp)
+            dist.all_gather_into_tensor(gathered, summ)
+            if full_gather is not None:
+                dist.all_gather_into_tensor(full_gather, jac)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = ev.launch_count()
+    barrier()
+    t_begin = time.time()
+    for i in range(args.steps):
+        flush.fill_(float(i))          # untimed: evict L2 between timed steps
+        starts[i].record(stream)
+        step()
+        stops[i].record(stream)
+    barrier()
+    t_end = time.time()
+    launches = ev.launch_count() - launches0
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = float(sum(per_step_ms))
+    clocks = sampler.stop(t_begin, t_end)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tt.item())
+    value = world * B * args.steps / (total_ms_max / 1e3)
+
+    # ---- roofline of the dominant kernel (k_eval): kernel-only timing on the same stream ------------
+    kern_ms = []
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, capi.MEM_DEVICE, sp)
+        e.record(stream)
+        torch.cuda.synchronize()
+        kern_ms.append(s.elapsed_time(e))
+    kern_avg_ms = float(np.mean(kern_ms))
+    inst_bytes = 8 * ev.dims.inst_stride
+    alg_bytes_unit = 8 * (nv + 1 + ng + nz) + inst_bytes
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    achieved = alg_bytes_unit * B / (kern_avg_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"k_eval_{args.jac}_C2_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"k_eval<pm3d> ({args.jac})", "kernel_ms": kern_avg_ms,
+                "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B, "peak_source": peak_src}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.from_numpy(wl.x).pin_memory()
+        hf = torch.empty(B, dtype=torch.float64).pin_memory()
+        hg = torch.empty((B, ng), dtype=torch.float64).pin_memory()
+        hj = torch.empty((B, nz), dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            ev.eval_ptr(hx.data_ptr(), hf.data_ptr(), hg.data_ptr(), hj.data_ptr(), jac_mode, capi.MEM_HOST, sp)
+
+        nsteps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(nsteps):
+            e2e_step()
+        e.record(stream)
+        barrier()
+        te = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * nsteps / (float(te.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(8 * B * nv), "d2h_bytes_per_step": int(8 * B * (1 + ng + nz)),
+               "steps": nsteps, "what": "ecuda_eval with pinned HOST x/f/g/J buffers: H2D of x, kernel, D2H of "
+                                        "f, g and all Jacobian values, every step"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_sample(wl, args.cpu_seconds, 1 if args.jac == "fd" else 0, style=0)
+        tight = cpu_sample(wl, max(2.0, args.cpu_seconds / 4), 1 if args.jac == "fd" else 0, style=1)
+        cpu_baseline.pop("seconds"), cpu_baseline.pop("n")
+        cpu_baseline["tight_loops_value"] = tight["value"]
+        cpu_baseline["note"] = ("oracle port (restatement, not PSOPT/ADOL-C binaries); value = reference-style "
+                                "callbacks on all host threads; tight_loops_value = same arithmetic, plain loops")
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(wl, args, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ecuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
-    "ecuda_summary", "ecuda_sync", "ecuda_launch_count", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
+    "ecuda_summary", "ecuda_summarize", "ecuda_sync", "ecuda_launch_count", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation",
 ]
@@ -75,6 +75,7 @@ def lib():
                              C.c_void_p]
     L.ecuda_eval_grad_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ecuda_summarize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ecuda_sync.argtypes = [C.c_void_p]
     L.ecuda_launch_count.restype = C.c_int64
     L.ecuda_launch_count.argtypes = [C.c_void_p]
@@ -259,6 +260,9 @@ class Evaluator:
 
     def summary_ptr(self, x_ptr, out_ptr, memkind, stream=None):
         self._check(self.L.ecuda_summary(self.h, x_ptr, out_ptr, memkind, stream))
+
+    def summarize_ptr(self, f_ptr, g_ptr, out_ptr, stream=None):
+        self._check(self.L.ecuda_summarize(self.h, f_ptr, g_ptr, out_ptr, stream))
 
     def summary_host(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)

@@ -560,6 +560,23 @@ int ecuda_summary(ecuda_handle h, const double* x, double* out, int memkind, voi
     return ECUDA_OK;
 }
 
+int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, double* out_dev, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_bounds) return fail(h, ECUDA_ERR_STATE, "upload_bounds has not been called");
+    if (!f_dev || !g_dev || !out_dev) return fail(h, ECUDA_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const size_t B = h->hp.desc.batch;
+    const int warps_per_block = 4;
+    k_summary<<<(unsigned)((B + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, st>>>(
+        f_dev, g_dev, static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), out_dev, (int)B,
+        h->pd.ncons);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return ECUDA_OK;
+}
+
 int ecuda_sync(ecuda_handle h) {
     if (!h) return ECUDA_ERR_ARG;
     CU(cudaSetDevice(h->device));

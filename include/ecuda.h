@@ -148,6 +148,9 @@ int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* ja
 int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream);
 /* per-instance summary [B][2] = { f, max bound violation of g } (needs ecuda_upload_bounds) */
 int ecuda_summary(ecuda_handle h, const double* x, double* out, int memkind, void* stream);
+/* same reduction over f [B] and g [B][ncons] already on the device (e.g. the outputs of a previous
+ * ecuda_eval on the same stream); out [B][2] on the device. One warp per instance, shuffle max. */
+int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, double* out_dev, void* stream);
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);

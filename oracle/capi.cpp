@@ -7,6 +7,7 @@
 #include <exception>
 #include <string>
 
+#include "../include/ecuda_detmath.h"
 #include "oracle.hpp"
 
 using namespace oracle;
@@ -205,5 +206,10 @@ double oracle_eval_batch(void* hv, int first, int count, const double* x, double
 }
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+
+// host build of the shared deterministic sincos, for tests/test_detmath.py
+void oracle_sincos(const double* x, int n, double* s, double* c) {
+    for (int i = 0; i < n; ++i) ecuda_sincos(x[i], s + i, c + i);
+}
 
 }  // extern "C"

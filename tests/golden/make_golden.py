@@ -1,0 +1,25 @@
+"""Generates tests/golden/c0_ocp_golden.npz: oracle outputs for the reference VGP (C0) at the
+committed seeded decision vector. The reference itself cannot run here (PSOPT/ADOL-C/IPOPT absent,
+SURVEY.md section 8c), so these are ORACLE-generated regression vectors, pinned in turn by the
+hand-derived known answers of appendix_b_kats.json. Run from the repo root:
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_binding as ob  # noqa: E402
+from etol_b200 import workloads as W  # noqa: E402
+
+wl = W.reference_vgp("ocp")
+o = ob.Oracle(wl)
+fd = o.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=1)
+ex = o.eval(wl.x, want=("jac",), jac_mode=0)
+irow, jcol, grp = o.structure()
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "c0_ocp_golden.npz"), x=wl.x, f=fd["f"], g=fd["g"],
+                    jac_fd=fd["jac"], jac_exact=ex["jac"], grad=fd["grad"], irow=irow, jcol=jcol, group_of_col=grp)
+print("wrote c0_ocp_golden.npz", o.nvars, o.ncons, o.nnz)

@@ -52,6 +52,7 @@ def lib():
         L.oracle_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                         C.c_int, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_sincos.argtypes = [_dp, C.c_int, _dp, _dp]
         _lib = L
     return _lib
 
@@ -156,3 +157,10 @@ class Oracle:
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def det_sincos(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s, c = np.zeros_like(x), np.zeros_like(x)
+    lib().oracle_sincos(_p(x), x.size, _p(s), _p(c))
+    return s, c

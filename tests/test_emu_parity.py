@@ -1,0 +1,45 @@
+"""CPU stepping of the kernel phases (tests/emu) against the oracle. This is NOT the parity gate
+(that is tests/test_gpu_parity.py on a B200, through the C ABI); it checks, where there is no GPU,
+that the kernel source computes every row and every triplet with the canonical operation order."""
+import numpy as np
+import pytest
+
+import emu_binding as eb
+import oracle_binding as ob
+from conftest import TOL_JAC, TOL_VALUE, rel_err
+from etol_b200 import workloads as W
+
+CASES = {
+    "C0-ocp": lambda: W.reference_vgp("ocp", batch=3, jitter=0.02),
+    "C0-mip": lambda: W.reference_vgp("mip", batch=2, jitter=0.01),
+    "C0-ocp-cheb-max": lambda: W.reference_vgp("ocp", collocation=W.CHEBYSHEV, maximize=True),
+    "C0-ocp-deps": lambda: W.reference_vgp("ocp", pattern_mode=W.MODEL_DEPS),
+    "C2-pm3d": lambda: W.pm3d(batch=3),
+    "C2-pm3d-scaled-deps": lambda: W.pm3d(batch=2, scaled=True, pattern_mode=W.MODEL_DEPS),
+    "C3-fw6-small": lambda: W.fw6(batch=2, nnodes=21, ncyl=5, scaled=True),
+    "C3-fw6-N200": lambda: W.fw6(batch=1),
+    "C4-multiphase": lambda: W.pm3d_multiphase(batch=2, scaled=True),
+    "C4-multiphase-ragged": lambda: W.pm3d_multiphase(batch=1, nphases=4, nnodes=7, ncyl=1),
+    "pm3d-N2": lambda: W.pm3d(batch=1, nnodes=2, ncyl=1),
+    "pm3d-no-obstacles": lambda: W.pm3d(batch=2, nnodes=9, ncyl=0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("nthr", [32, 256])
+def test_phases_match_oracle(name, nthr):
+    wl = CASES[name]()
+    if name == "C3-fw6-N200" and nthr == 32:
+        pytest.skip("one thread count is enough for the large case")
+    o = ob.Oracle(wl)
+    style = 1 if name == "C3-fw6-N200" else 0
+    for mode in (W.JAC_FD, W.JAC_EXACT):
+        ref = o.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style, nthreads=4)
+        got = eb.emu_eval(wl, wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, nthr=nthr)
+        assert rel_err(got["f"], ref["f"]) <= TOL_VALUE
+        assert rel_err(got["g"], ref["g"]) <= TOL_VALUE
+        assert rel_err(got["grad"], ref["grad"]) <= TOL_VALUE
+        assert not np.isnan(got["jac"]).any(), "a triplet was never written"
+        assert rel_err(got["jac"], ref["jac"]) <= TOL_JAC
+        if mode == W.JAC_FD:  # same operation sequence => identical bits
+            assert np.array_equal(got["g"], ref["g"]) and np.array_equal(got["jac"], ref["jac"])

@@ -1,0 +1,220 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/ecuda.h), against the CPU
+oracle on the same seeded inputs. Bars (BASELINE.json north_star): sparsity pattern and colouring
+bit-exact; f and g within 1e-12 relative; Jacobian entries within 1e-9 relative under the same
+perturbation step. FD mode additionally asserts identical bits (same IEEE operation sequence)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from conftest import TOL_JAC, TOL_VALUE, rel_err
+from etol_b200 import capi, workloads as W
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # C0: the reference VGP (ocp_2d_ex1.xml shape) and the mip_2d_ex1.xml variant the Singularity app runs
+    "C0-ocp": lambda: W.reference_vgp("ocp", batch=5, jitter=0.02),
+    "C0-mip": lambda: W.reference_vgp("mip", batch=3, jitter=0.01),
+    "C0-ocp-cheb-max": lambda: W.reference_vgp("ocp", collocation=W.CHEBYSHEV, maximize=True),
+    "C0-ocp-deps-base1": lambda: W.reference_vgp("ocp", pattern_mode=W.MODEL_DEPS, index_base=1),
+    # C1/C2: 3-D point mass, 8 cylinders, 40 LGL nodes
+    "C1-pm3d": lambda: W.pm3d(batch=1),
+    "C2-pm3d-64": lambda: W.pm3d(batch=64),
+    "C2-pm3d-scaled-deps": lambda: W.pm3d(batch=7, scaled=True, pattern_mode=W.MODEL_DEPS),
+    # C3: fixed wing, 200 nodes, 64 cylinders
+    "C3-fw6": lambda: W.fw6(batch=2),
+    "C3-fw6-small-scaled": lambda: W.fw6(batch=3, nnodes=21, ncyl=5, scaled=True),
+    # C4: three linked phases
+    "C4-multiphase": lambda: W.pm3d_multiphase(batch=6, scaled=True),
+    "C4-multiphase-ragged": lambda: W.pm3d_multiphase(batch=2, nphases=4, nnodes=7, ncyl=1),
+    # edge cases: minimum node count, no obstacles, node counts off the block size
+    "pm3d-N2": lambda: W.pm3d(batch=2, nnodes=2, ncyl=1),
+    "pm3d-no-obstacles": lambda: W.pm3d(batch=2, nnodes=9, ncyl=0),
+    "pm3d-N65": lambda: W.pm3d(batch=2, nnodes=65, ncyl=3),
+}
+
+
+@pytest.fixture(scope="module")
+def evaluators():
+    cache = {}
+    yield cache
+    for ev, _, _ in cache.values():
+        ev.close()
+
+
+def _get(evaluators, name):
+    if name not in evaluators:
+        wl = CASES[name]()
+        evaluators[name] = (capi.Evaluator(wl, device=0), ob.Oracle(wl), wl)
+    return evaluators[name]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_structure_bit_exact(evaluators, name):
+    ev, orc, wl = _get(evaluators, name)
+    for a, b in zip(ev.structure(), orc.structure()):
+        assert np.array_equal(a, b)
+    assert (ev.nvars, ev.ncons, ev.nnz, ev.dims.ngroups) == (orc.nvars, orc.ncons, orc.nnz, orc.ngroups)
+    for p, N in enumerate(wl.nnodes):
+        for a, b in zip(ev.collocation(p), orc.collocation(p, N)):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("mode", [W.JAC_FD, W.JAC_EXACT])
+def test_values_match_oracle(evaluators, name, mode):
+    ev, orc, wl = _get(evaluators, name)
+    style = 1 if name == "C3-fw6" else 0  # tight oracle for the 200-node case (bit-identical to style 0)
+    ref = orc.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style, nthreads=ob.max_threads())
+    got = ev.eval_host(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode)
+    assert rel_err(got["f"], ref["f"]) <= TOL_VALUE
+    assert rel_err(got["g"], ref["g"]) <= TOL_VALUE
+    assert rel_err(got["grad"], ref["grad"]) <= TOL_VALUE
+    assert rel_err(got["jac"], ref["jac"]) <= TOL_JAC
+    if mode == W.JAC_FD:
+        assert np.array_equal(got["f"], ref["f"]) and np.array_equal(got["g"], ref["g"])
+        assert np.array_equal(got["jac"], ref["jac"]), "FD Jacobian is not bit-identical to the oracle"
+
+
+def test_golden_fixture_c0(evaluators):
+    """committed oracle outputs for the reference VGP at a committed decision vector"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "c0_ocp_golden.npz"))
+    wl = W.reference_vgp("ocp")
+    assert np.array_equal(wl.x, gold["x"]), "workload generator drifted from the committed fixture"
+    ev = capi.Evaluator(wl)
+    fd = ev.eval_host(wl.x, jac_mode=W.JAC_FD)
+    ex = ev.eval_host(wl.x, want=("jac",), jac_mode=W.JAC_EXACT)
+    assert rel_err(fd["f"], gold["f"]) <= TOL_VALUE and rel_err(fd["g"], gold["g"]) <= TOL_VALUE
+    assert rel_err(fd["jac"], gold["jac_fd"]) <= TOL_JAC and rel_err(ex["jac"], gold["jac_exact"]) <= TOL_JAC
+    irow, jcol, grp = ev.structure()
+    assert np.array_equal(irow, gold["irow"]) and np.array_equal(jcol, gold["jcol"])
+    assert np.array_equal(grp, gold["group_of_col"])
+    ev.close()
+
+
+def test_device_pointer_path_and_partial_outputs(evaluators):
+    import torch
+    ev, orc, wl = _get(evaluators, "C2-pm3d-64")
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(wl.x).to(dev)
+    f = torch.full((wl.batch,), float("nan"), dtype=torch.float64, device=dev)
+    g = torch.full((wl.batch, ev.ncons), float("nan"), dtype=torch.float64, device=dev)
+    jac = torch.full((wl.batch, ev.nnz), float("nan"), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), W.JAC_FD, capi.MEM_DEVICE, st)
+    torch.cuda.synchronize()
+    ref = orc.eval(wl.x, jac_mode=W.JAC_FD, nthreads=ob.max_threads())
+    assert np.array_equal(f.cpu().numpy(), ref["f"])
+    assert np.array_equal(g.cpu().numpy(), ref["g"])
+    assert np.array_equal(jac.cpu().numpy(), ref["jac"])
+    # g only: f and jac buffers must stay untouched
+    g2 = torch.zeros_like(g)
+    ev.eval_ptr(x.data_ptr(), None, g2.data_ptr(), None, W.JAC_FD, capi.MEM_DEVICE, st)
+    torch.cuda.synchronize()
+    assert torch.equal(g2, g)
+
+
+def test_full_size_batch_properties():
+    """BASELINE config C2 at full size (4096 instances): properties that need no 4096-instance oracle run."""
+    import torch
+    wl = W.pm3d(batch=4096)
+    ev = capi.Evaluator(wl)
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(wl.x).to(dev)
+    out = {}
+    for mode in (W.JAC_FD, W.JAC_EXACT):
+        f = torch.empty(wl.batch, dtype=torch.float64, device=dev)
+        g = torch.empty((wl.batch, ev.ncons), dtype=torch.float64, device=dev)
+        jac = torch.full((wl.batch, ev.nnz), float("nan"), dtype=torch.float64, device=dev)
+        ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), mode, capi.MEM_DEVICE, None)
+        ev.sync()
+        out[mode] = (f.cpu().numpy(), g.cpu().numpy(), jac.cpu().numpy())
+    f, g, jfd = out[W.JAC_FD]
+    _, _, jex = out[W.JAC_EXACT]
+    assert not np.isnan(jfd).any() and not np.isnan(jex).any()
+    # (1) FD ~ exact on every instance
+    assert np.abs(jfd - jex).max() <= 2e-6 * np.abs(jex).max()
+    # (2) a random sample of instances is bit-identical to the oracle
+    idx = np.random.default_rng(3).choice(wl.batch, 12, replace=False)
+    orc = ob.Oracle(wl)
+    for b in idx:
+        ref = orc.eval(wl.x[b:b + 1], jac_mode=W.JAC_FD, first=int(b), count=1)
+        assert np.array_equal(ref["f"][0], f[b]) and np.array_equal(ref["g"][0], g[b])
+        assert np.array_equal(ref["jac"][0], jfd[b])
+    # (3) instances are independent: a permuted batch gives the permuted result
+    perm = np.random.default_rng(4).permutation(wl.batch)
+    wl2 = W.pm3d(batch=4096)
+    wl2.cylinders, wl2.x = wl.cylinders[perm], wl.x[perm]
+    ev2 = capi.Evaluator(wl2)
+    got = ev2.eval_host(wl2.x, jac_mode=W.JAC_FD)
+    assert np.array_equal(got["g"], g[perm]) and np.array_equal(got["jac"], jfd[perm])
+    # (4) the duration row equals tf - t0 and the event rows equal the boundary states
+    N = 40
+    assert np.array_equal(g[:, -1], wl.x[:, wl.itf(0)] - wl.x[:, wl.it0(0)])
+    assert np.array_equal(g[:, 6 * N:6 * N + 6], wl.x[:, wl.ix(0, 0, 0):wl.ix(0, 0, 0) + 6])
+    ev.close()
+    ev2.close()
+
+
+def test_summary_matches_numpy(evaluators):
+    ev, orc, wl = _get(evaluators, "C2-pm3d-64")
+    s = ev.summary_host(wl.x)
+    ref = ev.eval_host(wl.x, want=("f", "g"))
+    viol = np.maximum(np.maximum(wl.gl - ref["g"], ref["g"] - wl.gu), 0.0).max(axis=1)
+    assert np.array_equal(s[:, 0], ref["f"]) and np.array_equal(s[:, 1], viol)
+
+
+def test_ipopt_shaped_shims():
+    wl = W.reference_vgp("ocp")
+    ev = capi.Evaluator(wl)
+    orc = ob.Oracle(wl)
+    L, h = ev.L, ev.h
+    n, m, nz = ev.nvars, ev.ncons, ev.nnz
+    x = np.ascontiguousarray(wl.x[0])
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int32)
+    obj = C.c_double()
+    assert L.ecuda_ipopt_eval_f(h, n, x.ctypes.data_as(dp), 1, C.byref(obj)) == 0
+    g = np.zeros(m)
+    assert L.ecuda_ipopt_eval_g(h, n, x.ctypes.data_as(dp), 0, m, g.ctypes.data_as(dp)) == 0
+    grad = np.zeros(n)
+    assert L.ecuda_ipopt_eval_grad_f(h, n, x.ctypes.data_as(dp), 0, grad.ctypes.data_as(dp)) == 0
+    irow, jcol = np.zeros(nz, dtype=np.int32), np.zeros(nz, dtype=np.int32)
+    assert L.ecuda_ipopt_eval_jac_g(h, n, x.ctypes.data_as(dp), 0, m, nz, irow.ctypes.data_as(ip),
+                                    jcol.ctypes.data_as(ip), None) == 0
+    vals = np.zeros(nz)
+    assert L.ecuda_ipopt_eval_jac_g(h, n, x.ctypes.data_as(dp), 0, m, nz, None, None, vals.ctypes.data_as(dp)) == 0
+    ref = orc.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=W.JAC_EXACT)
+    oi, oj, _ = orc.structure()
+    assert obj.value == ref["f"][0] and np.array_equal(g, ref["g"][0])
+    assert rel_err(grad, ref["grad"][0]) <= TOL_VALUE and rel_err(vals, ref["jac"][0]) <= TOL_JAC
+    assert np.array_equal(irow, oi) and np.array_equal(jcol, oj)
+    assert L.ecuda_ipopt_eval_g(h, n + 1, x.ctypes.data_as(dp), 0, m, g.ctypes.data_as(dp)) == -1
+    ev.close()
+
+
+def test_error_behaviour_on_gpu():
+    wl = W.pm3d(batch=2)
+    ev = capi.Evaluator(wl, upload=False)
+    with pytest.raises(capi.EcudaError, match="upload_instances"):
+        ev.eval_host(wl.x)
+    h = C.c_void_p()
+    assert capi.lib().ecuda_create(999, C.byref(h)) == -1
+    ev.close()
+
+
+def test_injected_collocation_is_used():
+    """ecuda_set_collocation: a perturbed D must change the defects exactly as the oracle formula says"""
+    wl = W.pm3d(batch=1, nnodes=9, ncyl=0)
+    ev = capi.Evaluator(wl)
+    tau, w, D = ev.collocation(0)
+    base = ev.eval_host(wl.x, want=("g",))["g"]
+    ev.set_collocation(0, tau, w, 2.0 * D)
+    twice = ev.eval_host(wl.x, want=("g",))["g"]
+    N, ns = 9, 6
+    X = np.stack([[wl.x[0, wl.ix(0, k, i)] for i in range(ns)] for k in range(N)])
+    assert np.allclose((twice - base)[0, :N * ns].reshape(N, ns), D @ X, rtol=1e-12, atol=1e-9)
+    ev.close()
