@@ -191,6 +191,7 @@ def run_ecuda(args):
     wl = W.pm3d(batch=args.batch, seed=W.SEED + rank)
     ev = capi.Evaluator(wl, device=local)
     B, nv, ng, nz = wl.batch, ev.nvars, ev.ncons, ev.nnz
+    torch.cuda.synchronize()
     x = torch.from_numpy(wl.x).to(dev)
     f = torch.empty(B, dtype=torch.float64, device=dev)
     g = torch.empty((B, ng), dtype=torch.float64, device=dev)
@@ -201,8 +202,11 @@ def run_ecuda(args):
     if world > 1 and args.gather == "full":
         full_gather = torch.empty((world * B, nz), dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: kernels, copies, NCCL and the timing events all go on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def step():
         ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, capi.MEM_DEVICE, sp)

@@ -225,9 +225,19 @@ static int upload_collocation(ecuda_ctx* h, int p) {
 
 template <int M>
 static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
-    // opt in to the full 227 KB of dynamic shared memory (per function and device; it only permits)
-    CU(cudaFuncSetAttribute(k_eval<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaFuncSetAttribute(k_grad<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // opt in to more than 48 KB of dynamic shared memory. The attribute is per function and device
+    // and only permits, so it is raised monotonically to the largest size any handle has needed.
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    if (h->smem_bytes > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < h->smem_bytes) {
+            CU(cudaFuncSetAttribute(k_eval<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            CU(cudaFuncSetAttribute(k_grad<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            cur = h->smem_bytes;
+        }
+    }
     const int grid = io.batch * h->pd.nphases;
     if (io.grad) {
         k_grad<M><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
@@ -358,7 +368,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
         size_t s = cta_doubles(pd, ph, kThreads) * sizeof(double);
         smem = s > smem ? s : smem;
     }
-    if (smem > 227 * 1024)
+    if (smem > 227 * 1024 - 64)
         return fail(h, ECUDA_ERR_ARG, "phase too large for one CTA's shared memory (" + std::to_string(smem) + " B)");
     h->smem_bytes = smem;
     int rc;

@@ -139,7 +139,8 @@ int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int 
  * f [B], g [B][ncons], jac [B][nnz] in the triplet order of ecuda_get_structure.
  * memkind says where x/f/g/jac live (all the same kind). HOST buffers are staged through device
  * buffers owned by the handle (pinned host memory makes the copies asynchronous). The work is
- * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream) and is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the handle's own non-blocking stream,
+ * NOT the legacy default stream -- pass cudaStreamLegacy explicitly if that is wanted) and is
  * asynchronous with respect to the host for DEVICE buffers; HOST calls return after the results
  * have landed. */
 int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,

@@ -103,9 +103,11 @@ def test_device_pointer_path_and_partial_outputs(evaluators):
     f = torch.full((wl.batch,), float("nan"), dtype=torch.float64, device=dev)
     g = torch.full((wl.batch, ev.ncons), float("nan"), dtype=torch.float64, device=dev)
     jac = torch.full((wl.batch, ev.nnz), float("nan"), dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream(device=dev)
+    st = stream.cuda_stream
+    stream.wait_stream(torch.cuda.current_stream())
     ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), W.JAC_FD, capi.MEM_DEVICE, st)
-    torch.cuda.synchronize()
+    stream.synchronize()
     ref = orc.eval(wl.x, jac_mode=W.JAC_FD, nthreads=ob.max_threads())
     assert np.array_equal(f.cpu().numpy(), ref["f"])
     assert np.array_equal(g.cpu().numpy(), ref["g"])
@@ -135,8 +137,9 @@ def test_full_size_batch_properties():
     f, g, jfd = out[W.JAC_FD]
     _, _, jex = out[W.JAC_EXACT]
     assert not np.isnan(jfd).any() and not np.isnan(jex).any()
-    # (1) FD ~ exact on every instance
-    assert np.abs(jfd - jex).max() <= 2e-6 * np.abs(jex).max()
+    # (1) FD ~ exact on every instance. The bound is the FD noise model eps*|g|/(2*delta): with
+    # PSOPT's step 2^-26*(1+|z|) a position clipped to ~0 and |g| ~ 1e6 m^2 gives ~7e-3 absolute.
+    assert np.abs(jfd - jex).max() <= 5e-5 * np.abs(jex).max()
     # (2) a random sample of instances is bit-identical to the oracle
     idx = np.random.default_rng(3).choice(wl.batch, 12, replace=False)
     orc = ob.Oracle(wl)
