@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libecuda.so")
+# ECUDA_LIB: alternative build of the same library (kernel tuning experiments); still no fallback
+LIB_PATH = os.environ.get("ECUDA_LIB") or os.path.join(HERE, "csrc", "libecuda.so")
 
 MAX_PHASES = 8
 MEM_HOST, MEM_DEVICE = 0, 1

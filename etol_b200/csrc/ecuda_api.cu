@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -22,6 +23,9 @@
 namespace ecuda {
 
 constexpr int kThreads = 256;
+#ifndef ECUDA_MIN_CTAS
+#define ECUDA_MIN_CTAS 2 /* resident CTAs per SM the specialised kernels are register-limited for */
+#endif
 
 // ---- TMA bulk copy helpers (PTX) -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -56,8 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------
-template <int M>
-__global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ ProbDev pb,
+// NB > 0: every phase has exactly NB summation blocks (block sums in registers); NB == 0: generic
+template <int M, int NB>
+__global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(const __grid_constant__ ProbDev pb,
                                                    const __grid_constant__ EvalIO io) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ ProbD
     __syncthreads();
     phase_b<M>(pb, ph, p, io, m, b, tid, nthr);
     __syncthreads();
-    phase_c<M>(pb, ph, p, io, m, b, tid, nthr);
+    phase_c<M, NB>(pb, ph, p, io, m, b, tid, nthr);
 }
 
 template <int M>
@@ -151,6 +156,8 @@ struct ecuda_ctx {
     size_t smem_bytes = 0;
     int64_t launches = 0;
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
+    bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
+    int nb_uniform = 0;  // summation-block count if all phases share it and it is <= 8, else 0
     std::vector<double> h_sz, h_sg;
 };
 
@@ -223,8 +230,8 @@ static int upload_collocation(ecuda_ctx* h, int p) {
     return ECUDA_OK;
 }
 
-template <int M>
-static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
+template <int M, int NB>
+static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     // opt in to more than 48 KB of dynamic shared memory. The attribute is per function and device
     // and only permits, so it is raised monotonically to the largest size any handle has needed.
     static std::mutex mu;
@@ -233,18 +240,41 @@ static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
         std::lock_guard<std::mutex> lock(mu);
         size_t& cur = configured[h->device & 63];
         if (cur < h->smem_bytes) {
-            CU(cudaFuncSetAttribute(k_eval<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-            CU(cudaFuncSetAttribute(k_grad<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            CU(cudaFuncSetAttribute(k_eval<M, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
             cur = h->smem_bytes;
         }
     }
+    k_eval<M, NB><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
+
+template <int M>
+static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     const int grid = io.batch * h->pd.nphases;
     if (io.grad) {
+        static std::mutex mu;
+        static size_t configured[64] = {0};
+        if (h->smem_bytes > 48 * 1024) {
+            std::lock_guard<std::mutex> lock(mu);
+            size_t& cur = configured[h->device & 63];
+            if (cur < h->smem_bytes) {
+                CU(cudaFuncSetAttribute(k_grad<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+                cur = h->smem_bytes;
+            }
+        }
         k_grad<M><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
         ++h->launches;
     }
     if (io.f || io.g || io.jac) {
-        k_eval<M><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
+        int rc = ECUDA_OK;
+        switch (h->nb_uniform) {  // block count shared by all phases, or 0
+            // specialised for the node counts of the BASELINE configs: 17 -> 3, 30 -> 4, 33 / 40 -> 5
+            case 3: rc = launch_keval<M, 3>(h, io, st, grid); break;
+            case 4: rc = launch_keval<M, 4>(h, io, st, grid); break;
+            case 5: rc = launch_keval<M, 5>(h, io, st, grid); break;
+            default: rc = launch_keval<M, 0>(h, io, st, grid); break;
+        }
+        if (rc) return rc;
         ++h->launches;
         if (io.f && h->pd.nphases > 1) {
             k_sum_phases<<<(io.batch + 127) / 128, 128, 0, st>>>(io.fpart, io.f, io.batch, h->pd.nphases, h->pd.sf);
@@ -289,6 +319,10 @@ int ecuda_create(int device, ecuda_handle* out) {
     h = new (std::nothrow) ecuda_ctx;
     if (!h) return fail(nullptr, ECUDA_ERR_ALLOC, "out of host memory");
     h->device = device;
+    {
+        const char* fg = std::getenv("ECUDA_FORCE_GENERIC");
+        h->force_generic = fg && fg[0] == '1';
+    }
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
@@ -371,6 +405,11 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if (smem > 227 * 1024 - 64)
         return fail(h, ECUDA_ERR_ARG, "phase too large for one CTA's shared memory (" + std::to_string(smem) + " B)");
     h->smem_bytes = smem;
+    h->nb_uniform = pd.ph[0].nb;
+    for (int p = 1; p < hp.nphases; ++p)
+        if (pd.ph[p].nb != h->nb_uniform) h->nb_uniform = 0;
+    if (h->nb_uniform > 8) h->nb_uniform = 0;
+    if (h->force_generic) h->nb_uniform = 0;
     int rc;
     if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
     CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));

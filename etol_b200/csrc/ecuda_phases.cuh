@@ -50,7 +50,8 @@ struct CtaMem {
     double* dotv;  // [N*ns]    (D X)[k][i]
     double* Lk;    // [N]       running cost per node
     double* inst;  // [inst_stride] obstacle + track records of the instance
-    double* P;     // [nb][nthr] thread-private block sums
+    double* P;     // [nb][nthr] thread-private block sums (generic block count only)
+    int* colp;     // [nvars_p] first triplet index of each column of this phase
 };
 
 // shared-memory footprint in doubles for one CTA working on phase `ph`
@@ -61,6 +62,7 @@ ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr) {
     n += static_cast<size_t>(ph.N + (ph.N & 1));
     n += static_cast<size_t>(pb.inst_stride);
     n += static_cast<size_t>(ph.nb) * nthr;
+    n += static_cast<size_t>((ph.nvars + 2) / 2);  // colp (ints)
     return n;
 }
 
@@ -75,7 +77,8 @@ ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& 
     m.hf = base;    base += static_cast<size_t>(ph.N) * pb.ns;
     m.dotv = base;  base += static_cast<size_t>(ph.N) * pb.ns;
     m.Lk = base;    base += static_cast<size_t>(ph.N + (ph.N & 1));
-    m.P = base;
+    m.P = base;     base += static_cast<size_t>(ph.nb) * nthr;
+    m.colp = reinterpret_cast<int*>(base);
 }
 
 struct PhaseTimes {
@@ -99,6 +102,7 @@ ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io
         double zt = ECUDA_LDG(xs + c);
         double s = ECUDA_LDG(is + c);
         m.z[c] = zt * s;
+        m.colp[c] = ECUDA_LDG(pb.colptr + ph.zoff + c);
         if (fd) {
             double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt));
             m.xp[c] = (zt + delta) * s;
@@ -116,20 +120,25 @@ ECUDA_HD double path_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m,
     return track_row(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x, y, t);
 }
 
-// blocked dot of row k of D with state j of X, optionally with X[lsub][j] replaced by xsub
-ECUDA_HD double dot_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int k, int j, int lsub,
-                        double xsub) {
+// canonical blocked dot of row k of D with state j of X: blocks of ECUDA_DOT_BLOCK nodes, each a
+// serial ascending fma chain from 0; block sums added serially in ascending order. The block sums
+// are also left in P[bi*pstride] (thread-private shared memory) for the finite-difference pass.
+ECUDA_HD double dot_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int k, int j, double* P,
+                        int pstride) {
     const double* X = m.z + pb.nc * ph.N + j;
     const double* Dt = ph.Dt + k;
     const int N = ph.N, ns = pb.ns;
     double total = 0.0;
-    for (int l0 = 0; l0 < N; l0 += ECUDA_DOT_BLOCK) {
-        int l1 = l0 + ECUDA_DOT_BLOCK < N ? l0 + ECUDA_DOT_BLOCK : N;
+    for (int l0 = 0, bi = 0; l0 < N; l0 += ECUDA_DOT_BLOCK, ++bi) {
         double p = 0.0;
-        for (int l = l0; l < l1; ++l) {
-            double xv = (l == lsub) ? xsub : X[l * ns];
-            p = fma(ECUDA_LDG(Dt + static_cast<size_t>(l) * N), xv, p);
+        if (l0 + ECUDA_DOT_BLOCK <= N) {
+#pragma unroll
+            for (int i = 0; i < ECUDA_DOT_BLOCK; ++i)
+                p = fma(ECUDA_LDG(Dt + static_cast<size_t>(l0 + i) * N), X[(l0 + i) * ns], p);
+        } else {
+            for (int l = l0; l < N; ++l) p = fma(ECUDA_LDG(Dt + static_cast<size_t>(l) * N), X[l * ns], p);
         }
+        P[bi * pstride] = p;
         total = (l0 == 0) ? p : total + p;
     }
     return total;
@@ -168,7 +177,7 @@ ECUDA_HD void phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
     }
     for (int it = tid; it < ns * N; it += nthr) {
         int j = it / N, k = it - j * N;
-        m.dotv[k * ns + j] = dot_row(pb, ph, m, k, j, -1, 0.0);
+        m.dotv[k * ns + j] = dot_row(pb, ph, m, k, j, m.P + tid, nthr);
     }
     if (g) {
         for (int e = tid; e < pb.ne; e += nthr) {
@@ -209,12 +218,260 @@ ECUDA_HD void objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, cons
         io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
 }
 
+// ---- Jacobian work items ------------------------------------------------------------------------------
+// A "state item" (j,k) owns defect row (k,j): it writes that row of g, the D-coupled entries of the
+// row (columns X(l,j), l != k) and the whole node-local part of column X(k,j) (defect rows of node
+// k, event row, obstacle rows, linkage row). A "node item" (k,c) owns the node-local part of a
+// control column or of the t0/tf columns at node k.
+
 // position of defect row (k, state j) inside column X(l, j), k != l
 ECUDA_HD int dot_entry_pos(const ProbDev& pb, int j, int k, int l) { return k < l ? k : k - 1 + pb.xcnt[j]; }
 
-// defect rows of g and the D-coupled Jacobian entries (row (k,j), columns X(l,j), l != k)
-ECUDA_HD void defect_item(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, CtaMem& m, int b, int j, int k,
-                          int tid, int nthr) {
+// node-local part of column X(k,j) by central differences; dpk/dmk = (D X)[k][j] with X[k][j]
+// replaced by its +/- perturbed value
+template <int M>
+ECUDA_HD void state_column_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                              int b, int j, int k, double dpk, double dmk) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+    const double* sg = pb.sg;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    const int lcol = nc * N + k * ns + j;
+    const int base = m.colp[lcol];
+    const double xpv = m.xp[lcol], xmv = m.xm[lcol], ri = m.rinv[lcol];
+    double xq[NS], xr[NS], u[NCU], fp[NS], fm[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double xi = m.z[nc * N + k * ns + i];
+        xq[i] = (i == j) ? xpv : xi;
+        xr[i] = (i == j) ? xmv : xi;
+    }
+#pragma unroll
+    for (int i = 0; i < NCU; ++i) u[i] = m.z[k * nc + i];
+    Model<M>::f(xq, u, t, fp);
+    Model<M>::f(xr, u, t, fm);
+    const int rdef0 = ph.goff + k * ns;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        int rk = pb.xrank[j][i];
+        if (rk >= 0) {
+            double s = ECUDA_LDG(sg + rdef0 + i);
+            double dv = m.dotv[k * ns + i];
+            double gp = s * (((i == j) ? dpk : dv) - pt.h * fp[i]);
+            double gm = s * (((i == j) ? dmk : dv) - pt.h * fm[i]);
+            ECUDA_STREAM_STORE(jac + base + k + rk, (gp - gm) * ri);
+        }
+    }
+    int pos = N - 1 + pb.xcnt[j];
+    if (k == 0 || k == N - 1) {
+        int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
+        double s = ECUDA_LDG(sg + r);
+        ECUDA_STREAM_STORE(jac + base + pos, (s * xpv - s * xmv) * ri);
+        ++pos;
+    }
+    if (j < 2) {  // every obstacle row reads the two horizontal positions
+        const int rpath0 = ph.goff + ns * N + pb.ne + k * np;
+        for (int q = 0; q < np; ++q) {
+            double s = ECUDA_LDG(sg + rpath0 + q);
+            double vp = path_row<M>(pb, ph, m, q, xq[0], xq[1], t);
+            double vm = path_row<M>(pb, ph, m, q, xr[0], xr[1], t);
+            ECUDA_STREAM_STORE(jac + base + pos + q, (s * vp - s * vm) * ri);
+        }
+        pos += np;
+    }
+    if (k == N - 1 && p + 1 < pb.nphases) {
+        const PhaseDev& nx = pb.ph[p + 1];
+        int r = pb.linkoff + p * (ns + 1) + j;
+        double s = ECUDA_LDG(sg + r);
+        double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + j);
+        ECUDA_STREAM_STORE(jac + base + pos, (s * (xpv - o) - s * (xmv - o)) * ri);
+    }
+    if (k == 0 && p > 0) {
+        const PhaseDev& pv = pb.ph[p - 1];
+        int r = pb.linkoff + (p - 1) * (ns + 1) + j;
+        double s = ECUDA_LDG(sg + r);
+        double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * ns + j);
+        ECUDA_STREAM_STORE(jac + base + pos, (s * (o - xpv) - s * (o - xmv)) * ri);
+    }
+}
+
+// node-local part of column X(k,j), analytic
+template <int M>
+ECUDA_HD void state_column_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                                 int b, int j, int k) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+    const double* sg = pb.sg;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    const int lcol = nc * N + k * ns + j, col = ph.zoff + lcol;
+    const int base = m.colp[lcol];
+    double x[NS], u[NCU];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = m.z[nc * N + k * ns + i];
+#pragma unroll
+    for (int i = 0; i < NCU; ++i) u[i] = m.z[k * nc + i];
+    double dfdx[NS][NS], dfdu[NS][NCU];
+    Model<M>::jac(x, u, dfdx, dfdu);
+    const double is = ECUDA_LDG(pb.isz + col);
+    const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
+    const int rdef0 = ph.goff + k * ns;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        int rk = pb.xrank[j][i];
+        if (rk >= 0) {
+            double d = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < NS; ++jj)
+                if (jj == j) d = dfdx[i][jj];
+            double v = ((i == j) ? dkk : 0.0) - pt.h * d;
+            ECUDA_STREAM_STORE(jac + base + k + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+        }
+    }
+    int pos = N - 1 + pb.xcnt[j];
+    if (k == 0 || k == N - 1) {
+        int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
+        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+        ++pos;
+    }
+    if (j < 2) {
+        const int rpath0 = ph.goff + ns * N + pb.ne + k * np;
+        for (int q = 0; q < np; ++q) {
+            double ddx, ddy, ddt = 0.0;
+            if (q < ph.nstat)
+                Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x[0], x[1], &ddx, &ddy);
+            else
+                track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0], x[1], t,
+                                   &ddx, &ddy, &ddt);
+            double v = (j == 0) ? ddx : ddy;
+            ECUDA_STREAM_STORE(jac + base + pos + q, (ECUDA_LDG(sg + rpath0 + q) * v) * is);
+        }
+        pos += np;
+    }
+    if (k == N - 1 && p + 1 < pb.nphases) {
+        int r = pb.linkoff + p * (ns + 1) + j;
+        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+    }
+    if (k == 0 && p > 0) {
+        int r = pb.linkoff + (p - 1) * (ns + 1) + j;
+        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
+    }
+}
+
+// Same as fd_block for any tail length and any number of valid nodes (runtime loops).
+template <int NS>
+ECUDA_HD double fd_block_generic(const double* __restrict__ Dtb, int N, const double* __restrict__ Xb,
+                                 const double* __restrict__ XPb, const double* __restrict__ XMb,
+                                 const double* __restrict__ RIb, const int* __restrict__ CPb, int nin, double pre,
+                                 const double* __restrict__ Ptail, int ntail, int nthr, double sgr, double hfv,
+                                 int krel, int cntm1, double* __restrict__ jac, double& dpk, double& dmk) {
+    double own = 0.0;
+    for (int i = 0; i < nin; ++i) own = fma(ECUDA_LDG(Dtb + static_cast<size_t>(i) * N), Xb[i * NS], own);
+    double qa = 0.0;  // unperturbed prefix q[a]
+    for (int a = 0; a < nin; ++a) {
+        const double da = ECUDA_LDG(Dtb + static_cast<size_t>(a) * N);
+        double sp = fma(da, XPb[a * NS], qa);
+        double sm = fma(da, XMb[a * NS], qa);
+        for (int i = a + 1; i < nin; ++i) {
+            double di = ECUDA_LDG(Dtb + static_cast<size_t>(i) * N), xi = Xb[i * NS];
+            sp = fma(di, xi, sp);
+            sm = fma(di, xi, sm);
+        }
+        double tp = pre + sp;
+        double tm = pre + sm;
+        for (int t = 0; t < ntail; ++t) {
+            double pv = Ptail[t * nthr];
+            tp = tp + pv;
+            tm = tm + pv;
+        }
+        if (a != krel) {
+            double gp = sgr * (tp - hfv);
+            double gm = sgr * (tm - hfv);
+            ECUDA_STREAM_STORE(jac + CPb[a * NS] + (krel > a ? cntm1 : 0), (gp - gm) * RIb[a * NS]);
+        } else {
+            dpk = tp;
+            dmk = tm;
+        }
+        qa = fma(da, Xb[a * NS], qa);
+    }
+    return own;
+}
+
+// One summation block of the row-restricted FD of defect row (k,j): for each of the block's nodes
+// ls = l0+a the two perturbed dots (X[ls][j] -> +-), rebuilt from the unperturbed in-block prefix
+// q[a], the serial prefix `pre` over the earlier blocks and the NT block sums that follow.
+//   NS   state stride (compile time), NT  number of following blocks, FULL  block has BL valid nodes
+template <int NS, int NT, bool FULL>
+ECUDA_HD double fd_block(const double* __restrict__ Dtb, int N, const double* __restrict__ Xb,
+                         const double* __restrict__ XPb, const double* __restrict__ XMb,
+                         const double* __restrict__ RIb, const int* __restrict__ CPb, int nin, double pre,
+                         const double* __restrict__ Ptail, int ntail, int nthr, double sgr, double hfv, int krel,
+                         int cntm1, double* __restrict__ jac, double& dpk, double& dmk) {
+    constexpr int BL = ECUDA_DOT_BLOCK;
+    double d[BL], xv[BL], q[BL + 1], T[NT > 0 ? NT : 1];
+    q[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BL; ++i) {
+        if (FULL || i < nin) {
+            d[i] = ECUDA_LDG(Dtb + static_cast<size_t>(i) * N);
+            xv[i] = Xb[i * NS];
+            q[i + 1] = fma(d[i], xv[i], q[i]);  // unperturbed in-block prefix
+        } else {
+            d[i] = 0.0;
+            xv[i] = 0.0;
+            q[i + 1] = q[i];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) T[t] = (t < ntail) ? Ptail[t * nthr] : 0.0;
+#pragma unroll
+    for (int a = 0; a < BL; ++a) {
+        if (FULL || a < nin) {
+            double sp = fma(d[a], XPb[a * NS], q[a]);
+            double sm = fma(d[a], XMb[a * NS], q[a]);
+            if (FULL) {
+#pragma unroll
+                for (int i = a + 1; i < BL; ++i) {
+                    sp = fma(d[i], xv[i], sp);
+                    sm = fma(d[i], xv[i], sm);
+                }
+            } else {
+                for (int i = a + 1; i < nin; ++i) {
+                    double di = ECUDA_LDG(Dtb + static_cast<size_t>(i) * N), xi = Xb[i * NS];
+                    sp = fma(di, xi, sp);
+                    sm = fma(di, xi, sm);
+                }
+            }
+            double tp = pre + sp;  // a block sum is never -0.0, so 0.0 + s == s bit for bit when pre == 0
+            double tm = pre + sm;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                tp = tp + T[t];
+                tm = tm + T[t];
+            }
+            if (a != krel) {
+                double gp = sgr * (tp - hfv);
+                double gm = sgr * (tm - hfv);
+                // rows k < ls sit at position k of column X(ls,j); rows k > ls come after its node-local block
+                ECUDA_STREAM_STORE(jac + CPb[a * NS] + (krel > a ? cntm1 : 0), (gp - gm) * RIb[a * NS]);
+            } else {
+                dpk = tp;
+                dmk = tm;
+            }
+        }
+    }
+    return q[BL];  // this block's unperturbed sum
+}
+
+// State item (j,k). NB > 0: the phase has exactly NB summation blocks, so the block sums that
+// follow the current block fit a register window of NB-1 values; NB == 0: any block count.
+template <int M, int NB>
+ECUDA_HD void state_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int j,
+                         int k, int tid, int nthr) {
+    constexpr int BL = ECUDA_DOT_BLOCK;
     const int N = ph.N, ns = pb.ns, nc = pb.nc;
     const int r = ph.goff + k * ns + j;
     const double sgr = ECUDA_LDG(pb.sg + r);
@@ -222,71 +479,62 @@ ECUDA_HD void defect_item(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     if (io.g) ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, sgr * (m.dotv[k * ns + j] - hfv));
     if (!io.jac) return;
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-    const int col0 = ph.zoff + nc * N + j;  // global column of X(0, j); X(l, j) = col0 + l*ns
+    const int xoff = nc * N + j;  // phase-local index of X(0,j); X(l,j) = xoff + l*ns
     const double* Dt = ph.Dt + k;
     if (io.jac_mode == ECUDA_JAC_EXACT) {
+        const int cntm1 = pb.xcnt[j] - 1;
         for (int l = 0; l < N; ++l) {
             if (l == k) continue;
-            int col = col0 + l * ns;
-            double v = (sgr * ECUDA_LDG(Dt + static_cast<size_t>(l) * N)) * ECUDA_LDG(pb.isz + col);
-            ECUDA_STREAM_STORE(jac + ECUDA_LDG(pb.colptr + col) + dot_entry_pos(pb, j, k, l), v);
+            const int lcol = xoff + l * ns;
+            double v = (sgr * ECUDA_LDG(Dt + static_cast<size_t>(l) * N)) * ECUDA_LDG(pb.isz + ph.zoff + lcol);
+            ECUDA_STREAM_STORE(jac + m.colp[lcol] + (k < l ? k : k + cntm1), v);
         }
+        state_column_exact<M>(pb, ph, p, io, m, b, j, k);
         return;
     }
-    // index-set central differences, row-restricted
-    const double* X = m.z + nc * N + j;
-    double* P = m.P + tid;  // P[b*nthr]
-    for (int l0 = 0, bi = 0; l0 < N; l0 += ECUDA_DOT_BLOCK, ++bi) {
-        int l1 = l0 + ECUDA_DOT_BLOCK < N ? l0 + ECUDA_DOT_BLOCK : N;
-        double s = 0.0;
-        for (int l = l0; l < l1; ++l) s = fma(ECUDA_LDG(Dt + static_cast<size_t>(l) * N), X[l * ns], s);
-        P[bi * nthr] = s;
-    }
-    double pre = 0.0;  // P[0] + ... + P[bi-1], serial
-    for (int l0 = 0, bi = 0; l0 < N; l0 += ECUDA_DOT_BLOCK, ++bi) {
-        double d[ECUDA_DOT_BLOCK], xv[ECUDA_DOT_BLOCK];
-#pragma unroll
-        for (int i = 0; i < ECUDA_DOT_BLOCK; ++i) {
-            bool in = l0 + i < N;
-            d[i] = in ? ECUDA_LDG(Dt + static_cast<size_t>(l0 + i) * N) : 0.0;
-            xv[i] = in ? X[(l0 + i) * ns] : 0.0;
+    // ---- index-set central differences, row-restricted ----------------------------------------------
+    const double* X = m.z + xoff;
+    const double* XP = m.xp + xoff;
+    const double* XM = m.xm + xoff;
+    const double* RI = m.rinv + xoff;
+    const int* CP = m.colp + xoff;
+    const int cntm1 = pb.xcnt[j] - 1;
+    double dpk = 0.0, dmk = 0.0;  // (D X)[k][j] with X[k][j] perturbed (column X(k,j) itself)
+    // block sums P[bi] of the unperturbed row in thread-private shared memory (P[bi*nthr]). When
+    // every thread owns at most one state item, phase B left them there; otherwise rebuild them.
+    double* P = m.P + tid;
+    if (ns * N > nthr) dot_row(pb, ph, m, k, j, P, nthr);
+    constexpr int NSC = Model<M>::NS;  // == pb.ns for every model
+    const int nb = NB > 0 ? NB : ph.nb;
+    double* jk = jac + k;  // entry of row k in column X(ls,j): colptr + k (+ cntm1 when k > ls)
+    double pre = 0.0;      // P[0] + ... + P[bi-1], serial
+#pragma unroll 1
+    for (int bi = 0; bi < nb; ++bi) {
+        const int l0 = bi * BL;
+        const int nin = (N - l0) < BL ? (N - l0) : BL;
+        const int ntail = nb - 1 - bi;
+        const double* Dtb = Dt + static_cast<size_t>(l0) * N;
+        const double* Ptail = P + (bi + 1) * nthr;
+        const int o = l0 * NSC;
+        const int krel = k - l0;  // position of the diagonal inside this block, or outside [0,BL)
+        double own;
+        constexpr int NTW = NB > 0 ? NB - 1 : 0;
+        if (NB > 0 && nin == BL) {
+            // one code path for every block: the register window always holds NB-1 following sums,
+            // padded with +0.0 (x + 0.0 == x bit for bit: no partial sum here is ever -0.0)
+            own = fd_block<NSC, NTW, true>(Dtb, N, X + o, XP + o, XM + o, RI + o, CP + o, nin, pre, Ptail, ntail, nthr,
+                                           sgr, hfv, krel, cntm1, jk, dpk, dmk);
+        } else {
+            // any block count / partial last block: runtime loops, tail sums read from shared memory
+            own = fd_block_generic<NSC>(Dtb, N, X + o, XP + o, XM + o, RI + o, CP + o, nin, pre, Ptail, ntail, nthr,
+                                        sgr, hfv, krel, cntm1, jk, dpk, dmk);
         }
-        const int nin = (N - l0) < ECUDA_DOT_BLOCK ? (N - l0) : ECUDA_DOT_BLOCK;
-#pragma unroll
-        for (int a = 0; a < ECUDA_DOT_BLOCK; ++a) {
-            const int ls = l0 + a;
-            if (a < nin && ls != k) {
-                const int lcol = nc * N + ls * ns + j;  // phase-local column
-                double sp = 0.0, sm = 0.0;
-                const double xpv = m.xp[lcol], xmv = m.xm[lcol];
-#pragma unroll
-                for (int i = 0; i < ECUDA_DOT_BLOCK; ++i) {
-                    if (i < nin) {
-                        sp = fma(d[i], (i == a) ? xpv : xv[i], sp);
-                        sm = fma(d[i], (i == a) ? xmv : xv[i], sm);
-                    }
-                }
-                double tp = (bi == 0) ? sp : pre + sp;
-                double tm = (bi == 0) ? sm : pre + sm;
-                for (int b2 = bi + 1; b2 < ph.nb; ++b2) {
-                    double pv = P[b2 * nthr];
-                    tp = tp + pv;
-                    tm = tm + pv;
-                }
-                double gp = sgr * (tp - hfv);
-                double gm = sgr * (tm - hfv);
-                int col = ph.zoff + lcol;
-                ECUDA_STREAM_STORE(jac + ECUDA_LDG(pb.colptr + col) + dot_entry_pos(pb, j, k, ls),
-                                   (gp - gm) * m.rinv[lcol]);
-            }
-        }
-        double own = P[bi * nthr];
-        pre = (bi == 0) ? own : pre + own;
+        pre = pre + own;
     }
+    state_column_fd<M>(pb, ph, p, io, m, b, j, k, dpk, dmk);
 }
 
-// node-local Jacobian entries of column c at node k: c in [0,nc) control, [nc,nc+ns) state,
-// nc+ns -> t0, nc+ns+1 -> tf
+// node-local Jacobian entries of column c at node k: c in [0,nc) control, nc -> t0, nc+1 -> tf
 template <int M>
 ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m, int b,
                         int k, int c) {
@@ -308,7 +556,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
 
     if (c < nc) {  // ---- control column U(k, j)
         const int j = c, lcol = k * nc + j, col = ph.zoff + lcol;
-        const int base = ECUDA_LDG(pb.colptr + col);
+        const int base = m.colp[lcol];
         if (fd) {
             double up[NCU], um[NCU], fp[NS], fm[NS];
 #pragma unroll
@@ -348,114 +596,10 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
         }
         return;
     }
-    if (c < nc + ns) {  // ---- state column X(k, j)
-        const int j = c - nc, lcol = nc * N + k * ns + j, col = ph.zoff + lcol;
-        const int base = ECUDA_LDG(pb.colptr + col);
-        const bool reads_path = (j < 2);  // every obstacle row reads the two horizontal positions
-        int pos = N - 1 + pb.xcnt[j];
-        if (fd) {
-            const double xpv = m.xp[lcol], xmv = m.xm[lcol], ri = m.rinv[lcol];
-            double xq[NS], xr[NS], fp[NS], fm[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                xq[i] = (i == j) ? xpv : x[i];
-                xr[i] = (i == j) ? xmv : x[i];
-            }
-            Model<M>::f(xq, u, t, fp);
-            Model<M>::f(xr, u, t, fm);
-            const double dp = dot_row(pb, ph, m, k, j, k, xpv);
-            const double dm = dot_row(pb, ph, m, k, j, k, xmv);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                int rk = pb.xrank[j][i];
-                if (rk >= 0) {
-                    double s = ECUDA_LDG(sg + rdef0 + i);
-                    double dvp = (i == j) ? dp : m.dotv[k * ns + i];
-                    double dvm = (i == j) ? dm : m.dotv[k * ns + i];
-                    double gp = s * (dvp - pt.h * fp[i]);
-                    double gm = s * (dvm - pt.h * fm[i]);
-                    ECUDA_STREAM_STORE(jac + base + k + rk, (gp - gm) * ri);
-                }
-            }
-            if (k == 0 || k == N - 1) {
-                int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
-                double s = ECUDA_LDG(sg + r);
-                ECUDA_STREAM_STORE(jac + base + pos, (s * xpv - s * xmv) * ri);
-                ++pos;
-            }
-            if (reads_path) {
-                for (int q = 0; q < np; ++q) {
-                    double s = ECUDA_LDG(sg + rpath0 + q);
-                    double vp = path_row<M>(pb, ph, m, q, xq[0], xq[1], t);
-                    double vm = path_row<M>(pb, ph, m, q, xr[0], xr[1], t);
-                    ECUDA_STREAM_STORE(jac + base + pos + q, (s * vp - s * vm) * ri);
-                }
-                pos += np;
-            }
-            if (k == N - 1 && p + 1 < pb.nphases) {
-                const PhaseDev& nx = pb.ph[p + 1];
-                int r = pb.linkoff + p * (ns + 1) + j;
-                double s = ECUDA_LDG(sg + r);
-                double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + j);
-                ECUDA_STREAM_STORE(jac + base + pos, (s * (xpv - o) - s * (xmv - o)) * ri);
-            }
-            if (k == 0 && p > 0) {
-                const PhaseDev& pv = pb.ph[p - 1];
-                int r = pb.linkoff + (p - 1) * (ns + 1) + j;
-                double s = ECUDA_LDG(sg + r);
-                double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * ns + j);
-                ECUDA_STREAM_STORE(jac + base + pos, (s * (o - xpv) - s * (o - xmv)) * ri);
-            }
-        } else {
-            double dfdx[NS][NS], dfdu[NS][NCU];
-            Model<M>::jac(x, u, dfdx, dfdu);
-            const double is = ECUDA_LDG(pb.isz + col);
-            const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                int rk = pb.xrank[j][i];
-                if (rk >= 0) {
-                    double d = 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < NS; ++jj)
-                        if (jj == j) d = dfdx[i][jj];
-                    double v = ((i == j) ? dkk : 0.0) - pt.h * d;
-                    ECUDA_STREAM_STORE(jac + base + k + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
-                }
-            }
-            if (k == 0 || k == N - 1) {
-                int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
-                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
-                ++pos;
-            }
-            if (reads_path) {
-                for (int q = 0; q < np; ++q) {
-                    double ddx, ddy, ddt = 0.0;
-                    if (q < ph.nstat)
-                        Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x[0], x[1], &ddx, &ddy);
-                    else
-                        track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0],
-                                           x[1], t, &ddx, &ddy, &ddt);
-                    double v = (j == 0) ? ddx : ddy;
-                    ECUDA_STREAM_STORE(jac + base + pos + q, (ECUDA_LDG(sg + rpath0 + q) * v) * is);
-                }
-                pos += np;
-            }
-            if (k == N - 1 && p + 1 < pb.nphases) {
-                int r = pb.linkoff + p * (ns + 1) + j;
-                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
-            }
-            if (k == 0 && p > 0) {
-                int r = pb.linkoff + (p - 1) * (ns + 1) + j;
-                ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
-            }
-        }
-        return;
-    }
     // ---- time columns t0 / tf
-    const int which = c - nc - ns;  // 0: t0, 1: tf
+    const int which = c - nc;  // 0: t0, 1: tf
     const int lcol = (ns + nc) * N + which, col = ph.zoff + lcol;
-    const int base = ECUDA_LDG(pb.colptr + col);
+    const int base = m.colp[lcol];
     const int ntr = np - ph.nstat;
     if (fd) {
         const double ri = m.rinv[lcol];
@@ -532,7 +676,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
     }
 }
 
-template <int M>
+template <int M, int NB>
 ECUDA_HD void phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
                       int nthr) {
     const int N = ph.N, ns = pb.ns, nc = pb.nc;
@@ -540,12 +684,12 @@ ECUDA_HD void phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
     if (io.g || io.jac)
         for (int it = tid; it < ns * N; it += nthr) {
             int j = it / N, k = it - j * N;
-            defect_item(pb, ph, io, m, b, j, k, tid, nthr);
+            state_item<M, NB>(pb, ph, p, io, m, b, j, k, tid, nthr);
         }
     if (io.jac) {
-        // handed out from the top of the thread range downwards: the threads that had no defect
-        // item above start on these first
-        const int nitems = (nc + ns + 2) * N;
+        // the lighter node items are handed out from the top of the thread range downwards, so the
+        // threads that had no state item above start on these first
+        const int nitems = (nc + 2) * N;
         for (int it = nthr - 1 - tid; it < nitems; it += nthr) {
             int c = it / N, k = it - c * N;
             node_item<M>(pb, ph, p, io, m, b, k, c);

@@ -14,8 +14,13 @@
 
 using namespace ecuda;
 
+template <int M, int NB>
+static void run_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int nthr) {
+    for (int t = 0; t < nthr; ++t) phase_c<M, NB>(pb, ph, p, io, m, b, t, nthr);
+}
+
 template <int M>
-static void run(const ProbDev& pb, const EvalIO& io, int nthr) {
+static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
     for (int b = 0; b < io.batch; ++b)
         for (int p = 0; p < pb.nphases; ++p) {
             const PhaseDev& ph = pb.ph[p];
@@ -31,7 +36,12 @@ static void run(const ProbDev& pb, const EvalIO& io, int nthr) {
             }
             if (io.f || io.g || io.jac) {
                 for (int t = 0; t < nthr; ++t) phase_b<M>(pb, ph, p, io, m, b, t, nthr);
-                for (int t = 0; t < nthr; ++t) phase_c<M>(pb, ph, p, io, m, b, t, nthr);
+                switch (generic ? 0 : ph.nb) {  // same dispatch as launch_eval_t
+                    case 3: run_c<M, 3>(pb, ph, p, io, m, b, nthr); break;
+                    case 4: run_c<M, 4>(pb, ph, p, io, m, b, nthr); break;
+                    case 5: run_c<M, 5>(pb, ph, p, io, m, b, nthr); break;
+                    default: run_c<M, 0>(pb, ph, p, io, m, b, nthr); break;
+                }
             }
         }
     if (io.f && pb.nphases > 1)
@@ -44,7 +54,7 @@ static void run(const ProbDev& pb, const EvalIO& io, int nthr) {
 
 extern "C" int emu_eval(const ecuda_problem_desc* desc, const double* sz, const double* sg, double sf,
                         const double* inst, const double* x, double* f, double* g, double* jac, double* grad,
-                        int jac_mode, int nthr) {
+                        int jac_mode, int nthr, int generic) {
     HostProblem hp;
     std::string err;
     if (!build_layout(*desc, &hp, &err)) return -1;
@@ -87,9 +97,9 @@ extern "C" int emu_eval(const ecuda_problem_desc* desc, const double* sz, const 
     io.x = x; io.inst = inst; io.f = f; io.fpart = fpart.data(); io.g = g; io.jac = jac; io.grad = grad;
     io.jac_mode = jac_mode; io.batch = desc->batch;
     switch (desc->model) {
-        case ECUDA_MODEL_SI2D: run<ECUDA_MODEL_SI2D>(pd, io, nthr); break;
-        case ECUDA_MODEL_PM3D: run<ECUDA_MODEL_PM3D>(pd, io, nthr); break;
-        case ECUDA_MODEL_FW6: run<ECUDA_MODEL_FW6>(pd, io, nthr); break;
+        case ECUDA_MODEL_SI2D: run<ECUDA_MODEL_SI2D>(pd, io, nthr, generic != 0); break;
+        case ECUDA_MODEL_PM3D: run<ECUDA_MODEL_PM3D>(pd, io, nthr, generic != 0); break;
+        case ECUDA_MODEL_FW6: run<ECUDA_MODEL_FW6>(pd, io, nthr, generic != 0); break;
         default: return -1;
     }
     return 0;

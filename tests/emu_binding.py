@@ -32,11 +32,11 @@ def lib():
             build()
         _lib = C.CDLL(LIB)
         _lib.emu_eval.argtypes = [C.POINTER(capi.ProblemDesc), _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp,
-                                  C.c_int, C.c_int]
+                                  C.c_int, C.c_int, C.c_int]
     return _lib
 
 
-def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64):
+def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False):
     dims = capi.host_dims(wl)
     inst = capi.pack_instances(wl, dims)
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(wl.batch, dims.nvars)
@@ -49,7 +49,7 @@ def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64):
     sg = None if wl.sg is None else np.ascontiguousarray(wl.sg, dtype=np.float64)
     desc = capi.make_desc(wl)
     rc = lib().emu_eval(C.byref(desc), p(sz), p(sg), float(wl.sf), p(inst), p(x), p(f), p(g), p(jac), p(grad),
-                        jac_mode, nthr)
+                        jac_mode, nthr, int(generic))
     if rc != 0:
         raise RuntimeError("emu_eval failed")
     return dict(f=f, g=g, jac=jac, grad=grad)

@@ -26,16 +26,16 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("nthr", [32, 256])
-def test_phases_match_oracle(name, nthr):
+@pytest.mark.parametrize("nthr,generic", [(32, False), (256, False), (256, True)])
+def test_phases_match_oracle(name, nthr, generic):
     wl = CASES[name]()
-    if name == "C3-fw6-N200" and nthr == 32:
+    if name == "C3-fw6-N200" and (nthr == 32 or generic):
         pytest.skip("one thread count is enough for the large case")
     o = ob.Oracle(wl)
     style = 1 if name == "C3-fw6-N200" else 0
     for mode in (W.JAC_FD, W.JAC_EXACT):
         ref = o.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style, nthreads=4)
-        got = eb.emu_eval(wl, wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, nthr=nthr)
+        got = eb.emu_eval(wl, wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, nthr=nthr, generic=generic)
         assert rel_err(got["f"], ref["f"]) <= TOL_VALUE
         assert rel_err(got["g"], ref["g"]) <= TOL_VALUE
         assert rel_err(got["grad"], ref["grad"]) <= TOL_VALUE
