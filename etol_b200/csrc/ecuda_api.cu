@@ -13,12 +13,14 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
-#include "ecuda_phases.cuh"
+#include "ecuda_fast.cuh"
 
 namespace ecuda {
 
@@ -87,6 +89,43 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
     phase_c<M, NB>(pb, ph, p, io, m, b, tid, nthr);
 }
 
+// Specialised kernel (ecuda_fast.cuh): one defect row per thread, NB summation blocks, separate
+// instantiations for finite differences and for the exact Jacobian (which needs neither the
+// perturbation data in shared memory nor the registers of the FD rows).
+#ifndef ECUDA_MIN_CTAS_FD
+#define ECUDA_MIN_CTAS_FD 3
+#endif
+#ifndef ECUDA_MIN_CTAS_EXACT
+#define ECUDA_MIN_CTAS_EXACT 4
+#endif
+template <int M, int NB, bool FD>
+__global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_FD : ECUDA_MIN_CTAS_EXACT)
+    k_eval_fast(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (!FD && io.jac) fast_copy_template(pb, ph, io, b, tid, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    RowRegs<NB> rr;
+    fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+    __syncthreads();
+    fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+}
+
 template <int M>
 __global__ void __launch_bounds__(kThreads) k_grad(const __grid_constant__ ProbDev pb,
                                                    const __grid_constant__ EvalIO io) {
@@ -150,10 +189,12 @@ struct ecuda_ctx {
     bool have_problem = false, have_inst = false, have_bounds = false;
     HostProblem hp;
     ProbDev pd{};
-    DevBuf colptr, isz, sg, inst, gl, gu, fpart;
+    DevBuf colptr, isz, sg, inst, gl, gu, fpart, jtmpl;
     DevBuf coll[ECUDA_MAX_PHASES];  // D | Dt | tau | w per phase
     DevBuf sx, sf_, sgv, sjac, sgrad, ssum;  // staging for host-memory calls
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_fast_fd = 0, smem_fast_exact = 0;
+    bool fast_ok = false;  // the specialised kernels (ecuda_fast.cuh) can run this problem
+    bool no_fast = false;  // ECUDA_NO_FAST=1 in the environment: never use them (A/B runs and tests)
     int64_t launches = 0;
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
@@ -194,6 +235,19 @@ static void release(DevBuf& b) {
     b.bytes = 0;
 }
 
+// exact-mode template of the instance-independent triplets; depends on the scaling and on D
+static int upload_template(ecuda_ctx* h) {
+    if (h->hp.col.empty()) return ECUDA_OK;  // collocation data not built yet
+    std::vector<double> isz(h->hp.dims.nvars), tmpl;
+    for (int c = 0; c < h->hp.dims.nvars; ++c) isz[c] = 1.0 / h->h_sz[c];
+    build_jac_template(h->hp, isz.data(), h->h_sg.data(), &tmpl);
+    int rc;
+    if ((rc = ensure(h, h->jtmpl, sizeof(double) * tmpl.size()))) return rc;
+    CU(cudaMemcpy(h->jtmpl.p, tmpl.data(), sizeof(double) * tmpl.size(), cudaMemcpyHostToDevice));
+    h->pd.jtmpl = static_cast<const double*>(h->jtmpl.p);
+    return ECUDA_OK;
+}
+
 static int upload_scaling(ecuda_ctx* h) {
     const int nv = h->hp.dims.nvars, ng = h->hp.dims.ncons;
     std::vector<double> isz(nv);
@@ -205,7 +259,7 @@ static int upload_scaling(ecuda_ctx* h) {
     CU(cudaMemcpy(h->sg.p, h->h_sg.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
     h->pd.isz = static_cast<const double*>(h->isz.p);
     h->pd.sg = static_cast<const double*>(h->sg.p);
-    return ECUDA_OK;
+    return upload_template(h);
 }
 
 static int upload_collocation(ecuda_ctx* h, int p) {
@@ -248,6 +302,28 @@ static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int gri
     return ECUDA_OK;
 }
 
+template <int M, int NB, bool FD>
+static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    const size_t smem = FD ? h->smem_fast_fd : h->smem_fast_exact;
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < smem) {
+            CU(cudaFuncSetAttribute(k_eval_fast<M, NB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    k_eval_fast<M, NB, FD><<<grid, kThreads, smem, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
+template <int M, int NB>
+static int launch_keval_fast_mode(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    if (io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET) return launch_keval_fast<M, NB, true>(h, io, st, grid);
+    return launch_keval_fast<M, NB, false>(h, io, st, grid);
+}
+
 template <int M>
 static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     const int grid = io.batch * h->pd.nphases;
@@ -267,6 +343,13 @@ static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     }
     if (io.f || io.g || io.jac) {
         int rc = ECUDA_OK;
+        if (h->fast_ok) {
+            switch (h->nb_uniform) {
+                case 3: rc = launch_keval_fast_mode<M, 3>(h, io, st, grid); break;
+                case 4: rc = launch_keval_fast_mode<M, 4>(h, io, st, grid); break;
+                default: rc = launch_keval_fast_mode<M, 5>(h, io, st, grid); break;
+            }
+        } else
         switch (h->nb_uniform) {  // block count shared by all phases, or 0
             // specialised for the node counts of the BASELINE configs: 17 -> 3, 30 -> 4, 33 / 40 -> 5
             case 3: rc = launch_keval<M, 3>(h, io, st, grid); break;
@@ -322,6 +405,8 @@ int ecuda_create(int device, ecuda_handle* out) {
     {
         const char* fg = std::getenv("ECUDA_FORCE_GENERIC");
         h->force_generic = fg && fg[0] == '1';
+        const char* nf = std::getenv("ECUDA_NO_FAST");
+        h->no_fast = nf && nf[0] == '1';
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -337,7 +422,7 @@ int ecuda_destroy(ecuda_handle h) {
     if (!h) return ECUDA_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->sx, &h->sf_, &h->sgv,
+    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->sx, &h->sf_, &h->sgv,
                       &h->sjac, &h->sgrad, &h->ssum})
         release(*b);
     for (auto& b : h->coll) release(b);
@@ -362,54 +447,30 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     h->have_inst = false;
     h->have_bounds = false;
     ProbDev& pd = h->pd;
-    std::memset(&pd, 0, sizeof(pd));
-    pd.model = desc->model;
-    pd.ns = hp.ns;
-    pd.nc = hp.nc;
-    pd.ne = hp.ne;
-    pd.nphases = hp.nphases;
-    pd.nvars = hp.dims.nvars;
-    pd.ncons = hp.dims.ncons;
-    pd.nnz = hp.dims.nnz;
-    pd.nlink = hp.dims.nlinkages;
-    pd.linkoff = hp.linkoff;
-    pd.ntracks = desc->ntracks;
-    pd.nway = desc->nwaypoints;
-    pd.track_off = hp.track_off;
-    pd.track_size = hp.dims.track_size;
-    pd.rec_size = hp.dims.rec_size;
-    pd.inst_stride = hp.dims.inst_stride;
-    pd.maximize = desc->maximize ? 1 : 0;
-    pd.dense = desc->pattern_mode == ECUDA_PATTERN_DENSE_NODE;
-    pd.sf = 1.0;
-    std::memcpy(pd.xrank, hp.xrank, sizeof(pd.xrank));
-    std::memcpy(pd.urank, hp.urank, sizeof(pd.urank));
-    std::memcpy(pd.xcnt, hp.xcnt, sizeof(pd.xcnt));
-    std::memcpy(pd.ucnt, hp.ucnt, sizeof(pd.ucnt));
-    size_t smem = 0;
+    fill_probdev(hp, &pd);
+    size_t smem = 0, smem_fd = 0, smem_ex = 0;
+    bool one_row_per_thread = true;
     for (int p = 0; p < hp.nphases; ++p) {
         PhaseDev& ph = pd.ph[p];
-        ph.N = hp.N[p];
-        ph.npath = hp.npath[p];
-        ph.nstat = hp.nstat[p];
-        ph.nb = (hp.N[p] + ECUDA_DOT_BLOCK - 1) / ECUDA_DOT_BLOCK;
-        ph.zoff = hp.zoff[p];
-        ph.goff = hp.goff[p];
-        ph.nvars = hp.nvars_p[p];
-        ph.inst_off = hp.inst_off[p];
         int rc = upload_collocation(h, p);
         if (rc) return rc;
-        size_t s = cta_doubles(pd, ph, kThreads) * sizeof(double);
-        smem = s > smem ? s : smem;
+        smem = std::max(smem, cta_doubles(pd, ph, kThreads) * sizeof(double));
+        smem_fd = std::max(smem_fd, cta_doubles(pd, ph, kThreads, CARVE_FD) * sizeof(double));
+        smem_ex = std::max(smem_ex, cta_doubles(pd, ph, kThreads, 0) * sizeof(double));
+        one_row_per_thread = one_row_per_thread && pd.ns * ph.N <= kThreads;
     }
     if (smem > 227 * 1024 - 64)
         return fail(h, ECUDA_ERR_ARG, "phase too large for one CTA's shared memory (" + std::to_string(smem) + " B)");
     h->smem_bytes = smem;
+    h->smem_fast_fd = smem_fd;
+    h->smem_fast_exact = smem_ex;
     h->nb_uniform = pd.ph[0].nb;
     for (int p = 1; p < hp.nphases; ++p)
         if (pd.ph[p].nb != h->nb_uniform) h->nb_uniform = 0;
     if (h->nb_uniform > 8) h->nb_uniform = 0;
     if (h->force_generic) h->nb_uniform = 0;
+    // the specialised kernels: block counts of the BASELINE configs, one defect row per thread
+    h->fast_ok = !h->no_fast && !h->force_generic && h->nb_uniform >= 3 && h->nb_uniform <= 5 && one_row_per_thread;
     int rc;
     if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
     CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));
@@ -469,7 +530,8 @@ int ecuda_set_collocation(ecuda_handle h, int phase, const double* tau, const do
     std::memcpy(c.tau.data(), tau, sizeof(double) * c.N);
     std::memcpy(c.w.data(), w, sizeof(double) * c.N);
     std::memcpy(c.D.data(), D, sizeof(double) * c.N * c.N);
-    return upload_collocation(h, phase);
+    int rc = upload_collocation(h, phase);
+    return rc ? rc : upload_template(h);
 }
 
 int ecuda_set_scaling(ecuda_handle h, const double* sz, const double* sg, double sf) {

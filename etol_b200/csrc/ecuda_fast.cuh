@@ -1,0 +1,285 @@
+// ecuda_fast.cuh -- the specialised per-instance evaluation used when every phase has at most one
+// defect row per thread (ns*N <= blockDim) and a compile-time number NB of summation blocks.
+//
+// Same arithmetic as ecuda_phases.cuh (every value is produced by the same operation sequence, so
+// the results are bit-identical to the generic path and to the oracle); what changes is how the work
+// is laid out on the CTA:
+//   * thread (j,k) owns defect row (k,j): its NB block sums of (D X)[k][j] stay in REGISTERS from
+//     phase B to phase C (no shared-memory round trip), the summation blocks are unrolled with the
+//     block index known at compile time, so the serial prefix / tail of block sums around a
+//     perturbed block are register operands and have exactly the length they need;
+//   * the diagonal column's perturbed dots are computed once per row instead of being carried as
+//     predicated moves through all N entries;
+//   * 32-bit triplet index arithmetic, one 64-bit multiply-add per store;
+//   * node-level work (path rows of g, path entries of the X columns, control and t0/tf columns) is
+//     handed out one item per thread from the top of the thread range, so threads without a defect
+//     row start on it and nobody evaluates eight obstacle rows in a row;
+//   * exact mode: the D-coupled triplets sg*D/sz do not depend on the instance, so they are copied
+//     from a per-problem template (L2 resident) with coalesced loads/stores instead of being
+//     recomputed.
+// Reference counterparts: as in ecuda_phases.cuh (PSOPT defect assembly + derivative drivers entered
+// at src/ePSOPT/ePSOPT.cpp:84, callbacks src/ePSOPT/ePSOPT.cpp:186-306).
+#ifndef ECUDA_FAST_CUH_
+#define ECUDA_FAST_CUH_
+
+#include "ecuda_phases.cuh"
+
+namespace ecuda {
+
+// per-thread state that lives in registers between phase B and phase C
+template <int NB>
+struct RowRegs {
+    double P[NB];   // block sums of (D X)[k][j]
+    double dp, dm;  // (D X)[k][j] with X[k][j] -> +-delta (finite differences only)
+};
+
+// block sums + total of row k of D times state j of X (canonical blocked order, see dot_row)
+template <int NS, int NB>
+ECUDA_HD double fast_dot(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj, double (&P)[NB]) {
+    constexpr int BL = ECUDA_DOT_BLOCK;
+    double total = 0.0;
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi) {
+        const int l0 = bi * BL;
+        double p = 0.0;
+#pragma unroll
+        for (int i = 0; i < BL; ++i)
+            if (bi < NB - 1 || l0 + i < N) p = fma(ECUDA_LDG(Dtk + (l0 + i) * N), Xj[(l0 + i) * NS], p);
+        P[bi] = p;
+        total = (bi == 0) ? p : total + p;
+    }
+    return total;
+}
+
+// perturbed dots of the diagonal column: same operation sequence as a D-coupled entry with l == k
+template <int NS, int NB>
+ECUDA_HD void fast_diag(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj, double xpk, double xmk,
+                        int k, const double (&P)[NB], double& dp, double& dm) {
+    constexpr int BL = ECUDA_DOT_BLOCK;
+    const int bk = k / BL, l0 = bk * BL, krel = k - l0;
+    double q = 0.0, sp = 0.0, sm = 0.0;
+#pragma unroll
+    for (int i = 0; i < BL; ++i) {
+        if (l0 + i < N) {
+            const double di = ECUDA_LDG(Dtk + (l0 + i) * N);
+            const double xi = Xj[(l0 + i) * NS];
+            if (i < krel) {
+                q = fma(di, xi, q);
+            } else if (i == krel) {
+                sp = fma(di, xpk, q);
+                sm = fma(di, xmk, q);
+            } else {
+                sp = fma(di, xi, sp);
+                sm = fma(di, xi, sm);
+            }
+        }
+    }
+    double pre = 0.0;
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        if (t < bk) pre = pre + P[t];  // 0.0 + P[0] == P[0] bit for bit (a block sum is never -0.0)
+    double tp = pre + sp, tm = pre + sm;
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        if (t > bk) {
+            tp = tp + P[t];
+            tm = tm + P[t];
+        }
+    dp = tp;
+    dm = tm;
+}
+
+// D-coupled triplets of row (k,j) in the state columns of summation block BI, by index-set central
+// differences (row-restricted: see ecuda_phases.cuh). jac = triplet array of the instance;
+// kpc = k + (number of node-local defect rows of column X(.,j)) - 1.
+template <int NS, int NB, int BI>
+ECUDA_HD void fast_fd_block(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj,
+                            const double* __restrict__ XPj, const double* __restrict__ XMj,
+                            const double* __restrict__ RIj, const int* __restrict__ CPj, const double (&P)[NB],
+                            double sgr, double hfv, int k, int kpc, double* __restrict__ jac) {
+    constexpr int BL = ECUDA_DOT_BLOCK;
+    constexpr int l0 = BI * BL;
+    constexpr bool LAST = BI == NB - 1;  // only the last block can be partial
+    double d[BL], xv[BL];
+#pragma unroll
+    for (int i = 0; i < BL; ++i) {
+        if (!LAST || l0 + i < N) {
+            d[i] = ECUDA_LDG(Dtk + (l0 + i) * N);
+            xv[i] = Xj[(l0 + i) * NS];
+        } else {
+            d[i] = 0.0;
+            xv[i] = 0.0;
+        }
+    }
+    double pre = 0.0;
+#pragma unroll
+    for (int t = 0; t < BI; ++t) pre = (t == 0) ? P[0] : pre + P[t];
+    double q = 0.0;  // unperturbed in-block prefix
+#pragma unroll
+    for (int a = 0; a < BL; ++a) {
+        if (!LAST || l0 + a < N) {
+            double sp = fma(d[a], XPj[(l0 + a) * NS], q);
+            double sm = fma(d[a], XMj[(l0 + a) * NS], q);
+#pragma unroll
+            for (int i = a + 1; i < BL; ++i)
+                if (!LAST || l0 + i < N) {
+                    sp = fma(d[i], xv[i], sp);
+                    sm = fma(d[i], xv[i], sm);
+                }
+            double tp = (BI > 0) ? pre + sp : sp;
+            double tm = (BI > 0) ? pre + sm : sm;
+#pragma unroll
+            for (int t = BI + 1; t < NB; ++t) {
+                tp = tp + P[t];
+                tm = tm + P[t];
+            }
+            const double gp = sgr * (tp - hfv);
+            const double gm = sgr * (tm - hfv);
+            const double v = (gp - gm) * RIj[(l0 + a) * NS];
+            // rows k < l sit at position k of column X(l,j); rows k > l come after its node-local block.
+            // For l == k the slot is the first node-local defect triplet of the thread's own column,
+            // which xcol_local_* overwrites later in this thread's program order: storing there
+            // unconditionally is cheaper than a branch around the store.
+            const unsigned idx = static_cast<unsigned>(CPj[(l0 + a) * NS] + ((l0 + a) < k ? kpc : k));
+            ECUDA_STREAM_STORE(jac + idx, v);
+            q = fma(d[a], xv[a], q);
+        }
+    }
+}
+
+template <int NS, int NB, int BI>
+struct FastFdBlocks {
+    ECUDA_HD static void run(const double* Dtk, int N, const double* Xj, const double* XPj, const double* XMj,
+                             const double* RIj, const int* CPj, const double (&P)[NB], double sgr, double hfv, int k,
+                             int kpc, double* jac) {
+        fast_fd_block<NS, NB, BI>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+        FastFdBlocks<NS, NB, BI + 1>::run(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+    }
+};
+template <int NS, int NB>
+struct FastFdBlocks<NS, NB, NB> {
+    ECUDA_HD static void run(const double*, int, const double*, const double*, const double*, const double*,
+                             const int*, const double (&)[NB], double, double, int, int, double*) {}
+};
+
+// exact mode: copy this phase's slice of the per-problem template into the instance's triplet array
+// (plain coalesced copies; the node-local triplets are overwritten after the next barrier)
+ECUDA_HD void fast_copy_template(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, int b, int tid, int nthr) {
+    const int e0 = ECUDA_LDG(pb.colptr + ph.zoff + pb.nc * ph.N);        // first state column of the phase
+    const int e1 = ECUDA_LDG(pb.colptr + ph.zoff + (pb.nc + pb.ns) * ph.N);  // its t0 column
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    for (int e = e0 + tid; e < e1; e += nthr) ECUDA_STREAM_STORE(jac + e, ECUDA_LDG(pb.jtmpl + e));
+}
+
+// ---- phase B ------------------------------------------------------------------------------------------
+template <int M, int NB, bool FD>
+ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
+                           int nthr, RowRegs<NB>& rr) {
+    constexpr int NS = Model<M>::NS;
+    const int N = ph.N, nc = pb.nc, np = ph.npath;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
+    const double* sg = pb.sg;
+    // defect rows: block sums into registers, totals into shared memory
+    if (tid < NS * N) {
+        const int j = tid / N, k = tid - j * N;
+        const double* Dtk = ph.Dt + k;
+        const double* Xj = m.z + nc * N + j;
+        m.dotv[k * NS + j] = fast_dot<NS, NB>(Dtk, N, Xj, rr.P);
+        if (FD && io.jac) {
+            const int lcol = nc * N + k * NS + j;
+            fast_diag<NS, NB>(Dtk, N, Xj, m.xp[lcol], m.xm[lcol], k, rr.P, rr.dp, rr.dm);
+        }
+    }
+    // node values, handed out from the top of the thread range (threads without a defect row first)
+    for (int k = nthr - 1 - tid; k < N; k += nthr) {
+        const double* x = m.z + nc * N + k * NS;
+        const double* u = m.z + k * nc;
+        const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+        double f[NS];
+        Model<M>::f(x, u, t, f);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) m.hf[k * NS + i] = pt.h * f[i];
+        const double L = Model<M>::cost(x, u, t);
+        m.Lk[k] = pb.maximize ? -1.0 * L : L;
+    }
+    if (g) {
+        // path rows: one row per thread
+        for (int it = nthr - 1 - tid; it < np * N; it += nthr) {
+            const int k = it / np, q = it - k * np;
+            const double* x = m.z + nc * N + k * NS;
+            const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+            const int r = ph.goff + NS * N + pb.ne + it;
+            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t));
+        }
+        for (int e = tid; e < pb.ne; e += nthr) {
+            const int r = ph.goff + NS * N + e;
+            const int node = (e < NS) ? 0 : N - 1;
+            const int i = (e < NS) ? e : e - NS;
+            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * m.z[nc * N + node * NS + i]);
+        }
+        if (tid == 0) {
+            const int r = ph.goff + NS * N + pb.ne + np * N;
+            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * (pt.tf - pt.t0));
+        }
+        if (p + 1 < pb.nphases) {
+            const PhaseDev& nx = pb.ph[p + 1];
+            for (int i = tid; i <= NS; i += nthr) {
+                const int r = pb.linkoff + p * (NS + 1) + i;
+                const double mine = (i < NS) ? m.z[nc * N + (N - 1) * NS + i] : pt.tf;
+                const int ocol = (i < NS) ? nx.zoff + nc * nx.N + i : nx.zoff + (NS + nc) * nx.N;
+                const double other = other_phase_value(pb, io, b, ocol);
+                ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * (mine - other));
+            }
+        }
+    }
+}
+
+// ---- phase C ------------------------------------------------------------------------------------------
+template <int M, int NB, bool FD>
+ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
+                           int nthr, const RowRegs<NB>& rr) {
+    constexpr int NS = Model<M>::NS;
+    const int N = ph.N, nc = pb.nc, np = ph.npath;
+    if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
+    double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
+    if (tid < NS * N && (io.g || jac)) {
+        const int j = tid / N, k = tid - j * N;
+        const int r = ph.goff + k * NS + j;
+        const double sgr = ECUDA_LDG(pb.sg + r);
+        const double hfv = m.hf[k * NS + j];
+        if (io.g) ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, sgr * (m.dotv[k * NS + j] - hfv));
+        if (jac) {
+            if (FD) {
+                const int xoff = nc * N + j;
+                FastFdBlocks<NS, NB, 0>::run(ph.Dt + k, N, m.z + xoff, m.xp + xoff, m.xm + xoff, m.rinv + xoff,
+                                             m.colp + xoff, rr.P, sgr, hfv, k, k + pb.xcnt[j] - 1, jac);
+                xcol_local_fd<M>(pb, ph, p, io, m, b, j, k, rr.dp, rr.dm, jac);
+            } else {
+                xcol_local_exact<M>(pb, ph, p, m, j, k, jac);
+            }
+        }
+    }
+    if (jac) {
+        // one item per thread from the top of the thread range: path triplets of the state columns
+        // (states 0 and 1 of every node), then the control and t0/tf columns
+        const int nP = (NS >= 2) ? N * 2 * np : 0, nU = (nc + 2) * N;
+        for (int it = nthr - 1 - tid; it < nP + nU; it += nthr) {
+            if (it < nP) {
+                const int k = it / (2 * np), rem = it - k * 2 * np;
+                const int j = rem / np, q = rem - j * np;
+                if (FD)
+                    xcol_path_fd<M>(pb, ph, m, j, k, q, jac);
+                else
+                    xcol_path_exact<M>(pb, ph, m, j, k, q, jac);
+            } else {
+                const int i2 = it - nP;
+                const int c = i2 / N, k = i2 - c * N;
+                node_item<M>(pb, ph, p, io, m, b, k, c);
+            }
+        }
+    }
+}
+
+}  // namespace ecuda
+#endif

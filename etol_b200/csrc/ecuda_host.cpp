@@ -9,6 +9,7 @@
 //   edge records static geometry of src/Examples/PSOPT/etol_psopt_example1.cpp:164-172,178-179
 // Compiled with -ffp-contract=off so that every expression below is a sequence of single IEEE
 // operations.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -304,6 +305,66 @@ void build_structure(HostProblem* hp) {
         hp->group_of_col[c] = static_cast<int32_t>(g);
     }
     hp->dims.ngroups = static_cast<int32_t>(cover.size());
+}
+
+void fill_probdev(const HostProblem& hp, ProbDev* out) {
+    ProbDev& pd = *out;
+    std::memset(&pd, 0, sizeof(pd));
+    const ecuda_problem_desc& d = hp.desc;
+    pd.model = d.model;
+    pd.ns = hp.ns;
+    pd.nc = hp.nc;
+    pd.ne = hp.ne;
+    pd.nphases = hp.nphases;
+    pd.nvars = hp.dims.nvars;
+    pd.ncons = hp.dims.ncons;
+    pd.nnz = hp.dims.nnz;
+    pd.nlink = hp.dims.nlinkages;
+    pd.linkoff = hp.linkoff;
+    pd.ntracks = d.ntracks;
+    pd.nway = d.nwaypoints;
+    pd.track_off = hp.track_off;
+    pd.track_size = hp.dims.track_size;
+    pd.rec_size = hp.dims.rec_size;
+    pd.inst_stride = hp.dims.inst_stride;
+    pd.maximize = d.maximize ? 1 : 0;
+    pd.dense = d.pattern_mode == ECUDA_PATTERN_DENSE_NODE;
+    pd.sf = 1.0;
+    std::memcpy(pd.xrank, hp.xrank, sizeof(pd.xrank));
+    std::memcpy(pd.urank, hp.urank, sizeof(pd.urank));
+    std::memcpy(pd.xcnt, hp.xcnt, sizeof(pd.xcnt));
+    std::memcpy(pd.ucnt, hp.ucnt, sizeof(pd.ucnt));
+    for (int p = 0; p < hp.nphases; ++p) {
+        PhaseDev& ph = pd.ph[p];
+        ph.N = hp.N[p];
+        ph.npath = hp.npath[p];
+        ph.nstat = hp.nstat[p];
+        ph.nb = (hp.N[p] + ECUDA_DOT_BLOCK - 1) / ECUDA_DOT_BLOCK;
+        ph.zoff = hp.zoff[p];
+        ph.goff = hp.goff[p];
+        ph.nvars = hp.nvars_p[p];
+        ph.inst_off = hp.inst_off[p];
+    }
+}
+
+void build_jac_template(const HostProblem& hp, const double* isz, const double* sg, std::vector<double>* tmpl) {
+    tmpl->assign(static_cast<size_t>(hp.dims.nnz), 0.0);
+    const int ns = hp.ns, nc = hp.nc;
+    for (int p = 0; p < hp.nphases; ++p) {
+        const int N = hp.N[p];
+        const double* D = hp.col[p].D.data();
+        for (int l = 0; l < N; ++l)
+            for (int j = 0; j < ns; ++j) {
+                const int col = hp.zoff[p] + nc * N + l * ns + j;
+                const int base = hp.colptr[col];
+                for (int k = 0; k < N; ++k) {
+                    if (k == l) continue;
+                    const int row = hp.goff[p] + k * ns + j;
+                    // same two roundings as the kernels: (sg * D) * (1/sz)
+                    (*tmpl)[base + (k < l ? k : k + hp.xcnt[j] - 1)] = (sg[row] * D[static_cast<size_t>(k) * N + l]) * isz[col];
+                }
+            }
+    }
 }
 
 }  // namespace ecuda

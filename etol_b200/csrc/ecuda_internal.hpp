@@ -40,6 +40,8 @@ struct ProbDev {
     int maximize, dense;
     double sf;
     const int* colptr;    // [nvars+1]
+    const double* jtmpl;  // [nnz] exact-mode template: the instance-independent D-coupled entries
+                          //       sg[row] * D[k][l] / sz[col]; other slots are 0
     const double* isz;    // [nvars]  1/sz
     const double* sg;     // [ncons]
     // position of defect row (k,i) inside the node-local part of column X(k,j) / U(k,j); -1 = absent
@@ -96,6 +98,12 @@ struct HostProblem {
 bool build_layout(const ecuda_problem_desc& d, HostProblem* hp, std::string* err);
 // pattern (CSC, rows ascending per column) + CPR grouping
 void build_structure(HostProblem* hp);
+// layout part of the kernel parameter block (everything except device pointers and sf); needs
+// build_layout + build_structure
+void fill_probdev(const HostProblem& hp, ProbDev* pd);
+// exact-mode Jacobian template: tmpl[e] = (sg[row] * D[k][l]) * isz[col] for every D-coupled triplet
+// (defect row (k,j) x state column X(l,j), k != l), 0 elsewhere. Needs the collocation data in hp.col.
+void build_jac_template(const HostProblem& hp, const double* isz, const double* sg, std::vector<double>* tmpl);
 
 }  // namespace ecuda
 #endif

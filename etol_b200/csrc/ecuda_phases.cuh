@@ -51,33 +51,43 @@ struct CtaMem {
     double* Lk;    // [N]       running cost per node
     double* inst;  // [inst_stride] obstacle + track records of the instance
     double* P;     // [nb][nthr] thread-private block sums (generic block count only)
-    int* colp;     // [nvars_p] first triplet index of each column of this phase
+    int* colp;     // [nvars_p + 1] first triplet index of each column of this phase (+ end of the phase)
 };
 
+// what a CTA keeps in shared memory: the generic kernels need everything; the fast kernels keep the
+// block sums in registers (no P) and, in exact mode, have no finite-difference data (no xp/xm/rinv)
+enum { CARVE_P = 1, CARVE_FD = 2, CARVE_ALL = 3 };
+
 // shared-memory footprint in doubles for one CTA working on phase `ph`
-ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr) {
+ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr, int what = CARVE_ALL) {
     size_t n = 0;
-    n += 4 * static_cast<size_t>(ph.nvars + (ph.nvars & 1));
+    n += ((what & CARVE_FD) ? 4 : 1) * static_cast<size_t>(ph.nvars + (ph.nvars & 1));
     n += 2 * static_cast<size_t>(ph.N) * pb.ns;
     n += static_cast<size_t>(ph.N + (ph.N & 1));
     n += static_cast<size_t>(pb.inst_stride);
-    n += static_cast<size_t>(ph.nb) * nthr;
-    n += static_cast<size_t>((ph.nvars + 2) / 2);  // colp (ints)
+    if (what & CARVE_P) n += static_cast<size_t>(ph.nb) * nthr;
+    n += static_cast<size_t>((ph.nvars + 3) / 2);  // colp (ints), nvars_p + 1 of them
     return n;
 }
 
-ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& ph, int nthr) {
+ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& ph, int nthr, int what = CARVE_ALL) {
     size_t nv = static_cast<size_t>(ph.nvars + (ph.nvars & 1));
     m.inst = base;  // first: 16-byte aligned destination of the bulk copy
     base += pb.inst_stride;
     m.z = base;     base += nv;
-    m.xp = base;    base += nv;
-    m.xm = base;    base += nv;
-    m.rinv = base;  base += nv;
+    m.xp = m.xm = m.rinv = m.P = nullptr;
+    if (what & CARVE_FD) {
+        m.xp = base;    base += nv;
+        m.xm = base;    base += nv;
+        m.rinv = base;  base += nv;
+    }
     m.hf = base;    base += static_cast<size_t>(ph.N) * pb.ns;
     m.dotv = base;  base += static_cast<size_t>(ph.N) * pb.ns;
     m.Lk = base;    base += static_cast<size_t>(ph.N + (ph.N & 1));
-    m.P = base;     base += static_cast<size_t>(ph.nb) * nthr;
+    if (what & CARVE_P) {
+        m.P = base;
+        base += static_cast<size_t>(ph.nb) * nthr;
+    }
     m.colp = reinterpret_cast<int*>(base);
 }
 
@@ -98,6 +108,7 @@ ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io
                          int nthr, bool fd) {
     const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
     const double* is = pb.isz + ph.zoff;
+    if (tid == 0) m.colp[ph.nvars] = ECUDA_LDG(pb.colptr + ph.zoff + ph.nvars);
     for (int c = tid; c < ph.nvars; c += nthr) {
         double zt = ECUDA_LDG(xs + c);
         double s = ECUDA_LDG(is + c);
@@ -227,17 +238,22 @@ ECUDA_HD void objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, cons
 // position of defect row (k, state j) inside column X(l, j), k != l
 ECUDA_HD int dot_entry_pos(const ProbDev& pb, int j, int k, int l) { return k < l ? k : k - 1 + pb.xcnt[j]; }
 
-// node-local part of column X(k,j) by central differences; dpk/dmk = (D X)[k][j] with X[k][j]
-// replaced by its +/- perturbed value
+// ---- node-local part of column X(k,j) -------------------------------------------------------------------
+// Column X(k,j) holds, in row order: the D-coupled defect rows (k',j), k' < k | the defect rows of
+// node k | the D-coupled rows k' > k | the event row (k = 0 or N-1) | the path rows of node k
+// (j < 2: every obstacle row reads the two horizontal positions) | the linkage row.
+// `jac` is the base such that jac[e] is the slot of triplet e of this instance.
+
+// defect rows of node k, event row, linkage row -- by central differences. dpk/dmk = (D X)[k][j]
+// with X[k][j] replaced by its +/- perturbed value.
 template <int M>
-ECUDA_HD void state_column_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
-                              int b, int j, int k, double dpk, double dmk) {
+ECUDA_HD void xcol_local_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m, int b,
+                            int j, int k, double dpk, double dmk, double* jac) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
     const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
     const PhaseTimes pt = phase_times(pb, ph, m.z);
     const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
     const double* sg = pb.sg;
-    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
     const int lcol = nc * N + k * ns + j;
     const int base = m.colp[lcol];
     const double xpv = m.xp[lcol], xmv = m.xm[lcol], ri = m.rinv[lcol];
@@ -271,16 +287,7 @@ ECUDA_HD void state_column_fd(const ProbDev& pb, const PhaseDev& ph, int p, cons
         ECUDA_STREAM_STORE(jac + base + pos, (s * xpv - s * xmv) * ri);
         ++pos;
     }
-    if (j < 2) {  // every obstacle row reads the two horizontal positions
-        const int rpath0 = ph.goff + ns * N + pb.ne + k * np;
-        for (int q = 0; q < np; ++q) {
-            double s = ECUDA_LDG(sg + rpath0 + q);
-            double vp = path_row<M>(pb, ph, m, q, xq[0], xq[1], t);
-            double vm = path_row<M>(pb, ph, m, q, xr[0], xr[1], t);
-            ECUDA_STREAM_STORE(jac + base + pos + q, (s * vp - s * vm) * ri);
-        }
-        pos += np;
-    }
+    if (j < 2) pos += np;
     if (k == N - 1 && p + 1 < pb.nphases) {
         const PhaseDev& nx = pb.ph[p + 1];
         int r = pb.linkoff + p * (ns + 1) + j;
@@ -297,16 +304,31 @@ ECUDA_HD void state_column_fd(const ProbDev& pb, const PhaseDev& ph, int p, cons
     }
 }
 
-// node-local part of column X(k,j), analytic
+// path row q of node k in column X(k,j), j < 2 -- by central differences
 template <int M>
-ECUDA_HD void state_column_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
-                                 int b, int j, int k) {
-    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+ECUDA_HD void xcol_path_fd(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int j, int k, int q, double* jac) {
     const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
     const PhaseTimes pt = phase_times(pb, ph, m.z);
     const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+    const int lcol = nc * N + k * ns + j;
+    const double xpv = m.xp[lcol], xmv = m.xm[lcol], ri = m.rinv[lcol];
+    const double x0 = m.z[nc * N + k * ns], x1 = m.z[nc * N + k * ns + 1];
+    const int r = ph.goff + ns * N + pb.ne + k * np + q;
+    const double s = ECUDA_LDG(pb.sg + r);
+    double vp = path_row<M>(pb, ph, m, q, j == 0 ? xpv : x0, j == 1 ? xpv : x1, t);
+    double vm = path_row<M>(pb, ph, m, q, j == 0 ? xmv : x0, j == 1 ? xmv : x1, t);
+    const int pos = N - 1 + pb.xcnt[j] + ((k == 0 || k == N - 1) ? 1 : 0) + q;
+    ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * vp - s * vm) * ri);
+}
+
+// defect rows of node k, event row, linkage row -- analytic
+template <int M>
+ECUDA_HD void xcol_local_exact(const ProbDev& pb, const PhaseDev& ph, int p, const CtaMem& m, int j, int k,
+                               double* jac) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
     const double* sg = pb.sg;
-    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
     const int lcol = nc * N + k * ns + j, col = ph.zoff + lcol;
     const int base = m.colp[lcol];
     double x[NS], u[NCU];
@@ -337,20 +359,7 @@ ECUDA_HD void state_column_exact(const ProbDev& pb, const PhaseDev& ph, int p, c
         ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
         ++pos;
     }
-    if (j < 2) {
-        const int rpath0 = ph.goff + ns * N + pb.ne + k * np;
-        for (int q = 0; q < np; ++q) {
-            double ddx, ddy, ddt = 0.0;
-            if (q < ph.nstat)
-                Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x[0], x[1], &ddx, &ddy);
-            else
-                track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0], x[1], t,
-                                   &ddx, &ddy, &ddt);
-            double v = (j == 0) ? ddx : ddy;
-            ECUDA_STREAM_STORE(jac + base + pos + q, (ECUDA_LDG(sg + rpath0 + q) * v) * is);
-        }
-        pos += np;
-    }
+    if (j < 2) pos += np;
     if (k == N - 1 && p + 1 < pb.nphases) {
         int r = pb.linkoff + p * (ns + 1) + j;
         ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
@@ -359,6 +368,44 @@ ECUDA_HD void state_column_exact(const ProbDev& pb, const PhaseDev& ph, int p, c
         int r = pb.linkoff + (p - 1) * (ns + 1) + j;
         ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
     }
+}
+
+// path row q of node k in column X(k,j), j < 2 -- analytic
+template <int M>
+ECUDA_HD void xcol_path_exact(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int j, int k, int q,
+                              double* jac) {
+    const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
+    const int lcol = nc * N + k * ns + j, col = ph.zoff + lcol;
+    const double x0 = m.z[nc * N + k * ns], x1 = m.z[nc * N + k * ns + 1];
+    double ddx, ddy, ddt = 0.0;
+    if (q < ph.nstat)
+        Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x0, x1, &ddx, &ddy);
+    else
+        track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x0, x1, t, &ddx, &ddy, &ddt);
+    const double v = (j == 0) ? ddx : ddy;
+    const int r = ph.goff + ns * N + pb.ne + k * np + q;
+    const int pos = N - 1 + pb.xcnt[j] + ((k == 0 || k == N - 1) ? 1 : 0) + q;
+    ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (ECUDA_LDG(pb.sg + r) * v) * ECUDA_LDG(pb.isz + col));
+}
+
+// whole node-local part of column X(k,j), written to the caller's global array (generic path)
+template <int M>
+ECUDA_HD void state_column_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                              int b, int j, int k, double dpk, double dmk) {
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    xcol_local_fd<M>(pb, ph, p, io, m, b, j, k, dpk, dmk, jac);
+    if (j < 2)
+        for (int q = 0; q < ph.npath; ++q) xcol_path_fd<M>(pb, ph, m, j, k, q, jac);
+}
+template <int M>
+ECUDA_HD void state_column_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                                 int b, int j, int k) {
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    xcol_local_exact<M>(pb, ph, p, m, j, k, jac);
+    if (j < 2)
+        for (int q = 0; q < ph.npath; ++q) xcol_path_exact<M>(pb, ph, m, j, k, q, jac);
 }
 
 // Same as fd_block for any tail length and any number of valid nodes (runtime loops).

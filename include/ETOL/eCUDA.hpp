@@ -1,0 +1,96 @@
+// eCUDA.hpp -- the eCUDA eSolver: ETOL's TrajectoryOptimizer interface in front of the B200
+// collocation-NLP evaluator (include/ecuda.h).
+//
+// It takes the place ePSOPT has in the reference (include/ETOL/ePSOPT.hpp, src/ePSOPT/ePSOPT.cpp):
+// the same XML, the same call sequence
+//     loadConfigs -> setMaximize -> [model + constraint registration] -> setup -> debug -> solve
+//     -> getScore / getXtraj / getUtraj / save -> close
+// (src/Examples/PSOPT/etol_psopt_example1.cpp:41-81), the same NLP dimensions and bounds
+// (ePSOPT::setup / addBounds, src/ePSOPT/ePSOPT.cpp:40-81,125-155). What differs is where the VGP
+// callbacks run. ePSOPT calls host std::function lambdas on adouble once per node
+// (ePSOPT.cpp:186-276); a GPU cannot call those, so -- like every eSolver, which fixes the scalar
+// type its callbacks are written in (src/docs/source/tutorials/vgp.rst:155) -- eCUDA takes its
+// callbacks as *device models*: setModel() selects dynamics + running cost, and
+// addObstacleConstraints() / addTrackConstraints() register the path constraints that the
+// reference example builds in obsConstraint() / saaConstraint()
+// (etol_psopt_example1.cpp:140-258), including the same "side_i_j_0" / "ball_i_0_0" parameters.
+#ifndef INCLUDE_ETOL_ECUDA_HPP_
+#define INCLUDE_ETOL_ECUDA_HPP_
+
+#include <array>
+#include <string>
+#include <vector>
+
+#include <ETOL/TrajectoryOptimizer.hpp>
+#include <ETOL/eCUDA_Types.hpp>
+
+namespace ETOL {
+
+class eCUDA : public TrajectoryOptimizer {
+ public:
+    eCUDA();
+    virtual ~eCUDA();
+
+    // ---- the eSolver interface (TrajectoryOptimizer.hpp:39-54) -----------------------------------
+    void setup();  // transcribe() + creates the device evaluator and uploads the problem to the GPU
+    void solve();  // runs the NLP solver with GPU callbacks; on success setScore() + trajectories
+    void debug();  // print_level = 5 (call after setup, before solve -- as ePSOPT::debug)
+    void close();  // releases the device handle
+
+    // host half of setup(): VGP -> NLP dimensions, bounds, scaling, guess, Jacobian structure and
+    // instance data in getProblem(); needs no device
+    void transcribe();
+
+    // ---- solver structs, as ePSOPT::getAlgorithm/getProblem/getSolution ---------------------------
+    ecuda_alg_t* getAlgorithm();
+    ecuda_prob_t* getProblem();
+    ecuda_sol_t* getSolution();
+
+    // ---- device-side VGP callbacks ----------------------------------------------------------------
+    // dynamics + running cost: ECUDA_MODEL_SI2D (the reference example's x'=u0, y'=u1, u0^2+u1^2),
+    // ECUDA_MODEL_PM3D, ECUDA_MODEL_FW6
+    void setModel(int model);
+    // one ellipse constraint per polygon edge of every exclusion zone (si2d) or one circumscribed
+    // vertical cylinder per exclusion zone (pm3d, fw6); adds parameters side_i_j_0 = {C,-1000,0,0,T}
+    void addObstacleConstraints();
+    // one keep-out circle per moving exclusion zone; adds parameters ball_i_0_0 = {C,-1000,0,0,T}
+    void addTrackConstraints();
+    // explicit vertical cylinder (pm3d / fw6), in addition to the XML exclusion zones
+    void addCylinder(double cx, double cy, double radius);
+
+    // ---- batches of independent instances (evaluation-only use, BASELINE configs 2 and 5) ---------
+    // B copies of the loaded VGP; instance b can then be given its own obstacle data
+    void setBatch(size_t nInstances);
+    size_t getBatch() const;
+    // raw instance-data block of instance b (layout: ecuda_upload_instances); valid after setup()
+    std::vector<double>& instanceData(size_t b);
+    void uploadInstances();  // push edited instance data to the device
+
+    // ---- evaluation (the hot path), host buffers --------------------------------------------------
+    // z: [B][nvars] unscaled decision vectors; outputs may be null. Values are returned in the
+    // solver's (scaled) space exactly as IPOPT would see them.
+    int evaluate(const double* z, double* f, double* g, double* jac);
+    int evaluateGradient(const double* z, double* grad);
+    ecuda_handle handle();  // the C-ABI handle, for callers that manage device buffers themselves
+
+ private:
+    void buildBounds();
+    void buildScaling();
+    void buildInstance(std::vector<double>* out) const;
+    void extractTrajectories(const std::vector<double>& z);
+    void fail(const std::string& what);
+
+    ecuda_alg_t _algorithm;
+    ecuda_prob_t _problem;
+    ecuda_sol_t _solution;
+    ecuda_handle _handle;
+    int _model;
+    bool _model_set, _obstacles_on, _tracks_on, _is_setup;
+    size_t _batch;
+    std::vector<std::array<double, 3>> _cylinders;
+    std::vector<std::vector<double>> _inst;  // per-instance data blocks
+    std::vector<double> _zscaled;            // scratch: z * sz
+};
+
+}  // namespace ETOL
+#endif  // INCLUDE_ETOL_ECUDA_HPP_

@@ -1,0 +1,452 @@
+// eCUDA.cpp -- the eCUDA eSolver: VGP -> collocation NLP on a B200 through the C ABI of include/ecuda.h.
+//
+// Mirrors src/ePSOPT/ePSOPT.cpp of the reference method by method:
+//   eCUDA::setup        <- ePSOPT::setup      :40-81   dimensions (nevents = 2*nstates, nodes = nsteps+1,
+//                                                       npath = #parameters), zero guess + linspace time
+//   eCUDA::buildBounds  <- ePSOPT::addBounds  :125-155 box / event / path / fixed-time bounds
+//   eCUDA::solve        <- ePSOPT::solve      :83-94   run the NLP solver, score with the sign undone
+//   extractTrajectories <- ePSOPT::getTraj    :157-182 one (t, values) pair per collocation node
+//   eCUDA::debug/close  <- ePSOPT::debug/close :100-107
+// The per-node callbacks ePSOPT::dae / integrand_cost / events (:186-291) are the device kernels.
+#include <ETOL/eCUDA.hpp>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <limits>
+
+#include "ecuda_nlp.hpp"
+
+namespace ETOL {
+
+namespace {
+std::string paramName(const std::string& name, size_t i, size_t j, size_t k) {
+    return name + "_" + std::to_string(i) + "_" + std::to_string(j) + "_" + std::to_string(k);
+}
+}  // namespace
+
+eCUDA::eCUDA()
+    : TrajectoryOptimizer(), _handle(nullptr), _model(ECUDA_MODEL_SI2D), _model_set(false), _obstacles_on(false),
+      _tracks_on(false), _is_setup(false), _batch(1) {}
+
+eCUDA::~eCUDA() { close(); }
+
+void eCUDA::fail(const std::string& what) {
+    // ETOL's error convention: message, then exit (TrajectoryOptimizer.cpp:1812-1817)
+    std::cerr << "eCUDA: " << what;
+    if (_handle) std::cerr << " [" << ecuda_last_error(_handle) << "]";
+    std::cerr << std::endl;
+    exit(EXIT_FAILURE);
+}
+
+ecuda_alg_t* eCUDA::getAlgorithm() { return &_algorithm; }
+ecuda_prob_t* eCUDA::getProblem() { return &_problem; }
+ecuda_sol_t* eCUDA::getSolution() { return &_solution; }
+ecuda_handle eCUDA::handle() { return _handle; }
+size_t eCUDA::getBatch() const { return _batch; }
+
+void eCUDA::setModel(int model) {
+    _model = model;
+    _model_set = true;
+}
+
+void eCUDA::setBatch(size_t n) { _batch = n ? n : 1; }
+
+void eCUDA::addCylinder(double cx, double cy, double radius) {
+    addParams({param_t(paramName("cyl", _cylinders.size(), 0, 0),
+                       {var_t::CONTINUOUS, -1000., 0., 0., getDt() * getNSteps()})});
+    _cylinders.push_back({cx, cy, radius});
+}
+
+// same parameters as obsConstraint() of the reference example (etol_psopt_example1.cpp:140-151)
+void eCUDA::addObstacleConstraints() {
+    const double tspan = getDt() * getNSteps();
+    size_t i = 0;
+    for (const border_t& border : *getObstacles_Raw()) {
+        const int model = _model_set ? _model : (getNStates() == 2 ? ECUDA_MODEL_SI2D : ECUDA_MODEL_PM3D);
+        const size_t rows = model == ECUDA_MODEL_SI2D ? border.size() : 1;  // one row per edge / per cylinder
+        for (size_t j = 0; j < rows; ++j)
+            addParams({param_t(paramName("side", i, j, 0), {var_t::CONTINUOUS, -1000., 0., 0., tspan})});
+        ++i;
+    }
+    _obstacles_on = true;
+}
+
+// same parameters as saaConstraint() of the reference example (etol_psopt_example1.cpp:199-223)
+void eCUDA::addTrackConstraints() {
+    const double tspan = getDt() * getNSteps();
+    size_t i = 0;
+    for (const track_t& track : *getTracks()) {
+        (void)track;
+        addParams({param_t(paramName("ball", i, 0, 0), {var_t::CONTINUOUS, -1000., 0., 0., tspan})});
+        ++i;
+    }
+    _tracks_on = true;
+}
+
+// ---- setup ------------------------------------------------------------------------------------------------
+void eCUDA::setup() {
+    transcribe();
+    // device side
+    if (_handle) {
+        ecuda_destroy(_handle);
+        _handle = nullptr;
+    }
+    if (ecuda_create(_algorithm.device, &_handle) != ECUDA_OK)
+        fail(std::string("cannot create the device evaluator: ") + ecuda_last_error(nullptr));
+    if (ecuda_set_problem(_handle, &_problem.desc) != ECUDA_OK) fail("ecuda_set_problem");
+    if (ecuda_set_scaling(_handle, _problem.sz.data(), _problem.sg.data(), _problem.sf) != ECUDA_OK)
+        fail("ecuda_set_scaling");
+    if (ecuda_set_ipopt_jac_mode(_handle, _algorithm.derivatives == "numerical" ? ECUDA_JAC_FD_INDEXSET
+                                                                                 : ECUDA_JAC_EXACT) != ECUDA_OK)
+        fail("ecuda_set_ipopt_jac_mode");
+    _is_setup = true;
+    uploadInstances();
+}
+
+// host half of setup(): VGP -> NLP description (no device needed)
+void eCUDA::transcribe() {
+    if (!_model_set) _model = getNStates() == 2 ? ECUDA_MODEL_SI2D : ECUDA_MODEL_PM3D;
+    const size_t ns = getNStates(), nc = getNControls();
+    ecuda_problem_desc& d = _problem.desc;
+    d = ecuda_problem_desc{};
+    d.model = _model;
+    d.nphases = 1;  // ePSOPT.cpp:27-28: one phase, no linkages
+    d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
+    size_t nstatic = 0;
+    if (_obstacles_on) {
+        if (_model == ECUDA_MODEL_SI2D)
+            for (const border_t& b : *getObstacles_Raw()) nstatic += b.size();
+        else
+            nstatic += getObstacles_Raw()->size();
+    }
+    if (_model != ECUDA_MODEL_SI2D) nstatic += _cylinders.size();
+    d.nstatic[0] = static_cast<int32_t>(nstatic);
+    d.ncontrols = static_cast<int32_t>(nc);
+    d.ntracks = 0;
+    d.nwaypoints = 0;
+    if (_tracks_on && !getTracks()->empty()) {
+        if (_model != ECUDA_MODEL_SI2D) fail("moving exclusion zones are only modelled for the si2d device model");
+        d.ntracks = static_cast<int32_t>(getTracks()->size());
+        d.nwaypoints = static_cast<int32_t>(getTracks()->front().trajectory.size());
+        for (const track_t& t : *getTracks())
+            if (static_cast<int32_t>(t.trajectory.size()) != d.nwaypoints)
+                fail("all tracks must have the same number of waypoints");
+    }
+    d.collocation = _algorithm.collocation_method == "Chebyshev" ? ECUDA_CHEBYSHEV : ECUDA_LEGENDRE;
+    d.pattern_mode = ECUDA_PATTERN_DENSE_NODE;
+    d.maximize = isMaximized() ? 1 : 0;
+    d.batch = static_cast<int32_t>(_batch);
+    d.index_base = 0;
+
+    if (ecuda_host_dims(&d, &_problem.dims) != ECUDA_OK)
+        fail("the VGP does not fit the selected device model (states/controls/nodes)");
+    if (static_cast<size_t>(_problem.dims.nstates) != ns)
+        fail("device model expects " + std::to_string(_problem.dims.nstates) + " states, the VGP has " +
+             std::to_string(ns));
+    // npath = #parameters (ePSOPT.cpp:58): every path row must have its parameter
+    const size_t npath = nstatic + static_cast<size_t>(d.ntracks);
+    if (npath != getParams()->size())
+        fail("path rows (" + std::to_string(npath) + ") and registered parameters (" +
+             std::to_string(getParams()->size()) + ") differ");
+
+    const int nnz = _problem.dims.nnz, nv = _problem.dims.nvars;
+    _problem.iRow.assign(nnz, 0);
+    _problem.jCol.assign(nnz, 0);
+    _problem.group_of_col.assign(nv, 0);
+    ecuda_host_structure(&d, _problem.iRow.data(), _problem.jCol.data(), _problem.group_of_col.data());
+    const int N = d.nnodes[0];
+    _problem.tau.assign(N, 0.0);
+    _problem.w.assign(N, 0.0);
+    std::vector<double> D(static_cast<size_t>(N) * N);
+    ecuda_host_collocation(d.collocation, N, _problem.tau.data(), _problem.w.data(), D.data());
+
+    buildBounds();
+    buildScaling();
+
+    // guess. ePSOPT starts PSOPT/IPOPT from all-zero states and controls (ePSOPT.cpp:47-53); here the
+    // default is the straight line from the initial to the terminal state with the constant control
+    // that flies it (dynamics- and event-feasible for the integrator models), clipped into the box.
+    // Like ePSOPT's guess it can be overwritten through getProblem()->guess before solve().
+    _problem.guess.assign(nv, 0.0);
+    {
+        const double T = getNSteps() * getDt();
+        for (int k = 0; k < N; ++k) {
+            const double sfrac = 0.5 * (_problem.tau[k] + 1.0);
+            for (size_t i = 0; i < ns; ++i) {
+                const double a = i < getX0().size() ? getX0()[i] : 0.0, b = i < getXf().size() ? getXf()[i] : a;
+                _problem.guess[nc * N + k * ns + i] = a + sfrac * (b - a);
+            }
+            if (_model == ECUDA_MODEL_SI2D)
+                for (size_t j = 0; j < std::min<size_t>(nc, 2); ++j)
+                    _problem.guess[k * nc + j] = (getXf()[j] - getX0()[j]) / T;
+        }
+        _problem.guess[(ns + nc) * N + 1] = T;
+    }
+    for (int c = 0; c < nv; ++c) _problem.guess[c] = std::min(std::max(_problem.guess[c], _problem.zl[c]), _problem.zu[c]);
+
+    // per-instance data: every instance starts as a copy of the loaded VGP
+    _inst.assign(_batch, std::vector<double>());
+    buildInstance(&_inst[0]);
+    for (size_t b = 1; b < _batch; ++b) _inst[b] = _inst[0];
+
+}
+
+// ePSOPT::addBounds (ePSOPT.cpp:125-155) in the NLP layout of include/ecuda.h
+void eCUDA::buildBounds() {
+    const size_t ns = getNStates(), nc = getNControls();
+    const int N = _problem.desc.nnodes[0];
+    const int nv = _problem.dims.nvars, ng = _problem.dims.ncons;
+    const double inf = std::numeric_limits<double>::infinity();
+    auto at = [](const state_t& v, size_t i, double dflt) { return i < v.size() ? v[i] : dflt; };
+    _problem.zl.assign(nv, -inf);
+    _problem.zu.assign(nv, inf);
+    for (int k = 0; k < N; ++k) {
+        for (size_t j = 0; j < nc; ++j) {
+            _problem.zl[k * nc + j] = at(getUlower(), j, -inf);
+            _problem.zu[k * nc + j] = at(getUupper(), j, inf);
+        }
+        for (size_t i = 0; i < ns; ++i) {
+            _problem.zl[nc * N + k * ns + i] = at(getXlower(), i, -inf);
+            _problem.zu[nc * N + k * ns + i] = at(getXupper(), i, inf);
+        }
+    }
+    const double T = getNSteps() * getDt();
+    _problem.zl[(ns + nc) * N] = _problem.zu[(ns + nc) * N] = 0.0;        // StartTime fixed at 0
+    _problem.zl[(ns + nc) * N + 1] = _problem.zu[(ns + nc) * N + 1] = T;  // EndTime fixed at nsteps*dt
+
+    _problem.gl.assign(ng, 0.0);  // defect rows: equality with 0
+    _problem.gu.assign(ng, 0.0);
+    const size_t e0 = ns * N;
+    for (size_t i = 0; i < ns; ++i) {
+        _problem.gl[e0 + i] = _problem.gu[e0 + i] = at(getX0(), i, 0.0);
+        _problem.gl[e0 + ns + i] = at(getXf(), i, 0.0) - at(getXtol(), i, 0.0);
+        _problem.gu[e0 + ns + i] = at(getXf(), i, 0.0) + at(getXtol(), i, 0.0);
+    }
+    // path rows. ePSOPT hands PSOPT the parameter bounds in std::map order while dae() fills the rows in
+    // callback order (ePSOPT.cpp:147-150 vs :262-270) -- harmless there because every parameter of the
+    // example has the same bounds. Here each row takes the bounds of the parameter it was registered
+    // under: static rows side_i_j_0 in obstacle/edge order, then track rows ball_i_0_0.
+    _problem.path_names.clear();
+    if (_obstacles_on) {
+        size_t i = 0;
+        for (const border_t& b : *getObstacles_Raw()) {
+            const size_t rows = _model == ECUDA_MODEL_SI2D ? b.size() : 1;
+            for (size_t j = 0; j < rows; ++j) _problem.path_names.push_back(paramName("side", i, j, 0));
+            ++i;
+        }
+    }
+    if (_model != ECUDA_MODEL_SI2D)
+        for (size_t c = 0; c < _cylinders.size(); ++c) _problem.path_names.push_back(paramName("cyl", c, 0, 0));
+    for (int i = 0; i < _problem.desc.ntracks; ++i) _problem.path_names.push_back(paramName("ball", i, 0, 0));
+    const size_t np = _problem.path_names.size();
+    const size_t p0 = e0 + 2 * ns;
+    for (int k = 0; k < N; ++k)
+        for (size_t q = 0; q < np; ++q) {
+            auto it = getParams()->find(_problem.path_names[q]);
+            const double lo = it != getParams()->end() ? it->second.lbnd : -1000.0;
+            const double hi = it != getParams()->end() ? it->second.ubnd : 0.0;
+            _problem.gl[p0 + k * np + q] = lo;
+            _problem.gu[p0 + k * np + q] = hi;
+        }
+    _problem.gl[ng - 1] = 0.0;  // tf - t0 >= 0
+    _problem.gu[ng - 1] = inf;
+}
+
+// PSOPT scaling = "automatic" (SURVEY.md appendix A.5): variable scale 1/max(|lb|,|ub|), defect and
+// event rows scaled like their state, path rows and the objective left at 1.
+void eCUDA::buildScaling() {
+    const int nv = _problem.dims.nvars, ng = _problem.dims.ncons;
+    const size_t ns = getNStates();
+    const int N = _problem.desc.nnodes[0];
+    _problem.sz.assign(nv, 1.0);
+    _problem.sg.assign(ng, 1.0);
+    _problem.sf = 1.0;
+    if (_algorithm.scaling != "automatic") return;
+    for (int c = 0; c < nv; ++c) {
+        const double m = std::max(std::fabs(_problem.zl[c]), std::fabs(_problem.zu[c]));
+        if (std::isfinite(m) && m > 0.0) _problem.sz[c] = 1.0 / m;
+    }
+    const size_t x0col = getNControls() * N;
+    for (int k = 0; k < N; ++k)
+        for (size_t i = 0; i < ns; ++i) _problem.sg[k * ns + i] = _problem.sz[x0col + i];
+    for (size_t i = 0; i < ns; ++i) {
+        _problem.sg[ns * N + i] = _problem.sz[x0col + i];
+        _problem.sg[ns * N + ns + i] = _problem.sz[x0col + i];
+    }
+}
+
+// obstacle / track records of the loaded VGP in the layout of ecuda_upload_instances
+void eCUDA::buildInstance(std::vector<double>* out) const {
+    out->assign(_problem.dims.inst_stride, 0.0);
+    size_t o = 0;
+    eCUDA* self = const_cast<eCUDA*>(this);
+    if (_obstacles_on) {
+        for (const border_t& border : *self->getObstacles_Raw()) {
+            std::vector<double> xy;
+            for (const corner_t& c : border) {
+                xy.push_back(c[0]);
+                xy.push_back(c[1]);
+            }
+            const int n = static_cast<int>(border.size());
+            if (_model == ECUDA_MODEL_SI2D) {  // one ellipse per polygon edge (etol_psopt_example1.cpp:164-179)
+                ecuda_si2d_edge_records(xy.data(), n, out->data() + o);
+                o += 6 * n;
+            } else {  // circumscribed vertical cylinder: centroid + farthest corner
+                double cx = 0, cy = 0, r2 = 0;
+                for (int i = 0; i < n; ++i) {
+                    cx += xy[2 * i];
+                    cy += xy[2 * i + 1];
+                }
+                cx /= n;
+                cy /= n;
+                for (int i = 0; i < n; ++i)
+                    r2 = std::max(r2, (xy[2 * i] - cx) * (xy[2 * i] - cx) + (xy[2 * i + 1] - cy) * (xy[2 * i + 1] - cy));
+                (*out)[o] = cx;
+                (*out)[o + 1] = cy;
+                (*out)[o + 2] = r2;
+                (*out)[o + 3] = 0.0;
+                o += 4;
+            }
+        }
+    }
+    if (_model != ECUDA_MODEL_SI2D)
+        for (const auto& c : _cylinders) {
+            (*out)[o] = c[0];
+            (*out)[o + 1] = c[1];
+            (*out)[o + 2] = c[2] * c[2];
+            (*out)[o + 3] = 0.0;
+            o += 4;
+        }
+    if (_problem.desc.ntracks > 0)
+        for (const track_t& t : *self->getTracks()) {
+            (*out)[o++] = t.radius;
+            for (const traj_elem_t& wp : t.trajectory) {
+                (*out)[o++] = wp.first;
+                (*out)[o++] = wp.second.size() > 0 ? wp.second[0] : 0.0;
+                (*out)[o++] = wp.second.size() > 1 ? wp.second[1] : 0.0;
+            }
+        }
+}
+
+std::vector<double>& eCUDA::instanceData(size_t b) { return _inst.at(b); }
+
+void eCUDA::uploadInstances() {
+    if (!_is_setup) fail("uploadInstances() before setup()");
+    const size_t stride = _problem.dims.inst_stride;
+    std::vector<double> all(_batch * stride, 0.0);
+    for (size_t b = 0; b < _batch; ++b) std::copy(_inst[b].begin(), _inst[b].end(), all.begin() + b * stride);
+    if (ecuda_upload_instances(_handle, all.data(), ECUDA_MEM_HOST) != ECUDA_OK) fail("ecuda_upload_instances");
+}
+
+// ---- evaluation ---------------------------------------------------------------------------------------------
+int eCUDA::evaluate(const double* z, double* f, double* g, double* jac) {
+    if (!_is_setup) fail("evaluate() before setup()");
+    const size_t nv = _problem.dims.nvars;
+    _zscaled.resize(_batch * nv);
+    for (size_t b = 0; b < _batch; ++b)
+        for (size_t c = 0; c < nv; ++c) _zscaled[b * nv + c] = z[b * nv + c] * _problem.sz[c];
+    const int mode = _algorithm.derivatives == "numerical" ? ECUDA_JAC_FD_INDEXSET : ECUDA_JAC_EXACT;
+    return ecuda_eval(_handle, _zscaled.data(), f, g, jac, mode, ECUDA_MEM_HOST, nullptr);
+}
+
+int eCUDA::evaluateGradient(const double* z, double* grad) {
+    if (!_is_setup) fail("evaluateGradient() before setup()");
+    const size_t nv = _problem.dims.nvars;
+    _zscaled.resize(_batch * nv);
+    for (size_t b = 0; b < _batch; ++b)
+        for (size_t c = 0; c < nv; ++c) _zscaled[b * nv + c] = z[b * nv + c] * _problem.sz[c];
+    return ecuda_eval_grad_f(_handle, _zscaled.data(), grad, ECUDA_MEM_HOST, nullptr);
+}
+
+// ---- solve ----------------------------------------------------------------------------------------------------
+void eCUDA::solve() {
+    if (!_is_setup) fail("solve() before setup()");
+    if (_batch != 1) fail("solve() drives one instance; batches are evaluated with evaluate()");
+    const int nv = _problem.dims.nvars, ng = _problem.dims.ncons, nnz = _problem.dims.nnz;
+    const int mode = _algorithm.derivatives == "numerical" ? ECUDA_JAC_FD_INDEXSET : ECUDA_JAC_EXACT;
+
+    // the solver works in the scaled space the device evaluates in (like IPOPT under PSOPT)
+    ecuda_nlp::Problem P;
+    P.n = nv;
+    P.m = ng;
+    P.nnz = nnz;
+    P.irow = _problem.iRow.data();
+    P.jcol = _problem.jCol.data();
+    P.zl.resize(nv);
+    P.zu.resize(nv);
+    P.gl.resize(ng);
+    P.gu.resize(ng);
+    for (int c = 0; c < nv; ++c) {
+        P.zl[c] = _problem.zl[c] * _problem.sz[c];
+        P.zu[c] = _problem.zu[c] * _problem.sz[c];
+    }
+    for (int r = 0; r < ng; ++r) {
+        P.gl[r] = _problem.gl[r] * _problem.sg[r];
+        P.gu[r] = _problem.gu[r] * _problem.sg[r];
+    }
+    ecuda_handle h = _handle;
+    P.eval = [h, mode](const double* zs, double* f, double* g, double* jac, double* grad) -> bool {
+        if ((f || g || jac) && ecuda_eval(h, zs, f, g, jac, mode, ECUDA_MEM_HOST, nullptr) != ECUDA_OK) return false;
+        if (grad && ecuda_eval_grad_f(h, zs, grad, ECUDA_MEM_HOST, nullptr) != ECUDA_OK) return false;
+        return true;
+    };
+    ecuda_nlp::Options opt;
+    opt.max_iter = _algorithm.nlp_iter_max;
+    opt.tol = _algorithm.nlp_tolerance;
+    opt.print_level = _algorithm.print_level;
+    std::vector<double> z(nv);
+    for (int c = 0; c < nv; ++c) z[c] = _problem.guess[c] * _problem.sz[c];
+    ecuda_nlp::Result R;
+    const bool want_ipopt = _algorithm.nlp_method == "IPOPT";
+    int rc;
+    if (want_ipopt && ecuda_nlp::have_ipopt())
+        rc = ecuda_nlp::solve_ipopt(P, opt, &z, &R);
+    else
+        rc = ecuda_nlp::solve_builtin(P, opt, &z, &R);
+
+    _solution.error_flag = rc;
+    _solution.error_msg = R.message;
+    _solution.nlp_iterations = R.iterations;
+    _solution.max_violation = R.max_violation;
+    if (rc != 0) {  // as ePSOPT::solve (:85-87): report, leave score and trajectories untouched
+        std::cout << "!!!!!Problem failed!!!!!" << std::endl << _solution.error_msg << std::endl;
+        return;
+    }
+    _solution.z.resize(nv);
+    for (int c = 0; c < nv; ++c) _solution.z[c] = z[c] / _problem.sz[c];
+    _solution.cost = R.objective / _problem.sf;
+    setScore(isMaximized() ? -_solution.cost : _solution.cost);
+    extractTrajectories(_solution.z);
+}
+
+void eCUDA::extractTrajectories(const std::vector<double>& z) {
+    const size_t ns = getNStates(), nc = getNControls();
+    const int N = _problem.desc.nnodes[0];
+    const double t0 = z[(ns + nc) * N], tf = z[(ns + nc) * N + 1];
+    traj_t* xt = getXtraj();
+    traj_t* ut = getUtraj();
+    xt->clear();
+    ut->clear();
+    for (int k = 0; k < N; ++k) {
+        const double t = 0.5 * (tf - t0) * _problem.tau[k] + 0.5 * (tf + t0);
+        state_t x(z.begin() + nc * N + k * ns, z.begin() + nc * N + (k + 1) * ns);
+        state_t u(z.begin() + k * nc, z.begin() + (k + 1) * nc);
+        xt->push_back(traj_elem_t(t, x));
+        ut->push_back(traj_elem_t(t, u));
+    }
+}
+
+void eCUDA::debug() { _algorithm.print_level = 5; }
+
+void eCUDA::close() {
+    if (_handle) {
+        ecuda_destroy(_handle);
+        _handle = nullptr;
+    }
+    _is_setup = false;
+}
+
+}  // namespace ETOL

@@ -6,11 +6,12 @@
 // that index/offset logic can be compared with the oracle in the CPU test suite. It is NOT a
 // fallback: libecuda.so does not contain it, nothing in etol_b200/ or src/ references it, and the
 // GPU parity tests (-m gpu) go through the real kernels via the C ABI.
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "../../etol_b200/csrc/ecuda_phases.cuh"
+#include "../../etol_b200/csrc/ecuda_fast.cuh"
 
 using namespace ecuda;
 
@@ -19,11 +20,60 @@ static void run_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io
     for (int t = 0; t < nthr; ++t) phase_c<M, NB>(pb, ph, p, io, m, b, t, nthr);
 }
 
+// the specialised kernel (k_eval_fast): per-thread registers that survive the barrier are an array here
+template <int M, int NB, bool FD>
+static void run_fast(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    std::vector<double> smem(cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0), 0.0);
+    CtaMem m;
+    carve(m, smem.data(), pb, ph, nthr, FD ? CARVE_FD : 0);
+    std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
+    if (!FD && io.jac)
+        for (int t = 0; t < nthr; ++t) fast_copy_template(pb, ph, io, b, t, nthr);
+    for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, FD && io.jac != nullptr);
+    std::vector<RowRegs<NB>> rr(nthr);
+    for (int t = 0; t < nthr; ++t) fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rr[t]);
+    for (int t = 0; t < nthr; ++t) fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rr[t]);
+}
+template <int M, int NB>
+static void run_fast_mode(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    if (io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET)
+        run_fast<M, NB, true>(pb, ph, p, io, b, nthr);
+    else
+        run_fast<M, NB, false>(pb, ph, p, io, b, nthr);
+}
+
+static long g_fast_runs = 0;
+extern "C" long emu_fast_runs() { return g_fast_runs; }
+
+static bool fast_ok(const ProbDev& pb, int nthr) {  // same rule as ecuda_set_problem
+    int nb = pb.ph[0].nb;
+    for (int p = 0; p < pb.nphases; ++p)
+        if (pb.ph[p].nb != nb || pb.ns * pb.ph[p].N > nthr) return false;
+    return nb >= 3 && nb <= 5;
+}
+
 template <int M>
 static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
     for (int b = 0; b < io.batch; ++b)
         for (int p = 0; p < pb.nphases; ++p) {
             const PhaseDev& ph = pb.ph[p];
+            if (!generic && (io.f || io.g || io.jac) && fast_ok(pb, nthr)) {
+                ++g_fast_runs;
+                if (io.grad) {  // k_grad is a separate launch
+                    std::vector<double> smem(cta_doubles(pb, ph, nthr), 0.0);
+                    CtaMem m;
+                    carve(m, smem.data(), pb, ph, nthr);
+                    for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, false);
+                    for (int t = 0; t < nthr; ++t) cost_nodes<M>(pb, ph, m, t, nthr);
+                    for (int t = 0; t < nthr; ++t) gradient_phase<M>(pb, ph, io, m, b, t, nthr);
+                }
+                switch (ph.nb) {
+                    case 3: run_fast_mode<M, 3>(pb, ph, p, io, b, nthr); break;
+                    case 4: run_fast_mode<M, 4>(pb, ph, p, io, b, nthr); break;
+                    default: run_fast_mode<M, 5>(pb, ph, p, io, b, nthr); break;
+                }
+                continue;
+            }
             std::vector<double> smem(cta_doubles(pb, ph, nthr), 0.0);
             CtaMem m;
             carve(m, smem.data(), pb, ph, nthr);
@@ -74,22 +124,13 @@ extern "C" int emu_eval(const ecuda_problem_desc* desc, const double* sz, const 
     if (sg)
         for (int r = 0; r < hp.dims.ncons; ++r) sgv[r] = sg[r];
     ProbDev pd;
-    std::memset(&pd, 0, sizeof(pd));
-    pd.model = desc->model; pd.ns = hp.ns; pd.nc = hp.nc; pd.ne = hp.ne; pd.nphases = hp.nphases;
-    pd.nvars = hp.dims.nvars; pd.ncons = hp.dims.ncons; pd.nnz = hp.dims.nnz; pd.nlink = hp.dims.nlinkages;
-    pd.linkoff = hp.linkoff; pd.ntracks = desc->ntracks; pd.nway = desc->nwaypoints; pd.track_off = hp.track_off;
-    pd.track_size = hp.dims.track_size; pd.rec_size = hp.dims.rec_size; pd.inst_stride = hp.dims.inst_stride;
-    pd.maximize = desc->maximize ? 1 : 0; pd.dense = desc->pattern_mode == ECUDA_PATTERN_DENSE_NODE; pd.sf = sf;
-    pd.colptr = hp.colptr.data(); pd.isz = isz.data(); pd.sg = sgv.data();
-    std::memcpy(pd.xrank, hp.xrank, sizeof(pd.xrank));
-    std::memcpy(pd.urank, hp.urank, sizeof(pd.urank));
-    std::memcpy(pd.xcnt, hp.xcnt, sizeof(pd.xcnt));
-    std::memcpy(pd.ucnt, hp.ucnt, sizeof(pd.ucnt));
+    fill_probdev(hp, &pd);
+    pd.sf = sf;
+    std::vector<double> tmpl;
+    build_jac_template(hp, isz.data(), sgv.data(), &tmpl);
+    pd.colptr = hp.colptr.data(); pd.isz = isz.data(); pd.sg = sgv.data(); pd.jtmpl = tmpl.data();
     for (int p = 0; p < hp.nphases; ++p) {
         PhaseDev& ph = pd.ph[p];
-        ph.N = hp.N[p]; ph.npath = hp.npath[p]; ph.nstat = hp.nstat[p];
-        ph.nb = (hp.N[p] + ECUDA_DOT_BLOCK - 1) / ECUDA_DOT_BLOCK;
-        ph.zoff = hp.zoff[p]; ph.goff = hp.goff[p]; ph.nvars = hp.nvars_p[p]; ph.inst_off = hp.inst_off[p];
         ph.D = hp.col[p].D.data(); ph.Dt = Dt[p].data(); ph.tau = hp.col[p].tau.data(); ph.w = hp.col[p].w.data();
     }
     std::vector<double> fpart(static_cast<size_t>(desc->batch) * hp.nphases, 0.0);

@@ -1,0 +1,131 @@
+// shim.cpp -- TEST-ONLY C entry points over the C++ plugin layer so that the python test-suite can
+// drive it with ctypes: XML -> VGP -> transcription (no GPU needed), CSV/XML writers, the built-in
+// NLP driver with a caller-supplied evaluation callback, and the full eCUDA setup/evaluate/solve
+// path (GPU needed). Nothing in the product links this file.
+#include <ETOL/eCUDA.hpp>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ecuda_nlp.hpp"
+
+using ETOL::eCUDA;
+
+extern "C" {
+
+void* shim_create() { return new eCUDA(); }
+void shim_destroy(void* h) { delete static_cast<eCUDA*>(h); }
+
+// load + register constraints + transcribe (host only). flags: bit0 obstacles, bit1 tracks
+int shim_load(void* h, const char* xml, int model, int flags, int batch, const char* scaling, const char* derivatives) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    t->loadConfigs(xml);
+    t->setMaximize(false);
+    if (model >= 0) t->setModel(model);
+    if (flags & 1) t->addObstacleConstraints();
+    if (flags & 2) t->addTrackConstraints();
+    t->setBatch(batch);
+    if (scaling) t->getAlgorithm()->scaling = scaling;
+    if (derivatives) t->getAlgorithm()->derivatives = derivatives;
+    t->transcribe();
+    return 0;
+}
+void shim_vgp(void* h, int* out /*nsteps,nstates,ncontrols,nzones,ntracks,nparams*/, double* dt) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    out[0] = (int)t->getNSteps(); out[1] = (int)t->getNStates(); out[2] = (int)t->getNControls();
+    out[3] = (int)t->getNExclZones(); out[4] = (int)t->getNTracks(); out[5] = (int)t->getParams()->size();
+    *dt = t->getDt();
+}
+void shim_dims(void* h, ecuda_dims* d) { *d = static_cast<eCUDA*>(h)->getProblem()->dims; }
+void shim_desc(void* h, ecuda_problem_desc* d) { *d = static_cast<eCUDA*>(h)->getProblem()->desc; }
+void shim_bounds(void* h, double* zl, double* zu, double* gl, double* gu, double* guess, double* sz, double* sg) {
+    ETOL::ecuda_prob_t* p = static_cast<eCUDA*>(h)->getProblem();
+    std::memcpy(zl, p->zl.data(), sizeof(double) * p->zl.size());
+    std::memcpy(zu, p->zu.data(), sizeof(double) * p->zu.size());
+    std::memcpy(gl, p->gl.data(), sizeof(double) * p->gl.size());
+    std::memcpy(gu, p->gu.data(), sizeof(double) * p->gu.size());
+    std::memcpy(guess, p->guess.data(), sizeof(double) * p->guess.size());
+    std::memcpy(sz, p->sz.data(), sizeof(double) * p->sz.size());
+    std::memcpy(sg, p->sg.data(), sizeof(double) * p->sg.size());
+}
+void shim_instance(void* h, int b, double* out) {
+    std::vector<double>& v = static_cast<eCUDA*>(h)->instanceData(b);
+    std::memcpy(out, v.data(), sizeof(double) * v.size());
+}
+void shim_structure(void* h, int32_t* irow, int32_t* jcol, int32_t* grp) {
+    ETOL::ecuda_prob_t* p = static_cast<eCUDA*>(h)->getProblem();
+    std::memcpy(irow, p->iRow.data(), sizeof(int32_t) * p->iRow.size());
+    std::memcpy(jcol, p->jCol.data(), sizeof(int32_t) * p->jCol.size());
+    std::memcpy(grp, p->group_of_col.data(), sizeof(int32_t) * p->group_of_col.size());
+}
+int shim_save_xml(void* h, const char* path) {
+    static_cast<eCUDA*>(h)->saveConfigs(path);
+    return 0;
+}
+// CSV writer on a synthetic trajectory: n rows (t = i*0.5, values i + 0.25*c)
+int shim_save_csv(const char* path, int n, int width, char* out_path, int out_len) {
+    ETOL::traj_t traj;
+    for (int i = 0; i < n; ++i) {
+        ETOL::state_t v;
+        for (int c = 0; c < width; ++c) v.push_back(i + 0.25 * c);
+        traj.push_back(ETOL::traj_elem_t(0.5 * i, v));
+    }
+    std::string p = ETOL::TrajectoryOptimizer::save(&traj, path);
+    std::strncpy(out_path, p.c_str(), out_len - 1);
+    out_path[out_len - 1] = 0;
+    return 0;
+}
+double shim_interp(double t, int n, const double* tv, const double* ref) {
+    ETOL::state_t a(tv, tv + n), b(ref, ref + n);
+    return ETOL::TrajectoryOptimizer::linear_interpolation<double>(t, a, b);
+}
+
+// ---- built-in NLP driver with a python callback -------------------------------------------------------
+typedef int (*eval_cb)(const double* z, double* f, double* g, double* jac, double* grad);
+int shim_nlp_solve(int n, int m, int nnz, const double* zl, const double* zu, const double* gl, const double* gu,
+                   const int32_t* irow, const int32_t* jcol, eval_cb cb, int max_iter, double tol, int print_level,
+                   double* z, double* result /*iters, objective, max_violation*/) {
+    ecuda_nlp::Problem P;
+    P.n = n; P.m = m; P.nnz = nnz;
+    P.zl.assign(zl, zl + n); P.zu.assign(zu, zu + n); P.gl.assign(gl, gl + m); P.gu.assign(gu, gu + m);
+    P.irow = irow; P.jcol = jcol;
+    P.eval = [cb](const double* zz, double* f, double* g, double* jac, double* grad) { return cb(zz, f, g, jac, grad) == 0; };
+    ecuda_nlp::Options opt;
+    opt.max_iter = max_iter; opt.tol = tol; opt.print_level = print_level;
+    std::vector<double> zz(z, z + n);
+    ecuda_nlp::Result R;
+    int rc = ecuda_nlp::solve_builtin(P, opt, &zz, &R);
+    std::memcpy(z, zz.data(), sizeof(double) * n);
+    result[0] = R.iterations; result[1] = R.objective; result[2] = R.max_violation;
+    return rc;
+}
+
+// ---- the device path (GPU needed) --------------------------------------------------------------------------
+int shim_setup(void* h) { static_cast<eCUDA*>(h)->setup(); return 0; }
+int shim_evaluate(void* h, const double* z, double* f, double* g, double* jac) {
+    return static_cast<eCUDA*>(h)->evaluate(z, f, g, jac);
+}
+int shim_solve(void* h, int max_iter, int print_level, double* score, int* iters, double* viol) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    t->getAlgorithm()->nlp_iter_max = max_iter;
+    t->getAlgorithm()->print_level = print_level;
+    t->solve();
+    *score = t->getScore();
+    *iters = t->getSolution()->nlp_iterations;
+    *viol = t->getSolution()->max_violation;
+    return t->getSolution()->error_flag;
+}
+int shim_traj(void* h, int which, double* out /* [N][1+width] */) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    ETOL::traj_t* tr = which == 0 ? t->getXtraj() : t->getUtraj();
+    size_t o = 0;
+    for (auto& e : *tr) {
+        out[o++] = e.first;
+        for (double v : e.second) out[o++] = v;
+    }
+    return (int)tr->size();
+}
+void shim_close(void* h) { static_cast<eCUDA*>(h)->close(); }
+
+}  // extern "C"

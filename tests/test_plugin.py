@@ -1,0 +1,171 @@
+"""The C++ plugin layer behind ETOL's TrajectoryOptimizer interface (src/TrajectoryOptimizer,
+src/eCUDA): XML wire format, transcription (ePSOPT::setup / addBounds semantics), CSV/XML writers,
+the built-in NLP driver -- on CPU -- and the full setup/evaluate/solve path on a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import plugin_binding as pb
+from conftest import TOL_JAC, TOL_VALUE, rel_err
+from etol_b200 import capi, workloads as W
+
+REF_XML = "/root/reference/resource/configs/ocp_2d_ex1.xml"
+
+
+@pytest.fixture
+def xml(tmp_path):
+    return pb.write_reference_xml(str(tmp_path / "ocp.xml"))
+
+
+def test_xml_load_counts(xml):
+    p = pb.Plugin().load(xml)
+    v = p.vgp()
+    assert v == dict(nsteps=32, nstates=2, ncontrols=2, nzones=2, ntracks=2, nparams=11, dt=0.5)
+    assert (p.dims.nvars, p.dims.ncons, p.dims.nnz, p.dims.ngroups) == (134, 434, 3372, 70)
+    p.close()
+
+
+def test_xml_caps_and_exponents(tmp_path):
+    # n* attributes cap how many children are read; exponents are accepted (documented deviation)
+    path = pb.write_reference_xml(str(tmp_path / "e.xml"), exponent=True)
+    txt = open(path).read().replace('nzones="2">\n  <border', 'nzones="1">\n  <border', 1)
+    open(path, "w").write(txt)
+    p = pb.Plugin().load(path)
+    v = p.vgp()
+    assert v["nzones"] == 1 and v["nparams"] == 5 + 2 and v["dt"] == 0.5
+    p.close()
+
+
+def test_mip_variant_dims(tmp_path):
+    # the file the reference's Singularity app runs the PSOPT example with: 17 nodes, 4 controls
+    p = pb.Plugin().load(pb.write_reference_xml(str(tmp_path / "mip.xml"), "mip"))
+    assert (p.dims.nvars, p.dims.ncons, p.dims.nnz, p.dims.ngroups) == (104, 226, 1264, 40)
+    p.close()
+
+
+def test_transcription_matches_workload(xml):
+    p = pb.Plugin().load(xml)
+    wl = W.reference_vgp("ocp")
+    b = p.bounds()
+    assert np.array_equal(b["zl"], wl.zl) and np.array_equal(b["zu"], wl.zu)
+    assert np.array_equal(b["gl"], wl.gl[0]) and np.array_equal(b["gu"], wl.gu[0])
+    assert np.array_equal(b["sz"], np.ones(134)) and np.array_equal(b["sg"], np.ones(434))
+    assert np.array_equal(p.instance(0), capi.pack_instances(wl)[0])
+    irow, jcol, grp = p.structure()
+    r2, c2, g2 = capi.host_structure(wl)
+    assert np.array_equal(irow, r2) and np.array_equal(jcol, c2) and np.array_equal(grp, g2)
+    # guess: straight line start -> goal with the constant control that flies it, fixed times
+    assert b["guess"][wl.itf(0)] == 16.0 and b["guess"][wl.it0(0)] == 0.0
+    assert np.all(b["guess"] >= wl.zl) and np.all(b["guess"] <= wl.zu)
+    assert np.allclose([b["guess"][wl.ix(0, 0, i)] for i in range(2)], [1.0, 2.0])
+    assert np.allclose([b["guess"][wl.ix(0, 32, i)] for i in range(2)], [5.0, 4.0])
+    assert np.allclose([b["guess"][wl.iu(0, 7, j)] for j in range(2)], [0.25, 0.125])
+    p.close()
+
+
+def test_automatic_scaling(xml):
+    p = pb.Plugin().load(xml, scaling="automatic")
+    b = p.bounds()
+    wl = W.reference_vgp("ocp")
+    assert np.allclose(b["sz"][wl.ix(0, 3, 0)], 1.0 / 7.0) and np.allclose(b["sz"][wl.iu(0, 3, 1)], 2.0)
+    assert np.allclose(b["sz"][wl.itf(0)], 1.0 / 16.0) and b["sz"][wl.it0(0)] == 1.0
+    assert np.allclose(b["sg"][:66], 1.0 / 7.0) and np.allclose(b["sg"][66:70], 1.0 / 7.0)
+    assert np.array_equal(b["sg"][70:], np.ones(434 - 70))
+    p.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_XML), reason="reference tree not mounted")
+def test_shipped_file_loads_unchanged(xml):
+    a, b = pb.Plugin().load(REF_XML), pb.Plugin().load(xml)
+    assert a.vgp() == b.vgp()
+    for k, v in a.bounds().items():
+        assert np.array_equal(v, b.bounds()[k]), k
+    assert np.array_equal(a.instance(0), b.instance(0))
+    a.close(), b.close()
+
+
+def test_xml_round_trip(xml, tmp_path):
+    p = pb.Plugin().load(xml)
+    out = str(tmp_path / "saved.xml")
+    p.save_xml(out)
+    q = pb.Plugin().load(out)
+    assert p.vgp() == q.vgp()
+    assert np.array_equal(p.bounds()["gl"], q.bounds()["gl"]) and np.array_equal(p.instance(0), q.instance(0))
+    p.close(), q.close()
+
+
+def test_csv_save_never_overwrites(tmp_path):
+    base = str(tmp_path / "traj.csv")
+    first = pb.save_csv(base, 3, 2)
+    second = pb.save_csv(base, 3, 2)
+    third = pb.save_csv(base, 3, 2)
+    assert [os.path.basename(x) for x in (first, second, third)] == ["traj.csv", "traj1.csv", "traj2.csv"]
+    txt = open(first).read()
+    assert txt == "time,traj0,traj1\n0.000000,0.000000,0.250000\n0.500000,1.000000,1.250000\n1.000000,2.000000,2.250000"
+
+
+def test_linear_interpolation_rule():
+    tv, ref = [0.0, 10.0, 20.0], [1.0, 2.0, 4.0]
+    assert pb.interp(5.0, tv, ref) == 1.5
+    assert pb.interp(10.0, tv, ref) == 2.0       # a shared knot belongs to the later interval
+    assert pb.interp(25.0, tv, ref) == 5.0       # above the table: last interval extrapolated
+    assert pb.interp(-10.0, tv, ref) == 0.0      # below: first interval extrapolated
+
+
+def _oracle_eval(wl):
+    o = ob.Oracle(wl)
+
+    def ev(z, want):
+        r = o.eval(z[None, :], want=tuple(want), jac_mode=W.JAC_EXACT, style=1, nthreads=1)
+        return {k: (v[0] if v is not None else None) for k, v in r.items() if k in ("f", "g", "jac", "grad")}
+    return ev
+
+
+def test_builtin_nlp_solves_reference_vgp():
+    """the built-in interior-point driver on the shipped VGP, evaluations by the CPU oracle"""
+    wl = W.reference_vgp("ocp")
+    irow, jcol, _ = capi.host_structure(wl)
+    tau, _, _ = capi.host_collocation(W.LEGENDRE, 33)
+    x0, xf = wl.meta["x0"], wl.meta["xf"]
+    z0 = np.zeros(wl.nvars)  # the plugin's default guess: straight line + constant control
+    for k in range(33):
+        for i in range(2):
+            z0[wl.ix(0, k, i)] = x0[i] + 0.5 * (tau[k] + 1.0) * (xf[i] - x0[i])
+            z0[wl.iu(0, k, i)] = (xf[i] - x0[i]) / 16.0
+    z0[wl.itf(0)] = 16.0
+    rc, z, info = pb.nlp_solve(wl.nvars, wl.ncons, wl.zl, wl.zu, wl.gl[0], wl.gu[0], irow, jcol, _oracle_eval(wl), z0,
+                               max_iter=150, tol=1e-6)
+    assert rc == 0, info
+    assert info["max_violation"] <= 1e-3 * 1.0
+    X = np.array([[z[wl.ix(0, k, i)] for i in range(2)] for k in range(33)])
+    assert np.allclose(X[0], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1], [5.0, 4.0], atol=0.0101)
+    # a feasible trajectory costs at least the straight-line minimum-energy solution
+    assert info["objective"] >= (4.0 ** 2 + 2.0 ** 2) / 16.0 - 1e-6
+    assert info["objective"] < 5.0
+
+
+@pytest.mark.gpu
+def test_plugin_evaluate_matches_oracle(xml):
+    p = pb.Plugin().load(xml, derivatives="numerical")
+    p.setup()
+    wl = W.reference_vgp("ocp")
+    f, g, jac = p.evaluate(wl.x[:1])
+    ref = ob.Oracle(wl).eval(wl.x[:1], want=("f", "g", "jac"), jac_mode=W.JAC_FD, style=0, nthreads=2)
+    assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
+    assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    p.close()
+
+
+@pytest.mark.gpu
+def test_plugin_solves_reference_vgp(xml):
+    p = pb.Plugin().load(xml, scaling="automatic")
+    p.setup()
+    rc, score, iters, viol = p.solve(max_iter=150)
+    assert rc == 0 and viol <= 1e-3
+    X = p.traj(0, 2, 33)
+    assert np.allclose(X[0, 1:], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1, 1:], [5.0, 4.0], atol=0.0101)
+    assert X[0, 0] == 0.0 and abs(X[-1, 0] - 16.0) < 1e-12
+    assert 1.25 - 1e-6 <= score < 5.0
+    p.close()
