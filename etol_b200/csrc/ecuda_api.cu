@@ -457,7 +457,8 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
         smem = std::max(smem, cta_doubles(pd, ph, kThreads) * sizeof(double));
         smem_fd = std::max(smem_fd, cta_doubles(pd, ph, kThreads, CARVE_FD) * sizeof(double));
         smem_ex = std::max(smem_ex, cta_doubles(pd, ph, kThreads, 0) * sizeof(double));
-        one_row_per_thread = one_row_per_thread && pd.ns * ph.N <= kThreads;
+        one_row_per_thread = one_row_per_thread && pd.ns * ph.N <= kThreads &&
+                             (2 * ph.npath + pd.nc + 2) * ph.N < 65536;  // fast_div range
     }
     if (smem > 227 * 1024 - 64)
         return fail(h, ECUDA_ERR_ARG, "phase too large for one CTA's shared memory (" + std::to_string(smem) + " B)");

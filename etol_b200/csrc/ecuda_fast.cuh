@@ -34,7 +34,8 @@ struct RowRegs {
 };
 
 // block sums + total of row k of D times state j of X (canonical blocked order, see dot_row)
-template <int NS, int NB>
+// PARTIAL: the last block has fewer than ECUDA_DOT_BLOCK nodes (N < NB*BL); otherwise no bounds tests
+template <int NS, int NB, bool PARTIAL>
 ECUDA_HD double fast_dot(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj, double (&P)[NB]) {
     constexpr int BL = ECUDA_DOT_BLOCK;
     double total = 0.0;
@@ -44,7 +45,7 @@ ECUDA_HD double fast_dot(const double* __restrict__ Dtk, int N, const double* __
         double p = 0.0;
 #pragma unroll
         for (int i = 0; i < BL; ++i)
-            if (bi < NB - 1 || l0 + i < N) p = fma(ECUDA_LDG(Dtk + (l0 + i) * N), Xj[(l0 + i) * NS], p);
+            if (!PARTIAL || bi < NB - 1 || l0 + i < N) p = fma(ECUDA_LDG(Dtk + (l0 + i) * N), Xj[(l0 + i) * NS], p);
         P[bi] = p;
         total = (bi == 0) ? p : total + p;
     }
@@ -92,14 +93,14 @@ ECUDA_HD void fast_diag(const double* __restrict__ Dtk, int N, const double* __r
 // D-coupled triplets of row (k,j) in the state columns of summation block BI, by index-set central
 // differences (row-restricted: see ecuda_phases.cuh). jac = triplet array of the instance;
 // kpc = k + (number of node-local defect rows of column X(.,j)) - 1.
-template <int NS, int NB, int BI>
+template <int NS, int NB, int BI, bool PARTIAL>
 ECUDA_HD void fast_fd_block(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj,
                             const double* __restrict__ XPj, const double* __restrict__ XMj,
                             const double* __restrict__ RIj, const int* __restrict__ CPj, const double (&P)[NB],
                             double sgr, double hfv, int k, int kpc, double* __restrict__ jac) {
     constexpr int BL = ECUDA_DOT_BLOCK;
     constexpr int l0 = BI * BL;
-    constexpr bool LAST = BI == NB - 1;  // only the last block can be partial
+    constexpr bool LAST = PARTIAL && BI == NB - 1;  // only the last block can be partial
     double d[BL], xv[BL];
 #pragma unroll
     for (int i = 0; i < BL; ++i) {
@@ -152,7 +153,10 @@ struct FastFdBlocks {
     ECUDA_HD static void run(const double* Dtk, int N, const double* Xj, const double* XPj, const double* XMj,
                              const double* RIj, const int* CPj, const double (&P)[NB], double sgr, double hfv, int k,
                              int kpc, double* jac) {
-        fast_fd_block<NS, NB, BI>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+        if (BI < NB - 1 || N == NB * ECUDA_DOT_BLOCK)  // uniform over the CTA
+            fast_fd_block<NS, NB, BI, false>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+        else
+            fast_fd_block<NS, NB, BI, true>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
         FastFdBlocks<NS, NB, BI + 1>::run(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
     }
 };
@@ -182,10 +186,11 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
     const double* sg = pb.sg;
     // defect rows: block sums into registers, totals into shared memory
     if (tid < NS * N) {
-        const int j = tid / N, k = tid - j * N;
+        const int j = fast_div(tid, ph.mN), k = tid - j * N;
         const double* Dtk = ph.Dt + k;
         const double* Xj = m.z + nc * N + j;
-        m.dotv[k * NS + j] = fast_dot<NS, NB>(Dtk, N, Xj, rr.P);
+        m.dotv[k * NS + j] = (N == NB * ECUDA_DOT_BLOCK) ? fast_dot<NS, NB, false>(Dtk, N, Xj, rr.P)
+                                                         : fast_dot<NS, NB, true>(Dtk, N, Xj, rr.P);
         if (FD && io.jac) {
             const int lcol = nc * N + k * NS + j;
             fast_diag<NS, NB>(Dtk, N, Xj, m.xp[lcol], m.xm[lcol], k, rr.P, rr.dp, rr.dm);
@@ -206,7 +211,7 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
     if (g) {
         // path rows: one row per thread
         for (int it = nthr - 1 - tid; it < np * N; it += nthr) {
-            const int k = it / np, q = it - k * np;
+            const int k = fast_div(it, ph.mnp), q = it - k * np;
             const double* x = m.z + nc * N + k * NS;
             const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
             const int r = ph.goff + NS * N + pb.ne + it;
@@ -244,7 +249,7 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
     if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
     double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
     if (tid < NS * N && (io.g || jac)) {
-        const int j = tid / N, k = tid - j * N;
+        const int j = fast_div(tid, ph.mN), k = tid - j * N;
         const int r = ph.goff + k * NS + j;
         const double sgr = ECUDA_LDG(pb.sg + r);
         const double hfv = m.hf[k * NS + j];
@@ -266,15 +271,15 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
         const int nP = (NS >= 2) ? N * 2 * np : 0, nU = (nc + 2) * N;
         for (int it = nthr - 1 - tid; it < nP + nU; it += nthr) {
             if (it < nP) {
-                const int k = it / (2 * np), rem = it - k * 2 * np;
-                const int j = rem / np, q = rem - j * np;
+                const int k = fast_div(it, ph.m2np), rem = it - k * 2 * np;
+                const int j = rem >= np ? 1 : 0, q = rem - j * np;
                 if (FD)
                     xcol_path_fd<M>(pb, ph, m, j, k, q, jac);
                 else
                     xcol_path_exact<M>(pb, ph, m, j, k, q, jac);
             } else {
                 const int i2 = it - nP;
-                const int c = i2 / N, k = i2 - c * N;
+                const int c = fast_div(i2, ph.mN), k = i2 - c * N;
                 node_item<M>(pb, ph, p, io, m, b, k, c);
             }
         }

@@ -344,6 +344,9 @@ void fill_probdev(const HostProblem& hp, ProbDev* out) {
         ph.goff = hp.goff[p];
         ph.nvars = hp.nvars_p[p];
         ph.inst_off = hp.inst_off[p];
+        ph.mN = fast_div_magic(ph.N);
+        ph.mnp = fast_div_magic(ph.npath);
+        ph.m2np = fast_div_magic(2 * ph.npath);
     }
 }
 

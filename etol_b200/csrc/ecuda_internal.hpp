@@ -17,6 +17,16 @@
 
 namespace ecuda {
 
+// a / d for 0 <= a < 65536 and 1 <= d < 65536 with magic = floor(2^32 / d) + 1 (0 when d <= 1)
+ECUDA_HD int fast_div(int a, unsigned magic) {
+#if defined(__CUDA_ARCH__)
+    return magic ? static_cast<int>(__umulhi(static_cast<unsigned>(a), magic)) : a;
+#else
+    return magic ? static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(a)) * magic) >> 32) : a;
+#endif
+}
+inline unsigned fast_div_magic(int d) { return d <= 1 ? 0u : static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(d)) + 1u; }
+
 // ---- what the kernels see (passed by value as a __grid_constant__ kernel parameter) -------------
 struct PhaseDev {
     int N;          // collocation nodes
@@ -27,6 +37,7 @@ struct PhaseDev {
     int goff;       // first constraint row of the phase
     int nvars;      // (ns+nc)*N + 2
     int inst_off;   // offset (doubles) of this phase's static records inside the instance block
+    unsigned mN, mnp, m2np;  // multiply-high reciprocals of N, npath, 2*npath (fast_div; 0 = divisor <= 1)
     const double* D;    // [N][N] row-major
     const double* Dt;   // [N][N] transposed (Dt[l*N+k] = D[k][l]) : coalesced over rows k
     const double* tau;  // [N]

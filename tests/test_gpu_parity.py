@@ -3,6 +3,7 @@ oracle on the same seeded inputs. Bars (BASELINE.json north_star): sparsity patt
 bit-exact; f and g within 1e-12 relative; Jacobian entries within 1e-9 relative under the same
 perturbation step. FD mode additionally asserts identical bits (same IEEE operation sequence)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -221,3 +222,23 @@ def test_injected_collocation_is_used():
     X = np.stack([[wl.x[0, wl.ix(0, k, i)] for i in range(ns)] for k in range(N)])
     assert np.allclose((twice - base)[0, :N * ns].reshape(N, ns), D @ X, rtol=1e-12, atol=1e-9)
     ev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C0-ocp", "C0-mip", "C2-pm3d-64", "C4-multiphase", "C2-pm3d-scaled-deps"])
+def test_fast_and_generic_kernels_agree_bitwise(name):
+    """the specialised kernels (k_eval_fast) and the generic ones (k_eval) must produce the same bits:
+    both are built from the same operation sequences, only the work layout differs"""
+    wl = CASES[name]()
+    out = {}
+    for tag, env in (("fast", "0"), ("generic", "1")):
+        os.environ["ECUDA_NO_FAST"] = env  # read by ecuda_create
+        try:
+            ev = capi.Evaluator(wl, device=0)
+        finally:
+            os.environ.pop("ECUDA_NO_FAST", None)
+        out[tag] = {m: ev.eval_host(wl.x, want=("f", "g", "jac"), jac_mode=m) for m in (W.JAC_FD, W.JAC_EXACT)}
+        ev.close()
+    for m in (W.JAC_FD, W.JAC_EXACT):
+        for key in ("f", "g", "jac"):
+            assert np.array_equal(out["fast"][m][key], out["generic"][m][key]), (name, m, key)
