@@ -28,6 +28,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
@@ -121,7 +124,12 @@ def cpu_sample(wl, seconds_budget, jac_mode, style=0):
     """times the oracle on a bounded sample of the workload, all host threads"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
-    nthr = ob.max_threads()
+    # all host threads this process may use; torchrun exports OMP_NUM_THREADS=1, which must not
+    # shrink the CPU arm (the oracle takes its thread count explicitly)
+    try:
+        nthr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthr = os.cpu_count() or 1
     probe_n = min(wl.batch, nthr)
     sub = wl.slice_batch(0, min(wl.batch, 64 * nthr))
     orc = ob.Oracle(sub)
@@ -277,16 +285,30 @@ def run_ecuda(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     achieved = alg_bytes_unit * B / (kern_avg_ms / 1e3) / 1e9
-    traffic = None
+    traffic, fp64 = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and B == BATCH_PER_GPU:  # the ncu captures were taken at the default batch
         try:
-            traffic = json.load(open(tpath)).get(f"k_eval_{args.jac}_C2_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"k_eval_{args.jac}_C2_bytes_per_launch")
+            ops = tj.get(f"k_eval_{args.jac}_C2_fp64_thread_instr_per_launch")
+            if ops:
+                # second roof of the finite-difference kernel: FP64 pipe. Peak measured now with a
+                # register-only DFMA microbenchmark; executed FP64 thread instructions from ncu.
+                peak_tf = ev.fp64_peak_tflops()
+                lane_instr = ops["dfma"] + ops["dadd"] + ops["dmul"]
+                fp64 = {"peak_tflops_measured": peak_tf, "thread_instr_per_launch": lane_instr,
+                        "executed_tflops": (2 * ops["dfma"] + ops["dadd"] + ops["dmul"]) / (kern_avg_ms / 1e3) / 1e12,
+                        "pipe_frac": lane_instr / (kern_avg_ms / 1e3) / (peak_tf * 1e12 / 2.0),
+                        "note": "row-restricted FD needs ~21.5 FP64 instructions per D-coupled triplet; "
+                                "pipe_frac = executed FP64 thread instructions / (time x measured DFMA issue rate)"}
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": f"k_eval_fast<pm3d> ({args.jac})", "kernel_ms": kern_avg_ms,
                 "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B, "peak_source": peak_src}
+    if fp64:
+        roofline["fp64"] = fp64
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
-    "ecuda_summary", "ecuda_summarize", "ecuda_sync", "ecuda_launch_count", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
+    "ecuda_summary", "ecuda_summarize", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.ecuda_sync.argtypes = [C.c_void_p]
     L.ecuda_launch_count.restype = C.c_int64
     L.ecuda_launch_count.argtypes = [C.c_void_p]
+    L.ecuda_fp64_peak.argtypes = [C.c_void_p, _dp]
     L.ecuda_ipopt_eval_f.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp]
     L.ecuda_ipopt_eval_grad_f.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp]
     L.ecuda_ipopt_eval_g.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, _dp]
@@ -276,3 +277,8 @@ class Evaluator:
 
     def launch_count(self):
         return int(self.L.ecuda_launch_count(self.h))
+
+    def fp64_peak_tflops(self):
+        out = C.c_double()
+        self._check(self.L.ecuda_fp64_peak(self.h, C.byref(out)))
+        return out.value

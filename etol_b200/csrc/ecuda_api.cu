@@ -47,6 +47,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (SASS: UBLKCP), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest bulk group committed by this thread have finished READING their shared source
+__device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all bulk groups committed by this thread are complete (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// barrier over the first `count` threads of the CTA only (count a multiple of 32)
+__device__ __forceinline__ void named_barrier(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -98,32 +113,170 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
 #ifndef ECUDA_MIN_CTAS_EXACT
 #define ECUDA_MIN_CTAS_EXACT 4
 #endif
+// Exact mode: the D-coupled triplets are instance independent, so an extra warp streams them from the
+// per-problem template (L2 resident) to the instance's triplet array with TMA bulk copies,
+// global -> shared ring -> global, while the 256 compute threads run stage and phase B. The ring has
+// kCopySlots buffers of kCopyChunk doubles; one lane drives it. Used when nnz is even, so that the
+// template element e and its destination b*nnz + e always agree modulo 16 bytes.
+constexpr int kCopyWarpThreads = 32;
+#ifndef ECUDA_COPY_SLOTS
+#define ECUDA_COPY_SLOTS 4
+#endif
+#ifndef ECUDA_COPY_CHUNK
+#define ECUDA_COPY_CHUNK 1024
+#endif
+constexpr int kCopySlots = ECUDA_COPY_SLOTS;
+constexpr int kCopyChunk = ECUDA_COPY_CHUNK;  // doubles (1024 = 8 KB)
+
+__device__ void copy_warp_template(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, int b, double* ring,
+                                   uint64_t* bars, int lane) {
+    const int e0 = __ldg(pb.colptr + ph.zoff + pb.nc * ph.N);             // first state column of the phase
+    const int e1 = __ldg(pb.colptr + ph.zoff + (pb.nc + pb.ns) * ph.N);   // its t0 column
+    const size_t g0 = static_cast<size_t>(b) * pb.nnz + e0;               // global element index of the first
+    const int n = e1 - e0;
+    const double* src = pb.jtmpl + e0;  // nnz even: e0 and g0 have the same parity
+    double* dst = io.jac + g0;
+    const int head = static_cast<int>(g0 & 1);        // first element sits at an odd index: copy it alone
+    const int nal = (n - head) & ~1;                  // doubles in the 16-byte aligned interior
+    if (lane == 1 && head && n > 0) __stcs(dst, __ldg(src));
+    if (lane == 2 && head + nal < n) __stcs(dst + n - 1, __ldg(src + n - 1));
+    if (lane != 0) return;
+    src += head;
+    dst += head;
+    const int nchunks = (nal + kCopyChunk - 1) / kCopyChunk;
+    auto chunk_bytes = [&](int c) { return static_cast<uint32_t>(min(kCopyChunk, nal - c * kCopyChunk)) * 8u; };
+    for (int c = 0; c < nchunks && c < kCopySlots; ++c) {
+        mbar_expect_tx(&bars[c], chunk_bytes(c));
+        bulk_g2s(ring + c * kCopyChunk, src + static_cast<size_t>(c) * kCopyChunk, chunk_bytes(c), &bars[c]);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c % kCopySlots;
+        mbar_wait(&bars[slot], (c / kCopySlots) & 1);
+        bulk_s2g(dst + static_cast<size_t>(c) * kCopyChunk, ring + slot * kCopyChunk, chunk_bytes(c));
+        bulk_commit();
+        // refill the slot of the PREVIOUS chunk: its store has had one iteration to read shared memory
+        // (bulk groups complete in order, so "all but the newest" covers it)
+        const int cn = c - 1 + kCopySlots;
+        if (c >= 1 && cn < nchunks) {
+            bulk_wait_read_but_one();
+            const int ps = (c - 1) % kCopySlots;
+            mbar_expect_tx(&bars[ps], chunk_bytes(cn));
+            bulk_g2s(ring + ps * kCopyChunk, src + static_cast<size_t>(cn) * kCopyChunk, chunk_bytes(cn), &bars[ps]);
+        }
+    }
+    bulk_wait_all();  // writes performed before the CTA-wide barrier that precedes the node-local stores
+}
+
 template <int M, int NB, bool FD>
-__global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_FD : ECUDA_MIN_CTAS_EXACT)
+__global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
+                                  FD ? ECUDA_MIN_CTAS_FD : ECUDA_MIN_CTAS_EXACT)
     k_eval_fast(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t copy_bars[kCopySlots];
     const int b = blockIdx.x / pb.nphases;
     const int p = blockIdx.x - b * pb.nphases;
     const PhaseDev& ph = pb.ph[p];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = kThreads;  // compute threads; exact mode launches one more warp
+    const bool copy_warp = !FD && blockDim.x > kThreads;  // uniform over the CTA
     CtaMem m;
     carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (copy_warp)
+            for (int c = 0; c < kCopySlots; ++c) mbar_init(&copy_bars[c], 1);
+    }
     __syncthreads();
+    if (!FD && tid >= kThreads) {
+        // ---- copy warp: template -> triplet array, then wait at the barrier before phase C
+        double* ring = smem + cta_doubles(pb, ph, nthr, 0);
+        ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;  // 16-byte aligned
+        if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
+        __syncthreads();
+        return;
+    }
     if (tid == 0) {
         const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
     }
-    if (!FD && io.jac) fast_copy_template(pb, ph, io, b, tid, nthr);
+    if (!FD && io.jac && !copy_warp) fast_copy_template(pb, ph, io, b, tid, nthr);
     stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
     mbar_wait(&bar, 0);
-    __syncthreads();
+    if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
     RowRegs<NB> rr;
     fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
-    __syncthreads();
+    __syncthreads();  // all threads: in exact mode the template has landed before the node-local stores
     fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+}
+
+// Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
+// element index of the first one, so that shared and global addresses are 16-byte aligned together)
+// to dst[0..n): the aligned interior by one bulk copy issued by thread `lead`, the at most two
+// boundary elements by plain stores from the next two threads.
+__device__ __forceinline__ void flush_range(double* dst, const double* src, int par, int n, int tid, int lead) {
+    const int start = par;             // par == 1: element 0 sits at an odd global index
+    const int nal = (n - start) & ~1;  // doubles in the 16-byte aligned interior
+    if (tid == lead) {
+        if (nal > 0) bulk_s2g(dst + start, src + par + start, static_cast<uint32_t>(nal) * 8u);
+        bulk_commit();
+    } else if (tid == lead + 1) {
+        if (start == 1 && n > 0) __stcs(dst, src[par]);
+    } else if (tid == lead + 2) {
+        if (start + nal < n) __stcs(dst + n - 1, src[par + n - 1]);
+    }
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Exact mode, persistent: a CTA keeps a shared-memory IMAGE of its phase's whole triplet range. The
+// instance-independent D-coupled triplets are loaded into it once from the per-problem template;
+// for every instance the CTA works on, phase C overwrites the node-local triplets in the image (every
+// one of them, the pattern is the same for all instances) and one bulk shared->global copy (TMA)
+// writes the range out while the CTA already stages and evaluates its next instance. No triplet is
+// stored by an LSU instruction, nothing is read back, and the template is read once per CTA instead
+// of once per instance. Two CTAs per SM (the image of the benchmark shape is 101 KB).
+template <int M, int NB>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_eval_image(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int p = blockIdx.x % pb.nphases;  // fixed per CTA: gridDim.x is a multiple of nphases
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, 0);
+    double* image = smem + cta_doubles(pb, ph, nthr, 0);
+    image += (reinterpret_cast<uintptr_t>(image) & 8) ? 1 : 0;  // 16-byte aligned
+    const int c0 = __ldg(pb.colptr + ph.zoff), c1 = __ldg(pb.colptr + ph.zoff + ph.nvars);
+    const int n = c1 - c0;
+    const int par = c0 & 1;  // nnz is even (checked on the host): triplet c0 of every instance has this parity
+    double* vimage = image + par - c0;  // vimage[e] = slot of triplet e
+    for (int e = c0 + tid; e < c1; e += nthr) vimage[e] = __ldg(pb.jtmpl + e);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    const int stride = gridDim.x / pb.nphases;
+    for (int b = blockIdx.x / pb.nphases; b < io.batch; b += stride) {
+        if (tid == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+        }
+        stage_vars(pb, ph, io, m, b, tid, nthr, false);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        __syncthreads();
+        RowRegs<NB> rr;
+        fast_phase_b<M, NB, false>(pb, ph, p, io, m, b, tid, nthr, rr);
+        if (tid == 0) bulk_wait_read_all();  // the previous instance's image has left shared memory
+        __syncthreads();
+        fast_phase_c<M, NB, false, true>(pb, ph, p, io, m, b, tid, nthr, rr, vimage);
+        fence_async_smem();  // generic-proxy writes to the image -> visible to the bulk copy
+        __syncthreads();
+        flush_range(io.jac + static_cast<size_t>(b) * pb.nnz + c0, image, par, n, tid, 0);
+    }
+    if (tid == 0) bulk_wait_read_all();
 }
 
 template <int M>
@@ -172,6 +325,19 @@ __global__ void k_summary(const double* f, const double* g, const double* gl, co
     }
 }
 
+// FP64 FMA microbenchmark: 8 independent dependent-chains per thread, no memory traffic. Defines the
+// FP64 roof the finite-difference kernel is compared with (MEASURED_PEAKS.json has no FP64 figure).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    const double r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (r == 123.456) sink[blockIdx.x * blockDim.x + threadIdx.x] = r;  // never true: keeps the chains alive
+}
+
 // ---- context ------------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
@@ -195,6 +361,13 @@ struct ecuda_ctx {
     size_t smem_bytes = 0, smem_fast_fd = 0, smem_fast_exact = 0;
     bool fast_ok = false;  // the specialised kernels (ecuda_fast.cuh) can run this problem
     bool no_fast = false;  // ECUDA_NO_FAST=1 in the environment: never use them (A/B runs and tests)
+    bool no_image = true;   // ECUDA_IMAGE=1 opts in to the persistent image kernel (exact mode); measured
+                            // slower than the copy-warp kernel on C2 (0.180 vs 0.157 ms: 2 CTAs/SM leave the
+                            // latency-bound node-local phases exposed), kept for the next round's pipelining work
+    bool image_ok = false;
+    size_t smem_image = 0;
+    int num_sms = 148;
+    bool no_copy_warp = false;  // ECUDA_NO_COPY_WARP=1: exact mode copies the template with plain loads/stores
     int64_t launches = 0;
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
@@ -241,6 +414,7 @@ static int upload_template(ecuda_ctx* h) {
     std::vector<double> isz(h->hp.dims.nvars), tmpl;
     for (int c = 0; c < h->hp.dims.nvars; ++c) isz[c] = 1.0 / h->h_sz[c];
     build_jac_template(h->hp, isz.data(), h->h_sg.data(), &tmpl);
+    tmpl.resize(tmpl.size() + 2, 0.0);  // bulk copies read whole 16-byte units
     int rc;
     if ((rc = ensure(h, h->jtmpl, sizeof(double) * tmpl.size()))) return rc;
     CU(cudaMemcpy(h->jtmpl.p, tmpl.data(), sizeof(double) * tmpl.size(), cudaMemcpyHostToDevice));
@@ -306,7 +480,11 @@ template <int M, int NB, bool FD>
 static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     static std::mutex mu;
     static size_t configured[64] = {0};
-    const size_t smem = FD ? h->smem_fast_fd : h->smem_fast_exact;
+    // exact mode with a Jacobian: one more warp and its shared-memory ring (see copy_warp_template)
+    const bool copy_warp = !FD && io.jac != nullptr && !h->no_copy_warp && (h->pd.nnz & 1) == 0 &&
+                           (reinterpret_cast<uintptr_t>(io.jac) & 15) == 0;
+    const size_t smem = FD ? h->smem_fast_fd
+                           : h->smem_fast_exact + (copy_warp ? (kCopySlots * kCopyChunk + 2) * sizeof(double) : 0);
     if (smem > 48 * 1024) {
         std::lock_guard<std::mutex> lock(mu);
         size_t& cur = configured[h->device & 63];
@@ -315,12 +493,36 @@ static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, in
             cur = smem;
         }
     }
-    k_eval_fast<M, NB, FD><<<grid, kThreads, smem, st>>>(h->pd, io);
+    k_eval_fast<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, st>>>(h->pd, io);
     return ECUDA_OK;
 }
 template <int M, int NB>
+static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    const size_t smem = h->smem_image;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < smem) {
+            CU(cudaFuncSetAttribute(k_eval_image<M, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    // persistent: as many CTAs as fit (2 per SM while the image allows it), a multiple of nphases
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    int grid = h->num_sms * per_sm;
+    grid = std::min(grid, io.batch * h->pd.nphases);
+    grid -= grid % h->pd.nphases;
+    if (grid < h->pd.nphases) grid = h->pd.nphases;
+    k_eval_image<M, NB><<<grid, kThreads, smem, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
+
+template <int M, int NB>
 static int launch_keval_fast_mode(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     if (io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET) return launch_keval_fast<M, NB, true>(h, io, st, grid);
+    if (io.jac && h->image_ok && (reinterpret_cast<uintptr_t>(io.jac) & 15) == 0) return launch_keval_image<M, NB>(h, io, st);
     return launch_keval_fast<M, NB, false>(h, io, st, grid);
 }
 
@@ -407,6 +609,11 @@ int ecuda_create(int device, ecuda_handle* out) {
         h->force_generic = fg && fg[0] == '1';
         const char* nf = std::getenv("ECUDA_NO_FAST");
         h->no_fast = nf && nf[0] == '1';
+        const char* ni = std::getenv("ECUDA_IMAGE");
+        h->no_image = !(ni && ni[0] == '1');
+        h->num_sms = prop.multiProcessorCount;
+        const char* nw = std::getenv("ECUDA_NO_COPY_WARP");
+        h->no_copy_warp = nw && nw[0] == '1';
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -465,6 +672,13 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     h->smem_bytes = smem;
     h->smem_fast_fd = smem_fd;
     h->smem_fast_exact = smem_ex;
+    // persistent image kernel: work area + the largest phase slice of the triplet array (+ alignment pad)
+    size_t smem_img = 0;
+    for (int p = 0; p < hp.nphases; ++p) {
+        const size_t slice = hp.colptr[hp.zoff[p] + hp.nvars_p[p]] - hp.colptr[hp.zoff[p]];
+        smem_img = std::max(smem_img, (cta_doubles(pd, pd.ph[p], kThreads, 0) + slice + 4) * sizeof(double));
+    }
+    h->smem_image = smem_img;
     h->nb_uniform = pd.ph[0].nb;
     for (int p = 1; p < hp.nphases; ++p)
         if (pd.ph[p].nb != h->nb_uniform) h->nb_uniform = 0;
@@ -472,6 +686,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if (h->force_generic) h->nb_uniform = 0;
     // the specialised kernels: block counts of the BASELINE configs, one defect row per thread
     h->fast_ok = !h->no_fast && !h->force_generic && h->nb_uniform >= 3 && h->nb_uniform <= 5 && one_row_per_thread;
+    h->image_ok = h->fast_ok && !h->no_image && (pd.nnz & 1) == 0 && smem_img <= 227 * 1024 - 1024;
     int rc;
     if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
     CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));
@@ -697,6 +912,37 @@ int ecuda_sync(ecuda_handle h) {
 }
 
 int64_t ecuda_launch_count(ecuda_handle h) { return h ? h->launches : 0; }
+
+int ecuda_fp64_peak(ecuda_handle h, double* tflops) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!tflops) return fail(h, ECUDA_ERR_ARG, "null output");
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    int rc;
+    if ((rc = ensure(h, h->ssum, sizeof(double) * blocks * threads))) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        CU(cudaEventRecord(e0, h->stream));
+        k_fp64_peak<<<blocks, threads, 0, h->stream>>>(static_cast<double*>(h->ssum.p), iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU(cudaGetLastError());
+    ++h->launches;
+    *tflops = best;
+    return ECUDA_OK;
+}
 
 // ---- IPOPT TNLP-shaped shims (single instance) -----------------------------------------------------------
 static int ipopt_guard(ecuda_handle h, int n) {

@@ -172,7 +172,18 @@ ECUDA_HD void fast_copy_template(const ProbDev& pb, const PhaseDev& ph, const Ev
     const int e0 = ECUDA_LDG(pb.colptr + ph.zoff + pb.nc * ph.N);        // first state column of the phase
     const int e1 = ECUDA_LDG(pb.colptr + ph.zoff + (pb.nc + pb.ns) * ph.N);  // its t0 column
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-    for (int e = e0 + tid; e < e1; e += nthr) ECUDA_STREAM_STORE(jac + e, ECUDA_LDG(pb.jtmpl + e));
+    // batches of UNR independent loads, then UNR stores: one L2 round trip per batch instead of one
+    // per element (the template is L2 resident, ~100 KB shared by every CTA)
+    constexpr int UNR = 12;
+    for (int e = e0 + tid; e < e1; e += UNR * nthr) {
+        double v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (e + u * nthr < e1) v[u] = ECUDA_LDG(pb.jtmpl + e + u * nthr);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (e + u * nthr < e1) ECUDA_STREAM_STORE(jac + e + u * nthr, v[u]);
+    }
 }
 
 // ---- phase B ------------------------------------------------------------------------------------------
@@ -241,13 +252,16 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
 }
 
 // ---- phase C ------------------------------------------------------------------------------------------
-template <int M, int NB, bool FD>
+// SM (exact mode only): triplets go to the shared-memory image whose virtual base is `image`
+// (image[e] = slot of triplet e of the instance) instead of the caller's global array.
+template <int M, int NB, bool FD, bool SM = false>
 ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
-                           int nthr, const RowRegs<NB>& rr) {
+                           int nthr, const RowRegs<NB>& rr, double* image = nullptr) {
+    static_assert(!(FD && SM), "the shared-memory image is an exact-mode path");
     constexpr int NS = Model<M>::NS;
     const int N = ph.N, nc = pb.nc, np = ph.npath;
     if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
-    double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
+    double* jac = SM ? image : (io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr);
     if (tid < NS * N && (io.g || jac)) {
         const int j = fast_div(tid, ph.mN), k = tid - j * N;
         const int r = ph.goff + k * NS + j;
@@ -261,7 +275,7 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
                                              m.colp + xoff, rr.P, sgr, hfv, k, k + pb.xcnt[j] - 1, jac);
                 xcol_local_fd<M>(pb, ph, p, io, m, b, j, k, rr.dp, rr.dm, jac);
             } else {
-                xcol_local_exact<M>(pb, ph, p, m, j, k, jac);
+                xcol_local_exact<M, SM>(pb, ph, p, m, j, k, jac);
             }
         }
     }
@@ -276,11 +290,11 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
                 if (FD)
                     xcol_path_fd<M>(pb, ph, m, j, k, q, jac);
                 else
-                    xcol_path_exact<M>(pb, ph, m, j, k, q, jac);
+                    xcol_path_exact<M, SM>(pb, ph, m, j, k, q, jac);
             } else {
                 const int i2 = it - nP;
                 const int c = fast_div(i2, ph.mN), k = i2 - c * N;
-                node_item<M>(pb, ph, p, io, m, b, k, c);
+                node_item<M, SM>(pb, ph, p, io, m, b, k, c, SM ? jac : nullptr);
             }
         }
     }

@@ -41,6 +41,17 @@ namespace ecuda {
 
 #define ECUDA_SQRT_EPS 1.4901161193847656e-08 /* 2^-26 */
 
+// Triplet sink. SM = false: streaming store to the caller's global array. SM = true: plain store into
+// the CTA's shared-memory image of the instance's triplet range (k_eval_image), which leaves through
+// one bulk copy.
+template <bool SM>
+ECUDA_HD void jstore(double* p, double v) {
+    if (SM)
+        *p = v;
+    else
+        ECUDA_STREAM_STORE(p, v);
+}
+
 struct CtaMem {
     double* z;     // [nvars_p] unscaled variables of this phase
     double* xp;    // [nvars_p] (z~ + delta) * isz
@@ -322,7 +333,7 @@ ECUDA_HD void xcol_path_fd(const ProbDev& pb, const PhaseDev& ph, const CtaMem& 
 }
 
 // defect rows of node k, event row, linkage row -- analytic
-template <int M>
+template <int M, bool SM = false>
 ECUDA_HD void xcol_local_exact(const ProbDev& pb, const PhaseDev& ph, int p, const CtaMem& m, int j, int k,
                                double* jac) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
@@ -350,28 +361,28 @@ ECUDA_HD void xcol_local_exact(const ProbDev& pb, const PhaseDev& ph, int p, con
             for (int jj = 0; jj < NS; ++jj)
                 if (jj == j) d = dfdx[i][jj];
             double v = ((i == j) ? dkk : 0.0) - pt.h * d;
-            ECUDA_STREAM_STORE(jac + base + k + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+            jstore<SM>(jac + base + k + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
         }
     }
     int pos = N - 1 + pb.xcnt[j];
     if (k == 0 || k == N - 1) {
         int r = ph.goff + ns * N + (k == 0 ? j : ns + j);
-        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+        jstore<SM>(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
         ++pos;
     }
     if (j < 2) pos += np;
     if (k == N - 1 && p + 1 < pb.nphases) {
         int r = pb.linkoff + p * (ns + 1) + j;
-        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
+        jstore<SM>(jac + base + pos, (ECUDA_LDG(sg + r) * 1.0) * is);
     }
     if (k == 0 && p > 0) {
         int r = pb.linkoff + (p - 1) * (ns + 1) + j;
-        ECUDA_STREAM_STORE(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
+        jstore<SM>(jac + base + pos, (ECUDA_LDG(sg + r) * -1.0) * is);
     }
 }
 
 // path row q of node k in column X(k,j), j < 2 -- analytic
-template <int M>
+template <int M, bool SM = false>
 ECUDA_HD void xcol_path_exact(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int j, int k, int q,
                               double* jac) {
     const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
@@ -387,7 +398,7 @@ ECUDA_HD void xcol_path_exact(const ProbDev& pb, const PhaseDev& ph, const CtaMe
     const double v = (j == 0) ? ddx : ddy;
     const int r = ph.goff + ns * N + pb.ne + k * np + q;
     const int pos = N - 1 + pb.xcnt[j] + ((k == 0 || k == N - 1) ? 1 : 0) + q;
-    ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (ECUDA_LDG(pb.sg + r) * v) * ECUDA_LDG(pb.isz + col));
+    jstore<SM>(jac + m.colp[lcol] + pos, (ECUDA_LDG(pb.sg + r) * v) * ECUDA_LDG(pb.isz + col));
 }
 
 // whole node-local part of column X(k,j), written to the caller's global array (generic path)
@@ -582,9 +593,9 @@ ECUDA_HD void state_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
 }
 
 // node-local Jacobian entries of column c at node k: c in [0,nc) control, nc -> t0, nc+1 -> tf
-template <int M>
+template <int M, bool SM = false>
 ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m, int b,
-                        int k, int c) {
+                        int k, int c, double* jacbase = nullptr) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
     const int N = ph.N, ns = pb.ns, nc = pb.nc, np = ph.npath;
     const bool fd = io.jac_mode == ECUDA_JAC_FD_INDEXSET;
@@ -592,7 +603,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
     const double tau = ECUDA_LDG(ph.tau + k);
     const double t = pt.h * tau + pt.m;
     const double* sg = pb.sg;
-    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    double* jac = jacbase ? jacbase : io.jac + static_cast<size_t>(b) * pb.nnz;
     double x[NS], u[NCU];
 #pragma unroll
     for (int i = 0; i < NS; ++i) x[i] = m.z[nc * N + k * ns + i];
@@ -621,7 +632,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
                     double s = ECUDA_LDG(sg + rdef0 + i), dv = m.dotv[k * ns + i];
                     double gp = s * (dv - pt.h * fp[i]);
                     double gm = s * (dv - pt.h * fm[i]);
-                    ECUDA_STREAM_STORE(jac + base + rk, (gp - gm) * ri);
+                    jstore<SM>(jac + base + rk, (gp - gm) * ri);
                 }
             }
         } else {
@@ -637,7 +648,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
                     for (int jj = 0; jj < NCU; ++jj)
                         if (jj == j) d = dfdu[i][jj];
                     double v = -(pt.h * d);
-                    ECUDA_STREAM_STORE(jac + base + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+                    jstore<SM>(jac + base + rk, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
                 }
             }
         }
@@ -663,31 +674,31 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
             double s = ECUDA_LDG(sg + rdef0 + i), dv = m.dotv[k * ns + i];
             double gp = s * (dv - hp * fp[i]);
             double gm = s * (dv - hm * fm[i]);
-            ECUDA_STREAM_STORE(jac + base + k * ns + i, (gp - gm) * ri);
+            jstore<SM>(jac + base + k * ns + i, (gp - gm) * ri);
         }
         for (int q = ph.nstat; q < np; ++q) {
             double s = ECUDA_LDG(sg + rpath0 + q);
             double vp = path_row<M>(pb, ph, m, q, x[0], x[1], tp);
             double vm = path_row<M>(pb, ph, m, q, x[0], x[1], tm);
-            ECUDA_STREAM_STORE(jac + base + ns * N + k * ntr + (q - ph.nstat), (s * vp - s * vm) * ri);
+            jstore<SM>(jac + base + ns * N + k * ntr + (q - ph.nstat), (s * vp - s * vm) * ri);
         }
         if (k == 0) {
             int r = ph.goff + ns * N + pb.ne + np * N;
             double s = ECUDA_LDG(sg + r);
-            ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
+            jstore<SM>(jac + base + ns * N + N * ntr, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
             if (which == 0 && p > 0) {
                 const PhaseDev& pv = pb.ph[p - 1];
                 int rl = pb.linkoff + (p - 1) * (ns + 1) + ns;
                 double sl = ECUDA_LDG(sg + rl);
                 double o = other_phase_value(pb, io, b, pv.zoff + (ns + nc) * pv.N + 1);
-                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
+                jstore<SM>(jac + base + ns * N + N * ntr + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
             }
             if (which == 1 && p + 1 < pb.nphases) {
                 const PhaseDev& nx = pb.ph[p + 1];
                 int rl = pb.linkoff + p * (ns + 1) + ns;
                 double sl = ECUDA_LDG(sg + rl);
                 double o = other_phase_value(pb, io, b, nx.zoff + (ns + nc) * nx.N);
-                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
+                jstore<SM>(jac + base + ns * N + N * ntr + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
             }
         }
     } else {
@@ -699,25 +710,25 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
         for (int i = 0; i < NS; ++i) {
             // d zeta / d t0 = +f/2 ; d zeta / d tf = -f/2   (the models have no explicit time dependence)
             double v = which == 0 ? 0.5 * f[i] : -0.5 * f[i];
-            ECUDA_STREAM_STORE(jac + base + k * ns + i, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
+            jstore<SM>(jac + base + k * ns + i, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
         }
         for (int q = ph.nstat; q < np; ++q) {
             double ddx, ddy, ddt;
             track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0], x[1], t, &ddx,
                                &ddy, &ddt);
-            ECUDA_STREAM_STORE(jac + base + ns * N + k * ntr + (q - ph.nstat),
+            jstore<SM>(jac + base + ns * N + k * ntr + (q - ph.nstat),
                                (ECUDA_LDG(sg + rpath0 + q) * (ddt * dtk)) * is);
         }
         if (k == 0) {
             int r = ph.goff + ns * N + pb.ne + np * N;
-            ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr, (ECUDA_LDG(sg + r) * (which == 0 ? -1.0 : 1.0)) * is);
+            jstore<SM>(jac + base + ns * N + N * ntr, (ECUDA_LDG(sg + r) * (which == 0 ? -1.0 : 1.0)) * is);
             if (which == 0 && p > 0) {
                 int rl = pb.linkoff + (p - 1) * (ns + 1) + ns;
-                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * -1.0) * is);
+                jstore<SM>(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * -1.0) * is);
             }
             if (which == 1 && p + 1 < pb.nphases) {
                 int rl = pb.linkoff + p * (ns + 1) + ns;
-                ECUDA_STREAM_STORE(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * 1.0) * is);
+                jstore<SM>(jac + base + ns * N + N * ntr + 1, (ECUDA_LDG(sg + rl) * 1.0) * is);
             }
         }
     }

@@ -155,6 +155,9 @@ int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, do
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);
+/* measured FP64 FMA throughput of the device (TFLOP/s, register-only microbenchmark): the FP64 roof
+ * the finite-difference Jacobian kernel is reported against */
+int ecuda_fp64_peak(ecuda_handle h, double* tflops);
 
 /* IPOPT TNLP-shaped single-instance shims (B must be 1; host pointers). values==NULL in
  * eval_jac_g returns the structure, as IPOPT's convention requires. */

@@ -42,6 +42,27 @@ static void run_fast_mode(const ProbDev& pb, const PhaseDev& ph, int p, const Ev
         run_fast<M, NB, false>(pb, ph, p, io, b, nthr);
 }
 
+// the persistent exact-mode kernel (k_eval_image): the CTA's image of the phase's triplet range is
+// loaded from the template once, phase C overwrites the node-local slots, a memcpy stands for the bulk copy
+template <int M, int NB>
+static void run_image(const ProbDev& pb, int p, const EvalIO& io, int nthr) {
+    const PhaseDev& ph = pb.ph[p];
+    std::vector<double> smem(cta_doubles(pb, ph, nthr, 0), 0.0);
+    CtaMem m;
+    carve(m, smem.data(), pb, ph, nthr, 0);
+    const int c0 = pb.colptr[ph.zoff], c1 = pb.colptr[ph.zoff + ph.nvars];
+    std::vector<double> image(pb.jtmpl + c0, pb.jtmpl + c1);
+    double* vimage = image.data() - c0;
+    for (int b = 0; b < io.batch; ++b) {
+        std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
+        for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, false);
+        std::vector<RowRegs<NB>> rr(nthr);
+        for (int t = 0; t < nthr; ++t) fast_phase_b<M, NB, false>(pb, ph, p, io, m, b, t, nthr, rr[t]);
+        for (int t = 0; t < nthr; ++t) fast_phase_c<M, NB, false, true>(pb, ph, p, io, m, b, t, nthr, rr[t], vimage);
+        std::memcpy(io.jac + static_cast<size_t>(b) * pb.nnz + c0, image.data(), sizeof(double) * (c1 - c0));
+    }
+}
+
 static long g_fast_runs = 0;
 extern "C" long emu_fast_runs() { return g_fast_runs; }
 
@@ -54,9 +75,30 @@ static bool fast_ok(const ProbDev& pb, int nthr) {  // same rule as ecuda_set_pr
 
 template <int M>
 static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
+    // exact mode with a Jacobian on the fast path: the persistent image kernel (one pass per phase)
+    const bool image = !generic && io.jac && io.jac_mode == ECUDA_JAC_EXACT && fast_ok(pb, nthr) && (pb.nnz & 1) == 0;
+    if (image) {
+        for (int p = 0; p < pb.nphases; ++p) {
+            switch (pb.ph[p].nb) {
+                case 3: run_image<M, 3>(pb, p, io, nthr); break;
+                case 4: run_image<M, 4>(pb, p, io, nthr); break;
+                default: run_image<M, 5>(pb, p, io, nthr); break;
+            }
+        }
+    }
     for (int b = 0; b < io.batch; ++b)
         for (int p = 0; p < pb.nphases; ++p) {
             const PhaseDev& ph = pb.ph[p];
+            if (image && !io.grad) continue;
+            if (image) {  // only the gradient is left (k_grad is a separate launch)
+                std::vector<double> smem(cta_doubles(pb, ph, nthr), 0.0);
+                CtaMem m;
+                carve(m, smem.data(), pb, ph, nthr);
+                for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, false);
+                for (int t = 0; t < nthr; ++t) cost_nodes<M>(pb, ph, m, t, nthr);
+                for (int t = 0; t < nthr; ++t) gradient_phase<M>(pb, ph, io, m, b, t, nthr);
+                continue;
+            }
             if (!generic && (io.f || io.g || io.jac) && fast_ok(pb, nthr)) {
                 ++g_fast_runs;
                 if (io.grad) {  // k_grad is a separate launch

@@ -231,14 +231,21 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
     both are built from the same operation sequences, only the work layout differs"""
     wl = CASES[name]()
     out = {}
-    for tag, env in (("fast", "0"), ("generic", "1")):
-        os.environ["ECUDA_NO_FAST"] = env  # read by ecuda_create
+    # "fast": k_eval_fast, exact mode streams the template with the TMA copy warp (the default);
+    # "fast-image": exact through the persistent k_eval_image (shared-memory image + bulk stores);
+    # "fast-ldst": template copied with plain loads/stores; "generic": k_eval
+    for tag, env in (("fast", {}), ("fast-image", {"ECUDA_IMAGE": "1"}), ("fast-ldst", {"ECUDA_NO_COPY_WARP": "1"}),
+                     ("generic", {"ECUDA_NO_FAST": "1"})):
+        os.environ.update(env)  # read by ecuda_create
         try:
             ev = capi.Evaluator(wl, device=0)
         finally:
-            os.environ.pop("ECUDA_NO_FAST", None)
+            for k in env:
+                os.environ.pop(k, None)
         out[tag] = {m: ev.eval_host(wl.x, want=("f", "g", "jac"), jac_mode=m) for m in (W.JAC_FD, W.JAC_EXACT)}
         ev.close()
     for m in (W.JAC_FD, W.JAC_EXACT):
         for key in ("f", "g", "jac"):
             assert np.array_equal(out["fast"][m][key], out["generic"][m][key]), (name, m, key)
+            assert np.array_equal(out["fast-ldst"][m][key], out["generic"][m][key]), (name, m, key)
+            assert np.array_equal(out["fast-image"][m][key], out["generic"][m][key]), (name, m, key)
