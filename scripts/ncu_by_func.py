@@ -8,7 +8,12 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]; ie, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+data = []
+for r in rows[hi + 1:]:
+    if r and r[0] == "Address":  # next launch in the report
+        break
+    if len(r) >= len(hdr):
+        data.append(r)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "host" not in f][0]
@@ -24,7 +29,7 @@ for ln in dis.splitlines():
 assert len(seq) == len(data), (len(seq), len(data))
 # function line ranges of the current source
 funcs = []
-for fn in ("ecuda_phases.cuh", "ecuda_models.cuh", "ecuda_api.cu"):
+for fn in ("ecuda_phases.cuh", "ecuda_models.cuh", "ecuda_api.cu", "ecuda_fast.cuh", "ecuda_internal.hpp"):
     lines = open(os.path.join(ROOT, "etol_b200", "csrc", fn)).read().splitlines()
     for i, l in enumerate(lines, 1):
         m = re.match(r"^(?:ECUDA_HD|__device__ __forceinline__|__global__)\s+[\w:<>\*& ]*?(\w+)\(", l)
