@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
     ap.add_argument("--jac", default="fd", choices=["fd", "exact"])
     ap.add_argument("--gather", default="summary", choices=["summary", "full", "none"])
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="exchange the per-instance summaries with NCCL all_gather instead of the fused P2P kernel")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -62,6 +64,7 @@ def workload_config(wl, args, n_gpus):
             "l2": "flushed between timed steps: 256 MiB write, then a 256 MiB read sweep so the flush buffer's "
                   "dirty lines are written back before the timed region; outputs per step (446 MB) exceed L2",
             "parallelism": f"instances sharded over {n_gpus} GPU(s), gather={args.gather if n_gpus > 1 else 'n/a'}"}
+
 
 
 # ---- clocks sampler (B200_PROFILING.md recipe) -----------------------------------------------------------
@@ -171,7 +174,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "oracle port of the reference CPU path (PSOPT/ADOL-C cannot be built here); host cores only"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -210,6 +213,24 @@ def run_ecuda(args):
     full_gather = None
     if world > 1 and args.gather == "full":
         full_gather = torch.empty((world * B, nz), dtype=torch.float64, device=dev)
+    # fused summary + all-gather over NVLink peer memory (ecuda_summarize_allgather): two symmetric
+    # buffers used alternately, so a rank that runs one step ahead never overwrites rows a peer may
+    # still be reading; falls back to NCCL all_gather when symmetric memory is unavailable
+    peers, hdls, gather_impl = None, None, "n/a"
+    if world > 1 and args.gather != "none":
+        gather_impl = "nccl all_gather_into_tensor"
+        if not args.nccl_gather:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                bufs = [symm.empty((world * B, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+                hdls = [symm.rendezvous(t, dist.group.WORLD) for t in bufs]
+                peers = [[int(p) for p in hd.buffer_ptrs] for hd in hdls]
+                sym_bufs = bufs
+                gather_impl = "fused summary + P2P stores over NVLink (symmetric memory), 1 barrier per step"
+            except Exception as exc:  # noqa: BLE001
+                peers, hdls = None, None
+                gather_impl = f"nccl all_gather_into_tensor (symmetric memory unavailable: {type(exc).__name__})"
+    step_no = [0]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     sweep = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
@@ -227,9 +248,15 @@ def run_ecuda(args):
     def step():
         ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, capi.MEM_DEVICE, sp)
         if world > 1 and args.gather != "none":
-            # per-instance {f, max violation} from the f, g just computed, then one all-gather
-            ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), sp)
-            dist.all_gather_into_tensor(gathered, summ)
+            # per-instance {f, max violation} from the f, g just computed, gathered on every rank
+            if peers is not None:
+                s = step_no[0] & 1
+                step_no[0] += 1
+                ev.summarize_allgather_ptr(f.data_ptr(), g.data_ptr(), peers[s], rank, sp)
+                hdls[s].barrier(channel=0)
+            else:
+                ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), sp)
+                dist.all_gather_into_tensor(gathered, summ)
             if full_gather is not None:
                 dist.all_gather_into_tensor(full_gather, jac)
 
@@ -241,6 +268,13 @@ def run_ecuda(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if peers is not None:  # the fused exchange must give what NCCL gives
+        ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), sp)
+        dist.all_gather_into_tensor(gathered, summ)
+        torch.cuda.synchronize()
+        last = sym_bufs[(step_no[0] - 1) & 1]
+        if not torch.equal(last, gathered):
+            raise SystemExit("bench.py: fused P2P all-gather disagrees with NCCL all_gather")
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -249,8 +283,19 @@ def run_ecuda(args):
     launches0 = ev.launch_count()
     barrier()
     t_begin = time.time()
+    def align():
+        # untimed, in-stream: all ranks leave their L2 flush before anyone starts the timed step, so the
+        # step's exchange does not absorb the skew of the flush kernels
+        if world > 1:
+            if hdls is not None:
+                hdls[0].barrier(channel=1)
+            else:
+                dist.all_reduce(skew_token)
+
+    skew_token = torch.zeros(1, device=dev)
     for i in range(args.steps):
         flush_l2(i)                    # untimed: evict L2 between timed steps
+        align()
         starts[i].record(stream)
         step()
         stops[i].record(stream)
@@ -352,11 +397,11 @@ def run_ecuda(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(wl, args, world), "clocks": clocks, "e2e": e2e,
+                "config": dict(workload_config(wl, args, world), gather_impl=gather_impl), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(line)
     ev.close()
     if world > 1:
         dist.destroy_process_group()
@@ -365,9 +410,27 @@ def run_ecuda(args):
 
 def main():
     args = parse()
+    # exactly one line on stdout (rank 0's JSON): anything a library prints (NCCL's version banner,
+    # torchrun notices) goes to stderr while the benchmark runs
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ecuda(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":

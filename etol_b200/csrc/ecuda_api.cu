@@ -325,6 +325,36 @@ __global__ void k_summary(const double* f, const double* g, const double* gl, co
     }
 }
 
+// Fused per-instance summary + all-gather over NVLink peer memory: one warp reduces instance i to
+// {f, max bound violation} (shuffle max) and lane r stores the 16-byte row straight into rank r's
+// gathered buffer at row rank*batch + i (P2P stores; the buffers come from a symmetric-memory
+// rendezvous). No staging buffer, no separate collective launch: the exchange of the sharded path
+//  is the epilogue of the reduction. A cross-GPU barrier after the kernel
+// (caller's stream) makes the rows visible everywhere.
+struct PeerPtrs {
+    double* p[16];
+};
+__global__ void k_summary_scatter(const double* f, const double* g, const double* gl, const double* gu, PeerPtrs peers,
+                                  int nranks, int rank, int batch, int ncons) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= batch) return;
+    const double* gb = g + static_cast<size_t>(warp) * ncons;
+    const double* lb = gl + static_cast<size_t>(warp) * ncons;
+    const double* ub = gu + static_cast<size_t>(warp) * ncons;
+    double v = 0.0;
+    for (int r = lane; r < ncons; r += 32) {
+        double gv = gb[r];
+        v = fmax(v, fmax(lb[r] - gv, gv - ub[r]));
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const double fv = f[warp];
+    if (lane < nranks) {
+        double2* dst = reinterpret_cast<double2*>(peers.p[lane] + (static_cast<size_t>(rank) * batch + warp) * 2);
+        *dst = make_double2(fv, v);
+    }
+    __threadfence_system();
+}
+
 // FP64 FMA microbenchmark: 8 independent dependent-chains per thread, no memory traffic. Defines the
 // FP64 roof the finite-difference kernel is compared with (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
@@ -899,6 +929,30 @@ int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, do
     k_summary<<<(unsigned)((B + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, st>>>(
         f_dev, g_dev, static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), out_dev, (int)B,
         h->pd.ncons);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return ECUDA_OK;
+}
+
+int ecuda_summarize_allgather(ecuda_handle h, const double* f_dev, const double* g_dev, void* const* peer_out,
+                              int nranks, int rank, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_bounds) return fail(h, ECUDA_ERR_STATE, "upload_bounds has not been called");
+    if (!f_dev || !g_dev || !peer_out) return fail(h, ECUDA_ERR_ARG, "null pointer");
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return fail(h, ECUDA_ERR_ARG, "bad rank / nranks (1..16)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    PeerPtrs pp{};
+    for (int r = 0; r < nranks; ++r) {
+        if (!peer_out[r] || (reinterpret_cast<uintptr_t>(peer_out[r]) & 15)) return fail(h, ECUDA_ERR_ARG, "peer buffer null or not 16-byte aligned");
+        pp.p[r] = static_cast<double*>(peer_out[r]);
+    }
+    const size_t B = h->hp.desc.batch;
+    const int warps_per_block = 4;
+    k_summary_scatter<<<(unsigned)((B + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, st>>>(
+        f_dev, g_dev, static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), pp, nranks, rank,
+        (int)B, h->pd.ncons);
     ++h->launches;
     CU(cudaGetLastError());
     return ECUDA_OK;

@@ -93,11 +93,14 @@ ECUDA_HD void fast_diag(const double* __restrict__ Dtk, int N, const double* __r
 // D-coupled triplets of row (k,j) in the state columns of summation block BI, by index-set central
 // differences (row-restricted: see ecuda_phases.cuh). jac = triplet array of the instance;
 // kpc = k + (number of node-local defect rows of column X(.,j)) - 1.
-template <int NS, int NB, int BI, bool PARTIAL>
+// DIAGSTORE: the l == k value is the finished diagonal triplet (models whose f_j does not read x_j:
+// h*f_j is the same at the perturbed points, so the row's own column needs nothing else) and goes to
+// its real slot kd = k + rank of row (k,j) among the node-local rows of column X(k,j).
+template <int NS, int NB, int BI, bool PARTIAL, bool DIAGSTORE>
 ECUDA_HD void fast_fd_block(const double* __restrict__ Dtk, int N, const double* __restrict__ Xj,
                             const double* __restrict__ XPj, const double* __restrict__ XMj,
                             const double* __restrict__ RIj, const int* __restrict__ CPj, const double (&P)[NB],
-                            double sgr, double hfv, int k, int kpc, double* __restrict__ jac) {
+                            double sgr, double hfv, int k, int kpc, int kd, double* __restrict__ jac) {
     constexpr int BL = ECUDA_DOT_BLOCK;
     constexpr int l0 = BI * BL;
     constexpr bool LAST = PARTIAL && BI == NB - 1;  // only the last block can be partial
@@ -138,32 +141,33 @@ ECUDA_HD void fast_fd_block(const double* __restrict__ Dtk, int N, const double*
             const double gm = sgr * (tm - hfv);
             const double v = (gp - gm) * RIj[(l0 + a) * NS];
             // rows k < l sit at position k of column X(l,j); rows k > l come after its node-local block.
-            // For l == k the slot is the first node-local defect triplet of the thread's own column,
-            // which xcol_local_* overwrites later in this thread's program order: storing there
-            // unconditionally is cheaper than a branch around the store.
-            const unsigned idx = static_cast<unsigned>(CPj[(l0 + a) * NS] + ((l0 + a) < k ? kpc : k));
+            // For l == k: DIAGSTORE -> the diagonal triplet's own slot; otherwise the first node-local
+            // defect triplet of the thread's own column, which xcol_local_fd overwrites later in this
+            // thread's program order (an unconditional store is cheaper than a branch around it).
+            const int kge = (DIAGSTORE && (l0 + a) == k) ? kd : k;
+            const unsigned idx = static_cast<unsigned>(CPj[(l0 + a) * NS] + ((l0 + a) < k ? kpc : kge));
             ECUDA_STREAM_STORE(jac + idx, v);
             q = fma(d[a], xv[a], q);
         }
     }
 }
 
-template <int NS, int NB, int BI>
+template <int NS, int NB, int BI, bool DS>
 struct FastFdBlocks {
     ECUDA_HD static void run(const double* Dtk, int N, const double* Xj, const double* XPj, const double* XMj,
                              const double* RIj, const int* CPj, const double (&P)[NB], double sgr, double hfv, int k,
-                             int kpc, double* jac) {
+                             int kpc, int kd, double* jac) {
         if (BI < NB - 1 || N == NB * ECUDA_DOT_BLOCK)  // uniform over the CTA
-            fast_fd_block<NS, NB, BI, false>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+            fast_fd_block<NS, NB, BI, false, DS>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, kd, jac);
         else
-            fast_fd_block<NS, NB, BI, true>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
-        FastFdBlocks<NS, NB, BI + 1>::run(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, jac);
+            fast_fd_block<NS, NB, BI, true, DS>(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, kd, jac);
+        FastFdBlocks<NS, NB, BI + 1, DS>::run(Dtk, N, Xj, XPj, XMj, RIj, CPj, P, sgr, hfv, k, kpc, kd, jac);
     }
 };
-template <int NS, int NB>
-struct FastFdBlocks<NS, NB, NB> {
+template <int NS, int NB, bool DS>
+struct FastFdBlocks<NS, NB, NB, DS> {
     ECUDA_HD static void run(const double*, int, const double*, const double*, const double*, const double*,
-                             const int*, const double (&)[NB], double, double, int, int, double*) {}
+                             const int*, const double (&)[NB], double, double, int, int, int, double*) {}
 };
 
 // exact mode: copy this phase's slice of the per-problem template into the instance's triplet array
@@ -202,7 +206,7 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
         const double* Xj = m.z + nc * N + j;
         m.dotv[k * NS + j] = (N == NB * ECUDA_DOT_BLOCK) ? fast_dot<NS, NB, false>(Dtk, N, Xj, rr.P)
                                                          : fast_dot<NS, NB, true>(Dtk, N, Xj, rr.P);
-        if (FD && io.jac) {
+        if (FD && io.jac && !Model<M>::DIAG_FREE) {
             const int lcol = nc * N + k * NS + j;
             fast_diag<NS, NB>(Dtk, N, Xj, m.xp[lcol], m.xm[lcol], k, rr.P, rr.dp, rr.dm);
         }
@@ -271,9 +275,11 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
         if (jac) {
             if (FD) {
                 const int xoff = nc * N + j;
-                FastFdBlocks<NS, NB, 0>::run(ph.Dt + k, N, m.z + xoff, m.xp + xoff, m.xm + xoff, m.rinv + xoff,
-                                             m.colp + xoff, rr.P, sgr, hfv, k, k + pb.xcnt[j] - 1, jac);
-                xcol_local_fd<M>(pb, ph, p, io, m, b, j, k, rr.dp, rr.dm, jac);
+                constexpr bool DS = Model<M>::DIAG_FREE;
+                FastFdBlocks<NS, NB, 0, DS>::run(ph.Dt + k, N, m.z + xoff, m.xp + xoff, m.xm + xoff, m.rinv + xoff,
+                                                 m.colp + xoff, rr.P, sgr, hfv, k, k + pb.xcnt[j] - 1,
+                                                 k + pb.xrank[j][j], jac);
+                xcol_local_fd<M, DS>(pb, ph, p, io, m, b, j, k, DS ? 0.0 : rr.dp, DS ? 0.0 : rr.dm, jac);
             } else {
                 xcol_local_exact<M, SM>(pb, ph, p, m, j, k, jac);
             }

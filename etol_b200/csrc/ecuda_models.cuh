@@ -100,6 +100,9 @@ ECUDA_HD void track_row_partials(const double* trk, int nway, double x, double y
 template <>
 struct Model<ECUDA_MODEL_SI2D> {
     static constexpr int NS = 2, NCU = 2, REC = 6;
+    // f_i never reads x_i: the defect row (k,i) depends on its own state column only through D, so the
+    // diagonal triplet of that column needs no second evaluation of the dynamics
+    static constexpr bool DIAG_FREE = true;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         out[0] = u[0];
         out[1] = u[1];
@@ -123,6 +126,7 @@ struct Model<ECUDA_MODEL_SI2D> {
 template <>
 struct Model<ECUDA_MODEL_PM3D> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
+    static constexpr bool DIAG_FREE = true;  // f_i never reads x_i
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         out[0] = x[3]; out[1] = x[4]; out[2] = x[5];
         out[3] = u[0]; out[4] = u[1]; out[5] = u[2];
@@ -149,6 +153,7 @@ struct Model<ECUDA_MODEL_PM3D> {
 template <>
 struct Model<ECUDA_MODEL_FW6> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
+    static constexpr bool DIAG_FREE = true;  // f_i never reads x_i (x,y,z,V,gamma,psi derivatives)
     static constexpr double G0 = 9.80665;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         double sg, cg, sp, cp;

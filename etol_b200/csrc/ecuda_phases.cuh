@@ -257,7 +257,7 @@ ECUDA_HD int dot_entry_pos(const ProbDev& pb, int j, int k, int l) { return k < 
 
 // defect rows of node k, event row, linkage row -- by central differences. dpk/dmk = (D X)[k][j]
 // with X[k][j] replaced by its +/- perturbed value.
-template <int M>
+template <int M, bool SKIPDIAG = false>
 ECUDA_HD void xcol_local_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m, int b,
                             int j, int k, double dpk, double dmk, double* jac) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
@@ -283,7 +283,7 @@ ECUDA_HD void xcol_local_fd(const ProbDev& pb, const PhaseDev& ph, int p, const 
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
         int rk = pb.xrank[j][i];
-        if (rk >= 0) {
+        if (rk >= 0 && !(SKIPDIAG && i == j)) {  // SKIPDIAG: the caller has written the diagonal triplet
             double s = ECUDA_LDG(sg + rdef0 + i);
             double dv = m.dotv[k * ns + i];
             double gp = s * (((i == j) ? dpk : dv) - pt.h * fp[i]);

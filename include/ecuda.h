@@ -152,6 +152,13 @@ int ecuda_summary(ecuda_handle h, const double* x, double* out, int memkind, voi
 /* same reduction over f [B] and g [B][ncons] already on the device (e.g. the outputs of a previous
  * ecuda_eval on the same stream); out [B][2] on the device. One warp per instance, shuffle max. */
 int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, double* out_dev, void* stream);
+/* sharded runs (one handle per GPU, one process per GPU): the same reduction fused with the all-gather
+ * of the rows over NVLink peer memory. peer_out[r] is rank r's gathered buffer [nranks*B][2] (device
+ * pointers valid on this device, e.g. from a symmetric-memory rendezvous; 16-byte aligned); this rank's
+ * rows land at [rank*B, (rank+1)*B) of every buffer. The caller issues a cross-GPU barrier on the same
+ * stream afterwards. nranks <= 16. */
+int ecuda_summarize_allgather(ecuda_handle h, const double* f_dev, const double* g_dev, void* const* peer_out,
+                              int nranks, int rank, void* stream);
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);

@@ -1,0 +1,61 @@
+"""Two ranks on two GPUs (NCCL): the sharded evaluation with the fused summary + all-gather over NVLink
+peer memory (ecuda_summarize_allgather) must give exactly what the single-GPU summary + NCCL
+all_gather gives. Skipped on boxes with fewer than two GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from etol_b200 import capi, shard, workloads as W
+import torch.distributed._symmetric_memory as symm
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B = 33
+wl = W.pm3d(batch=B, nnodes=17, ncyl=3, seed=W.SEED + rank)   # every rank its own shard
+ev = capi.Evaluator(wl, device=local)
+x = torch.from_numpy(wl.x).to(dev)
+f = torch.empty(B, dtype=torch.float64, device=dev)
+g = torch.empty((B, ev.ncons), dtype=torch.float64, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), None, capi.JAC_EXACT, capi.MEM_DEVICE, st)
+summ = torch.empty((B, 2), dtype=torch.float64, device=dev)
+ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), st)
+ref = shard.gather_rows(summ)                                   # NCCL all_gather
+buf = symm.empty((world * B, 2), dtype=torch.float64, device=dev)
+buf.fill_(float("nan"))
+hdl = symm.rendezvous(buf, dist.group.WORLD)
+hdl.barrier(channel=0)                                          # everyone has cleared its buffer
+ev.summarize_allgather_ptr(f.data_ptr(), g.data_ptr(), [int(p) for p in hdl.buffer_ptrs], rank, st)
+hdl.barrier(channel=0)
+torch.cuda.synchronize()
+ok = torch.equal(buf, ref)
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    open(sys.argv[2], "w").write("ok" if int(flag.item()) == 1 else "mismatch")
+ev.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+def test_fused_allgather_matches_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script, out = tmp_path / "worker.py", tmp_path / "result.txt"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29547", str(script), ROOT, str(out)],
+                   check=True, env=env, timeout=600)
+    assert out.read_text() == "ok"
