@@ -226,7 +226,8 @@ def run_ecuda(args):
                 hdls = [symm.rendezvous(t, dist.group.WORLD) for t in bufs]
                 peers = [[int(p) for p in hd.buffer_ptrs] for hd in hdls]
                 sym_bufs = bufs
-                gather_impl = "fused summary + P2P stores over NVLink (symmetric memory), 1 barrier per step"
+                gather_impl = ("fused into k_eval: CTA epilogue stores {f, max violation} to every rank over NVLink "
+                               "(symmetric memory), 1 barrier per step")
             except Exception as exc:  # noqa: BLE001
                 peers, hdls = None, None
                 gather_impl = f"nccl all_gather_into_tensor (symmetric memory unavailable: {type(exc).__name__})"
@@ -246,14 +247,21 @@ def run_ecuda(args):
     assert sp != 0
 
     def step():
+        if world > 1 and args.gather != "none" and peers is not None:
+            # ONE kernel: evaluation, and every CTA's epilogue stores its instance's {f, max violation}
+            # row into all ranks' gathered buffers over NVLink; then one cross-GPU barrier
+            s = step_no[0] & 1
+            step_no[0] += 1
+            ev.eval_allgather_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, peers[s], rank, sp)
+            hdls[s].barrier(channel=0)
+            if full_gather is not None:
+                dist.all_gather_into_tensor(full_gather, jac)
+            return
         ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, capi.MEM_DEVICE, sp)
         if world > 1 and args.gather != "none":
             # per-instance {f, max violation} from the f, g just computed, gathered on every rank
-            if peers is not None:
-                s = step_no[0] & 1
-                step_no[0] += 1
-                ev.summarize_allgather_ptr(f.data_ptr(), g.data_ptr(), peers[s], rank, sp)
-                hdls[s].barrier(channel=0)
+            if False:
+                pass
             else:
                 ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), sp)
                 dist.all_gather_into_tensor(gathered, summ)

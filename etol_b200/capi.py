@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
-    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
+    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation",
 ]
@@ -79,6 +79,8 @@ def lib():
     L.ecuda_summarize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ecuda_summarize_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                             C.c_void_p]
+    L.ecuda_eval_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
     L.ecuda_sync.argtypes = [C.c_void_p]
     L.ecuda_launch_count.restype = C.c_int64
     L.ecuda_launch_count.argtypes = [C.c_void_p]
@@ -271,6 +273,11 @@ class Evaluator:
     def summarize_allgather_ptr(self, f_ptr, g_ptr, peer_ptrs, rank, stream=None):
         arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
         self._check(self.L.ecuda_summarize_allgather(self.h, f_ptr, g_ptr, arr, len(peer_ptrs), rank, stream))
+
+    def eval_allgather_ptr(self, x_ptr, f_ptr, g_ptr, jac_ptr, jac_mode, peer_ptrs, rank, stream=None):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        self._check(self.L.ecuda_eval_allgather(self.h, x_ptr, f_ptr, g_ptr, jac_ptr, jac_mode, arr, len(peer_ptrs), rank,
+                                                stream))
 
     def summary_host(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)

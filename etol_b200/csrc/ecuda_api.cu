@@ -208,6 +208,26 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
     __syncthreads();  // all threads: in exact mode the template has landed before the node-local stores
     fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+    if (io.nranks > 0) {
+        // fused summary + all-gather epilogue: {f, max bound violation} of this instance goes straight
+        // into every rank's gathered buffer over NVLink (P2P stores), row rank*batch + b
+        __shared__ double red[kThreads / 32 + 1];
+        double v = rr.viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = rr.fval;
+        named_barrier(2, kThreads);  // the copy warp (exact mode) has already left
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                // fire and forget: the kernel boundary orders the store before the caller's cross-GPU barrier
+                // (a system-scope fence here would keep the CTA resident for an NVLink round trip)
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
 }
 
 // Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
@@ -350,9 +370,8 @@ __global__ void k_summary_scatter(const double* f, const double* g, const double
     const double fv = f[warp];
     if (lane < nranks) {
         double2* dst = reinterpret_cast<double2*>(peers.p[lane] + (static_cast<size_t>(rank) * batch + warp) * 2);
-        *dst = make_double2(fv, v);
+        *dst = make_double2(fv, v);  // ordered before the caller's cross-GPU barrier by the kernel boundary
     }
-    __threadfence_system();
 }
 
 // FP64 FMA microbenchmark: 8 independent dependent-chains per thread, no memory traffic. Defines the
@@ -872,6 +891,40 @@ static int eval_common(ecuda_handle h, const double* x, double* f, double* g, do
 int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode, int memkind,
                void* stream) {
     return eval_common(h, x, f, g, jac, nullptr, jac_mode, memkind, stream);
+}
+
+int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,
+                         void* const* peer_out, int nranks, int rank, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
+    if (!h->have_bounds) return fail(h, ECUDA_ERR_STATE, "upload_bounds has not been called");
+    if (!h->fast_ok || h->pd.nphases != 1)
+        return fail(h, ECUDA_ERR_STATE, "the fused summary needs a single-phase problem on the specialised kernels; "
+                                        "use ecuda_eval + ecuda_summarize_allgather");
+    if (!x || !f || !g || !peer_out) return fail(h, ECUDA_ERR_ARG, "x, f, g and peer_out are required");
+    if (jac_mode != ECUDA_JAC_EXACT && jac_mode != ECUDA_JAC_FD_INDEXSET) return fail(h, ECUDA_ERR_ARG, "bad jac_mode");
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return fail(h, ECUDA_ERR_ARG, "bad rank / nranks (1..16)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    EvalIO io{};
+    io.inst = static_cast<const double*>(h->inst.p);
+    io.fpart = static_cast<double*>(h->fpart.p);
+    io.jac_mode = jac_mode;
+    io.batch = h->hp.desc.batch;
+    io.x = x;
+    io.f = f;
+    io.g = g;
+    io.jac = jac;
+    io.bl = static_cast<const double*>(h->gl.p);
+    io.bu = static_cast<const double*>(h->gu.p);
+    io.nranks = nranks;
+    io.rank = rank;
+    for (int r = 0; r < nranks; ++r) {
+        if (!peer_out[r] || (reinterpret_cast<uintptr_t>(peer_out[r]) & 15)) return fail(h, ECUDA_ERR_ARG, "peer buffer null or not 16-byte aligned");
+        io.peer[r] = static_cast<double*>(peer_out[r]);
+    }
+    return launch_eval(h, io, st);
 }
 
 int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream) {

@@ -31,7 +31,15 @@ template <int NB>
 struct RowRegs {
     double P[NB];   // block sums of (D X)[k][j]
     double dp, dm;  // (D X)[k][j] with X[k][j] -> +-delta (finite differences only)
+    double viol;    // fused summary: max bound violation over the g rows this thread has written
+    double fval;    // fused summary: the objective (thread that ran the quadrature)
 };
+
+// bound violation of one constraint value (fused summary; io.nranks > 0)
+ECUDA_HD double row_violation(const EvalIO& io, const ProbDev& pb, int b, int r, double val) {
+    const size_t o = static_cast<size_t>(b) * pb.ncons + r;
+    return fmax(ECUDA_LDG(io.bl + o) - val, val - ECUDA_LDG(io.bu + o));
+}
 
 // block sums + total of row k of D times state j of X (canonical blocked order, see dot_row)
 // PARTIAL: the last block has fewer than ECUDA_DOT_BLOCK nodes (N < NB*BL); otherwise no bounds tests
@@ -199,6 +207,8 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
     const PhaseTimes pt = phase_times(pb, ph, m.z);
     double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
     const double* sg = pb.sg;
+    rr.viol = 0.0;
+    rr.fval = 0.0;
     // defect rows: block sums into registers, totals into shared memory
     if (tid < NS * N) {
         const int j = fast_div(tid, ph.mN), k = tid - j * N;
@@ -230,17 +240,23 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
             const double* x = m.z + nc * N + k * NS;
             const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
             const int r = ph.goff + NS * N + pb.ne + it;
-            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t));
+            const double val = ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t);
+            ECUDA_STREAM_STORE(g + r, val);
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
         }
         for (int e = tid; e < pb.ne; e += nthr) {
             const int r = ph.goff + NS * N + e;
             const int node = (e < NS) ? 0 : N - 1;
             const int i = (e < NS) ? e : e - NS;
-            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * m.z[nc * N + node * NS + i]);
+            const double val = ECUDA_LDG(sg + r) * m.z[nc * N + node * NS + i];
+            ECUDA_STREAM_STORE(g + r, val);
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
         }
         if (tid == 0) {
             const int r = ph.goff + NS * N + pb.ne + np * N;
-            ECUDA_STREAM_STORE(g + r, ECUDA_LDG(sg + r) * (pt.tf - pt.t0));
+            const double val = ECUDA_LDG(sg + r) * (pt.tf - pt.t0);
+            ECUDA_STREAM_STORE(g + r, val);
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
         }
         if (p + 1 < pb.nphases) {
             const PhaseDev& nx = pb.ph[p + 1];
@@ -260,18 +276,22 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
 // (image[e] = slot of triplet e of the instance) instead of the caller's global array.
 template <int M, int NB, bool FD, bool SM = false>
 ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
-                           int nthr, const RowRegs<NB>& rr, double* image = nullptr) {
+                           int nthr, RowRegs<NB>& rr, double* image = nullptr) {
     static_assert(!(FD && SM), "the shared-memory image is an exact-mode path");
     constexpr int NS = Model<M>::NS;
     const int N = ph.N, nc = pb.nc, np = ph.npath;
-    if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
+    if (tid == nthr - 1) rr.fval = objective_phase(pb, ph, p, io, m, b);
     double* jac = SM ? image : (io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr);
     if (tid < NS * N && (io.g || jac)) {
         const int j = fast_div(tid, ph.mN), k = tid - j * N;
         const int r = ph.goff + k * NS + j;
         const double sgr = ECUDA_LDG(pb.sg + r);
         const double hfv = m.hf[k * NS + j];
-        if (io.g) ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, sgr * (m.dotv[k * NS + j] - hfv));
+        if (io.g) {
+            const double val = sgr * (m.dotv[k * NS + j] - hfv);
+            ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
+        }
         if (jac) {
             if (FD) {
                 const int xoff = nc * N + j;

@@ -74,6 +74,12 @@ struct EvalIO {
     double* grad;        // [B][nvars] or null
     int jac_mode;
     int batch;
+    // fused per-instance summary {f, max bound violation} + all-gather over peer memory (single-phase
+    // problems, specialised kernels): active when nranks > 0
+    const double* bl;    // [B][ncons] constraint bounds
+    const double* bu;
+    double* peer[16];    // rank r's gathered buffer [nranks*B][2]
+    int nranks, rank;
 };
 
 // ---- host-side problem description ------------------------------------------------------------------

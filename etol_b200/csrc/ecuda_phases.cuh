@@ -227,9 +227,9 @@ ECUDA_HD void phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
 
 // ---- phase C ------------------------------------------------------------------------------------------
 // objective of this phase: h * sum_k w_k L_k, serial ascending fma chain
-ECUDA_HD void objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
-                              int b) {
-    if (!io.f) return;
+ECUDA_HD double objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const CtaMem& m,
+                                int b) {
+    if (!io.f) return 0.0;
     const PhaseTimes pt = phase_times(pb, ph, m.z);
     double acc = 0.0;
     for (int k = 0; k < ph.N; ++k) acc = fma(ECUDA_LDG(ph.w + k), m.Lk[k], acc);
@@ -238,6 +238,7 @@ ECUDA_HD void objective_phase(const ProbDev& pb, const PhaseDev& ph, int p, cons
         io.f[b] = pb.sf * fp;
     else
         io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
+    return pb.sf * fp;  // the instance's scaled objective when there is one phase
 }
 
 // ---- Jacobian work items ------------------------------------------------------------------------------

@@ -159,6 +159,11 @@ int ecuda_summarize(ecuda_handle h, const double* f_dev, const double* g_dev, do
  * stream afterwards. nranks <= 16. */
 int ecuda_summarize_allgather(ecuda_handle h, const double* f_dev, const double* g_dev, void* const* peer_out,
                               int nranks, int rank, void* stream);
+/* evaluation and exchange in ONE kernel (single-phase problems on the specialised kernels): as ecuda_eval
+ * with device pointers, and every CTA finishes by storing its instance's {f, max bound violation} row
+ * into all ranks' gathered buffers, as ecuda_summarize_allgather does. f and g are required. */
+int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,
+                         void* const* peer_out, int nranks, int rank, void* stream);
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);

@@ -38,6 +38,17 @@ ev.summarize_allgather_ptr(f.data_ptr(), g.data_ptr(), [int(p) for p in hdl.buff
 hdl.barrier(channel=0)
 torch.cuda.synchronize()
 ok = torch.equal(buf, ref)
+# evaluation and exchange fused in one kernel (ecuda_eval_allgather), both Jacobian modes
+jac = torch.empty((B, ev.nnz), dtype=torch.float64, device=dev)
+for mode in (capi.JAC_FD, capi.JAC_EXACT):
+    buf.fill_(float("nan"))
+    torch.cuda.synchronize()
+    hdl.barrier(channel=0)
+    ev.eval_allgather_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), mode,
+                          [int(p) for p in hdl.buffer_ptrs], rank, st)
+    hdl.barrier(channel=0)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(buf, ref)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
