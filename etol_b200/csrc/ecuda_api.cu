@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
     stage_vars(pb, ph, io, m, b, tid, nthr, io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET);
     mbar_wait(&bar, 0);
     __syncthreads();
-    phase_b<M>(pb, ph, p, io, m, b, tid, nthr);
+    // blockIdx.y: slice of the phase (instances whose phases have more defect rows than threads)
+    phase_b<M>(pb, ph, p, io, m, b, tid, nthr, blockIdx.y, gridDim.y);
     __syncthreads();
-    phase_c<M, NB>(pb, ph, p, io, m, b, tid, nthr);
+    phase_c<M, NB>(pb, ph, p, io, m, b, tid, nthr, blockIdx.y, gridDim.y);
 }
 
 // Specialised kernel (ecuda_fast.cuh): one defect row per thread, NB summation blocks, separate
@@ -521,7 +522,9 @@ static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int gri
             cur = h->smem_bytes;
         }
     }
-    k_eval<M, NB><<<grid, kThreads, h->smem_bytes, st>>>(h->pd, io);
+    int nslices = 1;  // the widest phase decides; extra slices of a narrower phase just own fewer nodes
+    for (int p = 0; p < h->pd.nphases; ++p) nslices = std::max(nslices, generic_slices(h->pd.ns, h->pd.ph[p].N, kThreads));
+    k_eval<M, NB><<<dim3(grid, nslices), kThreads, h->smem_bytes, st>>>(h->pd, io);
     return ECUDA_OK;
 }
 

@@ -171,12 +171,23 @@ ECUDA_HD double other_phase_value(const ProbDev& pb, const EvalIO& io, int b, in
     return ECUDA_LDG(io.x + static_cast<size_t>(b) * pb.nvars + gcol) * ECUDA_LDG(pb.isz + gcol);
 }
 
+// Generic kernels: a phase may be split over `nslices` CTAs (one instance whose phase has more defect
+// rows than a CTA has threads, e.g. the 200-node fixed-wing problem). Slice s owns the nodes
+// k = s, s + nslices, ...: their defect rows, path rows and node-local triplets; slice 0 also owns the
+// objective and the event, duration and linkage rows. Every slice stages the whole decision vector.
+ECUDA_HD int slice_nodes(int N, int slice, int nslices) { return (N - slice + nslices - 1) / nslices; }
+ECUDA_HD int generic_slices(int ns, int N, int nthr) {
+    const int s = (ns * N + nthr - 1) / nthr;
+    return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+
 // ---- phase B: node evaluations, dots, event/duration/linkage rows --------------------------------------
 template <int M>
 ECUDA_HD void phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
-                      int nthr) {
+                      int nthr, int slice = 0, int nslices = 1) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
     const int N = ph.N, ns = pb.ns, nc = pb.nc;
+    const int nown = slice_nodes(N, slice, nslices);
     const PhaseTimes pt = phase_times(pb, ph, m.z);
     double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
     const double* sg = pb.sg;
@@ -190,18 +201,18 @@ ECUDA_HD void phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
         for (int i = 0; i < NS; ++i) m.hf[k * ns + i] = pt.h * f[i];
         double L = Model<M>::cost(x, u, t);
         m.Lk[k] = pb.maximize ? -1.0 * L : L;
-        if (g) {
+        if (g && k % nslices == slice) {  // path rows of the slice's own nodes
             const int r0 = ph.goff + ns * N + pb.ne + k * ph.npath;
             for (int q = 0; q < ph.npath; ++q)
                 ECUDA_STREAM_STORE(g + r0 + q, ECUDA_LDG(sg + r0 + q) * path_row<M>(pb, ph, m, q, x[0], x[1], t));
         }
         (void)NCU;
     }
-    for (int it = tid; it < ns * N; it += nthr) {
-        int j = it / N, k = it - j * N;
+    for (int it = tid; it < ns * nown; it += nthr) {  // defect rows of the slice's own nodes
+        int j = it / nown, k = slice + (it - j * nown) * nslices;
         m.dotv[k * ns + j] = dot_row(pb, ph, m, k, j, m.P + tid, nthr);
     }
-    if (g) {
+    if (g && slice == 0) {
         for (int e = tid; e < pb.ne; e += nthr) {
             int r = ph.goff + ns * N + e;
             int node = (e < ns) ? 0 : N - 1;
@@ -529,7 +540,7 @@ ECUDA_HD double fd_block(const double* __restrict__ Dtb, int N, const double* __
 // follow the current block fit a register window of NB-1 values; NB == 0: any block count.
 template <int M, int NB>
 ECUDA_HD void state_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int j,
-                         int k, int tid, int nthr) {
+                         int k, int tid, int nthr, bool recompute) {
     constexpr int BL = ECUDA_DOT_BLOCK;
     const int N = ph.N, ns = pb.ns, nc = pb.nc;
     const int r = ph.goff + k * ns + j;
@@ -562,7 +573,7 @@ ECUDA_HD void state_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     // block sums P[bi] of the unperturbed row in thread-private shared memory (P[bi*nthr]). When
     // every thread owns at most one state item, phase B left them there; otherwise rebuild them.
     double* P = m.P + tid;
-    if (ns * N > nthr) dot_row(pb, ph, m, k, j, P, nthr);
+    if (recompute) dot_row(pb, ph, m, k, j, P, nthr);
     constexpr int NSC = Model<M>::NS;  // == pb.ns for every model
     const int nb = NB > 0 ? NB : ph.nb;
     double* jk = jac + k;  // entry of row k in column X(ls,j): colptr + k (+ cntm1 when k > ls)
@@ -737,20 +748,24 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
 
 template <int M, int NB>
 ECUDA_HD void phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int tid,
-                      int nthr) {
+                      int nthr, int slice = 0, int nslices = 1) {
     const int N = ph.N, ns = pb.ns, nc = pb.nc;
-    if (tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
-    if (io.g || io.jac)
-        for (int it = tid; it < ns * N; it += nthr) {
-            int j = it / N, k = it - j * N;
-            state_item<M, NB>(pb, ph, p, io, m, b, j, k, tid, nthr);
+    const int nown = slice_nodes(N, slice, nslices);
+    if (slice == 0 && tid == nthr - 1) objective_phase(pb, ph, p, io, m, b);
+    if (io.g || io.jac) {
+        // when a thread owns more than one defect row, phase B left only the last row's block sums
+        const bool recompute = ns * nown > nthr;
+        for (int it = tid; it < ns * nown; it += nthr) {
+            int j = it / nown, k = slice + (it - j * nown) * nslices;
+            state_item<M, NB>(pb, ph, p, io, m, b, j, k, tid, nthr, recompute);
         }
+    }
     if (io.jac) {
         // the lighter node items are handed out from the top of the thread range downwards, so the
         // threads that had no state item above start on these first
-        const int nitems = (nc + 2) * N;
+        const int nitems = (nc + 2) * nown;
         for (int it = nthr - 1 - tid; it < nitems; it += nthr) {
-            int c = it / N, k = it - c * N;
+            int c = it / nown, k = slice + (it - c * nown) * nslices;
             node_item<M>(pb, ph, p, io, m, b, k, c);
         }
     }

@@ -2,13 +2,14 @@
 //
 // solve_builtin: primal-dual interior point on the slack formulation
 //     min f(z)  s.t.  c_E(z) = b_E,   c_I(z) - s = 0,   gl_I <= s <= gu_I,   zl <= z <= zu
-// with a diagonal model of the Lagrangian Hessian (the running costs of the device models are
-// separable, so diag(d2f) is recovered exactly from one extra gradient evaluation; constraint
-// curvature is left out, which convexifies the obstacle rows). With a diagonal Hessian block the
-// Newton system reduces to an m x m symmetric positive definite Schur complement
+// with a damped-BFGS model B of the Lagrangian Hessian over the free variables (started from
+// diag(d2f), which one extra gradient evaluation gives exactly for the separable running costs of the
+// device models; Powell damping keeps B positive definite, so the nonconvex obstacle rows are
+// handled like in an SQP method). With H = B + barrier terms positive definite the Newton system
+// reduces to an m x m symmetric positive definite Schur complement
 //     (J H^-1 J' + E S^-1 E' + dc I) dlambda = rhs
-// assembled from the sparse Jacobian triplets the GPU returns and factorised by dense Cholesky on
-// the host -- the KKT solve stays on the host, as it does with IPOPT in the reference
+// built from the Jacobian triplets the GPU returns and factorised by dense Cholesky on the host --
+// the KKT solve stays on the host, as it does with IPOPT in the reference
 // (src/ePSOPT/ePSOPT.cpp:62). An l1 merit function with backtracking and the fraction-to-boundary
 // rule globalises it; the barrier parameter follows the monotone Fiacco-McCormick schedule.
 #include "ecuda_nlp.hpp"
@@ -123,9 +124,20 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
     };
     if (!refresh_hessian()) return finish(3, "builtin NLP driver: gradient evaluation failed");
 
+    // free variables and the dense quasi-Newton matrix over them
+    std::vector<int> fidx(n, -1), fvars;
+    for (int c = 0; c < n; ++c)
+        if (!fixed[c]) {
+            fidx[c] = static_cast<int>(fvars.size());
+            fvars.push_back(c);
+        }
+    const int nf = static_cast<int>(fvars.size());
+    std::vector<double> Bq(static_cast<size_t>(nf) * nf, 0.0), Hq(static_cast<size_t>(nf) * nf), Jf(static_cast<size_t>(m) * nf),
+        Tq(static_cast<size_t>(nf) * m), uq(nf), grad_old(n), jac_old(nnz), sk(nf), yk(nf), Bs(nf);
+    for (int i = 0; i < nf; ++i) Bq[static_cast<size_t>(i) * nf + i] = std::max(hdiag[fvars[i]], 1e-2);
+
     double mu = 0.1;
     const double tau_min = 0.99, kappa_eps = 10.0, mu_min = opt.tol / 10.0, kappa_sigma = 1e10;
-    double nu = 10.0;      // l1 penalty
     double delta = 1e-4;   // primal (proximal) regularisation of the diagonal Hessian model
     std::vector<double> S(static_cast<size_t>(m) * m), rhs(m), dz(n), ds(m), dl(m), hz(n), hs(m), rz(n), rs(m), rc(m);
     std::vector<double> ztrial(n), strial(m), gtrial(m), bzv(n, 0.0), bsv(m, 0.0);
@@ -162,10 +174,19 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
         return v;
     };
 
-    int it = 0;
+    const double theta_init = infeasibility(W.g, s);
+    int it = 0, last_progress = 0;
     for (; it < opt.max_iter; ++it) {
+        // a quasi-Newton matrix that has grown ill-conditioned shows up as steps that shrink while the
+        // dual infeasibility does not: restart it from the diagonal when a barrier problem takes long
+        if (it - last_progress >= 25) {
+            std::fill(Bq.begin(), Bq.end(), 0.0);
+            for (int i = 0; i < nf; ++i) Bq[static_cast<size_t>(i) * nf + i] = std::max(hdiag[fvars[i]], 1e-2);
+            last_progress = it;
+        }
         // ---- optimality error of the barrier problem (primal-dual form) and Newton data
         double err_dual = 0.0, err_prim = 0.0, err_comp = 0.0;
+        int worst_dual = 0;  // variable index, or -1 - row for a slack
         for (int c = 0; c < n; ++c) {
             double v = W.grad[c];
             for (int e = colptr[c]; e < colptr[c + 1]; ++e) v += W.jac[e] * lam[P.irow[e]];
@@ -183,7 +204,10 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
                     sig += vU[c] / dhi;
                     err_comp = std::max(err_comp, std::fabs(vU[c] * dhi - mu));
                 }
-                err_dual = std::max(err_dual, std::fabs(v - vL[c] + vU[c]));
+                if (std::fabs(v - vL[c] + vU[c]) > err_dual) {
+                    err_dual = std::fabs(v - vL[c] + vU[c]);
+                    worst_dual = c;
+                }
             }
             rz[c] = fixed[c] ? 0.0 : v + bz;  // barrier form of the dual residual (multipliers eliminated)
             bzv[c] = bz;
@@ -204,7 +228,10 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
                     sig += wU[r] / dhi;
                     err_comp = std::max(err_comp, std::fabs(wU[r] * dhi - mu));
                 }
-                err_dual = std::max(err_dual, std::fabs(-lam[r] - wL[r] + wU[r]));
+                if (std::fabs(-lam[r] - wL[r] + wU[r]) > err_dual) {
+                    err_dual = std::fabs(-lam[r] - wL[r] + wU[r]);
+                    worst_dual = -1 - r;
+                }
                 rs[r] = -lam[r] + bs;
                 bsv[r] = bs;
                 hs[r] = sig + 1e-12;
@@ -220,31 +247,68 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
         if (opt.print_level > 0)
             std::printf("iter %3d  f %.8e  inf_pr %.2e  inf_du %.2e  compl %.2e  mu %.1e  delta %.1e\n", it, W.f,
                         err_prim, err_dual, err_comp, mu, delta);
+        if (opt.print_level > 2) {
+            if (worst_dual >= 0)
+                std::printf("          worst dual: var %d z %.6e [%.3e, %.3e] vL %.3e vU %.3e\n", worst_dual, z[worst_dual],
+                            P.zl[worst_dual], P.zu[worst_dual], vL[worst_dual], vU[worst_dual]);
+            else {
+                const int r = -1 - worst_dual;
+                std::printf("          worst dual: slack of row %d s %.6e [%.3e, %.3e] lam %.3e wL %.3e wU %.3e g %.6e\n", r, s[r],
+                            P.gl[r], P.gu[r], lam[r], wL[r], wU[r], W.g[r]);
+            }
+        }
         if (err <= opt.tol && mu <= mu_min * 1.0001) break;
         if (err <= kappa_eps * mu && mu > mu_min) {
             mu = std::max(mu_min, std::min(0.2 * mu, std::pow(mu, 1.5)));
+            last_progress = it;
             continue;  // re-evaluate the residuals with the new barrier parameter
         }
 
-        // ---- Schur complement S = J Hz^-1 J' + E Hs^-1 E' + dc I   (lower triangle)
-        std::fill(S.begin(), S.end(), 0.0);
+        // ---- H = B + barrier diagonal (+ proximal delta), Cholesky over the free variables
+        for (int i = 0; i < nf; ++i) {
+            for (int j2 = 0; j2 <= i; ++j2) Hq[static_cast<size_t>(i) * nf + j2] = Bq[static_cast<size_t>(i) * nf + j2];
+            Hq[static_cast<size_t>(i) * nf + i] += hz[fvars[i]] - hdiag[fvars[i]];  // sigma + delta
+        }
+        if (!cholesky(Hq, nf)) {
+            delta = std::max(1e-4, delta * 100.0);
+            if (delta > 1e8) return finish(4, "builtin NLP driver: Hessian model not positive definite");
+            continue;
+        }
+        // dense Jacobian over the free columns, T = L^-1 Jf'  (nf x m, column r = constraint row r)
+        std::fill(Jf.begin(), Jf.end(), 0.0);
         for (int c = 0; c < n; ++c) {
             if (fixed[c]) continue;
-            const double w = 1.0 / hz[c];
-            for (int e1 = colptr[c]; e1 < colptr[c + 1]; ++e1) {
-                const int r1 = P.irow[e1];
-                const double a = w * W.jac[e1];
+            for (int e = colptr[c]; e < colptr[c + 1]; ++e) Jf[static_cast<size_t>(P.irow[e]) * nf + fidx[c]] = W.jac[e];
+        }
+        for (int r = 0; r < m; ++r) {
+            const double* jr = &Jf[static_cast<size_t>(r) * nf];
+            for (int i = 0; i < nf; ++i) {  // forward substitution with L
+                const double* Li = &Hq[static_cast<size_t>(i) * nf];
+                double v = jr[i];
+                for (int k2 = 0; k2 < i; ++k2) v -= Li[k2] * Tq[static_cast<size_t>(k2) * m + r];
+                Tq[static_cast<size_t>(i) * m + r] = v / Li[i];
+            }
+        }
+        // ---- Schur complement S = T'T + E Hs^-1 E' + dc I   (lower triangle)
+        std::fill(S.begin(), S.end(), 0.0);
+        for (int i = 0; i < nf; ++i) {
+            const double* Ti = &Tq[static_cast<size_t>(i) * m];
+            for (int r1 = 0; r1 < m; ++r1) {
+                const double a = Ti[r1];
+                if (a == 0.0) continue;
                 double* Sr = &S[static_cast<size_t>(r1) * m];
-                for (int e2 = colptr[c]; e2 <= e1; ++e2) Sr[P.irow[e2]] += a * W.jac[e2];  // rows ascending
+                for (int r2 = 0; r2 <= r1; ++r2) Sr[r2] += a * Ti[r2];
             }
         }
         for (int r = 0; r < m; ++r) S[static_cast<size_t>(r) * m + r] += (ineq[r] ? 1.0 / hs[r] : 0.0) + 1e-9;
-        // rhs = rc - J Hz^-1 rz + E Hs^-1 rs
-        for (int r = 0; r < m; ++r) rhs[r] = rc[r] + (ineq[r] ? rs[r] / hs[r] : 0.0);
-        for (int c = 0; c < n; ++c) {
-            if (fixed[c]) continue;
-            const double v = rz[c] / hz[c];
-            for (int e = colptr[c]; e < colptr[c + 1]; ++e) rhs[P.irow[e]] -= W.jac[e] * v;
+        // rhs = rc - Jf H^-1 rz + E Hs^-1 rs
+        for (int i = 0; i < nf; ++i) uq[i] = rz[fvars[i]];
+        chol_solve(Hq, nf, uq);
+        for (int r = 0; r < m; ++r) {
+            const double* jr = &Jf[static_cast<size_t>(r) * nf];
+            double v = rc[r] + (ineq[r] ? rs[r] / hs[r] : 0.0);
+            for (int i = 0; i < nf; ++i) v -= jr[i] * uq[i];
+            rhs[r] = v;
         }
         if (!cholesky(S, m)) {
             delta = std::max(1e-4, delta * 100.0);
@@ -253,15 +317,16 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
         }
         dl = rhs;
         chol_solve(S, m, dl);
-        for (int c = 0; c < n; ++c) {
-            if (fixed[c]) {
-                dz[c] = 0.0;
-                continue;
-            }
-            double v = rz[c];
-            for (int e = colptr[c]; e < colptr[c + 1]; ++e) v += W.jac[e] * dl[P.irow[e]];
-            dz[c] = -v / hz[c];
+        // dz = -H^-1 (rz + Jf' dlambda)
+        for (int i = 0; i < nf; ++i) uq[i] = rz[fvars[i]];
+        for (int r = 0; r < m; ++r) {
+            const double* jr = &Jf[static_cast<size_t>(r) * nf];
+            const double d = dl[r];
+            for (int i = 0; i < nf; ++i) uq[i] += jr[i] * d;
         }
+        chol_solve(Hq, nf, uq);
+        std::fill(dz.begin(), dz.end(), 0.0);
+        for (int i = 0; i < nf; ++i) dz[fvars[i]] = -uq[i];
         for (int r = 0; r < m; ++r) ds[r] = ineq[r] ? -(rs[r] - dl[r]) / hs[r] : 0.0;
         // bound-multiplier steps from the linearised complementarity conditions
         for (int c = 0; c < n; ++c) {
@@ -312,10 +377,11 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
                 limit_dual(wU[r], dwU[r]);
             }
 
-        // ---- l1 merit, backtracking
-        double lam_inf = 0.0;
-        for (int r = 0; r < m; ++r) lam_inf = std::max(lam_inf, std::fabs(lam[r] + dl[r]));
-        nu = std::max(nu, std::min(1.1 * lam_inf + 1.0, 1e8));
+        // ---- backtracking line search with a filter-style acceptance test (no filter history):
+        // away from feasibility a trial point must reduce the infeasibility theta or the barrier
+        // objective phi sufficiently; once theta is negligible it must satisfy the Armijo condition on
+        // phi while staying (nearly) feasible -- an l1 merit with a penalty tied to |lambda| rejects
+        // good steps there (Maratos effect)
         const double theta0 = infeasibility(W.g, s);
         const double phi0 = W.f + barrier_terms(z, s, mu);
         double dphi = 0.0;  // directional derivative of the barrier objective
@@ -323,7 +389,8 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
             if (!fixed[c]) dphi += (W.grad[c] + bzv[c]) * dz[c];
         for (int r = 0; r < m; ++r)
             if (ineq[r]) dphi += bsv[r] * ds[r];
-        const double dmerit = dphi - nu * theta0;
+        const double theta_small = 1e-7 * std::max(1.0, theta_init);
+        const double dmerit = dphi;
         double alpha = amax;
         bool accepted = false;
         double ftrial = 0.0;
@@ -332,13 +399,17 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
             for (int r = 0; r < m; ++r) strial[r] = s[r] + alpha * ds[r];
             if (!P.eval(ztrial.data(), &ftrial, gtrial.data(), nullptr, nullptr))
                 return finish(3, "builtin NLP driver: evaluation failed in the line search");
-            const double merit_t = ftrial + barrier_terms(ztrial, strial, mu) + nu * infeasibility(gtrial, strial);
-            const double merit_0 = phi0 + nu * theta0;
-            if (std::isfinite(merit_t) &&
-                merit_t <= merit_0 + 1e-4 * alpha * std::min(dmerit, 0.0) + 1e-10 * std::max(1.0, std::fabs(merit_0))) {
-                accepted = true;
-                break;
+            const double phit = ftrial + barrier_terms(ztrial, strial, mu);
+            const double thetat = infeasibility(gtrial, strial);
+            if (std::isfinite(phit) && std::isfinite(thetat)) {
+                if (theta0 > theta_small || dphi >= 0.0) {  // (no descent in phi: the step is a feasibility step)
+                    if (thetat <= (1.0 - 1e-5) * theta0 || phit <= phi0 - 1e-5 * theta0) accepted = true;
+                } else if (phit <= phi0 + 1e-4 * alpha * std::min(dphi, 0.0) + 1e-13 * std::fabs(phi0) &&
+                           thetat <= 10.0 * theta_small) {
+                    accepted = true;
+                }
             }
+            if (accepted) break;
             alpha *= 0.5;
         }
         if (!accepted) {
@@ -373,9 +444,45 @@ int solve_builtin(const Problem& P, const Options& opt, std::vector<double>* zio
             if (P.gl[r] != -INF) upd(wL[r], dwL[r], s[r] - P.gl[r]);
             if (P.gu[r] != INF) upd(wU[r], dwU[r], P.gu[r] - s[r]);
         }
+        grad_old = W.grad;
+        jac_old = W.jac;
         if (!P.eval(z.data(), &W.f, W.g.data(), W.jac.data(), W.grad.data()))
             return finish(3, "builtin NLP driver: evaluation failed");
-        if ((it + 1) % 10 == 0 && !refresh_hessian()) return finish(3, "builtin NLP driver: gradient evaluation failed");
+        // damped BFGS update with s = step, y = change of the Lagrangian gradient at the new multipliers
+        double sy = 0.0, sBs = 0.0;
+        for (int i = 0; i < nf; ++i) {
+            const int c = fvars[i];
+            sk[i] = alpha * dz[c];
+            double yn = W.grad[c], yo = grad_old[c];
+            for (int e = colptr[c]; e < colptr[c + 1]; ++e) {
+                yn += W.jac[e] * lam[P.irow[e]];
+                yo += jac_old[e] * lam[P.irow[e]];
+            }
+            yk[i] = yn - yo;
+        }
+        for (int i = 0; i < nf; ++i) {
+            double v = 0.0;
+            for (int j2 = 0; j2 < nf; ++j2) {
+                const double bij = j2 <= i ? Bq[static_cast<size_t>(i) * nf + j2] : Bq[static_cast<size_t>(j2) * nf + i];
+                v += bij * sk[j2];
+            }
+            Bs[i] = v;
+            sBs += sk[i] * v;
+            sy += sk[i] * yk[i];
+        }
+        if (sBs > 1e-16) {
+            double theta = 1.0;
+            if (sy < 0.2 * sBs) theta = 0.8 * sBs / (sBs - sy);  // Powell damping
+            double sr = 0.0;
+            for (int i = 0; i < nf; ++i) {
+                yk[i] = theta * yk[i] + (1.0 - theta) * Bs[i];
+                sr += sk[i] * yk[i];
+            }
+            if (sr > 1e-16)
+                for (int i = 0; i < nf; ++i)
+                    for (int j2 = 0; j2 <= i; ++j2)
+                        Bq[static_cast<size_t>(i) * nf + j2] += yk[i] * yk[j2] / sr - Bs[i] * Bs[j2] / sBs;
+        }
     }
 
     R.iterations = it;

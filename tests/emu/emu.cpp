@@ -6,6 +6,7 @@
 // that index/offset logic can be compared with the oracle in the CPU test suite. It is NOT a
 // fallback: libecuda.so does not contain it, nothing in etol_b200/ or src/ references it, and the
 // GPU parity tests (-m gpu) go through the real kernels via the C ABI.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -16,8 +17,9 @@
 using namespace ecuda;
 
 template <int M, int NB>
-static void run_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int nthr) {
-    for (int t = 0; t < nthr; ++t) phase_c<M, NB>(pb, ph, p, io, m, b, t, nthr);
+static void run_c(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, CtaMem& m, int b, int nthr, int slice,
+                  int nslices) {
+    for (int t = 0; t < nthr; ++t) phase_c<M, NB>(pb, ph, p, io, m, b, t, nthr, slice, nslices);
 }
 
 // the specialised kernel (k_eval_fast): per-thread registers that survive the barrier are an array here
@@ -127,12 +129,24 @@ static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
                 for (int t = 0; t < nthr; ++t) gradient_phase<M>(pb, ph, io, m, b, t, nthr);
             }
             if (io.f || io.g || io.jac) {
-                for (int t = 0; t < nthr; ++t) phase_b<M>(pb, ph, p, io, m, b, t, nthr);
-                switch (generic ? 0 : ph.nb) {  // same dispatch as launch_eval_t
-                    case 3: run_c<M, 3>(pb, ph, p, io, m, b, nthr); break;
-                    case 4: run_c<M, 4>(pb, ph, p, io, m, b, nthr); break;
-                    case 5: run_c<M, 5>(pb, ph, p, io, m, b, nthr); break;
-                    default: run_c<M, 0>(pb, ph, p, io, m, b, nthr); break;
+                // gridDim.y slices of the phase, each its own CTA (fresh shared memory, same staging)
+                int nslices = 1;
+                for (int q = 0; q < pb.nphases; ++q) nslices = std::max(nslices, generic_slices(pb.ns, pb.ph[q].N, nthr));
+                for (int slice = 0; slice < nslices; ++slice) {
+                    if (slice > 0) {
+                        std::fill(smem.begin(), smem.end(), 0.0);
+                        carve(m, smem.data(), pb, ph, nthr);
+                        std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride,
+                                    sizeof(double) * pb.inst_stride);
+                        for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, fd);
+                    }
+                    for (int t = 0; t < nthr; ++t) phase_b<M>(pb, ph, p, io, m, b, t, nthr, slice, nslices);
+                    switch (generic ? 0 : ph.nb) {  // same dispatch as launch_eval_t
+                        case 3: run_c<M, 3>(pb, ph, p, io, m, b, nthr, slice, nslices); break;
+                        case 4: run_c<M, 4>(pb, ph, p, io, m, b, nthr, slice, nslices); break;
+                        case 5: run_c<M, 5>(pb, ph, p, io, m, b, nthr, slice, nslices); break;
+                        default: run_c<M, 0>(pb, ph, p, io, m, b, nthr, slice, nslices); break;
+                    }
                 }
             }
         }
