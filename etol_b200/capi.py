@@ -45,7 +45,8 @@ ABI_SYMBOLS = [
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
     "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
-    "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation",
+    "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
+    "ecuda_host_path_eval",
 ]
 
 _lib = None

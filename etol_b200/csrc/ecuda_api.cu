@@ -631,6 +631,12 @@ static int launch_eval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     return fail(h, ECUDA_ERR_ARG, "unknown model");
 }
 
+// ---- host evaluation of the device models (callback verification in the plugin; no GPU) ------------------
+template <int M>
+static void host_model_eval_t(const double* x, const double* u, double t, double* f_out, double* cost_out) {
+    Model<M>::f(x, u, t, f_out);
+    *cost_out = Model<M>::cost(x, u, t);
+}
 extern "C" {
 
 const char* ecuda_last_error(ecuda_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -1022,6 +1028,30 @@ int ecuda_sync(ecuda_handle h) {
 }
 
 int64_t ecuda_launch_count(ecuda_handle h) { return h ? h->launches : 0; }
+
+int ecuda_host_model_eval(int model, const double* x, const double* u, double t, double* f_out, double* cost_out) {
+    if (!x || !u || !f_out || !cost_out) return ECUDA_ERR_ARG;
+    switch (model) {
+        case ECUDA_MODEL_SI2D: host_model_eval_t<ECUDA_MODEL_SI2D>(x, u, t, f_out, cost_out); return ECUDA_OK;
+        case ECUDA_MODEL_PM3D: host_model_eval_t<ECUDA_MODEL_PM3D>(x, u, t, f_out, cost_out); return ECUDA_OK;
+        case ECUDA_MODEL_FW6: host_model_eval_t<ECUDA_MODEL_FW6>(x, u, t, f_out, cost_out); return ECUDA_OK;
+    }
+    return ECUDA_ERR_ARG;
+}
+int ecuda_host_path_eval(const ecuda_problem_desc* desc, const double* inst, double x, double y, double t, double* rows) {
+    if (!desc || !inst || !rows) return ECUDA_ERR_ARG;
+    HostProblem hp;
+    std::string err;
+    if (!build_layout(*desc, &hp, &err)) return ECUDA_ERR_ARG;
+    const int nstat = hp.nstat[0], rec = hp.dims.rec_size;
+    for (int q = 0; q < nstat; ++q) {
+        const double* r = inst + hp.inst_off[0] + q * rec;
+        rows[q] = desc->model == ECUDA_MODEL_SI2D ? edge_row(r, x, y) : cylinder_row(r, x, y);
+    }
+    for (int i = 0; i < desc->ntracks; ++i)
+        rows[nstat + i] = track_row(inst + hp.track_off + i * hp.dims.track_size, desc->nwaypoints, x, y, t);
+    return ECUDA_OK;
+}
 
 int ecuda_fp64_peak(ecuda_handle h, double* tflops) {
     if (!h) return ECUDA_ERR_ARG;

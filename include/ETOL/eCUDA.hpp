@@ -23,6 +23,7 @@
 
 #include <ETOL/TrajectoryOptimizer.hpp>
 #include <ETOL/eCUDA_Types.hpp>
+#include <ETOL/eCUDA_var.hpp>
 
 namespace ETOL {
 
@@ -46,7 +47,18 @@ class eCUDA : public TrajectoryOptimizer {
     ecuda_prob_t* getProblem();
     ecuda_sol_t* getSolution();
 
-    // ---- device-side VGP callbacks ----------------------------------------------------------------
+    // ---- VGP callbacks written for eCUDA -----------------------------------------------------------
+    // setObjective / setGradient / setConstraints work as for ePSOPT, with ecuda::var in place of
+    // adouble: x, u hold `ecuda::var*`, k is `ecuda::var*` (time), dt a double; objective and state
+    // derivatives return ecuda::var, constraint callbacks return fout_ecuda_t (eCUDA_var.hpp). At
+    // setup() every callback is run once on symbolic inputs; the recorded expressions are evaluated at
+    // sample points of the state/control box and compared with the device models and with the path
+    // constraints the VGP data generates. The match selects what the GPU runs -- the callbacks
+    // themselves never run on the hot path. False (with a reason) when nothing matches; setup() then
+    // fails like ePSOPT does on a bad callback. Called by transcribe() when callbacks are registered.
+    bool matchCallbacks(std::string* why = nullptr);
+
+    // ---- device-side VGP callbacks, selected directly ------------------------------------------------
     // dynamics + running cost: ECUDA_MODEL_SI2D (the reference example's x'=u0, y'=u1, u0^2+u1^2),
     // ECUDA_MODEL_PM3D, ECUDA_MODEL_FW6
     void setModel(int model);
@@ -74,9 +86,12 @@ class eCUDA : public TrajectoryOptimizer {
     ecuda_handle handle();  // the C-ABI handle, for callers that manage device buffers themselves
 
  private:
+    void fillDesc(ecuda_problem_desc* d, int model, bool obstacles, bool tracks);
     void buildBounds();
     void buildScaling();
     void buildInstance(std::vector<double>* out) const;
+    void buildInstanceFor(std::vector<double>* out, int model, bool obstacles, bool tracks, const ecuda_problem_desc& d,
+                          int inst_stride) const;
     void extractTrajectories(const std::vector<double>& z);
     void fail(const std::string& what);
 

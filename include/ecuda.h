@@ -188,6 +188,12 @@ int ecuda_host_dims(const ecuda_problem_desc* desc, ecuda_dims* out);
 int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t* jCol,
                          int32_t* group_of_col);
 int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double* D);
+/* the device models evaluated on the host at one point: state derivatives f_out[nstates] and running
+ * cost. Used by the eCUDA plugin to verify that user callbacks and device model agree (eCUDA.hpp); not
+ * an evaluation path. u holds the model's controls (2 for si2d, 3 for pm3d / fw6). */
+int ecuda_host_model_eval(int model, const double* x, const double* u, double t, double* f_out, double* cost_out);
+/* path rows of phase 0 of one instance block (layout of ecuda_upload_instances) at position (x,y), time t */
+int ecuda_host_path_eval(const ecuda_problem_desc* desc, const double* inst, double x, double y, double t, double* rows);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,174 @@ void eCUDA::addTrackConstraints() {
     _tracks_on = true;
 }
 
+// problem description for a given choice of device model and constraint sets
+void eCUDA::fillDesc(ecuda_problem_desc* out, int model, bool obstacles, bool tracks) {
+    ecuda_problem_desc& d = *out;
+    d = ecuda_problem_desc{};
+    d.model = model;
+    d.nphases = 1;  // ePSOPT.cpp:27-28: one phase, no linkages
+    d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
+    size_t nstatic = 0;
+    if (obstacles) {
+        if (model == ECUDA_MODEL_SI2D)
+            for (const border_t& b : *getObstacles_Raw()) nstatic += b.size();
+        else
+            nstatic += getObstacles_Raw()->size();
+    }
+    if (model != ECUDA_MODEL_SI2D) nstatic += _cylinders.size();
+    d.nstatic[0] = static_cast<int32_t>(nstatic);
+    d.ncontrols = static_cast<int32_t>(getNControls());
+    d.ntracks = 0;
+    d.nwaypoints = 0;
+    if (tracks && !getTracks()->empty()) {
+        if (model != ECUDA_MODEL_SI2D) fail("moving exclusion zones are only modelled for the si2d device model");
+        d.ntracks = static_cast<int32_t>(getTracks()->size());
+        d.nwaypoints = static_cast<int32_t>(getTracks()->front().trajectory.size());
+        for (const track_t& t : *getTracks())
+            if (static_cast<int32_t>(t.trajectory.size()) != d.nwaypoints)
+                fail("all tracks must have the same number of waypoints");
+    }
+    d.collocation = _algorithm.collocation_method == "Chebyshev" ? ECUDA_CHEBYSHEV : ECUDA_LEGENDRE;
+    d.pattern_mode = ECUDA_PATTERN_DENSE_NODE;
+    d.maximize = isMaximized() ? 1 : 0;
+    d.batch = static_cast<int32_t>(_batch);
+    d.index_base = 0;
+}
+
+// ---- callbacks -> device model ------------------------------------------------------------------------------
+namespace {
+// deterministic sample points (SplitMix64)
+struct Rng {
+    uint64_t s;
+    double uniform() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (z >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+bool agree(double a, double b) {
+    const double d = std::fabs(a - b), m = std::max(std::fabs(a), std::fabs(b));
+    return d <= 1e-11 * std::max(m, 1e-3);
+}
+}  // namespace
+
+bool eCUDA::matchCallbacks(std::string* why) {
+    auto no = [&](const std::string& msg) {
+        if (why) *why = msg;
+        return false;
+    };
+    const size_t ns = getNStates(), nc = getNControls();
+    if (!_objective || _gradient.size() != ns) return no("setObjective and one setGradient entry per state are required");
+
+    // ---- run every callback once on symbolic inputs (the calling convention of ePSOPT::dae, :225-270)
+    ecuda::Tape tape;
+    ecuda::Tape::active() = &tape;
+    std::vector<ecuda::var> xs(ns), us(nc);
+    for (size_t i = 0; i < ns; ++i) xs[i] = ecuda::var::input(static_cast<int>(i));
+    for (size_t j = 0; j < nc; ++j) us[j] = ecuda::var::input(static_cast<int>(ns + j));
+    ecuda::var tv = ecuda::var::input(static_cast<int>(ns + nc));
+    vector_t x, u;
+    for (size_t i = 0; i < ns; ++i) x.push_back(&xs[i]);
+    for (size_t j = 0; j < nc; ++j) u.push_back(&us[j]);
+    const vector_t params = {std::string()};
+    const std::vector<std::string> pnames = {std::string("")};
+    int cost_id = -1;
+    std::vector<int> f_ids, row_ids;
+    try {
+        cost_id = std::any_cast<ecuda::var>((*_objective)(x, u, params, pnames, &tv, getDt())).id();
+        for (size_t i = 0; i < ns; ++i)
+            f_ids.push_back(std::any_cast<ecuda::var>((*_gradient[i])(x, u, params, pnames, &tv, getDt())).id());
+        for (f_t* c : _constraints)
+            for (const ecuda::var& r : std::any_cast<fout_ecuda_t>((*c)(x, u, params, pnames, &tv, getDt())))
+                row_ids.push_back(r.id());
+    } catch (std::bad_any_cast& e) {
+        ecuda::Tape::active() = nullptr;
+        return no(std::string("a callback did not take/return ecuda::var values (") + e.what() + ")");
+    }
+    ecuda::Tape::active() = nullptr;
+
+    // ---- sample points inside the state / control box and the time span
+    const int npts = 24;
+    Rng rng{0xE701u};
+    std::vector<std::vector<double>> pts;
+    auto pick = [&](const state_t& lo, const state_t& hi, size_t i) {
+        const double a = i < lo.size() ? lo[i] : -1.0, b = i < hi.size() ? hi[i] : 1.0;
+        return a + rng.uniform() * (b - a);
+    };
+    for (int p = 0; p < npts; ++p) {
+        std::vector<double> in(ns + nc + 1);
+        for (size_t i = 0; i < ns; ++i) in[i] = pick(getXlower(), getXupper(), i);
+        for (size_t j = 0; j < nc; ++j) in[ns + j] = pick(getUlower(), getUupper(), j);
+        in[ns + nc] = rng.uniform() * getNSteps() * getDt();
+        pts.push_back(in);
+    }
+    std::vector<std::vector<double>> vals(npts);
+    for (int p = 0; p < npts; ++p) tape.eval(pts[p].data(), &vals[p]);
+
+    // ---- dynamics + running cost against the device models
+    int found = -1;
+    for (int model : {ECUDA_MODEL_SI2D, ECUDA_MODEL_PM3D, ECUDA_MODEL_FW6}) {
+        if (_model_set && model != _model) continue;
+        ecuda_problem_desc d{};
+        d.model = model;
+        d.nphases = 1;
+        d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
+        d.ncontrols = static_cast<int32_t>(nc);
+        d.batch = 1;
+        ecuda_dims dims{};
+        if (ecuda_host_dims(&d, &dims) != ECUDA_OK || static_cast<size_t>(dims.nstates) != ns) continue;
+        bool ok = true;
+        for (int p = 0; p < npts && ok; ++p) {
+            double f[ECUDA_MAX_STATES], cost = 0.0;
+            ecuda_host_model_eval(model, pts[p].data(), pts[p].data() + ns, pts[p][ns + nc], f, &cost);
+            ok = agree(vals[p][cost_id], cost);
+            for (size_t i = 0; i < ns && ok; ++i) ok = agree(vals[p][f_ids[i]], f[i]);
+        }
+        if (ok) {
+            found = model;
+            break;
+        }
+    }
+    if (found < 0) return no("objective / state derivatives agree with none of the device models (si2d, pm3d, fw6)");
+
+    // ---- constraint rows against the path constraints the VGP data generates (static rows, then tracks)
+    bool matched = row_ids.empty();
+    bool use_obs = false, use_trk = false;
+    for (int combo = 3; combo >= 1 && !matched; --combo) {
+        const bool obs = combo & 1, trk = combo & 2;
+        if (trk && found != ECUDA_MODEL_SI2D) continue;
+        if ((obs && getObstacles_Raw()->empty() && _cylinders.empty()) || (trk && getTracks()->empty())) continue;
+        ecuda_problem_desc d;
+        fillDesc(&d, found, obs, trk);
+        d.batch = 1;
+        ecuda_dims dims{};
+        if (ecuda_host_dims(&d, &dims) != ECUDA_OK) continue;
+        if (static_cast<size_t>(d.nstatic[0] + d.ntracks) != row_ids.size()) continue;
+        std::vector<double> inst, rows(row_ids.size());
+        buildInstanceFor(&inst, found, obs, trk, d, dims.inst_stride);
+        bool ok = true;
+        for (int p = 0; p < npts && ok; ++p) {
+            ecuda_host_path_eval(&d, inst.data(), pts[p][0], pts[p][1], pts[p][ns + nc], rows.data());
+            for (size_t q = 0; q < rows.size() && ok; ++q) ok = agree(vals[p][row_ids[q]], rows[q]);
+        }
+        if (ok) {
+            matched = true;
+            use_obs = obs;
+            use_trk = trk;
+        }
+    }
+    if (!matched)
+        return no("the " + std::to_string(row_ids.size()) +
+                  " constraint rows are not the exclusion-zone / moving-zone constraints of the loaded VGP");
+    _model = found;
+    _model_set = true;
+    _obstacles_on = use_obs;
+    _tracks_on = use_trk;
+    return true;
+}
+
 // ---- setup ------------------------------------------------------------------------------------------------
 void eCUDA::setup() {
     transcribe();
@@ -108,38 +276,15 @@ void eCUDA::setup() {
 
 // host half of setup(): VGP -> NLP description (no device needed)
 void eCUDA::transcribe() {
+    if (_objective || !_gradient.empty() || !_constraints.empty()) {
+        std::string why;
+        if (!matchCallbacks(&why)) fail("the registered callbacks match no device model: " + why);
+    }
     if (!_model_set) _model = getNStates() == 2 ? ECUDA_MODEL_SI2D : ECUDA_MODEL_PM3D;
     const size_t ns = getNStates(), nc = getNControls();
     ecuda_problem_desc& d = _problem.desc;
-    d = ecuda_problem_desc{};
-    d.model = _model;
-    d.nphases = 1;  // ePSOPT.cpp:27-28: one phase, no linkages
-    d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
-    size_t nstatic = 0;
-    if (_obstacles_on) {
-        if (_model == ECUDA_MODEL_SI2D)
-            for (const border_t& b : *getObstacles_Raw()) nstatic += b.size();
-        else
-            nstatic += getObstacles_Raw()->size();
-    }
-    if (_model != ECUDA_MODEL_SI2D) nstatic += _cylinders.size();
-    d.nstatic[0] = static_cast<int32_t>(nstatic);
-    d.ncontrols = static_cast<int32_t>(nc);
-    d.ntracks = 0;
-    d.nwaypoints = 0;
-    if (_tracks_on && !getTracks()->empty()) {
-        if (_model != ECUDA_MODEL_SI2D) fail("moving exclusion zones are only modelled for the si2d device model");
-        d.ntracks = static_cast<int32_t>(getTracks()->size());
-        d.nwaypoints = static_cast<int32_t>(getTracks()->front().trajectory.size());
-        for (const track_t& t : *getTracks())
-            if (static_cast<int32_t>(t.trajectory.size()) != d.nwaypoints)
-                fail("all tracks must have the same number of waypoints");
-    }
-    d.collocation = _algorithm.collocation_method == "Chebyshev" ? ECUDA_CHEBYSHEV : ECUDA_LEGENDRE;
-    d.pattern_mode = ECUDA_PATTERN_DENSE_NODE;
-    d.maximize = isMaximized() ? 1 : 0;
-    d.batch = static_cast<int32_t>(_batch);
-    d.index_base = 0;
+    fillDesc(&d, _model, _obstacles_on, _tracks_on);
+    const size_t nstatic = static_cast<size_t>(d.nstatic[0]);
 
     if (ecuda_host_dims(&d, &_problem.dims) != ECUDA_OK)
         fail("the VGP does not fit the selected device model (states/controls/nodes)");
@@ -280,10 +425,16 @@ void eCUDA::buildScaling() {
 
 // obstacle / track records of the loaded VGP in the layout of ecuda_upload_instances
 void eCUDA::buildInstance(std::vector<double>* out) const {
-    out->assign(_problem.dims.inst_stride, 0.0);
+    buildInstanceFor(out, _model, _obstacles_on, _tracks_on, _problem.desc, _problem.dims.inst_stride);
+}
+
+void eCUDA::buildInstanceFor(std::vector<double>* out, int model, bool obstacles, bool tracks,
+                             const ecuda_problem_desc& d, int inst_stride) const {
+    (void)tracks;
+    out->assign(inst_stride, 0.0);
     size_t o = 0;
     eCUDA* self = const_cast<eCUDA*>(this);
-    if (_obstacles_on) {
+    if (obstacles) {
         for (const border_t& border : *self->getObstacles_Raw()) {
             std::vector<double> xy;
             for (const corner_t& c : border) {
@@ -291,7 +442,7 @@ void eCUDA::buildInstance(std::vector<double>* out) const {
                 xy.push_back(c[1]);
             }
             const int n = static_cast<int>(border.size());
-            if (_model == ECUDA_MODEL_SI2D) {  // one ellipse per polygon edge (etol_psopt_example1.cpp:164-179)
+            if (model == ECUDA_MODEL_SI2D) {  // one ellipse per polygon edge (etol_psopt_example1.cpp:164-179)
                 ecuda_si2d_edge_records(xy.data(), n, out->data() + o);
                 o += 6 * n;
             } else {  // circumscribed vertical cylinder: centroid + farthest corner
@@ -312,7 +463,7 @@ void eCUDA::buildInstance(std::vector<double>* out) const {
             }
         }
     }
-    if (_model != ECUDA_MODEL_SI2D)
+    if (model != ECUDA_MODEL_SI2D)
         for (const auto& c : _cylinders) {
             (*out)[o] = c[0];
             (*out)[o + 1] = c[1];
@@ -320,7 +471,7 @@ void eCUDA::buildInstance(std::vector<double>* out) const {
             (*out)[o + 3] = 0.0;
             o += 4;
         }
-    if (_problem.desc.ntracks > 0)
+    if (d.ntracks > 0)
         for (const track_t& t : *self->getTracks()) {
             (*out)[o++] = t.radius;
             for (const traj_elem_t& wp : t.trajectory) {

@@ -5,10 +5,12 @@
 #include <ETOL/eCUDA.hpp>
 
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "ecuda_nlp.hpp"
+#include "vgp_si2d_callbacks.hpp"
 
 using ETOL::eCUDA;
 
@@ -30,6 +32,46 @@ int shim_load(void* h, const char* xml, int model, int flags, int batch, const c
     if (derivatives) t->getAlgorithm()->derivatives = derivatives;
     t->transcribe();
     return 0;
+}
+// load + register USER CALLBACKS (ecuda::var) like the reference example does, then try to match them.
+// variant 0: the example's callbacks; 1: a different objective; 2: exclusion zones only; 3: zones
+// registered in the opposite order (moving zones first). Returns 1 when matched; *model, *flags
+// (bit0 obstacles, bit1 tracks) report what was recognised, why (<= 255 chars) the reason otherwise.
+int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* flags, char* why) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    t->loadConfigs(xml);
+    t->setMaximize(false);
+    static std::vector<std::unique_ptr<ETOL::f_t>> keep;  // callbacks must outlive the optimizer calls
+    auto hold = [&](ETOL::f_t f) {
+        keep.push_back(std::make_unique<ETOL::f_t>(std::move(f)));
+        return keep.back().get();
+    };
+    ETOL::f_t other = [](F_ARGS) -> ETOL::scalar_t {
+        ecuda::var a = vgp_si2d::at(u, 0), b = vgp_si2d::at(u, 1);
+        return a * a + 2.0 * (b * b);
+    };
+    t->setObjective(hold(variant == 1 ? other : ETOL::f_t(&vgp_si2d::effort)));
+    t->setGradient({hold(&vgp_si2d::xdot), hold(&vgp_si2d::ydot)});
+    ETOL::f_t* zones = hold(vgp_si2d::exclusionZones(t));
+    if (variant == 2) {
+        t->setConstraints({zones});
+    } else {
+        ETOL::f_t* movers = hold(vgp_si2d::movingZones(t));
+        if (variant == 3)
+            t->setConstraints({movers, zones});
+        else
+            t->setConstraints({zones, movers});
+    }
+    std::string reason;
+    const bool ok = t->matchCallbacks(&reason);
+    std::strncpy(why, reason.c_str(), 255);
+    why[255] = 0;
+    if (ok) {
+        t->transcribe();
+        *model = t->getProblem()->desc.model;
+        *flags = (t->getProblem()->desc.nstatic[0] > 0 ? 1 : 0) | (t->getProblem()->desc.ntracks > 0 ? 2 : 0);
+    }
+    return ok ? 1 : 0;
 }
 void shim_vgp(void* h, int* out /*nsteps,nstates,ncontrols,nzones,ntracks,nparams*/, double* dt) {
     eCUDA* t = static_cast<eCUDA*>(h);

@@ -24,6 +24,7 @@ def lib():
         L.shim_create.restype = C.c_void_p
         L.shim_destroy.argtypes = [C.c_void_p]
         L.shim_load.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+        L.shim_load_callbacks.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         L.shim_vgp.argtypes = [C.c_void_p, C.POINTER(C.c_int), _dp]
         L.shim_dims.argtypes = [C.c_void_p, C.POINTER(capi.Dims)]
         L.shim_desc.argtypes = [C.c_void_p, C.POINTER(capi.ProblemDesc)]
@@ -90,6 +91,15 @@ class Plugin:
         self.dims = capi.Dims()
         self.L.shim_dims(self.h, C.byref(self.dims))
         return self
+
+    def load_callbacks(self, xml, variant=0):
+        """register the example's ecuda::var callbacks (tests/plugin/shim.cpp) and match them"""
+        model, flags, why = C.c_int(-1), C.c_int(0), C.create_string_buffer(256)
+        ok = self.L.shim_load_callbacks(self.h, xml.encode(), variant, C.byref(model), C.byref(flags), why)
+        if ok:
+            self.dims = capi.Dims()
+            self.L.shim_dims(self.h, C.byref(self.dims))
+        return bool(ok), model.value, flags.value, why.value.decode()
 
     def vgp(self):
         out, dt = (C.c_int * 6)(), C.c_double()

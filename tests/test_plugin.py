@@ -142,6 +142,39 @@ def test_builtin_nlp_solves_reference_vgp(xml, scaling):
     assert abs(info["objective"] - 1.51287) < 1e-3
 
 
+def test_user_callbacks_are_recognised(xml):
+    """callbacks written with ecuda::var (the reference example's mathematics) are traced and matched:
+    single-integrator model + exclusion-zone + moving-zone constraints; the transcription is then the
+    same as with the explicit registration"""
+    p = pb.Plugin()
+    ok, model, flags, why = p.load_callbacks(xml, 0)
+    assert ok, why
+    assert model == W.SI2D and flags == 3
+    q = pb.Plugin().load(xml, scaling="automatic")  # the plugin's default, as in load_callbacks
+    assert (p.dims.nvars, p.dims.ncons, p.dims.nnz) == (q.dims.nvars, q.dims.ncons, q.dims.nnz) == (134, 434, 3372)
+    for k, v in p.bounds().items():
+        assert np.array_equal(v, q.bounds()[k]), k
+    assert np.array_equal(p.instance(0), q.instance(0))
+    p.close(), q.close()
+
+
+def test_user_callbacks_zones_only(xml):
+    p = pb.Plugin()
+    ok, model, flags, why = p.load_callbacks(xml, 2)
+    assert ok and model == W.SI2D and flags == 1, why
+    assert (p.dims.nvars, p.dims.ncons) == (134, 66 + 4 + 9 * 33 + 1)
+    p.close()
+
+
+@pytest.mark.parametrize("variant,needle", [(1, "device models"), (3, "constraint rows")])
+def test_user_callbacks_that_match_nothing_are_rejected(xml, variant, needle):
+    # a different running cost; constraint callbacks in an order the device kernels do not produce
+    p = pb.Plugin()
+    ok, model, flags, why = p.load_callbacks(xml, variant)
+    assert not ok and needle in why
+    p.close()
+
+
 @pytest.mark.gpu
 def test_plugin_evaluate_matches_oracle(xml):
     p = pb.Plugin().load(xml, derivatives="numerical")
@@ -155,8 +188,14 @@ def test_plugin_evaluate_matches_oracle(xml):
 
 
 @pytest.mark.gpu
-def test_plugin_solves_reference_vgp(xml):
-    p = pb.Plugin().load(xml, scaling="automatic")
+@pytest.mark.parametrize("callbacks", [False, True])
+def test_plugin_solves_reference_vgp(xml, callbacks):
+    if callbacks:  # the example-2 route: user callbacks, recognised at setup
+        p = pb.Plugin()
+        ok, _, _, why = p.load_callbacks(xml, 0)
+        assert ok, why
+    else:
+        p = pb.Plugin().load(xml, scaling="automatic")
     p.setup()
     rc, score, iters, viol = p.solve(max_iter=200)
     assert rc == 0 and viol <= 1e-8 and iters < 200
