@@ -20,7 +20,7 @@
 #include <string>
 #include <vector>
 
-#include "ecuda_fast.cuh"
+#include "ecuda_rows.cuh"
 
 namespace ecuda {
 
@@ -231,6 +231,76 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     }
 }
 
+// Row-owner kernel (ecuda_rows.cuh): one barrier after staging, then every thread writes whole rows.
+// Same launch shape as k_eval_fast (exact mode with a Jacobian: a 9th warp streams the template).
+#ifndef ECUDA_MIN_CTAS_ROWS_FD
+#define ECUDA_MIN_CTAS_ROWS_FD 3
+#endif
+template <int M, int NB, bool FD>
+__global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
+                                  FD ? ECUDA_MIN_CTAS_ROWS_FD : ECUDA_MIN_CTAS_EXACT)
+    k_eval_rows(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t copy_bars[kCopySlots];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = kThreads;
+    const bool copy_warp = !FD && blockDim.x > kThreads;  // uniform over the CTA
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (copy_warp)
+            for (int c = 0; c < kCopySlots; ++c) mbar_init(&copy_bars[c], 1);
+    }
+    __syncthreads();
+    if (!FD && tid >= kThreads) {  // copy warp: template -> triplet array, then the barrier before the triplets
+        double* ring = smem + cta_doubles(pb, ph, nthr, 0);
+        ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;
+        if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (!FD && io.jac && !copy_warp) fast_copy_template(pb, ph, io, b, tid, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
+    mbar_wait(&bar, 0);
+    if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
+    RowState<M, NB> rs;
+    rows_values<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+    if (FD) {
+        rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, true);
+    } else {
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, false);
+        __syncthreads();  // all threads: the template has landed before the node-local triplets overwrite it
+        rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, false, true);
+    }
+    if (io.nranks > 0) {  // fused summary + all-gather epilogue (see k_eval_fast)
+        __shared__ double red[kThreads / 32 + 1];
+        double v = rs.viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = rs.fval;
+        named_barrier(2, kThreads);
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
+}
+
 // Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
 // element index of the first one, so that shared and global addresses are 16-byte aligned together)
 // to dst[0..n): the aligned interior by one bulk copy issued by thread `lead`, the at most two
@@ -417,6 +487,7 @@ struct ecuda_ctx {
     bool image_ok = false;
     size_t smem_image = 0;
     int num_sms = 148;
+    bool no_rows = false;   // ECUDA_NO_ROWS=1: use the column-owner kernels (k_eval_fast) instead of k_eval_rows
     bool no_copy_warp = false;  // ECUDA_NO_COPY_WARP=1: exact mode copies the template with plain loads/stores
     int64_t launches = 0;
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
@@ -545,6 +616,19 @@ static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, in
             cur = smem;
         }
     }
+    if (!h->no_rows) {
+        static size_t configured_rows[64] = {0};
+        if (smem > 48 * 1024) {
+            std::lock_guard<std::mutex> lock(mu);
+            size_t& cur = configured_rows[h->device & 63];
+            if (cur < smem) {
+                CU(cudaFuncSetAttribute(k_eval_rows<M, NB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cur = smem;
+            }
+        }
+        k_eval_rows<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, st>>>(h->pd, io);
+        return ECUDA_OK;
+    }
     k_eval_fast<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, st>>>(h->pd, io);
     return ECUDA_OK;
 }
@@ -670,6 +754,8 @@ int ecuda_create(int device, ecuda_handle* out) {
         const char* ni = std::getenv("ECUDA_IMAGE");
         h->no_image = !(ni && ni[0] == '1');
         h->num_sms = prop.multiProcessorCount;
+        const char* nr = std::getenv("ECUDA_NO_ROWS");
+        h->no_rows = nr && nr[0] == '1';
         const char* nw = std::getenv("ECUDA_NO_COPY_WARP");
         h->no_copy_warp = nw && nw[0] == '1';
     }

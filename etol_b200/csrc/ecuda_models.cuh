@@ -26,6 +26,12 @@ namespace ecuda {
 template <int M>
 struct Model;
 
+// does f_i of model M read state j / control c? (FX / FU: 8 bits per i)
+template <int M>
+ECUDA_HD bool reads_state(int i, int j) { return (Model<M>::FX >> (8 * i + j)) & 1ull; }
+template <int M>
+ECUDA_HD bool reads_control(int i, int c) { return (Model<M>::FU >> (8 * i + c)) & 1ull; }
+
 // ------------------------------------------------------------------------------------------------------
 // path rows shared by the models
 // cylinder record: cx, cy, r^2, 0
@@ -103,6 +109,9 @@ struct Model<ECUDA_MODEL_SI2D> {
     // f_i never reads x_i: the defect row (k,i) depends on its own state column only through D, so the
     // diagonal triplet of that column needs no second evaluation of the dynamics
     static constexpr bool DIAG_FREE = true;
+    // which states / controls f_i reads, 8 bits per i (same data as model_info() on the host): a
+    // finite-difference triplet of a variable f_i does not read is exactly +0.0 and is stored as such
+    static constexpr unsigned long long FX = 0x0000ull, FU = 0x0201ull;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         out[0] = u[0];
         out[1] = u[1];
@@ -127,6 +136,8 @@ template <>
 struct Model<ECUDA_MODEL_PM3D> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i
+    // 8 bits per i: f_0..f_2 read x_3..x_5, f_3..f_5 read u_0..u_2
+    static constexpr unsigned long long FX = 0x000000201008ull, FU = 0x040201000000ull;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         out[0] = x[3]; out[1] = x[4]; out[2] = x[5];
         out[3] = u[0]; out[4] = u[1]; out[5] = u[2];
@@ -154,6 +165,8 @@ template <>
 struct Model<ECUDA_MODEL_FW6> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i (x,y,z,V,gamma,psi derivatives)
+    // 8 bits per i: f_0, f_1 read V, gamma, psi; f_2 reads V, gamma; f_3 reads gamma and u_0; f_4, f_5 read u_1, u_2
+    static constexpr unsigned long long FX = 0x000010183838ull, FU = 0x040201000000ull;
     static constexpr double G0 = 9.80665;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
         double sg, cg, sp, cp;

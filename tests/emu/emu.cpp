@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../etol_b200/csrc/ecuda_fast.cuh"
+#include "../../etol_b200/csrc/ecuda_rows.cuh"
 
 using namespace ecuda;
 
@@ -36,12 +36,43 @@ static void run_fast(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO&
     for (int t = 0; t < nthr; ++t) fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rr[t]);
     for (int t = 0; t < nthr; ++t) fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rr[t]);
 }
+// the row-owner kernel (k_eval_rows)
+template <int M, int NB, bool FD>
+static void run_rows(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    std::vector<double> smem(cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0), 0.0);
+    CtaMem m;
+    carve(m, smem.data(), pb, ph, nthr, FD ? CARVE_FD : 0);
+    std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
+    if (!FD && io.jac)
+        for (int t = 0; t < nthr; ++t) fast_copy_template(pb, ph, io, b, t, nthr);
+    for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, FD && io.jac != nullptr);
+    std::vector<RowState<M, NB>> rs(nthr);
+    for (int t = 0; t < nthr; ++t) {  // no barrier after staging: a thread runs to the end on its own
+        rows_values<M, NB, FD>(pb, ph, io, m, b, t, rs[t]);
+        if (FD) {
+            rows_jacobian<M, NB, FD>(pb, ph, io, m, b, t, rs[t]);
+            rows_other<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rs[t], true, true);
+        } else {
+            rows_other<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rs[t], true, false);
+        }
+    }
+    if (!FD)
+        for (int t = 0; t < nthr; ++t) {
+            rows_jacobian<M, NB, FD>(pb, ph, io, m, b, t, rs[t]);
+            rows_other<M, NB, FD>(pb, ph, p, io, m, b, t, nthr, rs[t], false, true);
+        }
+}
+static int g_use_rows = 1;
+extern "C" void emu_use_rows(int on) { g_use_rows = on; }
+
 template <int M, int NB>
 static void run_fast_mode(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
-    if (io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET)
-        run_fast<M, NB, true>(pb, ph, p, io, b, nthr);
-    else
-        run_fast<M, NB, false>(pb, ph, p, io, b, nthr);
+    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    if (g_use_rows) {
+        if (fd) run_rows<M, NB, true>(pb, ph, p, io, b, nthr); else run_rows<M, NB, false>(pb, ph, p, io, b, nthr);
+    } else {
+        if (fd) run_fast<M, NB, true>(pb, ph, p, io, b, nthr); else run_fast<M, NB, false>(pb, ph, p, io, b, nthr);
+    }
 }
 
 // the persistent exact-mode kernel (k_eval_image): the CTA's image of the phase's triplet range is
@@ -65,6 +96,8 @@ static void run_image(const ProbDev& pb, int p, const EvalIO& io, int nthr) {
     }
 }
 
+static int g_use_image = 0;
+extern "C" void emu_use_image(int on) { g_use_image = on; }
 static long g_fast_runs = 0;
 extern "C" long emu_fast_runs() { return g_fast_runs; }
 
@@ -78,7 +111,7 @@ static bool fast_ok(const ProbDev& pb, int nthr) {  // same rule as ecuda_set_pr
 template <int M>
 static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
     // exact mode with a Jacobian on the fast path: the persistent image kernel (one pass per phase)
-    const bool image = !generic && io.jac && io.jac_mode == ECUDA_JAC_EXACT && fast_ok(pb, nthr) && (pb.nnz & 1) == 0;
+    const bool image = g_use_image && !generic && io.jac && io.jac_mode == ECUDA_JAC_EXACT && fast_ok(pb, nthr) && (pb.nnz & 1) == 0;
     if (image) {
         for (int p = 0; p < pb.nphases; ++p) {
             switch (pb.ph[p].nb) {

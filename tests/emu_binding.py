@@ -36,7 +36,11 @@ def lib():
     return _lib
 
 
-def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False):
+def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False, variant="rows"):
+    """variant: which specialised kernel the emulator steps when the problem qualifies -- "rows"
+    (k_eval_rows, the default), "columns" (k_eval_fast) or "image" (k_eval_image, exact mode)"""
+    lib().emu_use_rows(1 if variant == "rows" else 0)
+    lib().emu_use_image(1 if variant == "image" else 0)
     dims = capi.host_dims(wl)
     inst = capi.pack_instances(wl, dims)
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(wl.batch, dims.nvars)

@@ -26,16 +26,18 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("nthr,generic", [(32, False), (256, False), (256, True)])
-def test_phases_match_oracle(name, nthr, generic):
+@pytest.mark.parametrize("nthr,generic,variant", [(32, False, "rows"), (256, False, "rows"), (256, False, "columns"),
+                                                  (256, False, "image"), (256, True, "rows")])
+def test_phases_match_oracle(name, nthr, generic, variant):
     wl = CASES[name]()
-    if name == "C3-fw6-N200" and (nthr == 32 or generic):
+    if name == "C3-fw6-N200" and (nthr == 32 or generic or variant != "rows"):
         pytest.skip("one thread count is enough for the large case")
     o = ob.Oracle(wl)
     style = 1 if name == "C3-fw6-N200" else 0
     for mode in (W.JAC_FD, W.JAC_EXACT):
         ref = o.eval(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style, nthreads=4)
-        got = eb.emu_eval(wl, wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, nthr=nthr, generic=generic)
+        got = eb.emu_eval(wl, wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode, nthr=nthr, generic=generic,
+                          variant=variant)
         assert rel_err(got["f"], ref["f"]) <= TOL_VALUE
         assert rel_err(got["g"], ref["g"]) <= TOL_VALUE
         assert rel_err(got["grad"], ref["grad"]) <= TOL_VALUE

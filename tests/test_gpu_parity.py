@@ -234,8 +234,9 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
     # "fast": k_eval_fast, exact mode streams the template with the TMA copy warp (the default);
     # "fast-image": exact through the persistent k_eval_image (shared-memory image + bulk stores);
     # "fast-ldst": template copied with plain loads/stores; "generic": k_eval
+    # ("fast" is k_eval_rows, the row-owner kernel; "columns" the column-owner k_eval_fast)
     for tag, env in (("fast", {}), ("fast-image", {"ECUDA_IMAGE": "1"}), ("fast-ldst", {"ECUDA_NO_COPY_WARP": "1"}),
-                     ("generic", {"ECUDA_NO_FAST": "1"})):
+                     ("columns", {"ECUDA_NO_ROWS": "1"}), ("generic", {"ECUDA_NO_FAST": "1"})):
         os.environ.update(env)  # read by ecuda_create
         try:
             ev = capi.Evaluator(wl, device=0)
@@ -249,3 +250,4 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
             assert np.array_equal(out["fast"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["fast-ldst"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["fast-image"][m][key], out["generic"][m][key]), (name, m, key)
+            assert np.array_equal(out["columns"][m][key], out["generic"][m][key]), (name, m, key)
