@@ -358,7 +358,7 @@ def run_ecuda(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"k_eval_fast<pm3d> ({args.jac})", "kernel_ms": kern_avg_ms,
+                "traffic": traffic, "kernel": f"k_eval_rows<pm3d> ({args.jac})", "kernel_ms": kern_avg_ms,
                 "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B, "peak_source": peak_src}
     if fp64:
         roofline["fp64"] = fp64
