@@ -25,7 +25,12 @@ ev = capi.Evaluator(wl, device=local)
 x = torch.from_numpy(wl.x).to(dev)
 f = torch.empty(B, dtype=torch.float64, device=dev)
 g = torch.empty((B, ev.ncons), dtype=torch.float64, device=dev)
-st = torch.cuda.current_stream().cuda_stream
+# one explicit stream for everything: a NULL stream pointer would select the handle's own non-blocking
+# stream (include/ecuda.h), which is not ordered with torch's current stream
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+st = stream.cuda_stream
+assert st != 0
 ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), None, capi.JAC_EXACT, capi.MEM_DEVICE, st)
 summ = torch.empty((B, 2), dtype=torch.float64, device=dev)
 ev.summarize_ptr(f.data_ptr(), g.data_ptr(), summ.data_ptr(), st)
