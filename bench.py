@@ -226,8 +226,15 @@ def run_ecuda(args):
                 hdls = [symm.rendezvous(t, dist.group.WORLD) for t in bufs]
                 peers = [[int(p) for p in hd.buffer_ptrs] for hd in hdls]
                 sym_bufs = bufs
+                # counters of ecuda_peer_barrier (one array of `world` 64-bit slots per rank)
+                flagbuf = symm.empty(64, dtype=torch.int64, device=dev)
+                flagbuf.zero_()
+                flag_hdl = symm.rendezvous(flagbuf, dist.group.WORLD)
+                flag_ptrs = [int(p) for p in flag_hdl.buffer_ptrs]
+                torch.cuda.synchronize()
+                flag_hdl.barrier(channel=0)  # every rank has zeroed its counters before anyone bumps them
                 gather_impl = ("fused into k_eval: CTA epilogue stores {f, max violation} to every rank over NVLink "
-                               "(symmetric memory), 1 barrier per step")
+                               "(symmetric memory), 1 flag barrier per step (ecuda_peer_barrier)")
             except Exception as exc:  # noqa: BLE001
                 peers, hdls = None, None
                 gather_impl = f"nccl all_gather_into_tensor (symmetric memory unavailable: {type(exc).__name__})"
@@ -253,7 +260,7 @@ def run_ecuda(args):
             s = step_no[0] & 1
             step_no[0] += 1
             ev.eval_allgather_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), jac_mode, peers[s], rank, sp)
-            hdls[s].barrier(channel=0)
+            ev.peer_barrier_ptr(flag_ptrs, rank, step_no[0], sp)
             if full_gather is not None:
                 dist.all_gather_into_tensor(full_gather, jac)
             return

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
-    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
+    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
     "ecuda_host_path_eval",
@@ -82,6 +82,7 @@ def lib():
                                             C.c_void_p]
     L.ecuda_eval_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    L.ecuda_peer_barrier.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint64, C.c_void_p]
     L.ecuda_sync.argtypes = [C.c_void_p]
     L.ecuda_launch_count.restype = C.c_int64
     L.ecuda_launch_count.argtypes = [C.c_void_p]
@@ -279,6 +280,10 @@ class Evaluator:
         arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
         self._check(self.L.ecuda_eval_allgather(self.h, x_ptr, f_ptr, g_ptr, jac_ptr, jac_mode, arr, len(peer_ptrs), rank,
                                                 stream))
+
+    def peer_barrier_ptr(self, flag_ptrs, rank, step, stream=None):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._check(self.L.ecuda_peer_barrier(self.h, arr, len(flag_ptrs), rank, step, stream))
 
     def summary_host(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)

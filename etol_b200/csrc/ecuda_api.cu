@@ -256,8 +256,11 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
             for (int c = 0; c < kCopySlots; ++c) mbar_init(&copy_bars[c], 1);
     }
     __syncthreads();
+    // fused summary: this phase's block of the instance's bounds is staged behind the work arrays
+    const int nbnd = io.nranks > 0 ? phase_ncons(pb, ph) + (phase_ncons(pb, ph) & 1) : 0;
+    double* bnd = smem + cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0);
     if (!FD && tid >= kThreads) {  // copy warp: template -> triplet array, then the barrier before the triplets
-        double* ring = smem + cta_doubles(pb, ph, nthr, 0);
+        double* ring = bnd + 2 * nbnd;
         ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;
         if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
         __syncthreads();
@@ -269,6 +272,27 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
     }
     if (!FD && io.jac && !copy_warp) fast_copy_template(pb, ph, io, b, tid, nthr);
+    if (io.nranks > 0) {  // coalesced, off the critical path: the values are needed after the barrier
+        const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
+        const int ncp = phase_ncons(pb, ph);
+        for (int c0 = tid; c0 < ncp; c0 += 4 * nthr) {  // loads of four strides in flight together
+            double lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * nthr < ncp) {
+                    lo[u] = __ldg(io.bl + o + c0 + u * nthr);
+                    hi[u] = __ldg(io.bu + o + c0 + u * nthr);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * nthr < ncp) {
+                    bnd[c0 + u * nthr] = lo[u];
+                    bnd[nbnd + c0 + u * nthr] = hi[u];
+                }
+        }
+        m.bl = bnd;
+        m.bu = bnd + nbnd;
+    }
     stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
     mbar_wait(&bar, 0);
     if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
@@ -445,6 +469,32 @@ __global__ void k_summary_scatter(const double* f, const double* g, const double
     }
 }
 
+// Cross-GPU barrier for the fused exchange: one block, thread r talks to rank r. Each rank owns an array
+// of counters in peer-visible memory; "I have finished step s" is a store of s into my slot of every
+// peer's array, after a system-scope fence that orders this GPU's earlier peer stores (the gathered
+// rows of the kernel before) ahead of it; then every thread waits until its peer's slot in the local
+// array has reached s. Counters only grow, so nothing is ever reset. The wait is bounded (about 0.1 s
+// of SM clocks): a lost peer turns into a wrong result the caller can detect, not into a hung GPU.
+struct PeerFlags {
+    unsigned long long* p[16];
+};
+__global__ void k_peer_barrier(PeerFlags flags, int nranks, int rank, unsigned long long step, int* timed_out) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    __threadfence_system();
+    volatile unsigned long long* theirs = flags.p[r] + rank;  // my slot in rank r's array
+    *theirs = step;
+    volatile unsigned long long* mine = flags.p[rank] + r;    // rank r's slot in my array
+    const long long t0 = clock64();
+    while (*mine < step) {
+        if (clock64() - t0 > 200000000ll) {
+            if (timed_out) *timed_out = 1;
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 // FP64 FMA microbenchmark: 8 independent dependent-chains per thread, no memory traffic. Defines the
 // FP64 roof the finite-difference kernel is compared with (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
@@ -475,7 +525,7 @@ struct ecuda_ctx {
     bool have_problem = false, have_inst = false, have_bounds = false;
     HostProblem hp;
     ProbDev pd{};
-    DevBuf colptr, isz, sg, inst, gl, gu, fpart, jtmpl;
+    DevBuf colptr, isz, sg, inst, gl, gu, fpart, jtmpl, bflag;
     DevBuf coll[ECUDA_MAX_PHASES];  // D | Dt | tau | w per phase
     DevBuf sx, sf_, sgv, sjac, sgrad, ssum;  // staging for host-memory calls
     size_t smem_bytes = 0, smem_fast_fd = 0, smem_fast_exact = 0;
@@ -618,15 +668,21 @@ static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, in
     }
     if (!h->no_rows) {
         static size_t configured_rows[64] = {0};
-        if (smem > 48 * 1024) {
+        size_t smem_rows = smem;
+        if (io.nranks > 0) {  // staged bounds (fused summary), largest phase
+            int ncp = 0;
+            for (int p = 0; p < h->pd.nphases; ++p) ncp = std::max(ncp, phase_ncons(h->pd, h->pd.ph[p]));
+            smem_rows += 2 * static_cast<size_t>(ncp + 2) * sizeof(double);
+        }
+        if (smem_rows > 48 * 1024) {
             std::lock_guard<std::mutex> lock(mu);
             size_t& cur = configured_rows[h->device & 63];
-            if (cur < smem) {
-                CU(cudaFuncSetAttribute(k_eval_rows<M, NB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cur = smem;
+            if (cur < smem_rows) {
+                CU(cudaFuncSetAttribute(k_eval_rows<M, NB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+                cur = smem_rows;
             }
         }
-        k_eval_rows<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, st>>>(h->pd, io);
+        k_eval_rows<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem_rows, st>>>(h->pd, io);
         return ECUDA_OK;
     }
     k_eval_fast<M, NB, FD><<<grid, kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, st>>>(h->pd, io);
@@ -773,7 +829,7 @@ int ecuda_destroy(ecuda_handle h) {
     if (!h) return ECUDA_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->sx, &h->sf_, &h->sgv,
+    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->bflag, &h->sx, &h->sf_, &h->sgv,
                       &h->sjac, &h->sgrad, &h->ssum})
         release(*b);
     for (auto& b : h->coll) release(b);
@@ -1101,6 +1157,25 @@ int ecuda_summarize_allgather(ecuda_handle h, const double* f_dev, const double*
     k_summary_scatter<<<(unsigned)((B + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, st>>>(
         f_dev, g_dev, static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), pp, nranks, rank,
         (int)B, h->pd.ncons);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return ECUDA_OK;
+}
+
+int ecuda_peer_barrier(ecuda_handle h, void* const* peer_flags, int nranks, int rank, uint64_t step, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!peer_flags || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || step == 0)
+        return fail(h, ECUDA_ERR_ARG, "bad peer_flags / rank / nranks (1..16) / step (>= 1)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    PeerFlags pf{};
+    for (int r = 0; r < nranks; ++r) {
+        if (!peer_flags[r]) return fail(h, ECUDA_ERR_ARG, "null peer flag array");
+        pf.p[r] = static_cast<unsigned long long*>(peer_flags[r]);
+    }
+    int rc;
+    if ((rc = ensure(h, h->bflag, sizeof(int)))) return rc;
+    k_peer_barrier<<<1, 32, 0, st>>>(pf, nranks, rank, static_cast<unsigned long long>(step), static_cast<int*>(h->bflag.p));
     ++h->launches;
     CU(cudaGetLastError());
     return ECUDA_OK;

@@ -36,7 +36,9 @@ struct RowRegs {
 };
 
 // bound violation of one constraint value (fused summary; io.nranks > 0)
-ECUDA_HD double row_violation(const EvalIO& io, const ProbDev& pb, int b, int r, double val) {
+ECUDA_HD double row_violation(const EvalIO& io, const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int b, int r,
+                              double val) {
+    if (m.bl) return fmax(m.bl[r - ph.goff] - val, val - m.bu[r - ph.goff]);
     const size_t o = static_cast<size_t>(b) * pb.ncons + r;
     return fmax(ECUDA_LDG(io.bl + o) - val, val - ECUDA_LDG(io.bu + o));
 }
@@ -242,7 +244,7 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
             const int r = ph.goff + NS * N + pb.ne + it;
             const double val = ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t);
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
         }
         for (int e = tid; e < pb.ne; e += nthr) {
             const int r = ph.goff + NS * N + e;
@@ -250,13 +252,13 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
             const int i = (e < NS) ? e : e - NS;
             const double val = ECUDA_LDG(sg + r) * m.z[nc * N + node * NS + i];
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
         }
         if (tid == 0) {
             const int r = ph.goff + NS * N + pb.ne + np * N;
             const double val = ECUDA_LDG(sg + r) * (pt.tf - pt.t0);
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
         }
         if (p + 1 < pb.nphases) {
             const PhaseDev& nx = pb.ph[p + 1];
@@ -290,7 +292,7 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
         if (io.g) {
             const double val = sgr * (m.dotv[k * NS + j] - hfv);
             ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
         }
         if (jac) {
             if (FD) {

@@ -63,6 +63,9 @@ struct ProbDev {
     PhaseDev ph[ECUDA_MAX_PHASES];
 };
 
+// constraint rows of one phase: defects, events, path rows, duration
+ECUDA_HD int phase_ncons(const ProbDev& pb, const PhaseDev& ph) { return (pb.ns + ph.npath) * ph.N + pb.ne + 1; }
+
 // per-call pointers (device memory)
 struct EvalIO {
     const double* x;     // [B][nvars] scaled decision vectors

@@ -63,11 +63,14 @@ struct CtaMem {
     double* inst;  // [inst_stride] obstacle + track records of the instance
     double* P;     // [nb][nthr] thread-private block sums (generic block count only)
     int* colp;     // [nvars_p + 1] first triplet index of each column of this phase (+ end of the phase)
+    const double* bl;  // fused summary only: this phase's block of the instance's constraint bounds,
+    const double* bu;  //   staged in shared memory by the kernel (null: read them from global memory)
 };
 
 // what a CTA keeps in shared memory: the generic kernels need everything; the fast kernels keep the
 // block sums in registers (no P) and, in exact mode, have no finite-difference data (no xp/xm/rinv)
 enum { CARVE_P = 1, CARVE_FD = 2, CARVE_ALL = 3 };
+#define ECUDA_STAGE_BATCH 2  // strides of the staging loops whose loads are in flight together
 
 // shared-memory footprint in doubles for one CTA working on phase `ph`
 ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr, int what = CARVE_ALL) {
@@ -87,6 +90,7 @@ ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& 
     base += pb.inst_stride;
     m.z = base;     base += nv;
     m.xp = m.xm = m.rinv = m.P = nullptr;
+    m.bl = m.bu = nullptr;
     if (what & CARVE_FD) {
         m.xp = base;    base += nv;
         m.xm = base;    base += nv;
@@ -120,16 +124,33 @@ ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io
     const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
     const double* is = pb.isz + ph.zoff;
     if (tid == 0) m.colp[ph.nvars] = ECUDA_LDG(pb.colptr + ph.zoff + ph.nvars);
-    for (int c = tid; c < ph.nvars; c += nthr) {
-        double zt = ECUDA_LDG(xs + c);
-        double s = ECUDA_LDG(is + c);
-        m.z[c] = zt * s;
-        m.colp[c] = ECUDA_LDG(pb.colptr + ph.zoff + c);
-        if (fd) {
-            double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt));
-            m.xp[c] = (zt + delta) * s;
-            m.xm[c] = (zt - delta) * s;
-            m.rinv[c] = 1.0 / (2.0 * delta);
+    // all global loads of a batch of ECUDA_STAGE_BATCH strides are issued before the first dependent
+    // store, so that a thread pays the DRAM latency once per batch instead of once per element
+    for (int c0 = tid; c0 < ph.nvars; c0 += ECUDA_STAGE_BATCH * nthr) {
+        double zt[ECUDA_STAGE_BATCH], s[ECUDA_STAGE_BATCH];
+        int cp[ECUDA_STAGE_BATCH];
+#pragma unroll
+        for (int u = 0; u < ECUDA_STAGE_BATCH; ++u) {
+            const int c = c0 + u * nthr;
+            if (c < ph.nvars) {
+                zt[u] = ECUDA_LDG(xs + c);
+                s[u] = ECUDA_LDG(is + c);
+                cp[u] = ECUDA_LDG(pb.colptr + ph.zoff + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ECUDA_STAGE_BATCH; ++u) {
+            const int c = c0 + u * nthr;
+            if (c < ph.nvars) {
+                m.z[c] = zt[u] * s[u];
+                m.colp[c] = cp[u];
+                if (fd) {
+                    double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt[u]));
+                    m.xp[c] = (zt[u] + delta) * s[u];
+                    m.xm[c] = (zt[u] - delta) * s[u];
+                    m.rinv[c] = 1.0 / (2.0 * delta);
+                }
+            }
         }
     }
 }

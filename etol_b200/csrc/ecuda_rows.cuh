@@ -60,7 +60,7 @@ ECUDA_HD void rows_values(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     if (io.g) {
         const double val = rs.sgr * (rs.dv - rs.hfv);
         ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, b, r, val));
+        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val));
     }
 }
 
@@ -242,7 +242,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
     const int tcol = (NS + nc) * N;
     auto note = [&](int r, double val) {
-        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, b, r, val));
+        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val));
     };
 
     if (it == 0) {  // ---- objective: running cost per node and quadrature            [phase_b + objective_phase]

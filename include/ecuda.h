@@ -164,6 +164,11 @@ int ecuda_summarize_allgather(ecuda_handle h, const double* f_dev, const double*
  * into all ranks' gathered buffers, as ecuda_summarize_allgather does. f and g are required. */
 int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,
                          void* const* peer_out, int nranks, int rank, void* stream);
+/* cross-GPU barrier for the fused exchanges above: peer_flags[r] is rank r's array of nranks 64-bit
+ * counters in peer-visible memory (zero-initialised once, e.g. a symmetric-memory buffer); step must
+ * grow by one per call (first call: 1). Enqueued on `stream` after the kernel whose peer stores it
+ * publishes; when it completes on every rank, every rank's rows of this step are visible everywhere. */
+int ecuda_peer_barrier(ecuda_handle h, void* const* peer_flags, int nranks, int rank, uint64_t step, void* stream);
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);

@@ -54,6 +54,21 @@ for mode in (capi.JAC_FD, capi.JAC_EXACT):
     hdl.barrier(channel=0)
     torch.cuda.synchronize()
     ok = ok and torch.equal(buf, ref)
+# the library's own flag barrier in place of the symmetric-memory handle's
+flags = symm.empty(64, dtype=torch.int64, device=dev)
+flags.zero_()
+fh = symm.rendezvous(flags, dist.group.WORLD)
+torch.cuda.synchronize()
+fh.barrier(channel=0)
+fptrs = [int(p) for p in fh.buffer_ptrs]
+for step in (1, 2, 3):
+    buf.fill_(float("nan"))
+    ev.peer_barrier_ptr(fptrs, rank, 2 * step - 1, st)      # everyone has cleared its buffer
+    ev.eval_allgather_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), capi.JAC_FD,
+                          [int(p) for p in hdl.buffer_ptrs], rank, st)
+    ev.peer_barrier_ptr(fptrs, rank, 2 * step, st)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(buf, ref)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
