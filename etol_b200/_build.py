@@ -45,12 +45,12 @@ def cuda_sources():
 
 
 def build_libecuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "ecuda_api.cu"), os.path.join(CSRC, "ecuda_host.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("ecuda_api.cu", "ecuda_host.cpp", "ecuda_usermodel.cpp")]
     if not force and not _stale(LIBECUDA, cuda_sources()):
         return LIBECUDA
     env = dict(os.environ)
     cmd = [_nvcc(), "-ccbin", _cxx()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-shared", "-o", LIBECUDA] + srcs
+          ["-shared", "-o", LIBECUDA] + srcs + ["-ldl"]
     subprocess.run(cmd, check=True, env=env)
     return LIBECUDA
 

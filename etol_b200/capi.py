@@ -34,6 +34,15 @@ class Dims(C.Structure):
                 ("inst_stride", C.c_int32), ("rec_size", C.c_int32), ("track_size", C.c_int32)]
 
 
+class TapeNode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("reserved", C.c_int32), ("imm", C.c_double)]
+
+
+class UserModel(C.Structure):
+    _fields_ = [("nstates", C.c_int32), ("ncontrols", C.c_int32), ("static_kind", C.c_int32), ("nnodes", C.c_int32),
+                ("nodes", C.POINTER(TapeNode)), ("f_out", C.c_int32 * 8), ("cost_out", C.c_int32)]
+
+
 class EcudaError(RuntimeError):
     pass
 
@@ -46,7 +55,7 @@ ABI_SYMBOLS = [
     "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
-    "ecuda_host_path_eval",
+    "ecuda_host_path_eval", "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
 ]
 
 _lib = None
@@ -96,12 +105,69 @@ def lib():
     L.ecuda_host_dims.argtypes = [C.POINTER(ProblemDesc), C.POINTER(Dims)]
     L.ecuda_host_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip, _ip]
     L.ecuda_host_collocation.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
+    L.ecuda_host_model_eval.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, _dp]
+    L.ecuda_register_user_model.argtypes = [C.POINTER(UserModel), _ip, C.c_char_p, C.c_size_t]
+    L.ecuda_user_model_source.argtypes = [C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.ecuda_user_model_compile_check.argtypes = [C.c_int32, C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
+
+
+_registered = {}
+
+
+def register_user_model(tape):
+    """etol_b200.tape.Tape -> model id for ProblemDesc.model (one registration per distinct tape and process)."""
+    key = tape.key()
+    if key in _registered:
+        return _registered[key]
+    nodes = (TapeNode * len(tape.nodes))()
+    for i, (op, a, b, imm) in enumerate(tape.nodes):
+        nodes[i].op, nodes[i].a, nodes[i].b, nodes[i].imm = op, a, b, imm
+    um = UserModel()
+    um.nstates, um.ncontrols, um.static_kind, um.nnodes = tape.ns, tape.nc, tape.static_kind, len(tape.nodes)
+    um.nodes = nodes
+    for i, v in enumerate(tape.f_out):
+        um.f_out[i] = v
+    um.cost_out = tape.cost_out
+    mid = C.c_int32(-1)
+    err = C.create_string_buffer(512)
+    if lib().ecuda_register_user_model(C.byref(um), C.byref(mid), err, len(err)) != 0:
+        raise EcudaError("ecuda_register_user_model: " + err.value.decode())
+    _registered[key] = mid.value
+    return mid.value
+
+
+def user_model_source(model_id):
+    n = C.c_size_t(0)
+    if lib().ecuda_user_model_source(model_id, None, 0, C.byref(n)) != 0:
+        raise EcudaError("not a registered user model")
+    buf = C.create_string_buffer(n.value)
+    lib().ecuda_user_model_source(model_id, buf, n.value, None)
+    return buf.value.decode()
+
+
+def user_model_compile_check(model_id, nnodes):
+    """NVRTC build of the kernels for a registered model (no device needed) -> size of the sm_100a image."""
+    n = C.c_size_t(0)
+    log = C.create_string_buffer(1 << 16)
+    rc = lib().ecuda_user_model_compile_check(model_id, nnodes, C.byref(n), log, len(log))
+    if rc != 0:
+        raise EcudaError("user model did not compile: " + log.value.decode())
+    return n.value
+
+
+def host_model_eval(model, x, u, t=0.0):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    f, cost = np.zeros(8), np.zeros(1)
+    if lib().ecuda_host_model_eval(model, _p(x), _p(u), float(t), _p(f), _p(cost)) != 0:
+        raise EcudaError("ecuda_host_model_eval: unknown model")
+    return f[:len(x)].copy(), float(cost[0])
 
 
 def make_desc(wl):
@@ -157,7 +223,7 @@ def pack_instances(wl, dims=None):
     B = wl.batch
     out = np.zeros((B, dims.inst_stride))
     off = 0
-    if wl.model == 0:  # si2d: polygons -> edge records (host helper of the library)
+    if wl.borders is not None:  # polygons -> edge records (host helper of the library), then tracks
         for b in range(B):
             o = 0
             for p in range(wl.nphases):
@@ -177,6 +243,12 @@ def pack_instances(wl, dims=None):
         rec[:, :, 1] = cyl[:, :, 1]
         rec[:, :, 2] = cyl[:, :, 2] * cyl[:, :, 2]
         out[:, off:off + 4 * n] = rec.reshape(B, 4 * n)
+        for b in range(B):
+            o = off + 4 * n
+            for (radius, t, x, y) in (wl.tracks[b] if wl.tracks else []):
+                trk = np.concatenate([[radius], np.stack([t, x, y], axis=1).ravel()])
+                out[b, o:o + trk.size] = trk
+                o += trk.size
     return np.ascontiguousarray(out)
 
 

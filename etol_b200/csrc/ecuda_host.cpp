@@ -37,8 +37,18 @@ bool model_info(int model, ModelInfo* m) {
             m->fx[3] = (1u << 4);
             m->fu[3] = 0x1u; m->fu[4] = 0x2u; m->fu[5] = 0x4u;
             return true;
-        default:
-            return false;
+        default: {
+            const UserModel* um = user_model(model);
+            if (!um) return false;
+            m->ns = um->ns;
+            m->nc_default = m->nc_used = um->nc;
+            m->rec_size = um->static_kind == ECUDA_STATIC_EDGE ? 6 : 4;
+            for (int i = 0; i < um->ns; ++i) {
+                m->fx[i] = um->fx[i];
+                m->fu[i] = um->fu[i];
+            }
+            return true;
+        }
     }
 }
 
@@ -167,8 +177,8 @@ bool build_layout(const ecuda_problem_desc& d, HostProblem* hp, std::string* err
     hp->nc = d.ncontrols > 0 ? d.ncontrols : hp->mi.nc_default;
     if (hp->nc < hp->mi.nc_default || hp->nc > ECUDA_MAX_CONTROLS) return fail("ncontrols out of range for model");
     if (d.model != ECUDA_MODEL_SI2D && hp->nc != hp->mi.nc_default) return fail("ncontrols is fixed for this model");
-    if (d.ntracks < 0 || (d.model != ECUDA_MODEL_SI2D && d.ntracks != 0))
-        return fail("moving-obstacle tracks are only defined for the si2d model");
+    if (d.ntracks < 0 || (d.model != ECUDA_MODEL_SI2D && d.model < ECUDA_MODEL_USER_BASE && d.ntracks != 0))
+        return fail("moving-obstacle tracks are only defined for the si2d model and user models");
     if (d.ntracks > 0 && d.nwaypoints < 2) return fail("tracks need at least 2 waypoints");
     hp->ne = 2 * hp->ns;  // ePSOPT.cpp:43
     hp->nphases = d.nphases;

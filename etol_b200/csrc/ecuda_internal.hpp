@@ -3,9 +3,11 @@
 #ifndef ECUDA_INTERNAL_HPP_
 #define ECUDA_INTERNAL_HPP_
 
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <string>
 #include <vector>
+#endif
 
 #include "../../include/ecuda.h"
 
@@ -25,7 +27,9 @@ ECUDA_HD int fast_div(int a, unsigned magic) {
     return magic ? static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(a)) * magic) >> 32) : a;
 #endif
 }
+#ifndef __CUDACC_RTC__
 inline unsigned fast_div_magic(int d) { return d <= 1 ? 0u : static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(d)) + 1u; }
+#endif
 
 // ---- what the kernels see (passed by value as a __grid_constant__ kernel parameter) -------------
 struct PhaseDev {
@@ -85,6 +89,7 @@ struct EvalIO {
     int nranks, rank;
 };
 
+#ifndef __CUDACC_RTC__
 // ---- host-side problem description ------------------------------------------------------------------
 struct ModelInfo {
     int ns, nc_default, nc_used, rec_size;
@@ -93,6 +98,33 @@ struct ModelInfo {
     unsigned path_x;                // states read by every path row
 };
 bool model_info(int model, ModelInfo* out);
+
+// ---- user models (ecuda_usermodel.cpp) -------------------------------------------------------------------
+struct UserModel {
+    int id = 0, ns = 0, nc = 0, static_kind = 0;
+    std::vector<ecuda_tape_node> nodes;  // the registered tape followed by the derivative nodes
+    int f_out[ECUDA_MAX_STATES];
+    int cost_out = -1;
+    // node ids of the partial derivatives, -1 = identically zero
+    int dfdx[ECUDA_MAX_STATES][ECUDA_MAX_STATES], dfdu[ECUDA_MAX_STATES][ECUDA_MAX_CONTROLS];
+    int dcdx[ECUDA_MAX_STATES], dcdu[ECUDA_MAX_CONTROLS];
+    unsigned fx[ECUDA_MAX_STATES], fu[ECUDA_MAX_STATES];  // states / controls read by f_i
+    std::string source;                                    // generated Model<ECUDA_MODEL_USER>
+};
+// compiled kernels of one user model for one dot-block count
+struct UserImage {
+    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, NKERNELS = 4 };
+    std::vector<char> cubin;
+    std::string name[NKERNELS];  // lowered kernel names ("" = not compiled)
+    std::string log;
+};
+const UserModel* user_model(int model_id);  // null when the id is not registered
+int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::string* err);
+void user_model_eval(const UserModel& m, const double* x, const double* u, double t, double* f_out, double* cost_out);
+void user_model_partials(const UserModel& m, const double* x, const double* u, double* dfdx, double* dfdu, double* dcdx,
+                         double* dcdu);
+// nb: template argument NB of the kernels (0 = generic block count); rows: also compile k_eval_rows
+bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, std::string* err);
 
 struct Collocation {
     int N = 0;
@@ -124,6 +156,8 @@ void fill_probdev(const HostProblem& hp, ProbDev* pd);
 // exact-mode Jacobian template: tmpl[e] = (sg[row] * D[k][l]) * isz[col] for every D-coupled triplet
 // (defect row (k,j) x state column X(l,j), k != l), 0 elsewhere. Needs the collocation data in hp.col.
 void build_jac_template(const HostProblem& hp, const double* isz, const double* sg, std::vector<double>* tmpl);
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace ecuda
 #endif

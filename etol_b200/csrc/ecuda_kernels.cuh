@@ -1,0 +1,409 @@
+// ecuda_kernels.cuh -- the evaluation kernels (sm_100a) of libecuda.so.
+//
+// One source, two compilers: ecuda_api.cu includes this file for the built-in device models, and the
+// user-model path (ecuda_usermodel.cpp) hands the same text to NVRTC together with a generated
+// Model<ECUDA_MODEL_USER>, so that a model traced from ETOL callbacks runs on exactly the kernels the
+// built-in ones do. Nothing here may use a host-only header.
+//
+// Kernel layout: one CTA per (VGP instance, phase). The instance's obstacle/track records are
+// fetched into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier, SASS: UBLKCP) while
+// the threads un-scale the decision vector into shared memory; then the barrier-free phases of
+// ecuda_phases.cuh run. Results are written with streaming stores straight into the caller's
+// f / g / Jacobian-triplet arrays (IPOPT layout), so the only HBM traffic is the algorithmic one:
+// 8*(nvars + 1 + ncons + nnz) bytes per instance plus its obstacle records.
+#ifndef ECUDA_KERNELS_CUH_
+#define ECUDA_KERNELS_CUH_
+
+#include "ecuda_rows.cuh"
+
+namespace ecuda {
+
+constexpr int kThreads = 256;
+#ifndef ECUDA_MIN_CTAS
+#define ECUDA_MIN_CTAS 2 /* resident CTAs per SM the specialised kernels are register-limited for */
+#endif
+
+// ---- TMA bulk copy helpers (PTX) -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (SASS: UBLKCP), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest bulk group committed by this thread have finished READING their shared source
+__device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all bulk groups committed by this thread are complete (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// barrier over the first `count` threads of the CTA only (count a multiple of 32)
+__device__ __forceinline__ void named_barrier(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------
+// NB > 0: every phase has exactly NB summation blocks (block sums in registers); NB == 0: generic
+template <int M, int NB>
+__global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(const __grid_constant__ ProbDev pb,
+                                                   const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    stage_vars(pb, ph, io, m, b, tid, nthr, io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    // blockIdx.y: slice of the phase (instances whose phases have more defect rows than threads)
+    phase_b<M>(pb, ph, p, io, m, b, tid, nthr, blockIdx.y, gridDim.y);
+    __syncthreads();
+    phase_c<M, NB>(pb, ph, p, io, m, b, tid, nthr, blockIdx.y, gridDim.y);
+}
+
+// Specialised kernel (ecuda_fast.cuh): one defect row per thread, NB summation blocks, separate
+// instantiations for finite differences and for the exact Jacobian (which needs neither the
+// perturbation data in shared memory nor the registers of the FD rows).
+#ifndef ECUDA_MIN_CTAS_FD
+#define ECUDA_MIN_CTAS_FD 3
+#endif
+#ifndef ECUDA_MIN_CTAS_EXACT
+#define ECUDA_MIN_CTAS_EXACT 4
+#endif
+// Exact mode: the D-coupled triplets are instance independent, so an extra warp streams them from the
+// per-problem template (L2 resident) to the instance's triplet array with TMA bulk copies,
+// global -> shared ring -> global, while the 256 compute threads run stage and phase B. The ring has
+// kCopySlots buffers of kCopyChunk doubles; one lane drives it. Used when nnz is even, so that the
+// template element e and its destination b*nnz + e always agree modulo 16 bytes.
+constexpr int kCopyWarpThreads = 32;
+#ifndef ECUDA_COPY_SLOTS
+#define ECUDA_COPY_SLOTS 4
+#endif
+#ifndef ECUDA_COPY_CHUNK
+#define ECUDA_COPY_CHUNK 1024
+#endif
+constexpr int kCopySlots = ECUDA_COPY_SLOTS;
+constexpr int kCopyChunk = ECUDA_COPY_CHUNK;  // doubles (1024 = 8 KB)
+
+__device__ void copy_warp_template(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, int b, double* ring,
+                                   uint64_t* bars, int lane) {
+    const int e0 = __ldg(pb.colptr + ph.zoff + pb.nc * ph.N);             // first state column of the phase
+    const int e1 = __ldg(pb.colptr + ph.zoff + (pb.nc + pb.ns) * ph.N);   // its t0 column
+    const size_t g0 = static_cast<size_t>(b) * pb.nnz + e0;               // global element index of the first
+    const int n = e1 - e0;
+    const double* src = pb.jtmpl + e0;  // nnz even: e0 and g0 have the same parity
+    double* dst = io.jac + g0;
+    const int head = static_cast<int>(g0 & 1);        // first element sits at an odd index: copy it alone
+    const int nal = (n - head) & ~1;                  // doubles in the 16-byte aligned interior
+    if (lane == 1 && head && n > 0) __stcs(dst, __ldg(src));
+    if (lane == 2 && head + nal < n) __stcs(dst + n - 1, __ldg(src + n - 1));
+    if (lane != 0) return;
+    src += head;
+    dst += head;
+    const int nchunks = (nal + kCopyChunk - 1) / kCopyChunk;
+    auto chunk_bytes = [&](int c) { return static_cast<uint32_t>(min(kCopyChunk, nal - c * kCopyChunk)) * 8u; };
+    for (int c = 0; c < nchunks && c < kCopySlots; ++c) {
+        mbar_expect_tx(&bars[c], chunk_bytes(c));
+        bulk_g2s(ring + c * kCopyChunk, src + static_cast<size_t>(c) * kCopyChunk, chunk_bytes(c), &bars[c]);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c % kCopySlots;
+        mbar_wait(&bars[slot], (c / kCopySlots) & 1);
+        bulk_s2g(dst + static_cast<size_t>(c) * kCopyChunk, ring + slot * kCopyChunk, chunk_bytes(c));
+        bulk_commit();
+        // refill the slot of the PREVIOUS chunk: its store has had one iteration to read shared memory
+        // (bulk groups complete in order, so "all but the newest" covers it)
+        const int cn = c - 1 + kCopySlots;
+        if (c >= 1 && cn < nchunks) {
+            bulk_wait_read_but_one();
+            const int ps = (c - 1) % kCopySlots;
+            mbar_expect_tx(&bars[ps], chunk_bytes(cn));
+            bulk_g2s(ring + ps * kCopyChunk, src + static_cast<size_t>(cn) * kCopyChunk, chunk_bytes(cn), &bars[ps]);
+        }
+    }
+    bulk_wait_all();  // writes performed before the CTA-wide barrier that precedes the node-local stores
+}
+
+template <int M, int NB, bool FD>
+__global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
+                                  FD ? ECUDA_MIN_CTAS_FD : ECUDA_MIN_CTAS_EXACT)
+    k_eval_fast(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t copy_bars[kCopySlots];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = kThreads;  // compute threads; exact mode launches one more warp
+    const bool copy_warp = !FD && blockDim.x > kThreads;  // uniform over the CTA
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (copy_warp)
+            for (int c = 0; c < kCopySlots; ++c) mbar_init(&copy_bars[c], 1);
+    }
+    __syncthreads();
+    if (!FD && tid >= kThreads) {
+        // ---- copy warp: template -> triplet array, then wait at the barrier before phase C
+        double* ring = smem + cta_doubles(pb, ph, nthr, 0);
+        ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;  // 16-byte aligned
+        if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (!FD && io.jac && !copy_warp) fast_copy_template(pb, ph, io, b, tid, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
+    mbar_wait(&bar, 0);
+    if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
+    RowRegs<NB> rr;
+    fast_phase_b<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+    __syncthreads();  // all threads: in exact mode the template has landed before the node-local stores
+    fast_phase_c<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rr);
+    if (io.nranks > 0) {
+        // fused summary + all-gather epilogue: {f, max bound violation} of this instance goes straight
+        // into every rank's gathered buffer over NVLink (P2P stores), row rank*batch + b
+        __shared__ double red[kThreads / 32 + 1];
+        double v = rr.viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = rr.fval;
+        named_barrier(2, kThreads);  // the copy warp (exact mode) has already left
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                // fire and forget: the kernel boundary orders the store before the caller's cross-GPU barrier
+                // (a system-scope fence here would keep the CTA resident for an NVLink round trip)
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
+}
+
+// Row-owner kernel (ecuda_rows.cuh): one barrier after staging, then every thread writes whole rows.
+// Same launch shape as k_eval_fast (exact mode with a Jacobian: a 9th warp streams the template).
+#ifndef ECUDA_MIN_CTAS_ROWS_FD
+#define ECUDA_MIN_CTAS_ROWS_FD 3
+#endif
+template <int M, int NB, bool FD>
+__global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
+                                  FD ? ECUDA_MIN_CTAS_ROWS_FD : ECUDA_MIN_CTAS_EXACT)
+    k_eval_rows(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t copy_bars[kCopySlots];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = kThreads;
+    const bool copy_warp = !FD && blockDim.x > kThreads;  // uniform over the CTA
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (copy_warp)
+            for (int c = 0; c < kCopySlots; ++c) mbar_init(&copy_bars[c], 1);
+    }
+    __syncthreads();
+    // fused summary: this phase's block of the instance's bounds is staged behind the work arrays
+    const int nbnd = io.nranks > 0 ? phase_ncons(pb, ph) + (phase_ncons(pb, ph) & 1) : 0;
+    double* bnd = smem + cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0);
+    if (!FD && tid >= kThreads) {  // copy warp: template -> triplet array, then the barrier before the triplets
+        double* ring = bnd + 2 * nbnd;
+        ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;
+        if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (!FD && io.jac && !copy_warp) fast_copy_template(pb, ph, io, b, tid, nthr);
+    if (io.nranks > 0) {  // coalesced, off the critical path: the values are needed after the barrier
+        const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
+        const int ncp = phase_ncons(pb, ph);
+        for (int c0 = tid; c0 < ncp; c0 += 4 * nthr) {  // loads of four strides in flight together
+            double lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * nthr < ncp) {
+                    lo[u] = __ldg(io.bl + o + c0 + u * nthr);
+                    hi[u] = __ldg(io.bu + o + c0 + u * nthr);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * nthr < ncp) {
+                    bnd[c0 + u * nthr] = lo[u];
+                    bnd[nbnd + c0 + u * nthr] = hi[u];
+                }
+        }
+        m.bl = bnd;
+        m.bu = bnd + nbnd;
+    }
+    stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
+    mbar_wait(&bar, 0);
+    if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
+    RowState<M, NB> rs;
+    rows_values<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+    if (FD) {
+        rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, true);
+    } else {
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, false);
+        __syncthreads();  // all threads: the template has landed before the node-local triplets overwrite it
+        rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
+        rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, false, true);
+    }
+    if (io.nranks > 0) {  // fused summary + all-gather epilogue (see k_eval_fast)
+        __shared__ double red[kThreads / 32 + 1];
+        double v = rs.viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = rs.fval;
+        named_barrier(2, kThreads);
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
+}
+
+// Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
+// element index of the first one, so that shared and global addresses are 16-byte aligned together)
+// to dst[0..n): the aligned interior by one bulk copy issued by thread `lead`, the at most two
+// boundary elements by plain stores from the next two threads.
+__device__ __forceinline__ void flush_range(double* dst, const double* src, int par, int n, int tid, int lead) {
+    const int start = par;             // par == 1: element 0 sits at an odd global index
+    const int nal = (n - start) & ~1;  // doubles in the 16-byte aligned interior
+    if (tid == lead) {
+        if (nal > 0) bulk_s2g(dst + start, src + par + start, static_cast<uint32_t>(nal) * 8u);
+        bulk_commit();
+    } else if (tid == lead + 1) {
+        if (start == 1 && n > 0) __stcs(dst, src[par]);
+    } else if (tid == lead + 2) {
+        if (start + nal < n) __stcs(dst + n - 1, src[par + n - 1]);
+    }
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Exact mode, persistent: a CTA keeps a shared-memory IMAGE of its phase's whole triplet range. The
+// instance-independent D-coupled triplets are loaded into it once from the per-problem template;
+// for every instance the CTA works on, phase C overwrites the node-local triplets in the image (every
+// one of them, the pattern is the same for all instances) and one bulk shared->global copy (TMA)
+// writes the range out while the CTA already stages and evaluates its next instance. No triplet is
+// stored by an LSU instruction, nothing is read back, and the template is read once per CTA instead
+// of once per instance. Two CTAs per SM (the image of the benchmark shape is 101 KB).
+template <int M, int NB>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_eval_image(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int p = blockIdx.x % pb.nphases;  // fixed per CTA: gridDim.x is a multiple of nphases
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr, 0);
+    double* image = smem + cta_doubles(pb, ph, nthr, 0);
+    image += (reinterpret_cast<uintptr_t>(image) & 8) ? 1 : 0;  // 16-byte aligned
+    const int c0 = __ldg(pb.colptr + ph.zoff), c1 = __ldg(pb.colptr + ph.zoff + ph.nvars);
+    const int n = c1 - c0;
+    const int par = c0 & 1;  // nnz is even (checked on the host): triplet c0 of every instance has this parity
+    double* vimage = image + par - c0;  // vimage[e] = slot of triplet e
+    for (int e = c0 + tid; e < c1; e += nthr) vimage[e] = __ldg(pb.jtmpl + e);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    const int stride = gridDim.x / pb.nphases;
+    for (int b = blockIdx.x / pb.nphases; b < io.batch; b += stride) {
+        if (tid == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+        }
+        stage_vars(pb, ph, io, m, b, tid, nthr, false);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        __syncthreads();
+        RowRegs<NB> rr;
+        fast_phase_b<M, NB, false>(pb, ph, p, io, m, b, tid, nthr, rr);
+        if (tid == 0) bulk_wait_read_all();  // the previous instance's image has left shared memory
+        __syncthreads();
+        fast_phase_c<M, NB, false, true>(pb, ph, p, io, m, b, tid, nthr, rr, vimage);
+        fence_async_smem();  // generic-proxy writes to the image -> visible to the bulk copy
+        __syncthreads();
+        flush_range(io.jac + static_cast<size_t>(b) * pb.nnz + c0, image, par, n, tid, 0);
+    }
+    if (tid == 0) bulk_wait_read_all();
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads) k_grad(const __grid_constant__ ProbDev pb,
+                                                   const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, false);
+    __syncthreads();
+    cost_nodes<M>(pb, ph, m, tid, nthr);
+    __syncthreads();
+    gradient_phase<M>(pb, ph, io, m, b, tid, nthr);
+}
+
+}  // namespace ecuda
+#endif

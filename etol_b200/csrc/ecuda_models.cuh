@@ -207,4 +207,10 @@ struct Model<ECUDA_MODEL_FW6> {
 };
 
 }  // namespace ecuda
+
+// Model<ECUDA_MODEL_USER>: generated from a callback tape (ecuda_usermodel.cpp) and compiled with the
+// kernels at run time (NVRTC), or on the host by the kernel-logic emulator of the test-suite
+#ifdef ECUDA_USER_MODEL_HEADER
+#include ECUDA_USER_MODEL_HEADER
+#endif
 #endif

@@ -25,7 +25,9 @@
 #ifndef ECUDA_PHASES_CUH_
 #define ECUDA_PHASES_CUH_
 
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 #include "ecuda_models.cuh"
 

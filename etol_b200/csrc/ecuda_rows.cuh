@@ -88,8 +88,10 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
         // D-coupled triplets (and, for DIAG_FREE models, the row's own diagonal triplet)
         constexpr bool DS = Model<M>::DIAG_FREE;
         const int xoff = nc * N + i;
-        FastFdBlocks<NS, NB, 0, DS>::run(ph.Dt + k, N, m.z + xoff, m.xp + xoff, m.xm + xoff, m.rinv + xoff, m.colp + xoff,
-                                         rs.P, sgr, rs.hfv, k, k + pb.xcnt[i] - 1, k + pb.xrank[i][i], jac);
+        // the l == k value always goes to the row's own diagonal slot: final for DIAG_FREE models, otherwise
+        // overwritten below by this same thread (j == i) -- never a slot another row's thread owns
+        FastFdBlocks<NS, NB, 0, true>::run(ph.Dt + k, N, m.z + xoff, m.xp + xoff, m.xm + xoff, m.rinv + xoff, m.colp + xoff,
+                                           rs.P, sgr, rs.hfv, k, k + pb.xcnt[i] - 1, k + pb.xrank[i][i], jac);
         double dpk = 0.0, dmk = 0.0;
         if (!DS) {
             const int lc = nc * N + k * NS + i;

@@ -51,6 +51,7 @@ class Workload:
     gu: Optional[np.ndarray] = None
     x: Optional[np.ndarray] = None    # [B][nvars] scaled decision vectors
     meta: dict = field(default_factory=dict)
+    tape: Optional[object] = None     # etol_b200.tape.Tape of a user model (model = its registered id)
 
     @property
     def nphases(self):
@@ -58,10 +59,12 @@ class Workload:
 
     @property
     def ns(self):
-        return MODEL_SHAPE[self.model][0]
+        return self.tape.ns if self.tape is not None else MODEL_SHAPE[self.model][0]
 
     @property
     def nc(self):
+        if self.tape is not None:
+            return self.tape.nc
         return self.ncontrols if self.ncontrols > 0 else MODEL_SHAPE[self.model][1]
 
     @property
@@ -323,3 +326,76 @@ def pm3d_multiphase(batch=1024, nphases=3, nnodes=30, ncyl=8, seed=SEED, scaled=
     """C4: takeoff/cruise/landing as 3 pm3d phases linked by state + time continuity."""
     return _uas(f"C4-pm3d-{nphases}x{nnodes}-B{batch}", PM3D, batch, [nnodes] * nphases, ncyl, seed, 90.0,
                 scaled, **kw)
+
+
+# ---- user models (dynamics and cost recorded from callbacks, etol_b200.tape) ---------------------------
+def pm3d_user(batch=8, **kw):
+    """pm3d written as callbacks and registered as a user model: same data as `pm3d`, runtime-compiled kernels."""
+    from . import capi, tape as T
+    wl = pm3d(batch=batch, **kw)
+    wl.tape = T.pm3d_tape()
+    wl.model = capi.register_user_model(wl.tape)
+    wl.name = wl.name.replace("pm3d", "pm3d-as-user-model")
+    return wl
+
+
+def planar_user(tape, batch=8, nnodes=33, ncyl=5, ntracks=0, nwaypoints=3, seed=SEED, name="user", scaled=False,
+                xlo=(0.0, 0.0, -8.0, -8.0), xhi=(1000.0, 1000.0, 8.0, 8.0), ulo=(-3.0, -3.0), uhi=(3.0, 3.0),
+                rest=(0.3, 5.0), **kw):
+    """A 4-state, 2-control planar user model (states 0, 1 = position) among cylinders and moving circles.
+    `rest` is the guess of states 2 and 3; tf is free in [30, 90] s."""
+    from . import capi
+    rng = _rng(seed)
+    wl = Workload(name=f"{name}-N{nnodes}-B{batch}", model=capi.register_user_model(tape), nnodes=[nnodes],
+                  nstatic=[ncyl], batch=batch, ntracks=ntracks, nwaypoints=nwaypoints if ntracks else 0, tape=tape, **kw)
+    ns, nc, N = wl.ns, wl.nc, nnodes
+    assert (ns, nc) == (4, 2)
+    start, goal = _start_goal(rng, batch)
+    wl.cylinders = _cylinder_field(rng, batch, ncyl, start, goal)
+    if ntracks:
+        wl.tracks = []
+        for b in range(batch):
+            trk = []
+            for _ in range(ntracks):
+                tt = np.linspace(0.0, 90.0, nwaypoints)
+                trk.append((float(rng.uniform(10.0, 30.0)), tt, rng.uniform(0.0, 1000.0, nwaypoints),
+                            rng.uniform(0.0, 1000.0, nwaypoints)))
+            wl.tracks.append(trk)
+    zl, zu = np.zeros(wl.nvars), np.zeros(wl.nvars)
+    guess = np.zeros((batch, wl.nvars))
+    s = np.linspace(0.0, 1.0, N)
+    for k in range(N):
+        zl[wl.ix(0, k, 0):wl.ix(0, k, 0) + ns], zu[wl.ix(0, k, 0):wl.ix(0, k, 0) + ns] = xlo, xhi
+        zl[wl.iu(0, k, 0):wl.iu(0, k, 0) + nc], zu[wl.iu(0, k, 0):wl.iu(0, k, 0) + nc] = ulo, uhi
+        for i in range(2):
+            guess[:, wl.ix(0, k, i)] = start[:, i] + s[k] * (goal[:, i] - start[:, i])
+        guess[:, wl.ix(0, k, 2)], guess[:, wl.ix(0, k, 3)] = rest
+    zl[wl.it0(0)] = zu[wl.it0(0)] = 0.0
+    zl[wl.itf(0)], zu[wl.itf(0)] = 30.0, 90.0
+    guess[:, wl.itf(0)] = 60.0
+    gl, gu = np.zeros((batch, wl.ncons)), np.zeros((batch, wl.ncons))
+    e0 = ns * N
+    xs = np.stack([guess[:, wl.ix(0, 0, i)] for i in range(ns)], axis=1)
+    xe = np.stack([guess[:, wl.ix(0, N - 1, i)] for i in range(ns)], axis=1)
+    gl[:, e0:e0 + ns], gu[:, e0:e0 + ns] = xs, xs
+    gl[:, e0 + ns:e0 + 2 * ns], gu[:, e0 + ns:e0 + 2 * ns] = xe - 0.5, xe + 0.5
+    p0 = e0 + 2 * ns
+    gl[:, p0:p0 + wl.npath[0] * N] = -1000.0
+    gu[:, p0 + wl.npath[0] * N] = np.inf
+    wl.zl, wl.zu, wl.gl, wl.gu = zl, zu, gl, gu
+    wl.meta = dict(start=start, goal=goal)
+    if scaled:
+        wl.sz = psopt_like_scaling(wl)
+    wl.x = _decision_vectors(wl, guess, rng)
+    return wl
+
+
+def unicycle(batch=8, **kw):
+    from . import tape as T
+    return planar_user(T.unicycle_tape(), batch=batch, name="user-unicycle", xlo=(0.0, 0.0, -3.2, 0.0),
+                       xhi=(1000.0, 1000.0, 3.2, 25.0), ulo=(-2.0, -0.5), uhi=(2.0, 0.5), rest=(0.6, 12.0), **kw)
+
+
+def dragmass(batch=8, **kw):
+    from . import tape as T
+    return planar_user(T.drag_tape(), batch=batch, name="user-dragmass", rest=(4.0, -3.0), **kw)

@@ -37,7 +37,17 @@
 #ifndef ECUDA_H_
 #define ECUDA_H_
 
+#ifndef __CUDACC_RTC__
+#include <stddef.h>
 #include <stdint.h>
+#else /* runtime compilation of the kernels for a user model: no host headers */
+typedef signed char int8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t;
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -60,8 +70,40 @@ extern "C" {
 enum ecuda_model {
     ECUDA_MODEL_SI2D = 0, /* 2-D single integrator + ellipse-per-edge + moving circles (reference VGP) */
     ECUDA_MODEL_PM3D = 1, /* 3-D point mass (6 states, 3 controls) + vertical cylinders */
-    ECUDA_MODEL_FW6 = 2   /* 6-state fixed-wing kinematics + vertical cylinders */
+    ECUDA_MODEL_FW6 = 2,  /* 6-state fixed-wing kinematics + vertical cylinders */
+    ECUDA_MODEL_USER = 3  /* internal tag of the runtime-compiled model; callers use the id returned by
+                             ecuda_register_user_model (>= ECUDA_MODEL_USER_BASE) */
 };
+#define ECUDA_MODEL_USER_BASE 16
+#define ECUDA_MAX_USER_MODELS 64
+
+/* ---- user models: dynamics and running cost recorded from callbacks -------------------------------
+ * What ePSOPT gets by running the VGP callbacks on ADOL-C adoubles (src/ePSOPT/ePSOPT.cpp:186-276),
+ * eCUDA gets as a tape: a straight-line program over the inputs [x_0..x_{ns-1} | u_0..u_{nc-1} | t].
+ * Node i may only refer to nodes < i. Semantics are normative (each node is one IEEE-754 double
+ * operation, no contraction): POW with an integral exponent e, |e| <= 8, is the left-to-right
+ * product a*a*...*a (1/(...) for e < 0, 1 for e = 0); SIN / COS are ecuda_sincos of
+ * include/ecuda_detmath.h; other POW exponents and EXP use the platform's pow / exp and are
+ * reproducible to rounding only. Dynamics and cost must be autonomous (must not read t). */
+enum ecuda_tape_op {
+    ECUDA_OP_INPUT = 0, ECUDA_OP_CONST = 1, ECUDA_OP_ADD = 2, ECUDA_OP_SUB = 3, ECUDA_OP_MUL = 4, ECUDA_OP_DIV = 5,
+    ECUDA_OP_NEG = 6, ECUDA_OP_POW = 7, ECUDA_OP_SQRT = 8, ECUDA_OP_SIN = 9, ECUDA_OP_COS = 10, ECUDA_OP_EXP = 11
+};
+typedef struct {
+    int32_t op;   /* enum ecuda_tape_op */
+    int32_t a, b; /* operand nodes (INPUT: a = input slot; unary: b = -1) */
+    int32_t reserved;
+    double imm;   /* CONST value / POW exponent */
+} ecuda_tape_node;
+enum ecuda_static_kind { ECUDA_STATIC_CYLINDER = 0, ECUDA_STATIC_EDGE = 1 };
+typedef struct {
+    int32_t nstates, ncontrols;        /* 2..ECUDA_MAX_STATES (path rows read states 0 and 1), 1..ECUDA_MAX_CONTROLS */
+    int32_t static_kind;               /* record type of the static path rows: enum ecuda_static_kind */
+    int32_t nnodes;                    /* tape length */
+    const ecuda_tape_node* nodes;
+    int32_t f_out[ECUDA_MAX_STATES];   /* node holding dx_i/dt */
+    int32_t cost_out;                  /* node holding the running cost */
+} ecuda_user_model;
 
 enum ecuda_collocation { ECUDA_LEGENDRE = 0, ECUDA_CHEBYSHEV = 1 };
 
@@ -106,6 +148,7 @@ typedef struct {
     int32_t track_size;   /* doubles per track record (1 + 3*nwaypoints) */
 } ecuda_dims;
 
+#ifndef __CUDACC_RTC__ /* entry points: host code only (the kernels include this file for the types) */
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int ecuda_abi_version(void);
 int ecuda_create(int device, ecuda_handle* out);
@@ -196,9 +239,22 @@ int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double*
 /* the device models evaluated on the host at one point: state derivatives f_out[nstates] and running
  * cost. Used by the eCUDA plugin to verify that user callbacks and device model agree (eCUDA.hpp); not
  * an evaluation path. u holds the model's controls (2 for si2d, 3 for pm3d / fw6). */
+/* Registers a user model (process-wide, thread-safe) and returns its id for ecuda_problem_desc.model.
+ * The library differentiates the tape symbolically, derives the dependency masks used by
+ * ECUDA_PATTERN_MODEL_DEPS and generates the CUDA source of the model; the kernels are compiled for it
+ * with NVRTC (libnvrtc.so.12 must be loadable) at the first ecuda_set_problem that uses the id.
+ * No GPU is needed to register. err (may be NULL) receives a message on failure. */
+int ecuda_register_user_model(const ecuda_user_model* m, int32_t* model_id, char* err, size_t errlen);
+/* the generated CUDA source of a registered model (NUL-terminated; *needed = bytes incl. NUL; buf may be NULL) */
+int ecuda_user_model_source(int32_t model_id, char* buf, size_t buflen, size_t* needed);
+/* compiles the kernels of a registered model for `nnodes` collocation nodes without a device and returns the
+ * size of the sm_100a image (0 on failure; log, if not NULL, receives the compiler log). Build check only. */
+int ecuda_user_model_compile_check(int32_t model_id, int nnodes, size_t* image_bytes, char* log, size_t loglen);
 int ecuda_host_model_eval(int model, const double* x, const double* u, double t, double* f_out, double* cost_out);
 /* path rows of phase 0 of one instance block (layout of ecuda_upload_instances) at position (x,y), time t */
 int ecuda_host_path_eval(const ecuda_problem_desc* desc, const double* inst, double x, double y, double t, double* rows);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,9 @@
 #ifndef ECUDA_DETMATH_H_
 #define ECUDA_DETMATH_H_
 
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define ECUDA_DETMATH_FN __host__ __device__ __forceinline__

@@ -19,6 +19,7 @@ struct Handle {
     std::string err;
 };
 thread_local std::string g_err;
+UserTape g_staged;  // consumed by the next oracle_create with model == USER
 }  // namespace
 
 extern "C" {
@@ -31,6 +32,19 @@ struct oracle_desc {  // field-for-field the same meaning as ecuda_problem_desc 
 };
 
 const char* oracle_last_error() { return g_err.c_str(); }
+
+// the tape of a user model (op / a / b / imm per node, include/ecuda.h "user models")
+void oracle_stage_user_tape(int ns, int nc, int edges, int n, const int32_t* op, const int32_t* a, const int32_t* b,
+                            const double* imm, const int32_t* f_out, int cost_out) {
+    UserTape t;
+    t.ns = ns;
+    t.nc = nc;
+    t.edges = edges != 0;
+    for (int i = 0; i < n; ++i) t.nodes.push_back(TapeNode{op[i], a[i], b[i], imm[i]});
+    t.f_out.assign(f_out, f_out + ns);
+    t.cost_out = cost_out;
+    g_staged = t;
+}
 
 void* oracle_create(const oracle_desc* d) {
     try {
@@ -48,6 +62,7 @@ void* oracle_create(const oracle_desc* d) {
         s.pattern_mode = d->pattern_mode;
         s.maximize = d->maximize != 0;
         s.index_base = d->index_base;
+        if (s.model == USER) s.user = g_staged;
         Handle* h = new Handle;
         h->P = new Problem(s);
         h->inst.resize(d->batch);

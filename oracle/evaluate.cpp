@@ -129,7 +129,7 @@ void check_instance(const Problem& P, const Instance& I) {
     if (static_cast<int>(I.phases.size()) != P.L.nphases) throw std::invalid_argument("instance phases");
     for (int p = 0; p < P.L.nphases; ++p) {
         int nstat = 0;
-        if (P.spec.model == SI2D)
+        if (P.spec.model == SI2D || (P.spec.model == USER && P.spec.user.edges))
             for (auto& b : I.phases[p].borders) nstat += static_cast<int>(b.size());
         else
             nstat = static_cast<int>(I.phases[p].cylinders.size());
@@ -179,7 +179,7 @@ template <class T>
 std::vector<Callbacks<T>> build_callbacks(const Problem& P, const Instance& I) {
     std::vector<Callbacks<T>> cbs;
     for (int p = 0; p < P.L.nphases; ++p)
-        cbs.push_back(make_callbacks<T>(P.spec.model, &I.phases[p], &I.tracks));
+        cbs.push_back(make_callbacks<T>(P.spec.model, &I.phases[p], &I.tracks, &P.spec.user));
     return cbs;
 }
 

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <iterator>
 #include <list>
+#include <stdexcept>
 #include <vector>
 
 #include "../include/ecuda_detmath.h"
@@ -64,6 +65,34 @@ inline void sincos_s(const Dual& a, Dual* s, Dual* c) {
         c->d[i] = -sv * a.d[i];
     }
 }
+inline double sqrt_s(const double& a) { return std::sqrt(a); }
+inline Dual sqrt_s(const Dual& a) {
+    Dual r(std::sqrt(a.v));
+    for (int i = 0; i < MAXD; ++i) r.d[i] = a.d[i] / (2.0 * r.v);
+    return r;
+}
+inline double exp_s(const double& a) { return std::exp(a); }
+inline Dual exp_s(const Dual& a) {
+    Dual r(std::exp(a.v));
+    for (int i = 0; i < MAXD; ++i) r.d[i] = r.v * a.d[i];
+    return r;
+}
+// a^e: integral |e| <= 8 is the left-to-right product (include/ecuda.h), anything else libm pow
+inline double pow_s(const double& a, double e) {
+    if (std::fabs(e) <= 8.0 && e == std::floor(e)) {
+        const int n = static_cast<int>(std::fabs(e));
+        double p = n == 0 ? 1.0 : a;
+        for (int r = 1; r < n; ++r) p = p * a;
+        return e < 0 ? 1.0 / p : p;
+    }
+    return std::pow(a, e);
+}
+inline Dual pow_s(const Dual& a, double e) {
+    Dual r(pow_s(a.v, e));
+    const double slope = e == 0.0 ? 0.0 : e * pow_s(a.v, e - 1.0);
+    for (int i = 0; i < MAXD; ++i) r.d[i] = slope * a.d[i];
+    return r;
+}
 inline double value_of(const double& a) { return a; }
 inline double value_of(const Dual& a) { return a.v; }
 
@@ -92,10 +121,57 @@ struct Callbacks {
 
 constexpr double kG0 = 9.80665;
 
+// replay of a recorded user tape at one node, in scalar type T; returns the value of node `want`
 template <class T>
-Callbacks<T> make_callbacks(int model, const PhaseData* pd, const std::vector<Track>* tracks) {
+T replay(const UserTape& ut, const vector_t& x, const vector_t& u, const std::any& k, int want) {
+    std::vector<T> v(static_cast<size_t>(want) + 1);
+    for (int i = 0; i <= want; ++i) {
+        const TapeNode& n = ut.nodes[i];
+        switch (n.op) {
+            case T_INPUT:
+                if (n.a < ut.ns) v[i] = *std::any_cast<T*>(x.at(n.a));
+                else if (n.a < ut.ns + ut.nc) v[i] = *std::any_cast<T*>(u.at(n.a - ut.ns));
+                else v[i] = *std::any_cast<T*>(k);
+                break;
+            case T_CONST: v[i] = T(n.imm); break;
+            case T_ADD: v[i] = v[n.a] + v[n.b]; break;
+            case T_SUB: v[i] = v[n.a] - v[n.b]; break;
+            case T_MUL: v[i] = v[n.a] * v[n.b]; break;
+            case T_DIV: v[i] = v[n.a] / v[n.b]; break;
+            case T_NEG: v[i] = -v[n.a]; break;
+            case T_POW: v[i] = pow_s(v[n.a], n.imm); break;
+            case T_SQRT: v[i] = sqrt_s(v[n.a]); break;
+            case T_EXP: v[i] = exp_s(v[n.a]); break;
+            case T_SIN:
+            case T_COS: {
+                T s, c;
+                sincos_s(v[n.a], &s, &c);
+                v[i] = n.op == T_SIN ? s : c;
+                break;
+            }
+            default: throw std::invalid_argument("bad tape op");
+        }
+    }
+    return v[want];
+}
+
+template <class T>
+Callbacks<T> make_callbacks(int model, const PhaseData* pd, const std::vector<Track>* tracks,
+                            const UserTape* ut = nullptr) {
     Callbacks<T> cb;
     auto X = [](const vector_t& v, size_t i) -> const T& { return *std::any_cast<T*>(v.at(i)); };
+    if (model == USER) {  // dynamics / cost from the tape; path rows of the declared kinds
+        Callbacks<T> path = make_callbacks<T>(ut->edges ? SI2D : PM3D, pd, tracks);
+        cb.objective = [ut](vector_t x, vector_t u, vector_t, std::vector<std::string>, std::any k,
+                            std::any) -> scalar_t { return replay<T>(*ut, x, u, k, ut->cost_out); };
+        for (int i = 0; i < ut->ns; ++i)
+            cb.gradient.push_back([ut, i](vector_t x, vector_t u, vector_t, std::vector<std::string>, std::any k,
+                                          std::any) -> scalar_t { return replay<T>(*ut, x, u, k, ut->f_out[i]); });
+        cb.constraints.push_back(path.constraints.at(0));       // ellipses per edge, or cylinders
+        if (ut->edges) cb.constraints.push_back(path.constraints.at(1));  // moving circles
+        else if (!tracks->empty()) cb.constraints.push_back(make_callbacks<T>(SI2D, pd, tracks).constraints.at(1));
+        return cb;
+    }
     if (model == SI2D) {
         // objFunction, etol_psopt_example1.cpp:101-114
         cb.objective = [X](vector_t x, vector_t u, vector_t, std::vector<std::string>, std::any,

@@ -30,7 +30,21 @@ using vector_t = std::vector<scalar_t>;
 using f_t = std::function<scalar_t(vector_t x, vector_t u, vector_t params,
                                    std::vector<std::string> pnames, std::any k, std::any dt)>;
 
-enum Model { SI2D = 0, PM3D = 1, FW6 = 2 };
+enum Model { SI2D = 0, PM3D = 1, FW6 = 2, USER = 3 };
+// USER: dynamics and running cost given as a recorded tape (semantics of include/ecuda.h,
+// "user models"): what a user's ePSOPT-style lambdas compute, replayed node by node
+enum TapeOp { T_INPUT = 0, T_CONST, T_ADD, T_SUB, T_MUL, T_DIV, T_NEG, T_POW, T_SQRT, T_SIN, T_COS, T_EXP };
+struct TapeNode {
+    int op, a, b;
+    double imm;
+};
+struct UserTape {
+    int ns = 0, nc = 0;
+    bool edges = false;  // static path rows: ellipse per polygon edge (true) or cylinders (false)
+    std::vector<TapeNode> nodes;
+    std::vector<int> f_out;
+    int cost_out = -1;
+};
 enum CollocationKind { LEGENDRE = 0, CHEBYSHEV = 1 };
 enum PatternMode { DENSE_NODE = 0, MODEL_DEPS = 1 };
 enum JacMode { JAC_EXACT = 0, JAC_FD_INDEXSET = 1 };
@@ -73,6 +87,7 @@ struct Spec {
     int pattern_mode = DENSE_NODE;
     bool maximize = false;
     int index_base = 0;
+    UserTape user;  // model == USER
 };
 
 // ---- NLP layout ------------------------------------------------------

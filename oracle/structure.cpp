@@ -19,9 +19,35 @@ struct ModelShape {
     std::vector<unsigned> fx, fu;
 };
 
-ModelShape model_shape(int model) {
+ModelShape model_shape(const Spec& s) {
     ModelShape m;
+    const int model = s.model;
     switch (model) {
+        case USER: {  // read sets by walking the tape backwards from every output
+            const UserTape& ut = s.user;
+            m.ns = ut.ns;
+            m.nc_default = ut.nc;
+            for (int i = 0; i < ut.ns; ++i) {
+                std::vector<char> live(ut.nodes.size(), 0);
+                live.at(ut.f_out.at(i)) = 1;
+                unsigned fx = 0, fu = 0;
+                for (int k = static_cast<int>(ut.nodes.size()) - 1; k >= 0; --k) {
+                    if (!live[k]) continue;
+                    const TapeNode& n = ut.nodes[k];
+                    if (n.op == T_INPUT) {
+                        if (n.a < ut.ns) fx |= 1u << n.a;
+                        else if (n.a < ut.ns + ut.nc) fu |= 1u << (n.a - ut.ns);
+                        continue;
+                    }
+                    if (n.op == T_CONST) continue;
+                    live.at(n.a) = 1;
+                    if (n.op >= T_ADD && n.op <= T_DIV) live.at(n.b) = 1;
+                }
+                m.fx.push_back(fx);
+                m.fu.push_back(fu);
+            }
+            break;
+        }
         case SI2D:  // xdot = u0, ydot = u1   (etol_psopt_example1.cpp:116-138)
             m.ns = 2;
             m.nc_default = 2;
@@ -51,13 +77,13 @@ ModelShape model_shape(int model) {
 }  // namespace
 
 Layout make_layout(const Spec& s) {
-    ModelShape m = model_shape(s.model);
+    ModelShape m = model_shape(s);
     Layout L;
     L.ns = m.ns;
     L.nc = s.ncontrols > 0 ? s.ncontrols : m.nc_default;
     if (L.nc < m.nc_default) throw std::invalid_argument("too few controls for model");
     if (s.model != SI2D && L.nc != m.nc_default) throw std::invalid_argument("ncontrols fixed for this model");
-    if (s.model != SI2D && s.ntracks != 0) throw std::invalid_argument("tracks are si2d-only");
+    if (s.model != SI2D && s.model != USER && s.ntracks != 0) throw std::invalid_argument("tracks are si2d-only");
     L.ne = 2 * L.ns;
     L.nphases = s.nphases;
     if (s.nphases < 1 || static_cast<int>(s.nnodes.size()) != s.nphases ||
@@ -87,7 +113,7 @@ Layout make_layout(const Spec& s) {
 }
 
 Structure make_structure(const Spec& s, const Layout& L) {
-    ModelShape m = model_shape(s.model);
+    ModelShape m = model_shape(s);
     const bool dense = (s.pattern_mode == DENSE_NODE);
     const unsigned all_x = (1u << L.ns) - 1u, all_u = (1u << L.nc) - 1u;
     std::vector<std::vector<int32_t>> rows(L.nvars);

@@ -54,8 +54,49 @@ double interp(double t, const std::vector<double>& tv, const std::vector<double>
     return (t - tv[j]) * (ref[j + 1] - ref[j]) / (tv[j + 1] - tv[j]) + ref[j];
 }
 
-void dynamics(int model, const double* x, const double* u, double* f) {
-    if (model == SI2D) {
+// plain-double replay of a user tape (the tight counterpart of replay<T> in models.hpp)
+void tape_values(const UserTape& ut, const double* x, const double* u, std::vector<double>& v) {
+    v.resize(ut.nodes.size());
+    for (size_t i = 0; i < ut.nodes.size(); ++i) {
+        const TapeNode& n = ut.nodes[i];
+        switch (n.op) {
+            case T_INPUT: v[i] = n.a < ut.ns ? x[n.a] : n.a < ut.ns + ut.nc ? u[n.a - ut.ns] : 0.0; break;
+            case T_CONST: v[i] = n.imm; break;
+            case T_ADD: v[i] = v[n.a] + v[n.b]; break;
+            case T_SUB: v[i] = v[n.a] - v[n.b]; break;
+            case T_MUL: v[i] = v[n.a] * v[n.b]; break;
+            case T_DIV: v[i] = v[n.a] / v[n.b]; break;
+            case T_NEG: v[i] = -v[n.a]; break;
+            case T_SQRT: v[i] = std::sqrt(v[n.a]); break;
+            case T_EXP: v[i] = std::exp(v[n.a]); break;
+            case T_POW: {
+                const double e = n.imm;
+                if (std::fabs(e) <= 8.0 && e == std::floor(e)) {
+                    const int c = static_cast<int>(std::fabs(e));
+                    double p = c == 0 ? 1.0 : v[n.a];
+                    for (int r = 1; r < c; ++r) p = p * v[n.a];
+                    v[i] = e < 0 ? 1.0 / p : p;
+                } else {
+                    v[i] = std::pow(v[n.a], e);
+                }
+                break;
+            }
+            default: {
+                double s, c;
+                ecuda_sincos(v[n.a], &s, &c);
+                v[i] = n.op == T_SIN ? s : c;
+            }
+        }
+    }
+}
+
+void dynamics(const Spec& spec, const double* x, const double* u, double* f) {
+    const int model = spec.model;
+    if (model == USER) {
+        static thread_local std::vector<double> v;
+        tape_values(spec.user, x, u, v);
+        for (int i = 0; i < spec.user.ns; ++i) f[i] = v[spec.user.f_out[i]];
+    } else if (model == SI2D) {
         f[0] = u[0];
         f[1] = u[1];
     } else if (model == PM3D) {
@@ -81,7 +122,13 @@ void dynamics(int model, const double* x, const double* u, double* f) {
 void path_rows(const Problem& P, const PhasePre& pre, const Instance& I, const double* x, double t,
                double* out) {
     int q = 0;
-    if (P.spec.model == SI2D) {
+    const bool user = P.spec.model == USER;
+    if (P.spec.model == SI2D || user) {
+        if (user)
+            for (size_t c = 0; c < pre.cyl.size(); c += 3) {
+                double dx = x[0] - pre.cyl[c], dy = x[1] - pre.cyl[c + 1];
+                out[q++] = pre.cyl[c + 2] - (dx * dx + dy * dy);
+            }
         for (const EdgeRec& e : pre.edges) {
             double dx = x[0] - e.xc, dy = x[1] - e.yc;
             double delx = e.ct * dx - e.st * dy;
@@ -102,8 +149,16 @@ void path_rows(const Problem& P, const PhasePre& pre, const Instance& I, const d
     }
 }
 
-double running_cost(int model, const double* u, bool maximize) {
-    double l = (model == SI2D) ? u[0] * u[0] + u[1] * u[1] : (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
+double running_cost(const Spec& spec, const double* x, const double* u, bool maximize) {
+    const int model = spec.model;
+    double l;
+    if (model == USER) {
+        static thread_local std::vector<double> v;
+        tape_values(spec.user, x, u, v);
+        l = v[spec.user.cost_out];
+    } else {
+        l = (model == SI2D) ? u[0] * u[0] + u[1] * u[1] : (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
+    }
     return maximize ? -1.0 * l : l;
 }
 
@@ -121,7 +176,7 @@ void g_tight(const Problem& P, const std::vector<PhasePre>& pre, const Instance&
         if (np > 256) throw std::invalid_argument("tight oracle supports <= 256 path rows per node");
         for (int k = 0; k < N; ++k) {
             double t = h * C.tau[k] + m;
-            dynamics(P.spec.model, &z[L.ix(p, k, 0)], &z[L.iu(p, k, 0)], &F[static_cast<size_t>(k) * ns]);
+            dynamics(P.spec, &z[L.ix(p, k, 0)], &z[L.iu(p, k, 0)], &F[static_cast<size_t>(k) * ns]);
             path_rows(P, pre[p], I, &z[L.ix(p, k, 0)], t, pathv);
             for (int q = 0; q < np; ++q) g[L.rpath(p, k, q)] = P.sc.sg[L.rpath(p, k, q)] * pathv[q];
         }
@@ -172,9 +227,10 @@ void Problem::eval_f_tight(const Instance& I, const double* zs, double* f) const
         double h = 0.5 * (tf - t0);
         double acc = 0.0;
         for (int k = 0; k < N; ++k) {
-            double u[8];
+            double u[8], x[8];
             for (int j = 0; j < L.nc; ++j) u[j] = zs[L.iu(p, k, j)] * sc.isz[L.iu(p, k, j)];
-            acc = std::fma(col[p].w[k], running_cost(spec.model, u, spec.maximize), acc);
+            for (int i = 0; i < L.ns; ++i) x[i] = zs[L.ix(p, k, i)] * sc.isz[L.ix(p, k, i)];
+            acc = std::fma(col[p].w[k], running_cost(spec, x, u, spec.maximize), acc);
         }
         double fp = h * acc;
         total = (p == 0) ? fp : total + fp;

@@ -226,11 +226,18 @@ extern "C" int emu_eval(const ecuda_problem_desc* desc, const double* sz, const 
     EvalIO io{};
     io.x = x; io.inst = inst; io.f = f; io.fpart = fpart.data(); io.g = g; io.jac = jac; io.grad = grad;
     io.jac_mode = jac_mode; io.batch = desc->batch;
+#ifdef ECUDA_USER_MODEL_HEADER
+    // a build of the emulator for one generated user model (tests/emu_binding.py): the id comes from this
+    // library's own registry
+    if (desc->model < ECUDA_MODEL_USER_BASE) return -1;
+    run<ECUDA_MODEL_USER>(pd, io, nthr, generic != 0);
+#else
     switch (desc->model) {
         case ECUDA_MODEL_SI2D: run<ECUDA_MODEL_SI2D>(pd, io, nthr, generic != 0); break;
         case ECUDA_MODEL_PM3D: run<ECUDA_MODEL_PM3D>(pd, io, nthr, generic != 0); break;
         case ECUDA_MODEL_FW6: run<ECUDA_MODEL_FW6>(pd, io, nthr, generic != 0); break;
         default: return -1;
     }
+#endif
     return 0;
 }

@@ -14,20 +14,64 @@ _dp = C.POINTER(C.c_double)
 _lib = None
 
 
-def build():
+def build(out=LIB, user_header=None):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas",
-                    "-shared", "-o", LIB, os.path.join(EMU_DIR, "emu.cpp"),
-                    os.path.join(ROOT, "etol_b200", "csrc", "ecuda_host.cpp")], check=True)
+    extra = [] if user_header is None else ['-DECUDA_USER_MODEL_HEADER="%s"' % user_header]
+    subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas"] + extra +
+                   ["-shared", "-o", out, os.path.join(EMU_DIR, "emu.cpp"),
+                    os.path.join(ROOT, "etol_b200", "csrc", "ecuda_host.cpp"),
+                    os.path.join(ROOT, "etol_b200", "csrc", "ecuda_usermodel.cpp"), "-ldl"], check=True)
+
+
+def _sources():
+    return [os.path.join(EMU_DIR, "emu.cpp")] + [
+        os.path.join(ROOT, "etol_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "etol_b200", "csrc"))
+        if f.endswith((".cuh", ".hpp", ".cpp"))] + [os.path.join(ROOT, "include", "ecuda_detmath.h"),
+                                                    os.path.join(ROOT, "include", "ecuda.h")]
+
+
+_user_libs = {}
+
+
+def user_lib(tape):
+    """The emulator compiled for one user model: the source libecuda.so generates for the tape is built into a
+    g++ copy of the kernel phases (the very text NVRTC compiles for the GPU). Returns (library, model id in it)."""
+    import hashlib
+    key = tape.key()
+    if key in _user_libs:
+        return _user_libs[key]
+    src = capi.user_model_source(capi.register_user_model(tape))
+    tag = hashlib.sha1(src.encode()).hexdigest()[:12]
+    udir = os.path.join(EMU_DIR, "_user")
+    os.makedirs(udir, exist_ok=True)
+    hdr, out = os.path.join(udir, tag + ".cuh"), os.path.join(udir, "libecuda_emu_" + tag + ".so")
+    if not os.path.exists(hdr) or open(hdr).read() != src:
+        with open(hdr, "w") as fh:
+            fh.write(src)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in _sources() + [hdr]):
+        build(out, hdr)
+    L = C.CDLL(out)
+    L.emu_eval.argtypes = lib().emu_eval.argtypes
+    L.ecuda_register_user_model.argtypes = capi.lib().ecuda_register_user_model.argtypes
+    nodes = (capi.TapeNode * len(tape.nodes))()
+    for i, (op, a, b, imm) in enumerate(tape.nodes):
+        nodes[i].op, nodes[i].a, nodes[i].b, nodes[i].imm = op, a, b, imm
+    um = capi.UserModel()
+    um.nstates, um.ncontrols, um.static_kind, um.nnodes = tape.ns, tape.nc, tape.static_kind, len(tape.nodes)
+    um.nodes = nodes
+    for i, v in enumerate(tape.f_out):
+        um.f_out[i] = v
+    um.cost_out = tape.cost_out
+    mid = C.c_int32(-1)
+    assert L.ecuda_register_user_model(C.byref(um), C.byref(mid), None, 0) == 0
+    _user_libs[key] = (L, mid.value)
+    return _user_libs[key]
 
 
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [
-            os.path.join(ROOT, "etol_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "etol_b200", "csrc"))
-            if f.endswith((".cuh", ".hpp", ".cpp"))] + [os.path.join(ROOT, "include", "ecuda_detmath.h")]
-        newest = max(os.path.getmtime(s) for s in srcs)
+        newest = max(os.path.getmtime(s) for s in _sources())
         if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
             build()
         _lib = C.CDLL(LIB)
@@ -39,8 +83,9 @@ def lib():
 def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False, variant="rows"):
     """variant: which specialised kernel the emulator steps when the problem qualifies -- "rows"
     (k_eval_rows, the default), "columns" (k_eval_fast) or "image" (k_eval_image, exact mode)"""
-    lib().emu_use_rows(1 if variant == "rows" else 0)
-    lib().emu_use_image(1 if variant == "image" else 0)
+    L, model = (lib(), wl.model) if getattr(wl, "tape", None) is None else user_lib(wl.tape)
+    L.emu_use_rows(1 if variant == "rows" else 0)
+    L.emu_use_image(1 if variant == "image" else 0)
     dims = capi.host_dims(wl)
     inst = capi.pack_instances(wl, dims)
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(wl.batch, dims.nvars)
@@ -52,7 +97,8 @@ def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False, 
     sz = None if wl.sz is None else np.ascontiguousarray(wl.sz, dtype=np.float64)
     sg = None if wl.sg is None else np.ascontiguousarray(wl.sg, dtype=np.float64)
     desc = capi.make_desc(wl)
-    rc = lib().emu_eval(C.byref(desc), p(sz), p(sg), float(wl.sf), p(inst), p(x), p(f), p(g), p(jac), p(grad),
+    desc.model = model
+    rc = L.emu_eval(C.byref(desc), p(sz), p(sg), float(wl.sf), p(inst), p(x), p(f), p(g), p(jac), p(grad),
                         jac_mode, nthr, int(generic))
     if rc != 0:
         raise RuntimeError("emu_eval failed")

@@ -51,6 +51,7 @@ def lib():
         L.oracle_eval_batch.restype = C.c_double
         L.oracle_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                         C.c_int, C.c_int]
+        L.oracle_stage_user_tape.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, C.c_int]
         L.oracle_max_threads.restype = C.c_int
         L.oracle_sincos.argtypes = [_dp, C.c_int, _dp, _dp]
         _lib = L
@@ -83,6 +84,17 @@ class Oracle:
         wl = workload
         d = OracleDesc()
         d.model, d.nphases = wl.model, wl.nphases
+        if getattr(wl, "tape", None) is not None:  # user model: the oracle replays the same tape (model 3)
+            t = wl.tape
+            ops = np.array([n[0] for n in t.nodes], dtype=np.int32)
+            aa = np.array([n[1] for n in t.nodes], dtype=np.int32)
+            bb = np.array([n[2] for n in t.nodes], dtype=np.int32)
+            imm = np.array([n[3] for n in t.nodes], dtype=np.float64)
+            fo = np.array(t.f_out, dtype=np.int32)
+            lib().oracle_stage_user_tape(t.ns, t.nc, int(t.static_kind == 1), len(t.nodes), ops.ctypes.data_as(_ip),
+                                         aa.ctypes.data_as(_ip), bb.ctypes.data_as(_ip), _p(imm),
+                                         fo.ctypes.data_as(_ip), t.cost_out)
+            d.model = 3
         for p in range(wl.nphases):
             d.nnodes[p] = wl.nnodes[p]
             d.nstatic[p] = wl.nstatic[p]

@@ -22,6 +22,10 @@ CASES = {
     "C4-multiphase-ragged": lambda: W.pm3d_multiphase(batch=1, nphases=4, nnodes=7, ncyl=1),
     "pm3d-N2": lambda: W.pm3d(batch=1, nnodes=2, ncyl=1),
     "pm3d-no-obstacles": lambda: W.pm3d(batch=2, nnodes=9, ncyl=0),
+    # user models: the generated Model<ECUDA_MODEL_USER> source compiled into a copy of the emulator
+    "user-unicycle-tracks": lambda: W.unicycle(batch=2, ntracks=1, scaled=True),
+    "user-dragmass-deps": lambda: W.dragmass(batch=2, ntracks=2, pattern_mode=W.MODEL_DEPS),
+    "user-dragmass-N12": lambda: W.dragmass(batch=2, nnodes=12, ncyl=2, collocation=W.CHEBYSHEV),
 }
 
 
@@ -32,6 +36,8 @@ def test_phases_match_oracle(name, nthr, generic, variant):
     wl = CASES[name]()
     if name == "C3-fw6-N200" and (nthr == 32 or generic or variant != "rows"):
         pytest.skip("one thread count is enough for the large case")
+    if name.startswith("user-") and variant != "rows":
+        pytest.skip("user models are compiled for the row-owner and the generic kernels only")
     o = ob.Oracle(wl)
     style = 1 if name == "C3-fw6-N200" else 0
     for mode in (W.JAC_FD, W.JAC_EXACT):

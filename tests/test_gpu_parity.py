@@ -34,6 +34,14 @@ CASES = {
     "pm3d-N2": lambda: W.pm3d(batch=2, nnodes=2, ncyl=1),
     "pm3d-no-obstacles": lambda: W.pm3d(batch=2, nnodes=9, ncyl=0),
     "pm3d-N65": lambda: W.pm3d(batch=2, nnodes=65, ncyl=3),
+    # user models: dynamics and cost recorded from callbacks, kernels compiled at run time (NVRTC)
+    "user-pm3d": lambda: W.pm3d_user(batch=9),
+    "user-unicycle-tracks": lambda: W.unicycle(batch=6, ntracks=2),
+    "user-unicycle-cheb-deps": lambda: W.unicycle(batch=3, nnodes=40, collocation=W.CHEBYSHEV, pattern_mode=W.MODEL_DEPS,
+                                                 scaled=True),
+    "user-dragmass": lambda: W.dragmass(batch=5, ntracks=1, scaled=True),
+    "user-dragmass-N12-generic": lambda: W.dragmass(batch=3, nnodes=12, ncyl=2),
+    "user-dragmass-N70-generic": lambda: W.dragmass(batch=2, nnodes=70, ncyl=3, maximize=True),
 }
 
 
@@ -77,6 +85,20 @@ def test_values_match_oracle(evaluators, name, mode):
     if mode == W.JAC_FD:
         assert np.array_equal(got["f"], ref["f"]) and np.array_equal(got["g"], ref["g"])
         assert np.array_equal(got["jac"], ref["jac"]), "FD Jacobian is not bit-identical to the oracle"
+
+
+def test_user_model_equals_builtin_bitwise(evaluators):
+    """pm3d written as callbacks and compiled at run time gives the bits of the built-in pm3d kernels"""
+    ev_u, _, wl_u = _get(evaluators, "user-pm3d")
+    wl_b = W.pm3d(batch=wl_u.batch)
+    ev_b = capi.Evaluator(wl_b, device=0)
+    assert np.array_equal(wl_u.x, wl_b.x)
+    for mode in (W.JAC_FD, W.JAC_EXACT):
+        a = ev_u.eval_host(wl_u.x, want=("f", "g", "jac", "grad"), jac_mode=mode)
+        b = ev_b.eval_host(wl_b.x, want=("f", "g", "jac", "grad"), jac_mode=mode)
+        for k in ("f", "g", "jac", "grad"):
+            assert np.array_equal(a[k], b[k]), (mode, k)
+    ev_b.close()
 
 
 def test_golden_fixture_c0(evaluators):

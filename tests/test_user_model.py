@@ -1,0 +1,142 @@
+"""User models: a tape recorded from callbacks is differentiated, printed as
+CUDA source and compiled with the kernels at run time. Everything here runs without a GPU: registration and
+validation, the generated source, the host evaluation, the NVRTC build (no device needed), structure
+against the oracle, and the oracle's replay of the same tape. Kernel logic with the generated source is
+covered by tests/test_emu_parity.py (user-* cases); the GPU run by tests/test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from etol_b200 import capi, tape as T, workloads as W
+
+
+def test_registration_is_idempotent_per_tape_and_ids_start_at_base():
+    a = capi.register_user_model(T.unicycle_tape())
+    b = capi.register_user_model(T.unicycle_tape())
+    assert a == b and a >= 16
+    assert capi.register_user_model(T.drag_tape()) != a
+
+
+def _raw_register(ns, nc, nodes, f_out, cost_out, kind=0):
+    arr = (capi.TapeNode * len(nodes))()
+    for i, (op, a, b, imm) in enumerate(nodes):
+        arr[i].op, arr[i].a, arr[i].b, arr[i].imm = op, a, b, imm
+    um = capi.UserModel()
+    um.nstates, um.ncontrols, um.static_kind, um.nnodes, um.nodes = ns, nc, kind, len(nodes), arr
+    for i, v in enumerate(f_out):
+        um.f_out[i] = v
+    um.cost_out = cost_out
+    mid, err = C.c_int32(-1), C.create_string_buffer(256)
+    rc = capi.lib().ecuda_register_user_model(C.byref(um), C.byref(mid), err, len(err))
+    return rc, err.value.decode()
+
+
+def test_bad_tapes_are_rejected_with_a_message():
+    inp = lambda s: (T.OP_INPUT, s, -1, 0.0)
+    ok = [inp(0), inp(1), inp(2), (T.OP_MUL, 2, 2, 0.0)]
+    assert _raw_register(2, 1, ok, [2, 2], 3)[0] == 0
+    rc, msg = _raw_register(2, 1, [inp(0), (T.OP_ADD, 0, 1, 0.0)], [0, 0], 0)
+    assert rc != 0 and "precede" in msg                      # operand refers to itself / a later node
+    rc, msg = _raw_register(2, 1, [inp(0), inp(3)], [0, 1], 0)
+    assert rc != 0 and "reads t" in msg                      # explicit time dependence of the dynamics
+    rc, msg = _raw_register(2, 1, [inp(7)], [0, 0], 0)
+    assert rc != 0 and "slot" in msg
+    rc, msg = _raw_register(1, 1, ok, [2], 3)
+    assert rc != 0 and "nstates" in msg
+    rc, msg = _raw_register(2, 1, ok, [2, 9], 3)
+    assert rc != 0 and "f_out" in msg
+    rc, msg = _raw_register(2, 1, [inp(0), (T.OP_CONST, -1, -1, float("inf"))], [0, 0], 1)
+    assert rc != 0 and "finite" in msg
+    rc, msg = _raw_register(2, 1, [inp(0), (99, 0, -1, 0.0)], [0, 0], 0)
+    assert rc != 0 and "unknown operation" in msg
+
+
+def test_generated_source_of_pm3d_tape_has_the_builtin_masks():
+    src = capi.user_model_source(capi.register_user_model(T.pm3d_tape()))
+    assert "struct Model<ECUDA_MODEL_USER>" in src
+    assert "NS = 6, NCU = 3, REC = 4" in src and "DIAG_FREE = true" in src
+    # the same dependency masks etol_b200/csrc/ecuda_models.cuh states for the built-in pm3d
+    assert "FX = 0x0000000000201008ull" in src and "FU = 0x0000040201000000ull" in src
+    drag = capi.user_model_source(capi.register_user_model(T.drag_tape()))
+    assert "DIAG_FREE = false" in drag and "sqrt(" in drag
+    edge = capi.user_model_source(capi.register_user_model(T.trace(2, 2, lambda x, u: [u[0], u[1]],
+                                                                   lambda x, u: u[0] * u[0] + u[1] * u[1],
+                                                                   static_kind=T.STATIC_EDGE)))
+    assert "REC = 6" in edge and "edge_row_dxy" in edge
+
+
+def test_host_evaluation_matches_builtin_and_closed_form():
+    rng = np.random.default_rng(5)
+    mid = capi.register_user_model(T.pm3d_tape())
+    for _ in range(20):
+        x, u = rng.uniform(-50, 50, 6), rng.uniform(-10, 10, 3)
+        fa, ca = capi.host_model_eval(mid, x, u)
+        fb, cb = capi.host_model_eval(W.PM3D, x, u)
+        assert np.array_equal(fa, fb) and ca == cb
+    mid = capi.register_user_model(T.unicycle_tape())
+    for _ in range(20):
+        x, u = rng.uniform(-3, 3, 4), rng.uniform(-1, 1, 2)
+        f, c = capi.host_model_eval(mid, x, u)
+        s, co = ob.det_sincos(np.array([x[2]]))
+        assert np.array_equal(f, [x[3] * co[0], x[3] * s[0], u[1], u[0]])
+        assert c == u[0] * u[0] + u[1] * u[1]
+
+
+def test_integer_powers_are_products():
+    t = T.trace(2, 1, lambda x, u: [x[0] ** 3, x[1] ** -2], lambda x, u: u[0] ** 2)
+    mid = capi.register_user_model(t)
+    x, u = np.array([1.1, 0.7]), np.array([0.3])
+    f, c = capi.host_model_eval(mid, x, u)
+    assert f[0] == (x[0] * x[0]) * x[0] and f[1] == 1.0 / (x[1] * x[1]) and c == u[0] * u[0]
+    assert "pow(" not in capi.user_model_source(mid)
+
+
+def test_kernels_compile_for_user_models_without_a_gpu():
+    """NVRTC builds the sm_100a image here (cross-compilation needs no device)"""
+    try:
+        C.CDLL("libnvrtc.so.12")
+    except OSError:
+        try:
+            C.CDLL("/usr/local/cuda/lib64/libnvrtc.so.12")
+        except OSError:
+            pytest.skip("libnvrtc.so.12 is not installed")
+    assert capi.user_model_compile_check(capi.register_user_model(T.drag_tape()), 33) > 100000    # rows + generic
+    assert capi.user_model_compile_check(capi.register_user_model(T.unicycle_tape()), 12) > 50000  # generic only
+
+
+@pytest.mark.parametrize("mk", [lambda: W.pm3d_user(batch=2), lambda: W.unicycle(batch=2, ntracks=1),
+                                lambda: W.dragmass(batch=2, pattern_mode=W.MODEL_DEPS),
+                                lambda: W.unicycle(batch=1, pattern_mode=W.MODEL_DEPS, index_base=1)])
+def test_structure_matches_oracle(mk):
+    wl = mk()
+    o = ob.Oracle(wl)
+    d = capi.host_dims(wl)
+    assert (d.nvars, d.ncons, d.nnz, d.ngroups) == (o.nvars, o.ncons, o.nnz, o.ngroups)
+    for a, b in zip(capi.host_structure(wl), o.structure()):
+        assert np.array_equal(a, b)
+
+
+def test_oracle_replay_of_pm3d_tape_equals_oracle_pm3d():
+    wu, wb = W.pm3d_user(batch=3, scaled=True), W.pm3d(batch=3, scaled=True)
+    ou, obb = ob.Oracle(wu), ob.Oracle(wb)
+    for mode in (W.JAC_FD, W.JAC_EXACT):
+        for style in (0, 1):
+            if mode == W.JAC_EXACT and style == 1:
+                continue
+            a = ou.eval(wu.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style)
+            b = obb.eval(wb.x, want=("f", "g", "jac", "grad"), jac_mode=mode, style=style)
+            for k in ("f", "g", "jac", "grad"):
+                assert np.array_equal(a[k], b[k]), (mode, style, k)
+
+
+def test_oracle_styles_agree_on_user_models():
+    for wl in (W.unicycle(batch=2, ntracks=1), W.dragmass(batch=2, scaled=True)):
+        o = ob.Oracle(wl)
+        a, b = o.eval(wl.x, jac_mode=W.JAC_FD, style=0), o.eval(wl.x, jac_mode=W.JAC_FD, style=1)
+        for k in ("f", "g", "jac"):
+            assert np.array_equal(a[k], b[k])
+        ex = o.eval(wl.x, want=("jac",), jac_mode=W.JAC_EXACT)
+        den = np.maximum(1.0, np.abs(ex["jac"]))
+        assert np.max(np.abs(ex["jac"] - a["jac"]) / den) < 1e-3  # central differences vs dual numbers
