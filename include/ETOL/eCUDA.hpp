@@ -54,9 +54,16 @@ class eCUDA : public TrajectoryOptimizer {
     // setup() every callback is run once on symbolic inputs; the recorded expressions are evaluated at
     // sample points of the state/control box and compared with the device models and with the path
     // constraints the VGP data generates. The match selects what the GPU runs -- the callbacks
-    // themselves never run on the hot path. False (with a reason) when nothing matches; setup() then
-    // fails like ePSOPT does on a bad callback. Called by transcribe() when callbacks are registered.
+    // themselves never run on the hot path. When objective and state derivatives are none of the
+    // built-in device models, their recording is registered as a user model
+    // (ecuda_register_user_model): the library differentiates it and compiles the evaluation kernels
+    // for it at setup(), so any autonomous dynamics / running cost written with ecuda::var runs on the
+    // GPU. The constraint callbacks must still be the exclusion-zone / moving-zone constraints of the
+    // VGP data. False (with a reason) when nothing matches; setup() then fails like ePSOPT does on a
+    // bad callback. Called by transcribe() when callbacks are registered.
     bool matchCallbacks(std::string* why = nullptr);
+    // true when setup() turned the callbacks into a user model (kernels compiled for them at run time)
+    bool isUserModel() const;
 
     // ---- device-side VGP callbacks, selected directly ------------------------------------------------
     // dynamics + running cost: ECUDA_MODEL_SI2D (the reference example's x'=u0, y'=u1, u0^2+u1^2),
@@ -87,6 +94,7 @@ class eCUDA : public TrajectoryOptimizer {
 
  private:
     void fillDesc(ecuda_problem_desc* d, int model, bool obstacles, bool tracks);
+    bool usesEdges(int model) const;
     void buildBounds();
     void buildScaling();
     void buildInstance(std::vector<double>* out) const;
@@ -101,6 +109,7 @@ class eCUDA : public TrajectoryOptimizer {
     ecuda_handle _handle;
     int _model;
     bool _model_set, _obstacles_on, _tracks_on, _is_setup;
+    bool _user_edges;  // user model: static path rows are edge ellipses (no explicit cylinders registered)
     size_t _batch;
     std::vector<std::array<double, 3>> _cylinders;
     std::vector<std::vector<double>> _inst;  // per-instance data blocks

@@ -28,6 +28,11 @@ inline ETOL::scalar_t effort(F_ARGS) {
 inline ETOL::scalar_t xdot(F_ARGS) { return at(u, 0); }
 inline ETOL::scalar_t ydot(F_ARGS) { return at(u, 1); }
 
+// a model no built-in device model implements (eCUDA then compiles the kernels for the recorded
+// callbacks): the same vehicle in a sheared wind field that depends on where it is
+inline ETOL::scalar_t windyXdot(F_ARGS) { return at(u, 0) + 0.05 * at(x, 1); }
+inline ETOL::scalar_t windyYdot(F_ARGS) { return at(u, 1) - 0.02 * (at(x, 0) * at(x, 0)); }
+
 inline std::string rowName(const char* kind, size_t i, size_t j) {
     return std::string(kind) + "_" + std::to_string(i) + "_" + std::to_string(j) + "_0";
 }

@@ -29,7 +29,7 @@ std::string paramName(const std::string& name, size_t i, size_t j, size_t k) {
 
 eCUDA::eCUDA()
     : TrajectoryOptimizer(), _handle(nullptr), _model(ECUDA_MODEL_SI2D), _model_set(false), _obstacles_on(false),
-      _tracks_on(false), _is_setup(false), _batch(1) {}
+      _tracks_on(false), _is_setup(false), _user_edges(true), _batch(1) {}
 
 eCUDA::~eCUDA() { close(); }
 
@@ -54,6 +54,13 @@ void eCUDA::setModel(int model) {
 
 void eCUDA::setBatch(size_t n) { _batch = n ? n : 1; }
 
+// static path rows are one ellipse per polygon edge (si2d, user models without explicit cylinders) or
+// vertical cylinders
+bool eCUDA::usesEdges(int model) const {
+    return model == ECUDA_MODEL_SI2D || (model >= ECUDA_MODEL_USER_BASE && _user_edges);
+}
+bool eCUDA::isUserModel() const { return _model_set && _model >= ECUDA_MODEL_USER_BASE; }
+
 void eCUDA::addCylinder(double cx, double cy, double radius) {
     addParams({param_t(paramName("cyl", _cylinders.size(), 0, 0),
                        {var_t::CONTINUOUS, -1000., 0., 0., getDt() * getNSteps()})});
@@ -66,7 +73,7 @@ void eCUDA::addObstacleConstraints() {
     size_t i = 0;
     for (const border_t& border : *getObstacles_Raw()) {
         const int model = _model_set ? _model : (getNStates() == 2 ? ECUDA_MODEL_SI2D : ECUDA_MODEL_PM3D);
-        const size_t rows = model == ECUDA_MODEL_SI2D ? border.size() : 1;  // one row per edge / per cylinder
+        const size_t rows = usesEdges(model) ? border.size() : 1;  // one row per edge / per cylinder
         for (size_t j = 0; j < rows; ++j)
             addParams({param_t(paramName("side", i, j, 0), {var_t::CONTINUOUS, -1000., 0., 0., tspan})});
         ++i;
@@ -95,18 +102,19 @@ void eCUDA::fillDesc(ecuda_problem_desc* out, int model, bool obstacles, bool tr
     d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
     size_t nstatic = 0;
     if (obstacles) {
-        if (model == ECUDA_MODEL_SI2D)
+        if (usesEdges(model))
             for (const border_t& b : *getObstacles_Raw()) nstatic += b.size();
         else
             nstatic += getObstacles_Raw()->size();
     }
-    if (model != ECUDA_MODEL_SI2D) nstatic += _cylinders.size();
+    if (!usesEdges(model)) nstatic += _cylinders.size();
     d.nstatic[0] = static_cast<int32_t>(nstatic);
     d.ncontrols = static_cast<int32_t>(getNControls());
     d.ntracks = 0;
     d.nwaypoints = 0;
     if (tracks && !getTracks()->empty()) {
-        if (model != ECUDA_MODEL_SI2D) fail("moving exclusion zones are only modelled for the si2d device model");
+        if (model != ECUDA_MODEL_SI2D && model < ECUDA_MODEL_USER_BASE)
+            fail("moving exclusion zones are only modelled for the si2d device model and for user models");
         d.ntracks = static_cast<int32_t>(getTracks()->size());
         d.nwaypoints = static_cast<int32_t>(getTracks()->front().trajectory.size());
         for (const track_t& t : *getTracks())
@@ -216,14 +224,42 @@ bool eCUDA::matchCallbacks(std::string* why) {
             break;
         }
     }
-    if (found < 0) return no("objective / state derivatives agree with none of the device models (si2d, pm3d, fw6)");
+    if (found < 0) {
+        // ---- no built-in model computes these callbacks: they become a user model. The recording of the
+        // objective and the state derivatives (everything up to the last of those nodes) is handed to the
+        // library, which differentiates it and compiles the kernels for it at setup().
+        if (_model_set && _model < ECUDA_MODEL_USER_BASE)
+            return no("objective / state derivatives do not agree with the device model selected by setModel()");
+        int last = cost_id;
+        for (int id : f_ids) last = std::max(last, id);
+        std::vector<ecuda_tape_node> nodes(static_cast<size_t>(last) + 1);
+        for (int k = 0; k <= last; ++k) {
+            const ecuda::Node& n = tape.nodes[k];
+            nodes[k] = ecuda_tape_node{static_cast<int32_t>(n.op), n.a, n.b, 0, n.imm};
+        }
+        ecuda_user_model um{};
+        um.nstates = static_cast<int32_t>(ns);
+        um.ncontrols = static_cast<int32_t>(nc);
+        _user_edges = _cylinders.empty();
+        um.static_kind = _user_edges ? ECUDA_STATIC_EDGE : ECUDA_STATIC_CYLINDER;
+        um.nnodes = static_cast<int32_t>(nodes.size());
+        um.nodes = nodes.data();
+        for (size_t i = 0; i < ns && i < ECUDA_MAX_STATES; ++i) um.f_out[i] = f_ids[i];
+        um.cost_out = cost_id;
+        int32_t id = -1;
+        char msg[256] = {0};
+        if (ns > ECUDA_MAX_STATES || ecuda_register_user_model(&um, &id, msg, sizeof msg) != ECUDA_OK)
+            return no(std::string("the callbacks match no built-in device model and cannot become a user model: ") +
+                      (ns > ECUDA_MAX_STATES ? "too many states" : msg));
+        found = id;
+    }
 
     // ---- constraint rows against the path constraints the VGP data generates (static rows, then tracks)
     bool matched = row_ids.empty();
     bool use_obs = false, use_trk = false;
     for (int combo = 3; combo >= 1 && !matched; --combo) {
         const bool obs = combo & 1, trk = combo & 2;
-        if (trk && found != ECUDA_MODEL_SI2D) continue;
+        if (trk && found != ECUDA_MODEL_SI2D && found < ECUDA_MODEL_USER_BASE) continue;
         if ((obs && getObstacles_Raw()->empty() && _cylinders.empty()) || (trk && getTracks()->empty())) continue;
         ecuda_problem_desc d;
         fillDesc(&d, found, obs, trk);
@@ -378,12 +414,12 @@ void eCUDA::buildBounds() {
     if (_obstacles_on) {
         size_t i = 0;
         for (const border_t& b : *getObstacles_Raw()) {
-            const size_t rows = _model == ECUDA_MODEL_SI2D ? b.size() : 1;
+            const size_t rows = usesEdges(_model) ? b.size() : 1;
             for (size_t j = 0; j < rows; ++j) _problem.path_names.push_back(paramName("side", i, j, 0));
             ++i;
         }
     }
-    if (_model != ECUDA_MODEL_SI2D)
+    if (!usesEdges(_model))
         for (size_t c = 0; c < _cylinders.size(); ++c) _problem.path_names.push_back(paramName("cyl", c, 0, 0));
     for (int i = 0; i < _problem.desc.ntracks; ++i) _problem.path_names.push_back(paramName("ball", i, 0, 0));
     const size_t np = _problem.path_names.size();
@@ -442,7 +478,7 @@ void eCUDA::buildInstanceFor(std::vector<double>* out, int model, bool obstacles
                 xy.push_back(c[1]);
             }
             const int n = static_cast<int>(border.size());
-            if (model == ECUDA_MODEL_SI2D) {  // one ellipse per polygon edge (etol_psopt_example1.cpp:164-179)
+            if (usesEdges(model)) {  // one ellipse per polygon edge (etol_psopt_example1.cpp:164-179)
                 ecuda_si2d_edge_records(xy.data(), n, out->data() + o);
                 o += 6 * n;
             } else {  // circumscribed vertical cylinder: centroid + farthest corner
@@ -463,7 +499,7 @@ void eCUDA::buildInstanceFor(std::vector<double>* out, int model, bool obstacles
             }
         }
     }
-    if (model != ECUDA_MODEL_SI2D)
+    if (!usesEdges(model))
         for (const auto& c : _cylinders) {
             (*out)[o] = c[0];
             (*out)[o + 1] = c[1];

@@ -35,7 +35,8 @@ int shim_load(void* h, const char* xml, int model, int flags, int batch, const c
 }
 // load + register USER CALLBACKS (ecuda::var) like the reference example does, then try to match them.
 // variant 0: the example's callbacks; 1: a different objective; 2: exclusion zones only; 3: zones
-// registered in the opposite order (moving zones first). Returns 1 when matched; *model, *flags
+// registered in the opposite order (moving zones first); 4: dynamics no built-in model has (wind field
+// depending on the position) -> user model. Returns 1 when matched; *model, *flags
 // (bit0 obstacles, bit1 tracks) report what was recognised, why (<= 255 chars) the reason otherwise.
 int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* flags, char* why) {
     eCUDA* t = static_cast<eCUDA*>(h);
@@ -51,7 +52,10 @@ int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* 
         return a * a + 2.0 * (b * b);
     };
     t->setObjective(hold(variant == 1 ? other : ETOL::f_t(&vgp_si2d::effort)));
-    t->setGradient({hold(&vgp_si2d::xdot), hold(&vgp_si2d::ydot)});
+    if (variant == 4)
+        t->setGradient({hold(&vgp_si2d::windyXdot), hold(&vgp_si2d::windyYdot)});
+    else
+        t->setGradient({hold(&vgp_si2d::xdot), hold(&vgp_si2d::ydot)});
     ETOL::f_t* zones = hold(vgp_si2d::exclusionZones(t));
     if (variant == 2) {
         t->setConstraints({zones});

@@ -166,13 +166,47 @@ def test_user_callbacks_zones_only(xml):
     p.close()
 
 
-@pytest.mark.parametrize("variant,needle", [(1, "device models"), (3, "constraint rows")])
-def test_user_callbacks_that_match_nothing_are_rejected(xml, variant, needle):
-    # a different running cost; constraint callbacks in an order the device kernels do not produce
+def test_constraint_callbacks_that_match_nothing_are_rejected(xml):
+    # constraint callbacks in an order the device kernels do not produce
+    p = pb.Plugin()
+    ok, model, flags, why = p.load_callbacks(xml, 3)
+    assert not ok and "constraint rows" in why
+    p.close()
+
+
+def _windy_workload():
+    """the VGP of shim variant 4 (tests/plugin/shim.cpp, vgp_si2d::windyXdot/windyYdot) as a Workload"""
+    from etol_b200 import capi, tape as T
+    wl = W.reference_vgp("ocp")
+    wl.tape = T.trace(2, 2, lambda x, u: [u[0] + 0.05 * x[1], u[1] - 0.02 * (x[0] * x[0])],
+                      lambda x, u: u[0] * u[0] + u[1] * u[1], static_kind=T.STATIC_EDGE)
+    wl.model = capi.register_user_model(wl.tape)
+    return wl
+
+
+@pytest.mark.parametrize("variant", [1, 4])
+def test_unknown_dynamics_or_cost_become_a_user_model(xml, variant):
+    """a running cost (1) or dynamics (4) that no built-in device model has: the recording is registered
+    as a user model; layout, bounds and instance data are those of the explicit registration"""
     p = pb.Plugin()
     ok, model, flags, why = p.load_callbacks(xml, variant)
-    assert not ok and needle in why
-    p.close()
+    assert ok, why
+    assert model >= 16 and flags == 3
+    q = pb.Plugin().load(xml, scaling="automatic")
+    assert (p.dims.nvars, p.dims.ncons) == (q.dims.nvars, q.dims.ncons) == (134, 434)
+    for k, v in p.bounds().items():
+        if k != "guess":  # the control guess is specific to the single-integrator model
+            assert np.array_equal(v, q.bounds()[k]), k
+    assert np.array_equal(p.instance(0), q.instance(0))
+    if variant == 4:  # the registered model computes what the callbacks compute, and reads the states
+        from etol_b200 import capi
+        f, cost = capi.host_model_eval(model, [3.0, -2.0], [0.5, 0.25])
+        assert np.array_equal(f, [0.5 + 0.05 * -2.0, 0.25 - 0.02 * (3.0 * 3.0)]) and cost == 0.5 * 0.5 + 0.25 * 0.25
+        wl = _windy_workload()
+        irow, jcol, _ = p.structure()
+        oi, oj, _ = ob.Oracle(wl).structure()
+        assert np.array_equal(irow, oi) and np.array_equal(jcol, oj)
+    p.close(), q.close()
 
 
 @pytest.mark.gpu
@@ -184,6 +218,30 @@ def test_plugin_evaluate_matches_oracle(xml):
     ref = ob.Oracle(wl).eval(wl.x[:1], want=("f", "g", "jac"), jac_mode=W.JAC_FD, style=0, nthreads=2)
     assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
     assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    p.close()
+
+
+@pytest.mark.gpu
+def test_plugin_user_model_evaluates_like_oracle_and_solves(xml):
+    """callbacks no built-in model implements, through the plugin: kernels compiled at setup(), values
+    against the oracle's replay of the same mathematics, then a full solve"""
+    p = pb.Plugin()
+    ok, model, _, why = p.load_callbacks(xml, 4)
+    assert ok and model >= 16, why
+    p.setup()
+    wl = _windy_workload()
+    o = ob.Oracle(wl)
+    bnd = p.bounds()
+    z = wl.x[:1] / (wl.sz if wl.sz is not None else 1.0)  # unscaled decision vector of the workload
+    o.set_scaling(bnd["sz"], bnd["sg"], 1.0)
+    f, g, jac = p.evaluate(z)
+    ref = o.eval(z * bnd["sz"], want=("f", "g", "jac"), jac_mode=W.JAC_EXACT, style=0)
+    assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
+    assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    rc, score, iters, viol = p.solve(max_iter=300)
+    assert rc == 0 and viol <= 1e-8
+    X = p.traj(0, 2, 33)
+    assert np.allclose(X[0, 1:], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1, 1:], [5.0, 4.0], atol=0.0101)
     p.close()
 
 
