@@ -45,7 +45,7 @@ def cuda_sources():
 
 
 def build_libecuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("ecuda_api.cu", "ecuda_host.cpp", "ecuda_usermodel.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("ecuda_api.cu", "ecuda_host.cpp", "ecuda_usermodel.cpp", "ecuda_mesh.cpp")]
     if not force and not _stale(LIBECUDA, cuda_sources()):
         return LIBECUDA
     env = dict(os.environ)

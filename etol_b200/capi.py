@@ -55,7 +55,8 @@ ABI_SYMBOLS = [
     "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
-    "ecuda_host_path_eval", "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
+    "ecuda_host_path_eval", "ecuda_ode_error", "ecuda_resample", "ecuda_host_error_mesh", "ecuda_host_resample_matrix",
+    "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
 ]
 
 _lib = None
@@ -106,6 +107,10 @@ def lib():
     L.ecuda_host_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip, _ip]
     L.ecuda_host_collocation.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
     L.ecuda_host_model_eval.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, _dp]
+    L.ecuda_ode_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ecuda_resample.argtypes = [C.c_void_p, C.c_void_p, _ip, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ecuda_host_error_mesh.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+    L.ecuda_host_resample_matrix.argtypes = [C.c_int, C.c_int, C.c_int, _dp]
     L.ecuda_register_user_model.argtypes = [C.POINTER(UserModel), _ip, C.c_char_p, C.c_size_t]
     L.ecuda_user_model_source.argtypes = [C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.ecuda_user_model_compile_check.argtypes = [C.c_int32, C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
@@ -356,6 +361,24 @@ class Evaluator:
     def peer_barrier_ptr(self, flag_ptrs, rank, step, stream=None):
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         self._check(self.L.ecuda_peer_barrier(self.h, arr, len(flag_ptrs), rank, step, stream))
+
+    def ode_error_host(self, x):
+        """relative local discretisation error per mesh interval, [B][sum_p (N_p - 1)] (host buffers)"""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)
+        out = np.zeros((self.batch, sum(n - 1 for n in self.wl.nnodes)))
+        self._check(lib().ecuda_ode_error(self.h, x.ctypes.data, out.ctypes.data, MEM_HOST, None))
+        return out
+
+    def resample_host(self, x, nnodes_new, sz_new=None):
+        """decision vectors interpolated onto meshes of nnodes_new[p] nodes (host buffers)"""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)
+        nn = np.asarray(nnodes_new, dtype=np.int32)
+        nv = sum((self.wl.ns + self.wl.nc) * int(n) + 2 for n in nn)
+        out = np.zeros((self.batch, nv))
+        sz = None if sz_new is None else np.ascontiguousarray(sz_new, dtype=np.float64)
+        self._check(lib().ecuda_resample(self.h, x.ctypes.data, nn.ctypes.data_as(_ip), None if sz is None else sz.ctypes.data,
+                                         out.ctypes.data, MEM_HOST, None))
+        return out
 
     def summary_host(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)

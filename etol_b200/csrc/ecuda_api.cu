@@ -125,6 +125,44 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, doub
 }
 
 // ---- context ------------------------------------------------------------------------------------------
+// decision vectors interpolated onto another mesh (ecuda_resample): new node values = R * old node values
+// per state / control, t0 and tf copied; input scaled with the problem's s_z, output with sz_new (or unscaled)
+struct ResampleDev {
+    const double* R;       // per phase [Nnew][N], back to back
+    int moff[ECUDA_MAX_PHASES], Nnew[ECUDA_MAX_PHASES], zoff_new[ECUDA_MAX_PHASES];
+    int nvars_new;
+    const double* x;       // [B][nvars]
+    double* x_new;         // [B][nvars_new]
+    const double* sz_new;  // [nvars_new] or null
+};
+__global__ void k_resample(const __grid_constant__ ProbDev pb, const __grid_constant__ ResampleDev rd) {
+    const int b = blockIdx.x / pb.nphases, p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int N = ph.N, Nn = rd.Nnew[p], ns = pb.ns, nc = pb.nc, per = ns + nc;
+    const double* x = rd.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
+    const double* isz = pb.isz + ph.zoff;
+    double* out = rd.x_new + static_cast<size_t>(b) * rd.nvars_new + rd.zoff_new[p];
+    const double* R = rd.R + rd.moff[p];
+    for (int it = threadIdx.x; it < Nn * per + 2; it += blockDim.x) {
+        double v;
+        int dst;
+        if (it >= Nn * per) {  // t0, tf
+            const int w = it - Nn * per;
+            v = x[per * N + w] * isz[per * N + w];
+            dst = per * Nn + w;
+        } else {
+            const int k = it / per, c = it - k * per;  // c < nc: control c, else state c - nc
+            const int stride = c < nc ? nc : ns, base = c < nc ? c : nc * N + (c - nc);
+            double acc = 0.0;
+            for (int l = 0; l < N; ++l) acc = fma(__ldg(R + k * N + l), x[base + l * stride] * isz[base + l * stride], acc);
+            v = acc;
+            dst = c < nc ? k * nc + c : nc * Nn + k * ns + (c - nc);
+        }
+        if (rd.sz_new) v = v * rd.sz_new[rd.zoff_new[p] + dst];
+        out[dst] = v;
+    }
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -163,8 +201,12 @@ struct ecuda_ctx {
     // user model (ecuda_register_user_model): kernels compiled with NVRTC, loaded per handle
     const UserModel* um = nullptr;
     cudaLibrary_t ulib = nullptr;
-    cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0};
+    cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0, 0};
+    // mesh-refinement support (ecuda_ode_error / ecuda_resample), built on first use
+    DevBuf mesh[ECUDA_MAX_PHASES];  // E | dE | wq | tq per phase
+    bool have_mesh = false;
+    DevBuf serr, resmat, sxnew, ssznew;
 };
 
 static std::string g_create_err;
@@ -419,14 +461,15 @@ static int load_user_kernels(ecuda_ctx* h) {
     return ECUDA_OK;
 }
 
-static int launch_user(ecuda_ctx* h, int which, dim3 grid, int threads, size_t smem, const EvalIO& io, cudaStream_t st) {
+static int launch_user(ecuda_ctx* h, int which, dim3 grid, int threads, size_t smem, const EvalIO& io, cudaStream_t st,
+                       const MeshDev* mesh = nullptr) {
     cudaKernel_t k = h->ukern[which];
     if (!k) return fail(h, ECUDA_ERR_STATE, "user-model kernel was not compiled");
     if (smem > 48 * 1024 && h->ukern_smem[which] < smem) {
         CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->ukern_smem[which] = smem;
     }
-    void* args[] = {const_cast<ProbDev*>(&h->pd), const_cast<EvalIO*>(&io)};
+    void* args[] = {const_cast<ProbDev*>(&h->pd), const_cast<EvalIO*>(&io), const_cast<MeshDev*>(mesh)};
     CU(cudaLaunchKernel(reinterpret_cast<const void*>(k), grid, dim3(threads), args, smem, st));
     ++h->launches;
     return ECUDA_OK;
@@ -534,6 +577,8 @@ int ecuda_destroy(ecuda_handle h) {
                       &h->sjac, &h->sgrad, &h->ssum})
         release(*b);
     for (auto& b : h->coll) release(b);
+    for (auto& b : h->mesh) release(b);
+    for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew}) release(*b);
     unload_user_kernels(h);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -555,6 +600,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     h->have_problem = false;
     h->have_inst = false;
     h->have_bounds = false;
+    h->have_mesh = false;
     ProbDev& pd = h->pd;
     fill_probdev(hp, &pd);
     size_t smem = 0, smem_fd = 0, smem_ex = 0;
@@ -786,6 +832,156 @@ int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, 
         io.peer[r] = static_cast<double*>(peer_out[r]);
     }
     return launch_eval(h, io, st);
+}
+
+}  // extern "C"
+
+// ---- mesh refinement support ---------------------------------------------------------------------------------
+template <int M>
+static int launch_ode_error_t(ecuda_ctx* h, const EvalIO& io, const MeshDev& mesh, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    if (h->smem_bytes > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < h->smem_bytes) {
+            CU(cudaFuncSetAttribute(k_ode_error<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            cur = h->smem_bytes;
+        }
+    }
+    k_ode_error<M><<<io.batch * h->pd.nphases, kThreads, h->smem_bytes, st>>>(h->pd, io, mesh);
+    ++h->launches;
+    return ECUDA_OK;
+}
+
+static int ensure_mesh(ecuda_ctx* h) {
+    if (h->have_mesh) return ECUDA_OK;
+    for (int p = 0; p < h->hp.nphases; ++p) {
+        MeshHost mh;
+        build_error_mesh(h->hp.col[p], &mh);
+        const size_t nE = mh.E.size(), nq = mh.wq.size();
+        int rc;
+        if ((rc = ensure(h, h->mesh[p], sizeof(double) * (2 * nE + 2 * nq)))) return rc;
+        double* base = static_cast<double*>(h->mesh[p].p);
+        CU(cudaMemcpy(base, mh.E.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(base + nE, mh.dE.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(base + 2 * nE, mh.wq.data(), sizeof(double) * nq, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(base + 2 * nE + nq, mh.tq.data(), sizeof(double) * nq, cudaMemcpyHostToDevice));
+    }
+    h->have_mesh = true;
+    return ECUDA_OK;
+}
+
+extern "C" {
+
+int ecuda_ode_error(ecuda_handle h, const double* x, double* err, int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!x || !err) return fail(h, ECUDA_ERR_ARG, "x and err are required");
+    if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    int rc;
+    if ((rc = ensure_mesh(h))) return rc;
+    const size_t B = h->hp.desc.batch, nv = h->pd.nvars;
+    MeshDev mesh{};
+    int nint = 0;
+    for (int p = 0; p < h->hp.nphases; ++p) {
+        const size_t N = h->hp.N[p], nE = (N - 1) * ECUDA_MESH_Q * N, nq = (N - 1) * ECUDA_MESH_Q;
+        const double* base = static_cast<const double*>(h->mesh[p].p);
+        mesh.E[p] = base;
+        mesh.dE[p] = base + nE;
+        mesh.wq[p] = base + 2 * nE;
+        mesh.tq[p] = base + 2 * nE + nq;
+        mesh.eoff[p] = nint;
+        nint += static_cast<int>(N) - 1;
+    }
+    mesh.nint = nint;
+    EvalIO io{};
+    io.inst = static_cast<const double*>(h->inst.p);
+    io.batch = static_cast<int>(B);
+    io.x = x;
+    mesh.out = err;
+    if (memkind == ECUDA_MEM_HOST) {
+        if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
+        if ((rc = ensure(h, h->serr, sizeof(double) * B * nint))) return rc;
+        CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * nv, cudaMemcpyHostToDevice, st));
+        io.x = static_cast<const double*>(h->sx.p);
+        mesh.out = static_cast<double*>(h->serr.p);
+    }
+    if (h->um) {
+        rc = launch_user(h, UserImage::ODE_ERROR, dim3(io.batch * h->pd.nphases), kThreads, h->smem_bytes, io, st, &mesh);
+    } else {
+        switch (h->pd.model) {
+            case ECUDA_MODEL_SI2D: rc = launch_ode_error_t<ECUDA_MODEL_SI2D>(h, io, mesh, st); break;
+            case ECUDA_MODEL_PM3D: rc = launch_ode_error_t<ECUDA_MODEL_PM3D>(h, io, mesh, st); break;
+            default: rc = launch_ode_error_t<ECUDA_MODEL_FW6>(h, io, mesh, st); break;
+        }
+    }
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    if (memkind == ECUDA_MEM_HOST) {
+        CU(cudaMemcpyAsync(err, mesh.out, sizeof(double) * B * nint, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_resample(ecuda_handle h, const double* x, const int32_t* nnodes_new, const double* sz_new, double* x_new,
+                   int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!x || !x_new || !nnodes_new) return fail(h, ECUDA_ERR_ARG, "x, nnodes_new and x_new are required");
+    if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const HostProblem& hp = h->hp;
+    // interpolation matrices of all phases, back to back, and the layout of the new decision vector
+    ResampleDev rd{};
+    std::vector<double> mats;
+    int zo = 0;
+    for (int p = 0; p < hp.nphases; ++p) {
+        Collocation to;
+        std::string err;
+        if (!build_collocation(hp.desc.collocation, nnodes_new[p], &to, &err)) return fail(h, ECUDA_ERR_ARG, err);
+        std::vector<double> R;
+        build_resample(hp.col[p], to, &R);
+        rd.moff[p] = static_cast<int>(mats.size());
+        rd.Nnew[p] = nnodes_new[p];
+        rd.zoff_new[p] = zo;
+        zo += (hp.ns + hp.nc) * nnodes_new[p] + 2;
+        mats.insert(mats.end(), R.begin(), R.end());
+    }
+    rd.nvars_new = zo;
+    const size_t B = hp.desc.batch, nv = h->pd.nvars;
+    int rc;
+    if ((rc = ensure(h, h->resmat, sizeof(double) * mats.size()))) return rc;
+    CU(cudaMemcpyAsync(h->resmat.p, mats.data(), sizeof(double) * mats.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // mats is a local
+    rd.R = static_cast<const double*>(h->resmat.p);
+    rd.x = x;
+    rd.x_new = x_new;
+    rd.sz_new = sz_new;
+    if (memkind == ECUDA_MEM_HOST) {
+        if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
+        if ((rc = ensure(h, h->sxnew, sizeof(double) * B * zo))) return rc;
+        CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * nv, cudaMemcpyHostToDevice, st));
+        rd.x = static_cast<const double*>(h->sx.p);
+        rd.x_new = static_cast<double*>(h->sxnew.p);
+        if (sz_new) {
+            if ((rc = ensure(h, h->ssznew, sizeof(double) * zo))) return rc;
+            CU(cudaMemcpyAsync(h->ssznew.p, sz_new, sizeof(double) * zo, cudaMemcpyHostToDevice, st));
+            rd.sz_new = static_cast<const double*>(h->ssznew.p);
+        }
+    }
+    k_resample<<<static_cast<unsigned>(B) * hp.nphases, 256, 0, st>>>(h->pd, rd);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (memkind == ECUDA_MEM_HOST) {
+        CU(cudaMemcpyAsync(x_new, rd.x_new, sizeof(double) * B * zo, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ECUDA_OK;
 }
 
 int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream) {

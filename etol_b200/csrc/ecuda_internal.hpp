@@ -70,6 +70,18 @@ struct ProbDev {
 // constraint rows of one phase: defects, events, path rows, duration
 ECUDA_HD int phase_ncons(const ProbDev& pb, const PhaseDev& ph) { return (pb.ns + ph.npath) * ph.N + pb.ne + 1; }
 
+// mesh-refinement support (ecuda_ode_error): interpolation data of every phase, device pointers
+#define ECUDA_MESH_Q 4  // Gauss-Legendre points per mesh interval
+struct MeshDev {
+    const double* E[ECUDA_MAX_PHASES];   // [(N-1)*Q][N] Lagrange basis at the quadrature points
+    const double* dE[ECUDA_MAX_PHASES];  // [(N-1)*Q][N] its derivative with respect to tau
+    const double* wq[ECUDA_MAX_PHASES];  // [(N-1)*Q]    quadrature weights (tau units)
+    const double* tq[ECUDA_MAX_PHASES];  // [(N-1)*Q]    quadrature points (tau)
+    int eoff[ECUDA_MAX_PHASES];          // first interval of the phase in the output row
+    int nint;                            // intervals per instance = sum (N_p - 1)
+    double* out;                         // [B][nint]
+};
+
 // per-call pointers (device memory)
 struct EvalIO {
     const double* x;     // [B][nvars] scaled decision vectors
@@ -102,6 +114,7 @@ bool model_info(int model, ModelInfo* out);
 // ---- user models (ecuda_usermodel.cpp) -------------------------------------------------------------------
 struct UserModel {
     int id = 0, ns = 0, nc = 0, static_kind = 0;
+    int nregistered = 0;                 // length of the registered tape (the first nodes)
     std::vector<ecuda_tape_node> nodes;  // the registered tape followed by the derivative nodes
     int f_out[ECUDA_MAX_STATES];
     int cost_out = -1;
@@ -113,7 +126,7 @@ struct UserModel {
 };
 // compiled kernels of one user model for one dot-block count
 struct UserImage {
-    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, NKERNELS = 4 };
+    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, ODE_ERROR = 4, NKERNELS = 5 };
     std::vector<char> cubin;
     std::string name[NKERNELS];  // lowered kernel names ("" = not compiled)
     std::string log;
@@ -131,6 +144,13 @@ struct Collocation {
     std::vector<double> tau, w, D;
 };
 bool build_collocation(int kind, int N, Collocation* out, std::string* err);
+// ecuda_mesh.cpp: quadrature points inside every mesh interval with the Lagrange basis (and its
+// derivative) there; interpolation matrix between two meshes
+struct MeshHost {
+    std::vector<double> E, dE, wq, tq;
+};
+void build_error_mesh(const Collocation& c, MeshHost* out);
+void build_resample(const Collocation& from, const Collocation& to, std::vector<double>* R);  // [to.N][from.N]
 
 struct HostProblem {
     ecuda_problem_desc desc{};

@@ -405,5 +405,26 @@ __global__ void __launch_bounds__(kThreads) k_grad(const __grid_constant__ ProbD
     gradient_phase<M>(pb, ph, io, m, b, tid, nthr);
 }
 
+// relative local discretisation error of every mesh interval (ecuda_ode_error)
+template <int M>
+__global__ void __launch_bounds__(kThreads) k_ode_error(const __grid_constant__ ProbDev pb,
+                                                        const __grid_constant__ EvalIO io,
+                                                        const __grid_constant__ MeshDev mesh) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    stage_vars(pb, ph, io, m, b, tid, nthr, false);
+    __syncthreads();
+    ode_error_dots<M>(pb, ph, m, tid, nthr);
+    __syncthreads();
+    ode_error_weights<M>(pb, ph, m, tid);
+    __syncthreads();
+    ode_error_intervals<M>(pb, ph, p, mesh, m, b, tid, nthr);
+}
+
 }  // namespace ecuda
 #endif

@@ -845,5 +845,72 @@ ECUDA_HD void gradient_phase(const ProbDev& pb, const PhaseDev& ph, const EvalIO
     }
 }
 
+// ---- discretisation error per mesh interval (ecuda_ode_error; the estimate is stated in ecuda_mesh.cpp) ----
+// step 1, all threads: (D X)[k][i] into m.dotv. Barrier. step 2, threads i < ns: the scale weights
+// w_i = max_k max(|x_ik|, |(D X)_ki / h|) into m.hf[i]. Barrier. step 3, thread k < N-1: Gauss-Legendre
+// quadrature of |dx~/dtau - h f(x~, u~)| over interval k, states and controls interpolated with the
+// Lagrange basis rows E / dE (serial ascending fma chains).
+template <int M>
+ECUDA_HD void ode_error_dots(const ProbDev& pb, const PhaseDev& ph, CtaMem& m, int tid, int nthr) {
+    const int ns = pb.ns;
+    for (int it = tid; it < ph.N * ns; it += nthr) {
+        const int k = it / ns, j = it - k * ns;
+        m.dotv[k * ns + j] = dot_row(pb, ph, m, k, j, m.P + tid, nthr);
+    }
+}
+template <int M>
+ECUDA_HD void ode_error_weights(const ProbDev& pb, const PhaseDev& ph, CtaMem& m, int tid) {
+    const int ns = pb.ns, N = ph.N;
+    if (tid >= ns) return;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    double w = 0.0;
+    for (int k = 0; k < N; ++k) {
+        w = fmax(w, fabs(m.z[pb.nc * N + k * ns + tid]));
+        w = fmax(w, fabs(m.dotv[k * ns + tid] / pt.h));
+    }
+    m.hf[tid] = w;
+}
+template <int M>
+ECUDA_HD void ode_error_intervals(const ProbDev& pb, const PhaseDev& ph, int p, const MeshDev& mesh, const CtaMem& m,
+                                  int b, int tid, int nthr) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    const int N = ph.N, nc = pb.nc;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    for (int k = tid; k < N - 1; k += nthr) {
+        double eta[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) eta[i] = 0.0;
+        for (int q = 0; q < ECUDA_MESH_Q; ++q) {
+            const size_t r = static_cast<size_t>(k) * ECUDA_MESH_Q + q;
+            const double* E = mesh.E[p] + r * N;
+            const double* dE = mesh.dE[p] + r * N;
+            double xq[NS], dxq[NS], uq[NCU], f[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) xq[i] = dxq[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NCU; ++j) uq[j] = 0.0;
+            for (int l = 0; l < N; ++l) {
+                const double e = ECUDA_LDG(E + l), de = ECUDA_LDG(dE + l);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    const double xv = m.z[nc * N + l * NS + i];
+                    xq[i] = fma(e, xv, xq[i]);
+                    dxq[i] = fma(de, xv, dxq[i]);
+                }
+#pragma unroll
+                for (int j = 0; j < NCU; ++j) uq[j] = fma(e, m.z[l * nc + j], uq[j]);
+            }
+            Model<M>::f(xq, uq, pt.h * ECUDA_LDG(mesh.tq[p] + r) + pt.m, f);
+            const double w = ECUDA_LDG(mesh.wq[p] + r);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) eta[i] = fma(w, fabs(dxq[i] - pt.h * f[i]), eta[i]);
+        }
+        double err = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) err = fmax(err, eta[i] / (m.hf[i] + 1.0));
+        mesh.out[static_cast<size_t>(b) * mesh.nint + mesh.eoff[p] + k] = err;
+    }
+}
+
 }  // namespace ecuda
 #endif

@@ -305,7 +305,27 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
     if (um->ncontrols < 1 || um->ncontrols > ECUDA_MAX_CONTROLS) return bad("ncontrols must be 1..8");
     if (um->static_kind != ECUDA_STATIC_CYLINDER && um->static_kind != ECUDA_STATIC_EDGE) return bad("bad static_kind");
     if (um->nnodes < 1 || um->nnodes > (1 << 16)) return bad("tape length must be 1..65536");
+    {  // the same model registered again (e.g. a plugin re-transcribing on a refined mesh): the same id
+        std::lock_guard<std::mutex> lock(g_mu);
+        for (const auto& e : g_models) {
+            if (e->ns != um->nstates || e->nc != um->ncontrols || e->static_kind != um->static_kind ||
+                e->nregistered != um->nnodes || e->cost_out != um->cost_out)
+                continue;
+            bool same = true;
+            for (int i = 0; i < um->nstates && same; ++i) same = e->f_out[i] == um->f_out[i];
+            for (int k = 0; k < um->nnodes && same; ++k) {
+                const ecuda_tape_node &a = e->nodes[k], &b = um->nodes[k];
+                same = a.op == b.op && a.imm == b.imm &&
+                       (a.op == ECUDA_OP_CONST || (a.a == b.a && (a.b == b.b || a.b < 0)));
+            }
+            if (same) {
+                *model_id = e->id;
+                return ECUDA_OK;
+            }
+        }
+    }
     std::unique_ptr<UserModel> m(new UserModel);
+    m->nregistered = um->nnodes;
     m->ns = um->nstates;
     m->nc = um->ncontrols;
     m->static_kind = um->static_kind;
@@ -506,6 +526,7 @@ bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, s
     std::vector<std::string> exprs(UserImage::NKERNELS);
     exprs[UserImage::GENERIC] = "ecuda::k_eval<" + M + ", " + NB + ">";
     exprs[UserImage::GRAD] = "ecuda::k_grad<" + M + ">";
+    exprs[UserImage::ODE_ERROR] = "ecuda::k_ode_error<" + M + ">";
     if (rows) {
         exprs[UserImage::ROWS_FD] = "ecuda::k_eval_rows<" + M + ", " + NB + ", true>";
         exprs[UserImage::ROWS_EXACT] = "ecuda::k_eval_rows<" + M + ", " + NB + ", false>";

@@ -85,6 +85,9 @@ class eCUDA : public TrajectoryOptimizer {
     std::vector<double>& instanceData(size_t b);
     void uploadInstances();  // push edited instance data to the device
 
+    // next node count of the automatic mesh refinement, from the (nodes, error) history of the solves so far
+    static int nextMeshSize(const std::vector<std::pair<int, double>>& history, const ecuda_alg_t& alg);
+
     // ---- evaluation (the hot path), host buffers --------------------------------------------------
     // z: [B][nvars] unscaled decision vectors; outputs may be null. Values are returned in the
     // solver's (scaled) space exactly as IPOPT would see them.
@@ -101,6 +104,8 @@ class eCUDA : public TrajectoryOptimizer {
     void buildInstanceFor(std::vector<double>* out, int model, bool obstacles, bool tracks, const ecuda_problem_desc& d,
                           int inst_stride) const;
     void extractTrajectories(const std::vector<double>& z);
+    int solveOnce();     // one NLP solve on the current mesh; fills _solution, returns its error flag
+    void deviceSetup();  // (re)creates the device evaluator for the current transcription
     void fail(const std::string& what);
 
     ecuda_alg_t _algorithm;
@@ -111,6 +116,7 @@ class eCUDA : public TrajectoryOptimizer {
     bool _model_set, _obstacles_on, _tracks_on, _is_setup;
     bool _user_edges;  // user model: static path rows are edge ellipses (no explicit cylinders registered)
     size_t _batch;
+    int _nodes;  // collocation nodes of the current mesh (0: nsteps + 1, the first mesh)
     std::vector<std::array<double, 3>> _cylinders;
     std::vector<std::vector<double>> _inst;  // per-instance data blocks
     std::vector<double> _zscaled;            // scratch: z * sz

@@ -14,6 +14,8 @@
 
 #include <ecuda.h>
 
+#include <utility>
+
 namespace ETOL {
 
 // algorithm options; defaults mirror ePSOPT::setup() (src/ePSOPT/ePSOPT.cpp:62-72)
@@ -24,6 +26,14 @@ struct ecuda_alg_t {
     std::string collocation_method = "Legendre";  // or "Chebyshev"
     int nlp_iter_max = 200;
     double nlp_tolerance = 1.e-6;
+    // mesh refinement between NLP solves, as ePSOPT configures PSOPT (ePSOPT.cpp:69-71): "automatic" re-solves
+    // on more nodes until the relative local discretisation error (ecuda_ode_error) is below ode_tolerance;
+    // "manual" solves once on nsteps+1 nodes
+    std::string mesh_refinement = "automatic";
+    int mr_max_iterations = 10;
+    double ode_tolerance = 1.e-4;
+    int mr_initial_increment = 10;          // nodes added by the first refinement
+    double mr_max_increment_factor = 0.4;   // later refinements add at most this fraction of the node count
     int print_level = 0;
     int device = 0;                            // CUDA device ordinal
 };
@@ -51,6 +61,8 @@ struct ecuda_sol_t {
     int nlp_iterations = 0;
     double max_violation = 0.0;
     std::vector<double> z;  // final decision vector (unscaled)
+    // one entry per NLP solve: node count and the largest relative local error of its solution
+    std::vector<std::pair<int, double>> mesh_history;
 };
 
 }  // namespace ETOL

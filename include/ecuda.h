@@ -228,6 +228,16 @@ int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, in
                            int32_t* iRow, int32_t* jCol, double* values);
 int ecuda_set_ipopt_jac_mode(ecuda_handle h, int jac_mode);
 
+/* ---- mesh refinement support (what PSOPT does between NLP solves, ePSOPT.cpp:69-71) ---------------- */
+/* Relative local discretisation error of the collocation solution x on every mesh interval (Betts'
+ * estimate, see etol_b200/csrc/ecuda_mesh.cpp): err[B][sum_p (nnodes[p] - 1)], phases back to back. */
+int ecuda_ode_error(ecuda_handle h, const double* x, double* err, int memkind, void* stream);
+/* The decision vectors x (this problem's layout and scaling) interpolated onto meshes with
+ * nnodes_new[p] nodes per phase: x_new[B][sum_p ((ns+nc)*nnodes_new[p] + 2)], multiplied by sz_new
+ * (same memory kind as x; NULL = unscaled). The warm start of the next solve. */
+int ecuda_resample(ecuda_handle h, const double* x, const int32_t* nnodes_new, const double* sz_new, double* x_new,
+                   int memkind, void* stream);
+
 /* ---- host-side helpers (no GPU needed) ------------------------------------------------------- */
 /* polygon (ncorners x,y pairs, closed implicitly) -> ncorners edge records of 6 doubles each */
 int ecuda_si2d_edge_records(const double* corners_xy, int ncorners, double* rec6);
@@ -236,6 +246,11 @@ int ecuda_host_dims(const ecuda_problem_desc* desc, ecuda_dims* out);
 int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t* jCol,
                          int32_t* group_of_col);
 int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double* D);
+/* interpolation data of ecuda_ode_error: quadrature points tq / weights wq [(N-1)*4] inside the mesh
+ * intervals, Lagrange basis E and its derivative dE there [(N-1)*4][N]; matrix R [N_to][N_from] of
+ * ecuda_resample. Any output may be NULL. */
+int ecuda_host_error_mesh(int kind, int nnodes, double* tq, double* wq, double* E, double* dE);
+int ecuda_host_resample_matrix(int kind, int nnodes_from, int nnodes_to, double* R);
 /* the device models evaluated on the host at one point: state derivatives f_out[nstates] and running
  * cost. Used by the eCUDA plugin to verify that user callbacks and device model agree (eCUDA.hpp); not
  * an evaluation path. u holds the model's controls (2 for si2d, 3 for pm3d / fw6). */

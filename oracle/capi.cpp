@@ -220,6 +220,37 @@ double oracle_eval_batch(void* hv, int first, int count, const double* x, double
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// mesh refinement support: err[count][sum_p (N_p - 1)]; x_new[count][nvars_new]
+int oracle_ode_error(void* hv, int first, int count, const double* x, double* err) {
+    Handle* h = static_cast<Handle*>(hv);
+    const Problem& P = *h->P;
+    size_t nint = 0;
+    for (int n : P.L.N) nint += n - 1;
+    try {
+        for (int b = 0; b < count; ++b) P.ode_error(h->inst[first + b], x + b * P.L.nvars, err + b * nint);
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+int oracle_resample(void* hv, int count, const double* x, const int32_t* nnew, const double* sz_new, double* x_new) {
+    Handle* h = static_cast<Handle*>(hv);
+    const Problem& P = *h->P;
+    try {
+        std::vector<int> nn(nnew, nnew + P.L.nphases);
+        std::vector<double> out;
+        for (int b = 0; b < count; ++b) {
+            P.resample(x + static_cast<size_t>(b) * P.L.nvars, nn, sz_new, &out);
+            std::memcpy(x_new + b * out.size(), out.data(), sizeof(double) * out.size());
+        }
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
 int oracle_max_threads() { return omp_get_max_threads(); }
 
 // host build of the shared deterministic sincos, for tests/test_detmath.py

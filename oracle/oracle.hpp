@@ -140,6 +140,10 @@ class Problem {
     void eval_g_tight(const Instance& I, const double* zs, double* g) const;
     void eval_f_tight(const Instance& I, const double* zs, double* f) const;
     void eval_jac_fd_tight(const Instance& I, const double* zs, double* vals) const;
+    // mesh refinement support (tight.cpp): relative local error per mesh interval [sum_p (N_p - 1)];
+    // decision vector interpolated onto meshes of nnew[p] nodes (scaled by sz_new when given)
+    void ode_error(const Instance& I, const double* zs, double* err) const;
+    void resample(const double* zs, const std::vector<int>& nnew, const double* sz_new, std::vector<double>* out) const;
 };
 
 // static geometry of one polygon edge, etol_psopt_example1.cpp:164-172,178-179

@@ -210,6 +210,140 @@ void g_tight(const Problem& P, const std::vector<PhasePre>& pre, const Instance&
 
 }  // namespace
 
+// ---- mesh refinement support: relative local discretisation error per mesh interval and interpolation
+// onto another mesh. PSOPT's own code is not in the reference tree (ePSOPT only sets mesh_refinement =
+// "automatic", ode_tolerance, mr_max_iterations: src/ePSOPT/ePSOPT.cpp:69-71); restated is the estimate it
+// documents (Betts): eta_ik = int_{t_k}^{t_k+1} |x~_i' - f_i(x~, u~)| dt by 4-point Gauss-Legendre, states
+// and controls interpolated by the Lagrange polynomial through the nodes; eps_k = max_i eta_ik / (w_i + 1),
+// w_i = max_k max(|x_ik|, |x'_ik|).
+namespace {
+const double kGX[4] = {-0.8611363115940526, -0.3399810435848563, 0.3399810435848563, 0.8611363115940526};
+const double kGW[4] = {0.3478548451374538, 0.6521451548625461, 0.6521451548625461, 0.3478548451374538};
+
+std::vector<double> barycentric(const std::vector<double>& tau) {
+    std::vector<double> w(tau.size());
+    for (size_t l = 0; l < tau.size(); ++l) {
+        double p = 1.0;
+        for (size_t m = 0; m < tau.size(); ++m)
+            if (m != l) p = p * (tau[l] - tau[m]);
+        w[l] = 1.0 / p;
+    }
+    return w;
+}
+// values (and tau-derivatives) of the Lagrange basis at t
+void basis_at(const std::vector<double>& tau, const std::vector<double>& bw, double t, std::vector<double>& L,
+              std::vector<double>* dL) {
+    const size_t N = tau.size();
+    L.assign(N, 0.0);
+    if (dL) dL->assign(N, 0.0);
+    for (size_t hit = 0; hit < N; ++hit) {
+        if (t != tau[hit]) continue;
+        L[hit] = 1.0;
+        if (dL) {
+            double s = 0.0;
+            for (size_t l = 0; l < N; ++l)
+                if (l != hit) {
+                    (*dL)[l] = (bw[l] / bw[hit]) / (tau[hit] - tau[l]);
+                    s = s + (*dL)[l];
+                }
+            (*dL)[hit] = -s;
+        }
+        return;
+    }
+    double s = 0.0, s2 = 0.0;
+    for (size_t l = 0; l < N; ++l) {
+        double r = bw[l] / (t - tau[l]);
+        s = s + r;
+        s2 = s2 + r / (t - tau[l]);
+    }
+    for (size_t l = 0; l < N; ++l) {
+        L[l] = (bw[l] / (t - tau[l])) / s;
+        if (dL) (*dL)[l] = L[l] * (s2 / s - 1.0 / (t - tau[l]));
+    }
+}
+}  // namespace
+
+void Problem::ode_error(const Instance& I, const double* zs, double* err) const {
+    (void)I;
+    std::vector<double> z(L.nvars);
+    for (int c = 0; c < L.nvars; ++c) z[c] = zs[c] * sc.isz[c];
+    const int ns = L.ns, nc = L.nc;
+    int eoff = 0;
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p];
+        const Collocation& C = col[p];
+        const double t0 = z[L.it0(p)], tf = z[L.itf(p)], h = 0.5 * (tf - t0);
+        const double* X = &z[L.ix(p, 0, 0)];
+        const double* U = &z[L.iu(p, 0, 0)];
+        std::vector<double> w(ns, 0.0);
+        for (int i = 0; i < ns; ++i)
+            for (int k = 0; k < N; ++k) {
+                const double* Dr = &C.D[static_cast<size_t>(k) * N];
+                double total = 0.0;
+                for (int b0 = 0; b0 < N; b0 += DOT_BLOCK) {
+                    int b1 = b0 + DOT_BLOCK < N ? b0 + DOT_BLOCK : N;
+                    double s = 0.0;
+                    for (int l = b0; l < b1; ++l) s = std::fma(Dr[l], X[static_cast<size_t>(l) * ns + i], s);
+                    total = (b0 == 0) ? s : total + s;
+                }
+                w[i] = std::fmax(w[i], std::fabs(X[static_cast<size_t>(k) * ns + i]));
+                w[i] = std::fmax(w[i], std::fabs(total / h));
+            }
+        std::vector<double> bw = barycentric(C.tau), E, dE;
+        for (int k = 0; k + 1 < N; ++k) {
+            const double half = 0.5 * (C.tau[k + 1] - C.tau[k]), mid = 0.5 * (C.tau[k + 1] + C.tau[k]);
+            std::vector<double> eta(ns, 0.0);
+            for (int q = 0; q < 4; ++q) {
+                basis_at(C.tau, bw, mid + half * kGX[q], E, &dE);
+                double xq[8] = {0}, dxq[8] = {0}, uq[8] = {0}, f[8];
+                for (int l = 0; l < N; ++l) {
+                    for (int i = 0; i < ns; ++i) {
+                        xq[i] = std::fma(E[l], X[static_cast<size_t>(l) * ns + i], xq[i]);
+                        dxq[i] = std::fma(dE[l], X[static_cast<size_t>(l) * ns + i], dxq[i]);
+                    }
+                    for (int j = 0; j < nc; ++j) uq[j] = std::fma(E[l], U[static_cast<size_t>(l) * nc + j], uq[j]);
+                }
+                dynamics(spec, xq, uq, f);
+                for (int i = 0; i < ns; ++i) eta[i] = std::fma(half * kGW[q], std::fabs(dxq[i] - h * f[i]), eta[i]);
+            }
+            double e = 0.0;
+            for (int i = 0; i < ns; ++i) e = std::fmax(e, eta[i] / (w[i] + 1.0));
+            err[eoff + k] = e;
+        }
+        eoff += N - 1;
+    }
+}
+
+void Problem::resample(const double* zs, const std::vector<int>& nnew, const double* sz_new, std::vector<double>* out) const {
+    const int ns = L.ns, nc = L.nc;
+    out->clear();
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p], Nn = nnew[p];
+        Collocation to = make_collocation(spec.collocation, Nn);
+        std::vector<double> bw = barycentric(col[p].tau), R;
+        const size_t o = out->size();
+        out->resize(o + static_cast<size_t>(ns + nc) * Nn + 2);
+        double* zn = out->data() + o;
+        for (int k = 0; k < Nn; ++k) {
+            basis_at(col[p].tau, bw, to.tau[k], R, nullptr);
+            for (int j = 0; j < nc; ++j) {
+                double a = 0.0;
+                for (int l = 0; l < N; ++l) a = std::fma(R[l], zs[L.iu(p, l, j)] * sc.isz[L.iu(p, l, j)], a);
+                zn[k * nc + j] = a;
+            }
+            for (int i = 0; i < ns; ++i) {
+                double a = 0.0;
+                for (int l = 0; l < N; ++l) a = std::fma(R[l], zs[L.ix(p, l, i)] * sc.isz[L.ix(p, l, i)], a);
+                zn[nc * Nn + k * ns + i] = a;
+            }
+        }
+        zn[(ns + nc) * Nn] = zs[L.it0(p)] * sc.isz[L.it0(p)];
+        zn[(ns + nc) * Nn + 1] = zs[L.itf(p)] * sc.isz[L.itf(p)];
+    }
+    if (sz_new)
+        for (size_t c = 0; c < out->size(); ++c) (*out)[c] = (*out)[c] * sz_new[c];
+}
+
 void Problem::eval_g_tight(const Instance& I, const double* zs, double* g) const {
     auto pre = precompute(*this, I);
     std::vector<double> z(L.nvars), F;

@@ -27,10 +27,15 @@ int main(int argc, char** argv) {
     ETOL::f_t zones = vgp_si2d::exclusionZones(t), movers = vgp_si2d::movingZones(t);
     t->setConstraints({&zones, &movers});
 
+    solver.getAlgorithm()->ode_tolerance = 1.e-6;  // tighter than ePSOPT's 1e-4 so that the refinement shows
     t->setup();
     printf("device model: %s\n", solver.isUserModel() ? "user model compiled from the callbacks" : "built-in");
     t->solve();
 
+    // the dynamics are nonlinear, so the collocation solution has a discretisation error between the nodes:
+    // eCUDA estimates it on the device and refines the mesh like PSOPT does for ePSOPT (ePSOPT.cpp:69-71)
+    for (const auto& m : solver.getSolution()->mesh_history)
+        printf("mesh: %d nodes, max relative local error %.3e\n", m.first, m.second);
     printf("\nMinimization Score:\t%f\n", t->getScore());
     printf("State variables saved in %s\n", ETOL::TrajectoryOptimizer::save(t->getXtraj(), "state_ecuda3.csv").c_str());
     printf("Control variables saved in %s\n",

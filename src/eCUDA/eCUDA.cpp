@@ -29,7 +29,7 @@ std::string paramName(const std::string& name, size_t i, size_t j, size_t k) {
 
 eCUDA::eCUDA()
     : TrajectoryOptimizer(), _handle(nullptr), _model(ECUDA_MODEL_SI2D), _model_set(false), _obstacles_on(false),
-      _tracks_on(false), _is_setup(false), _user_edges(true), _batch(1) {}
+      _tracks_on(false), _is_setup(false), _user_edges(true), _batch(1), _nodes(0) {}
 
 eCUDA::~eCUDA() { close(); }
 
@@ -99,7 +99,7 @@ void eCUDA::fillDesc(ecuda_problem_desc* out, int model, bool obstacles, bool tr
     d = ecuda_problem_desc{};
     d.model = model;
     d.nphases = 1;  // ePSOPT.cpp:27-28: one phase, no linkages
-    d.nnodes[0] = static_cast<int32_t>(getNSteps() + 1);
+    d.nnodes[0] = static_cast<int32_t>(_nodes > 0 ? _nodes : getNSteps() + 1);
     size_t nstatic = 0;
     if (obstacles) {
         if (usesEdges(model))
@@ -292,8 +292,12 @@ bool eCUDA::matchCallbacks(std::string* why) {
 
 // ---- setup ------------------------------------------------------------------------------------------------
 void eCUDA::setup() {
+    _nodes = 0;  // the first mesh: nsteps + 1 nodes (ePSOPT.cpp:44)
     transcribe();
-    // device side
+    deviceSetup();
+}
+
+void eCUDA::deviceSetup() {
     if (_handle) {
         ecuda_destroy(_handle);
         _handle = nullptr;
@@ -549,9 +553,80 @@ int eCUDA::evaluateGradient(const double* z, double* grad) {
 }
 
 // ---- solve ----------------------------------------------------------------------------------------------------
+// Automatic mesh refinement: what PSOPT does around its NLP solves when ePSOPT sets mesh_refinement =
+// "automatic" (ePSOPT.cpp:69-71). PSOPT's own rule is not in the reference tree; this one is eCUDA's: the
+// first refinement adds mr_initial_increment nodes; later ones extrapolate the straight line through
+// (nodes, log10 error) of the last two solves to the tolerance, and add at least 2 nodes and at most
+// mr_max_increment_factor * nodes.
+int eCUDA::nextMeshSize(const std::vector<std::pair<int, double>>& hist, const ecuda_alg_t& alg) {
+    const int N = hist.back().first;
+    if (hist.size() < 2) return N + std::max(2, alg.mr_initial_increment);
+    const int N0 = hist[hist.size() - 2].first;
+    const double e0 = hist[hist.size() - 2].second, e1 = hist.back().second;
+    const int cap = N + std::max(2, static_cast<int>(std::ceil(alg.mr_max_increment_factor * N)));
+    if (!(e0 > 0.0) || !(e1 > 0.0) || e1 >= e0 || N == N0) return cap;  // no measurable decay: the full step
+    const double slope = (std::log10(e1) - std::log10(e0)) / (N - N0);   // decades per node, negative
+    const double need = N + (std::log10(alg.ode_tolerance) - std::log10(e1)) / slope;
+    const int want = static_cast<int>(std::ceil(need));
+    return std::min(cap, std::max(N + 2, want));
+}
+
 void eCUDA::solve() {
     if (!_is_setup) fail("solve() before setup()");
     if (_batch != 1) fail("solve() drives one instance; batches are evaluated with evaluate()");
+    _solution.mesh_history.clear();
+    ecuda_sol_t best;
+    bool have_best = false;
+    for (int it = 0;; ++it) {
+        const int rc = solveOnce();
+        if (rc != 0) {
+            if (!have_best) return;  // first mesh failed: as ePSOPT::solve (:85-87)
+            std::cout << "eCUDA: the solve on " << _problem.desc.nnodes[0]
+                      << " nodes failed; keeping the solution of the previous mesh" << std::endl;
+            const std::vector<std::pair<int, double>> hist = _solution.mesh_history;
+            _solution = best;
+            _solution.mesh_history = hist;
+            _nodes = hist.back().first;  // back to the mesh that solution lives on
+            transcribe();
+            deviceSetup();
+            break;
+        }
+        // relative local discretisation error of this solution, per mesh interval (device)
+        const int N = _problem.desc.nnodes[0], nv = _problem.dims.nvars;
+        std::vector<double> zs(nv), err(N - 1, 0.0);
+        for (int c = 0; c < nv; ++c) zs[c] = _solution.z[c] * _problem.sz[c];
+        if (ecuda_ode_error(_handle, zs.data(), err.data(), ECUDA_MEM_HOST, nullptr) != ECUDA_OK) fail("ecuda_ode_error");
+        double emax = 0.0;
+        for (double e : err) emax = std::max(emax, e);
+        _solution.mesh_history.push_back({N, emax});
+        if (_algorithm.print_level > 0)
+            std::cout << "mesh " << it << ": " << N << " nodes, max relative local error " << emax << std::endl;
+        if (_algorithm.mesh_refinement != "automatic" || emax <= _algorithm.ode_tolerance ||
+            it >= _algorithm.mr_max_iterations)
+            break;
+        // next mesh: interpolate the solution onto it as the starting point, re-transcribe, re-create the evaluator
+        best = _solution;
+        have_best = true;
+        const int32_t Nn = nextMeshSize(_solution.mesh_history, _algorithm);
+        std::vector<double> znew((getNStates() + getNControls()) * static_cast<size_t>(Nn) + 2);
+        if (ecuda_resample(_handle, zs.data(), &Nn, nullptr, znew.data(), ECUDA_MEM_HOST, nullptr) != ECUDA_OK)
+            fail("ecuda_resample");
+        _nodes = Nn;
+        const std::vector<std::pair<int, double>> hist = _solution.mesh_history;
+        transcribe();
+        deviceSetup();
+        _problem.guess = znew;
+        for (int c = 0; c < _problem.dims.nvars; ++c)
+            _problem.guess[c] = std::min(std::max(_problem.guess[c], _problem.zl[c]), _problem.zu[c]);
+        _solution.mesh_history = hist;
+    }
+    if (_solution.error_flag == 0) {
+        setScore(isMaximized() ? -_solution.cost : _solution.cost);
+        extractTrajectories(_solution.z);
+    }
+}
+
+int eCUDA::solveOnce() {
     const int nv = _problem.dims.nvars, ng = _problem.dims.ncons, nnz = _problem.dims.nnz;
     const int mode = _algorithm.derivatives == "numerical" ? ECUDA_JAC_FD_INDEXSET : ECUDA_JAC_EXACT;
 
@@ -600,13 +675,12 @@ void eCUDA::solve() {
     _solution.max_violation = R.max_violation;
     if (rc != 0) {  // as ePSOPT::solve (:85-87): report, leave score and trajectories untouched
         std::cout << "!!!!!Problem failed!!!!!" << std::endl << _solution.error_msg << std::endl;
-        return;
+        return rc;
     }
     _solution.z.resize(nv);
     for (int c = 0; c < nv; ++c) _solution.z[c] = z[c] / _problem.sz[c];
     _solution.cost = R.objective / _problem.sf;
-    setScore(isMaximized() ? -_solution.cost : _solution.cost);
-    extractTrajectories(_solution.z);
+    return 0;
 }
 
 void eCUDA::extractTrajectories(const std::vector<double>& z) {

@@ -52,6 +52,8 @@ def lib():
         L.oracle_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                         C.c_int, C.c_int]
         L.oracle_stage_user_tape.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, C.c_int]
+        L.oracle_ode_error.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.oracle_resample.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _dp, _dp]
         L.oracle_max_threads.restype = C.c_int
         L.oracle_sincos.argtypes = [_dp, C.c_int, _dp, _dp]
         _lib = L
@@ -165,6 +167,26 @@ class Oracle:
             raise RuntimeError(lib().oracle_last_error().decode())
         out.update(f=f, g=g, jac=jac, grad=grad, seconds=secs)
         return out
+
+
+def ode_error(o, wl, x):
+    """relative local discretisation error per mesh interval, [B][sum_p (N_p - 1)]"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros((x.shape[0], sum(n - 1 for n in wl.nnodes)))
+    if lib().oracle_ode_error(o.h, 0, x.shape[0], _p(x), _p(out)) != 0:
+        raise RuntimeError(lib().oracle_last_error().decode())
+    return out
+
+
+def resample(o, wl, x, nnodes_new, sz_new=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nn = np.asarray(nnodes_new, dtype=np.int32)
+    nv = sum((wl.ns + wl.nc) * int(n) + 2 for n in nn)
+    out = np.zeros((x.shape[0], nv))
+    sz = None if sz_new is None else np.ascontiguousarray(sz_new, dtype=np.float64)
+    if lib().oracle_resample(o.h, x.shape[0], _p(x), nn.ctypes.data_as(_ip), _p(sz), _p(out)) != 0:
+        raise RuntimeError(lib().oracle_last_error().decode())
+    return out
 
 
 def max_threads():

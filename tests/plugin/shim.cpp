@@ -162,6 +162,30 @@ int shim_solve(void* h, int max_iter, int print_level, double* score, int* iters
     *viol = t->getSolution()->max_violation;
     return t->getSolution()->error_flag;
 }
+// mesh refinement controls / report (mode "automatic" | "manual")
+void shim_set_mesh(void* h, const char* mode, double ode_tolerance, int max_iterations) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    t->getAlgorithm()->mesh_refinement = mode;
+    t->getAlgorithm()->ode_tolerance = ode_tolerance;
+    t->getAlgorithm()->mr_max_iterations = max_iterations;
+}
+int shim_mesh_history(void* h, int cap, int* nodes, double* err) {
+    const auto& hist = static_cast<eCUDA*>(h)->getSolution()->mesh_history;
+    for (size_t i = 0; i < hist.size() && static_cast<int>(i) < cap; ++i) {
+        nodes[i] = hist[i].first;
+        err[i] = hist[i].second;
+    }
+    return static_cast<int>(hist.size());
+}
+int shim_next_mesh_size(int n, const int* nodes, const double* err, double tol, int initial_increment, double factor) {
+    std::vector<std::pair<int, double>> hist;
+    for (int i = 0; i < n; ++i) hist.push_back({nodes[i], err[i]});
+    ETOL::ecuda_alg_t alg;
+    alg.ode_tolerance = tol;
+    alg.mr_initial_increment = initial_increment;
+    alg.mr_max_increment_factor = factor;
+    return eCUDA::nextMeshSize(hist, alg);
+}
 int shim_traj(void* h, int which, double* out /* [N][1+width] */) {
     eCUDA* t = static_cast<eCUDA*>(h);
     ETOL::traj_t* tr = which == 0 ? t->getXtraj() : t->getUtraj();

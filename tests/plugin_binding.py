@@ -41,6 +41,9 @@ def lib():
         L.shim_evaluate.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
         L.shim_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp]
         L.shim_traj.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.shim_set_mesh.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
+        L.shim_mesh_history.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), _dp]
+        L.shim_next_mesh_size.argtypes = [C.c_int, C.POINTER(C.c_int), _dp, C.c_double, C.c_int, C.c_double]
         L.shim_close.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -146,6 +149,14 @@ class Plugin:
         rc = self.L.shim_solve(self.h, max_iter, print_level, C.byref(score), C.byref(iters), C.byref(viol))
         return rc, score.value, iters.value, viol.value
 
+    def set_mesh(self, mode="automatic", ode_tolerance=1e-4, max_iterations=10):
+        self.L.shim_set_mesh(self.h, mode.encode(), ode_tolerance, max_iterations)
+
+    def mesh_history(self):
+        nodes, err = (C.c_int * 32)(), np.zeros(32)
+        n = self.L.shim_mesh_history(self.h, 32, nodes, err.ctypes.data_as(_dp))
+        return [(nodes[i], float(err[i])) for i in range(n)]
+
     def traj(self, which, width, n):
         out = np.zeros((n, 1 + width))
         got = self.L.shim_traj(self.h, which, out.ctypes.data_as(_dp))
@@ -157,6 +168,12 @@ class Plugin:
             self.L.shim_close(self.h)
             self.L.shim_destroy(self.h)
             self.h = None
+
+
+def next_mesh_size(history, tol=1e-4, initial_increment=10, factor=0.4):
+    nodes = (C.c_int * len(history))(*[h[0] for h in history])
+    err = np.array([h[1] for h in history], dtype=np.float64)
+    return lib().shim_next_mesh_size(len(history), nodes, err.ctypes.data_as(_dp), tol, initial_increment, factor)
 
 
 def save_csv(path, n, width):

@@ -87,6 +87,52 @@ def test_values_match_oracle(evaluators, name, mode):
         assert np.array_equal(got["jac"], ref["jac"]), "FD Jacobian is not bit-identical to the oracle"
 
 
+MESH_CASES = ["C0-ocp", "C0-ocp-cheb-max", "C2-pm3d-scaled-deps", "C3-fw6", "C3-fw6-small-scaled", "C4-multiphase",
+              "C4-multiphase-ragged", "pm3d-N2", "pm3d-N65", "user-unicycle-tracks", "user-dragmass",
+              "user-dragmass-N70-generic"]
+
+
+@pytest.mark.parametrize("name", MESH_CASES)
+def test_ode_error_matches_oracle(evaluators, name):
+    """relative local discretisation error per mesh interval (mesh-refinement input)"""
+    ev, orc, wl = _get(evaluators, name)
+    ref = ob.ode_error(orc, wl, wl.x)
+    got = ev.ode_error_host(wl.x)
+    assert got.shape == ref.shape and np.isfinite(got).all() and (got >= 0).all()
+    assert rel_err(got, ref) <= TOL_VALUE
+
+
+@pytest.mark.parametrize("name", MESH_CASES)
+def test_resample_matches_oracle(evaluators, name):
+    """decision vectors interpolated onto a finer and a coarser mesh, unscaled and re-scaled"""
+    ev, orc, wl = _get(evaluators, name)
+    for nn in ([n + 7 for n in wl.nnodes], [max(2, n // 2) for n in wl.nnodes]):
+        nv = sum((wl.ns + wl.nc) * n + 2 for n in nn)
+        sz = np.linspace(0.5, 2.0, nv)
+        for s in (None, sz):
+            ref = ob.resample(orc, wl, wl.x, nn, sz_new=s)
+            got = ev.resample_host(wl.x, nn, sz_new=s)
+            assert got.shape == ref.shape
+            assert rel_err(got, ref) <= TOL_VALUE
+
+
+def test_resample_round_trip_on_device(evaluators):
+    """up-sampling does not change the interpolating polynomial: 40 -> 61 -> 40 nodes returns the decision
+    vectors (a size-independent property of the kernel), and the finer mesh sees an error profile of the
+    same size"""
+    ev, _, wl = _get(evaluators, "C2-pm3d-64")
+    fine = W.pm3d(batch=wl.batch, nnodes=61)
+    ev2 = capi.Evaluator(fine, device=0)
+    up = ev.resample_host(wl.x, [61])
+    back = ev2.resample_host(up, [40])
+    assert np.abs(back - wl.x).max() <= 1e-9 * np.abs(wl.x).max()
+    e1, e2 = ev.ode_error_host(wl.x), ev2.ode_error_host(up)
+    assert e1.shape == (wl.batch, 39) and e2.shape == (wl.batch, 60)
+    ratio = e2.sum(axis=1) / e1.sum(axis=1)   # sum of per-interval maxima: comparable, not identical
+    assert (ratio > 0.8).all() and (ratio < 1.5).all()
+    ev2.close()
+
+
 def test_user_model_equals_builtin_bitwise(evaluators):
     """pm3d written as callbacks and compiled at run time gives the bits of the built-in pm3d kernels"""
     ev_u, _, wl_u = _get(evaluators, "user-pm3d")

@@ -238,11 +238,52 @@ def test_plugin_user_model_evaluates_like_oracle_and_solves(xml):
     ref = o.eval(z * bnd["sz"], want=("f", "g", "jac"), jac_mode=W.JAC_EXACT, style=0)
     assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
     assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    p.set_mesh("manual")
     rc, score, iters, viol = p.solve(max_iter=300)
     assert rc == 0 and viol <= 1e-8
     X = p.traj(0, 2, 33)
     assert np.allclose(X[0, 1:], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1, 1:], [5.0, 4.0], atol=0.0101)
+    hist = p.mesh_history()
+    assert len(hist) == 1 and hist[0][0] == 33 and 0.0 < hist[0][1] < 1.0   # nonlinear dynamics: a defect between nodes
     p.close()
+
+
+@pytest.mark.gpu
+def test_plugin_mesh_refinement(xml):
+    """automatic mesh refinement (what PSOPT does around its NLP solves, ePSOPT.cpp:69-71): solve, estimate the
+    discretisation error on the device, interpolate onto more nodes, re-solve -- until below the tolerance"""
+    p = pb.Plugin()
+    ok, _, _, why = p.load_callbacks(xml, 4)
+    assert ok, why
+    p.setup()
+    p.set_mesh("manual")
+    rc, score0, _, _ = p.solve(max_iter=300)
+    e0 = p.mesh_history()[0][1]
+    assert rc == 0
+    p.set_mesh("automatic", ode_tolerance=e0 / 50.0, max_iterations=3)
+    p.setup()
+    rc, score, _, viol = p.solve(max_iter=400)
+    hist = p.mesh_history()
+    assert rc == 0 and viol <= 1e-8
+    assert len(hist) >= 2 and hist[0][0] == 33 and hist[1][0] == 43       # first refinement: + mr_initial_increment
+    assert all(b[0] > a[0] for a, b in zip(hist, hist[1:]))
+    assert hist[-1][1] < hist[0][1]                                        # the error went down with the mesh
+    # same optimum, better resolved: the exclusion zones are now enforced at more nodes, which costs a few per cent
+    assert score >= score0 - 1e-6 and abs(score - score0) < 0.10 * abs(score0)
+    n = hist[-1][0]
+    X = p.traj(0, 2, n)
+    assert np.allclose(X[0, 1:], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1, 1:], [5.0, 4.0], atol=0.0101)
+    p.close()
+
+
+def test_linear_dynamics_need_no_refinement_rule():
+    """the refinement rule alone (host): first step adds the initial increment, later steps extrapolate the
+    error decay of the last two solves and are capped by the increment factor"""
+    assert pb.next_mesh_size([(33, 1e-2)]) == 43
+    assert pb.next_mesh_size([(33, 1e-2), (43, 1e-3)]) == 53               # one decade per 10 nodes, one to go
+    assert pb.next_mesh_size([(33, 1e-2), (43, 9e-3)]) == 43 + 18          # slow decay: capped at +40 %
+    assert pb.next_mesh_size([(33, 1e-2), (43, 2e-2)]) == 43 + 18          # no decay: the full step
+    assert pb.next_mesh_size([(33, 1e-2), (43, 1.0001e-4)]) == 45          # nearly there: at least two nodes
 
 
 @pytest.mark.gpu
