@@ -55,7 +55,8 @@ ABI_SYMBOLS = [
     "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
-    "ecuda_host_path_eval", "ecuda_ode_error", "ecuda_resample", "ecuda_host_error_mesh", "ecuda_host_resample_matrix",
+    "ecuda_host_path_eval", "ecuda_get_hess_structure", "ecuda_eval_hess", "ecuda_ipopt_eval_h", "ecuda_host_hess_structure",
+    "ecuda_ode_error", "ecuda_resample", "ecuda_host_error_mesh", "ecuda_host_resample_matrix",
     "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
 ]
 
@@ -107,6 +108,10 @@ def lib():
     L.ecuda_host_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip, _ip]
     L.ecuda_host_collocation.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
     L.ecuda_host_model_eval.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, _dp]
+    L.ecuda_get_hess_structure.argtypes = [C.c_void_p, _ip, _ip, _ip]
+    L.ecuda_host_hess_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip, _ip]
+    L.ecuda_eval_hess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ecuda_ipopt_eval_h.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, C.c_int, _dp, C.c_int, C.c_int, _ip, _ip, _dp]
     L.ecuda_ode_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_resample.argtypes = [C.c_void_p, C.c_void_p, _ip, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_host_error_mesh.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
@@ -204,6 +209,16 @@ def host_structure(wl):
     if rc != 0:
         raise EcudaError("ecuda_host_structure failed")
     return irow, jcol, grp
+
+
+def host_hess_structure(wl):
+    """lower triangle of the Lagrangian Hessian: (iRow, jCol), sorted by (column, row)"""
+    d, n = make_desc(wl), C.c_int32(0)
+    if lib().ecuda_host_hess_structure(C.byref(d), C.byref(n), None, None) != 0:
+        raise EcudaError("ecuda_host_hess_structure rejected the problem description")
+    irow, jcol = np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+    lib().ecuda_host_hess_structure(C.byref(d), None, irow.ctypes.data_as(_ip), jcol.ctypes.data_as(_ip))
+    return irow, jcol
 
 
 def host_collocation(kind, N):
@@ -361,6 +376,18 @@ class Evaluator:
     def peer_barrier_ptr(self, flag_ptrs, rank, step, stream=None):
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         self._check(self.L.ecuda_peer_barrier(self.h, arr, len(flag_ptrs), rank, step, stream))
+
+    def hess_host(self, x, sigma, lam):
+        """Hessian of the Lagrangian per instance (host buffers): sigma [B], lam [B][ncons] -> [B][nnz_h]"""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(self.batch)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(self.batch, self.ncons)
+        n = C.c_int32(0)
+        self._check(lib().ecuda_get_hess_structure(self.h, C.byref(n), None, None))
+        out = np.zeros((self.batch, n.value))
+        self._check(lib().ecuda_eval_hess(self.h, x.ctypes.data, sigma.ctypes.data, 0.0, lam.ctypes.data, out.ctypes.data,
+                                          MEM_HOST, None))
+        return out
 
     def ode_error_host(self, x):
         """relative local discretisation error per mesh interval, [B][sum_p (N_p - 1)] (host buffers)"""

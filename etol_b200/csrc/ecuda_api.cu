@@ -201,8 +201,9 @@ struct ecuda_ctx {
     // user model (ecuda_register_user_model): kernels compiled with NVRTC, loaded per handle
     const UserModel* um = nullptr;
     cudaLibrary_t ulib = nullptr;
-    cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0, 0};
+    cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0, 0, 0};
+    DevBuf slam, ssig, shess;  // staging for ecuda_eval_hess with host buffers
     // mesh-refinement support (ecuda_ode_error / ecuda_resample), built on first use
     DevBuf mesh[ECUDA_MAX_PHASES];  // E | dE | wq | tq per phase
     bool have_mesh = false;
@@ -462,14 +463,14 @@ static int load_user_kernels(ecuda_ctx* h) {
 }
 
 static int launch_user(ecuda_ctx* h, int which, dim3 grid, int threads, size_t smem, const EvalIO& io, cudaStream_t st,
-                       const MeshDev* mesh = nullptr) {
+                       const void* mesh = nullptr) {
     cudaKernel_t k = h->ukern[which];
     if (!k) return fail(h, ECUDA_ERR_STATE, "user-model kernel was not compiled");
     if (smem > 48 * 1024 && h->ukern_smem[which] < smem) {
         CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->ukern_smem[which] = smem;
     }
-    void* args[] = {const_cast<ProbDev*>(&h->pd), const_cast<EvalIO*>(&io), const_cast<MeshDev*>(mesh)};
+    void* args[] = {const_cast<ProbDev*>(&h->pd), const_cast<EvalIO*>(&io), const_cast<void*>(mesh)};
     CU(cudaLaunchKernel(reinterpret_cast<const void*>(k), grid, dim3(threads), args, smem, st));
     ++h->launches;
     return ECUDA_OK;
@@ -578,7 +579,7 @@ int ecuda_destroy(ecuda_handle h) {
         release(*b);
     for (auto& b : h->coll) release(b);
     for (auto& b : h->mesh) release(b);
-    for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew}) release(*b);
+    for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew, &h->slam, &h->ssig, &h->shess}) release(*b);
     unload_user_kernels(h);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -854,6 +855,23 @@ static int launch_ode_error_t(ecuda_ctx* h, const EvalIO& io, const MeshDev& mes
     return ECUDA_OK;
 }
 
+template <int M>
+static int launch_hess_t(ecuda_ctx* h, const EvalIO& io, const HessIO& hio, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    if (h->smem_bytes > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < h->smem_bytes) {
+            CU(cudaFuncSetAttribute(k_hess<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            cur = h->smem_bytes;
+        }
+    }
+    k_hess<M><<<io.batch * h->pd.nphases, kThreads, h->smem_bytes, st>>>(h->pd, io, hio);
+    ++h->launches;
+    return ECUDA_OK;
+}
+
 static int ensure_mesh(ecuda_ctx* h) {
     if (h->have_mesh) return ECUDA_OK;
     for (int p = 0; p < h->hp.nphases; ++p) {
@@ -922,6 +940,79 @@ int ecuda_ode_error(ecuda_handle h, const double* x, double* err, int memkind, v
     CU(cudaGetLastError());
     if (memkind == ECUDA_MEM_HOST) {
         CU(cudaMemcpyAsync(err, mesh.out, sizeof(double) * B * nint, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_get_hess_structure(ecuda_handle h, int32_t* nnz_h, int32_t* iRow, int32_t* jCol) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    std::vector<int32_t> ir, jc;
+    build_hess_structure(h->hp, &ir, &jc);
+    if (nnz_h) *nnz_h = static_cast<int32_t>(ir.size());
+    const int base = h->hp.desc.index_base;
+    for (size_t e = 0; e < ir.size(); ++e) {
+        if (iRow) iRow[e] = ir[e] + base;
+        if (jCol) jCol[e] = jc[e] + base;
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_eval_hess(ecuda_handle h, const double* x, const double* sigma, double sigma0, const double* lambda,
+                    double* vals, int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
+    if (!x || !lambda || !vals) return fail(h, ECUDA_ERR_ARG, "x, lambda and vals are required");
+    if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const size_t B = h->hp.desc.batch, nv = h->pd.nvars, ng = h->pd.ncons;
+    HessIO hio{};
+    int nnz_h = 0;
+    for (int p = 0; p < h->hp.nphases; ++p) {
+        hio.hoff[p] = nnz_h;
+        nnz_h += hess_phase_nnz(h->hp.ns, h->hp.nc, h->hp.N[p]);
+    }
+    hio.nnz_h = nnz_h;
+    hio.sigma0 = sigma0;
+    hio.sigma = sigma;
+    hio.lambda = lambda;
+    hio.vals = vals;
+    EvalIO io{};
+    io.inst = static_cast<const double*>(h->inst.p);
+    io.batch = static_cast<int>(B);
+    io.x = x;
+    int rc;
+    if (memkind == ECUDA_MEM_HOST) {
+        if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
+        if ((rc = ensure(h, h->slam, sizeof(double) * B * ng))) return rc;
+        if ((rc = ensure(h, h->shess, sizeof(double) * B * nnz_h))) return rc;
+        CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * nv, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->slam.p, lambda, sizeof(double) * B * ng, cudaMemcpyHostToDevice, st));
+        io.x = static_cast<const double*>(h->sx.p);
+        hio.lambda = static_cast<const double*>(h->slam.p);
+        hio.vals = static_cast<double*>(h->shess.p);
+        if (sigma) {
+            if ((rc = ensure(h, h->ssig, sizeof(double) * B))) return rc;
+            CU(cudaMemcpyAsync(h->ssig.p, sigma, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+            hio.sigma = static_cast<const double*>(h->ssig.p);
+        }
+    }
+    if (h->um) {
+        rc = launch_user(h, UserImage::HESS, dim3(io.batch * h->pd.nphases), kThreads, h->smem_bytes, io, st, &hio);
+    } else {
+        switch (h->pd.model) {
+            case ECUDA_MODEL_SI2D: rc = launch_hess_t<ECUDA_MODEL_SI2D>(h, io, hio, st); break;
+            case ECUDA_MODEL_PM3D: rc = launch_hess_t<ECUDA_MODEL_PM3D>(h, io, hio, st); break;
+            default: rc = launch_hess_t<ECUDA_MODEL_FW6>(h, io, hio, st); break;
+        }
+    }
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    if (memkind == ECUDA_MEM_HOST) {
+        CU(cudaMemcpyAsync(vals, hio.vals, sizeof(double) * B * nnz_h, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return ECUDA_OK;
@@ -1187,6 +1278,18 @@ int ecuda_ipopt_eval_g(ecuda_handle h, int n, const double* x, int new_x, int m,
     if (rc) return rc;
     if (m != h->pd.ncons) return fail(h, ECUDA_ERR_ARG, "m does not match ncons");
     return eval_common(h, x, nullptr, g, nullptr, nullptr, ECUDA_JAC_EXACT, ECUDA_MEM_HOST, nullptr);
+}
+int ecuda_ipopt_eval_h(ecuda_handle h, int n, const double* x, int new_x, double obj_factor, int m, const double* lambda,
+                       int new_lambda, int nele_hess, int32_t* iRow, int32_t* jCol, double* values) {
+    (void)new_x;
+    (void)new_lambda;
+    int rc = ipopt_guard(h, n);
+    if (rc) return rc;
+    int32_t nnz_h = 0;
+    if ((rc = ecuda_get_hess_structure(h, &nnz_h, nullptr, nullptr))) return rc;
+    if (m != h->pd.ncons || nele_hess != nnz_h) return fail(h, ECUDA_ERR_ARG, "m / nele_hess mismatch");
+    if (!values) return ecuda_get_hess_structure(h, nullptr, iRow, jCol);
+    return ecuda_eval_hess(h, x, nullptr, obj_factor, lambda, values, ECUDA_MEM_HOST, nullptr);
 }
 int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, int m, int nele_jac, int32_t* iRow,
                            int32_t* jCol, double* values) {

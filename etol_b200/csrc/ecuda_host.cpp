@@ -385,7 +385,54 @@ void build_jac_template(const HostProblem& hp, const double* isz, const double* 
 // ---- extern "C" host helpers ---------------------------------------------------------------------------
 using namespace ecuda;
 
+// lower triangle of the Lagrangian Hessian, sorted by (column, row); see HessIO in ecuda_internal.hpp
+void ecuda::build_hess_structure(const HostProblem& hp, std::vector<int32_t>* irow, std::vector<int32_t>* jcol) {
+    irow->clear();
+    jcol->clear();
+    const int ns = hp.ns, nc = hp.nc;
+    for (int p = 0; p < hp.nphases; ++p) {
+        const int N = hp.N[p], z0 = hp.zoff[p], t0 = z0 + (ns + nc) * N, tf = t0 + 1;
+        auto put = [&](int r, int c) {
+            irow->push_back(r);
+            jcol->push_back(c);
+        };
+        for (int k = 0; k < N; ++k)
+            for (int j = 0; j < nc; ++j) {
+                const int c = z0 + k * nc + j;
+                for (int j2 = j; j2 < nc; ++j2) put(z0 + k * nc + j2, c);
+                for (int i = 0; i < ns; ++i) put(z0 + nc * N + k * ns + i, c);
+                put(t0, c);
+                put(tf, c);
+            }
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < ns; ++i) {
+                const int c = z0 + nc * N + k * ns + i;
+                for (int i2 = i; i2 < ns; ++i2) put(z0 + nc * N + k * ns + i2, c);
+                put(t0, c);
+                put(tf, c);
+            }
+        put(t0, t0);
+        put(tf, t0);
+        put(tf, tf);
+    }
+}
+
 extern "C" {
+
+int ecuda_host_hess_structure(const ecuda_problem_desc* desc, int32_t* nnz_h, int32_t* iRow, int32_t* jCol) {
+    if (!desc) return ECUDA_ERR_ARG;
+    ecuda::HostProblem hp;
+    std::string err;
+    if (!ecuda::build_layout(*desc, &hp, &err)) return ECUDA_ERR_ARG;
+    std::vector<int32_t> ir, jc;
+    ecuda::build_hess_structure(hp, &ir, &jc);
+    if (nnz_h) *nnz_h = static_cast<int32_t>(ir.size());
+    for (size_t e = 0; e < ir.size(); ++e) {
+        if (iRow) iRow[e] = ir[e] + desc->index_base;
+        if (jCol) jCol[e] = jc[e] + desc->index_base;
+    }
+    return ECUDA_OK;
+}
 
 int ecuda_abi_version(void) { return ECUDA_ABI_VERSION; }
 

@@ -82,6 +82,22 @@ struct MeshDev {
     double* out;                         // [B][nint]
 };
 
+// Hessian of the Lagrangian (ecuda_eval_hess): sigma * f + sum_r lambda_r g_r in the solver's scaled space.
+// Lower triangle, sorted by (column, row). Per phase: the dense block of every node's variables
+// [u_k | x_k], their couplings with t0 and tf, and the 3 time-time entries; everything else is
+// structurally zero (D X, events, duration and linkages are linear).
+struct HessIO {
+    const double* lambda;  // [B][ncons]
+    const double* sigma;   // [B] or null (sigma0 for every instance)
+    double sigma0;
+    double* vals;          // [B][nnz_h]
+    int nnz_h;
+    int hoff[ECUDA_MAX_PHASES];  // first entry of each phase
+};
+ECUDA_HD int hess_cu(int ns, int nc) { return nc * (nc + 1) / 2 + nc * (ns + 2); }  // entries of a node's control columns
+ECUDA_HD int hess_cx(int ns) { return ns * (ns + 1) / 2 + 2 * ns; }                  // ... of its state columns
+ECUDA_HD int hess_phase_nnz(int ns, int nc, int N) { return N * (hess_cu(ns, nc) + hess_cx(ns)) + 3; }
+
 // per-call pointers (device memory)
 struct EvalIO {
     const double* x;     // [B][nvars] scaled decision vectors
@@ -121,12 +137,14 @@ struct UserModel {
     // node ids of the partial derivatives, -1 = identically zero
     int dfdx[ECUDA_MAX_STATES][ECUDA_MAX_STATES], dfdu[ECUDA_MAX_STATES][ECUDA_MAX_CONTROLS];
     int dcdx[ECUDA_MAX_STATES], dcdu[ECUDA_MAX_CONTROLS];
+    // second derivatives over [x | u]: d2[(o * nv + a) * nv + b], a <= b, o < ns: f_o, o == ns: cost
+    std::vector<int> d2;
     unsigned fx[ECUDA_MAX_STATES], fu[ECUDA_MAX_STATES];  // states / controls read by f_i
     std::string source;                                    // generated Model<ECUDA_MODEL_USER>
 };
 // compiled kernels of one user model for one dot-block count
 struct UserImage {
-    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, ODE_ERROR = 4, NKERNELS = 5 };
+    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, ODE_ERROR = 4, HESS = 5, NKERNELS = 6 };
     std::vector<char> cubin;
     std::string name[NKERNELS];  // lowered kernel names ("" = not compiled)
     std::string log;
@@ -170,6 +188,8 @@ struct HostProblem {
 bool build_layout(const ecuda_problem_desc& d, HostProblem* hp, std::string* err);
 // pattern (CSC, rows ascending per column) + CPR grouping
 void build_structure(HostProblem* hp);
+// lower triangle of the Lagrangian Hessian (0-based), sorted by (column, row)
+void build_hess_structure(const HostProblem& hp, std::vector<int32_t>* irow, std::vector<int32_t>* jcol);
 // layout part of the kernel parameter block (everything except device pointers and sf); needs
 // build_layout + build_structure
 void fill_probdev(const HostProblem& hp, ProbDev* pd);

@@ -426,5 +426,32 @@ __global__ void __launch_bounds__(kThreads) k_ode_error(const __grid_constant__ 
     ode_error_intervals<M>(pb, ph, p, mesh, m, b, tid, nthr);
 }
 
+// Hessian of the Lagrangian, lower triangle (ecuda_eval_hess)
+template <int M>
+__global__ void __launch_bounds__(kThreads) k_hess(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io,
+                                                   const __grid_constant__ HessIO hio) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CtaMem m;
+    carve(m, smem, pb, ph, nthr);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    stage_vars(pb, ph, io, m, b, tid, nthr, false);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    hess_nodes<M>(pb, ph, p, hio, m, b, tid, nthr);
+    __syncthreads();
+    hess_time_block(pb, ph, p, hio, m, b, tid);
+}
+
 }  // namespace ecuda
 #endif

@@ -45,6 +45,14 @@ ECUDA_HD void cylinder_row_dxy(const double* rec, double x, double y, double* dd
     *ddy = -2.0 * (y - rec[1]);
 }
 
+// second derivatives of the cylinder row: d2/dx2 = d2/dy2 = -2, d2/dxdy = 0
+ECUDA_HD void cylinder_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {
+    (void)rec;
+    *hxx = -2.0;
+    *hxy = 0.0;
+    *hyy = -2.0;
+}
+
 // si2d edge record: xc, yc, cos(tt), sin(tt), asq, bsq
 ECUDA_HD double edge_row(const double* rec, double x, double y) {
     double dx = x - rec[0];
@@ -61,6 +69,13 @@ ECUDA_HD void edge_row_dxy(const double* rec, double x, double y, double* ddx, d
     double dely = st * dx + ct * dy;
     *ddx = -2.0 * (bsq * delx * ct + asq * dely * st);
     *ddy = -2.0 * (-bsq * delx * st + asq * dely * ct);
+}
+
+ECUDA_HD void edge_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {
+    const double ct = rec[2], st = rec[3], asq = rec[4], bsq = rec[5];
+    *hxx = -2.0 * (bsq * (ct * ct) + asq * (st * st));
+    *hxy = -2.0 * ((asq - bsq) * (ct * st));
+    *hyy = -2.0 * (bsq * (st * st) + asq * (ct * ct));
 }
 
 // track record: radius, then nway x (t, x, y). Interval choice and formula as in ETOL's
@@ -102,7 +117,22 @@ ECUDA_HD void track_row_partials(const double* trk, int nway, double x, double y
     *ddt = 2.0 * (dx * sx + dy * sy);
 }
 
+// second derivatives of the moving-circle row inside the waypoint interval of t:
+// d2/dx2 = d2/dy2 = -2, d2/dxdt = 2 sx, d2/dydt = 2 sy, d2/dt2 = -2 (sx^2 + sy^2)
+ECUDA_HD void track_row_hess(const double* trk, int nway, double t, double* hxt, double* hyt, double* htt) {
+    int j = track_interval(trk, nway, t);
+    const double* a = trk + 1 + 3 * j;
+    const double* b = a + 3;
+    double sx = (b[1] - a[1]) / (b[0] - a[0]);
+    double sy = (b[2] - a[2]) / (b[0] - a[0]);
+    *hxt = 2.0 * sx;
+    *hyt = 2.0 * sy;
+    *htt = -2.0 * (sx * sx + sy * sy);
+}
+
 // ------------------------------------------------------------------------------------------------------
+// Every model also provides hess(x, u, lam, lamL, H): H[a][b] = sum_i lam[i] d2 f_i + lamL d2 L over the
+// node variables ordered [x_0..x_NS-1, u_0..u_NCU-1] (full symmetric matrix), for the Lagrangian Hessian.
 template <>
 struct Model<ECUDA_MODEL_SI2D> {
     static constexpr int NS = 2, NCU = 2, REC = 6;
@@ -126,9 +156,17 @@ struct Model<ECUDA_MODEL_SI2D> {
         dfdx[0][0] = 0.0; dfdx[0][1] = 0.0; dfdx[1][0] = 0.0; dfdx[1][1] = 0.0;
         dfdu[0][0] = 1.0; dfdu[0][1] = 0.0; dfdu[1][0] = 0.0; dfdu[1][1] = 1.0;
     }
+    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+                              double (*H)[NS + NCU]) {
+        for (int a = 0; a < NS + NCU; ++a)
+            for (int b = 0; b < NS + NCU; ++b) H[a][b] = (a == b && a >= NS) ? 2.0 * lamL : 0.0;
+    }
     ECUDA_HD static double static_row(const double* rec, double x, double y) { return edge_row(rec, x, y); }
     ECUDA_HD static void static_row_dxy(const double* rec, double x, double y, double* a, double* b) {
         edge_row_dxy(rec, x, y, a, b);
+    }
+    ECUDA_HD static void static_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {
+        edge_row_hess(rec, hxx, hxy, hyy);
     }
 };
 
@@ -154,6 +192,14 @@ struct Model<ECUDA_MODEL_PM3D> {
             for (int j = 0; j < NS; ++j) dfdx[i][j] = (i < 3 && j == i + 3) ? 1.0 : 0.0;
             for (int j = 0; j < NCU; ++j) dfdu[i][j] = (i >= 3 && j == i - 3) ? 1.0 : 0.0;
         }
+    }
+    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+                              double (*H)[NS + NCU]) {
+        for (int a = 0; a < NS + NCU; ++a)
+            for (int b = 0; b < NS + NCU; ++b) H[a][b] = (a == b && a >= NS) ? 2.0 * lamL : 0.0;
+    }
+    ECUDA_HD static void static_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {
+        cylinder_row_hess(rec, hxx, hxy, hyy);
     }
     ECUDA_HD static double static_row(const double* rec, double x, double y) { return cylinder_row(rec, x, y); }
     ECUDA_HD static void static_row_dxy(const double* rec, double x, double y, double* a, double* b) {
@@ -199,6 +245,29 @@ struct Model<ECUDA_MODEL_FW6> {
         dfdx[1][3] = cg * sp;  dfdx[1][4] = -(V * sg) * sp;  dfdx[1][5] = (V * cg) * cp;
         dfdx[2][3] = sg;       dfdx[2][4] = V * cg;
         dfdx[3][4] = -G0 * cg;
+    }
+    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+                              double (*H)[NS + NCU]) {
+        double sg, cg, sp, cp;
+        ecuda_sincos(x[4], &sg, &cg);
+        ecuda_sincos(x[5], &sp, &cp);
+        const double V = x[3];
+        for (int a = 0; a < NS + NCU; ++a)
+            for (int b = 0; b < NS + NCU; ++b) H[a][b] = (a == b && a >= NS) ? 2.0 * lamL : 0.0;
+        // f0 = V cg cp, f1 = V cg sp, f2 = V sg, f3 = u0 - G0 sg   over (V, gamma, psi) = x[3..5]
+        const double vg = lam[0] * (-(sg * cp)) + lam[1] * (-(sg * sp)) + lam[2] * cg;
+        const double vp = lam[0] * (-(cg * sp)) + lam[1] * (cg * cp);
+        const double gg = lam[0] * (-(V * cg) * cp) + lam[1] * (-(V * cg) * sp) + lam[2] * (-(V * sg)) + lam[3] * (G0 * sg);
+        const double gp = lam[0] * ((V * sg) * sp) + lam[1] * (-(V * sg) * cp);
+        const double pp = lam[0] * (-(V * cg) * cp) + lam[1] * (-(V * cg) * sp);
+        H[3][4] = H[4][3] = vg;
+        H[3][5] = H[5][3] = vp;
+        H[4][4] = gg;
+        H[4][5] = H[5][4] = gp;
+        H[5][5] = pp;
+    }
+    ECUDA_HD static void static_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {
+        cylinder_row_hess(rec, hxx, hxy, hyy);
     }
     ECUDA_HD static double static_row(const double* rec, double x, double y) { return cylinder_row(rec, x, y); }
     ECUDA_HD static void static_row_dxy(const double* rec, double x, double y, double* a, double* b) {

@@ -912,5 +912,147 @@ ECUDA_HD void ode_error_intervals(const ProbDev& pb, const PhaseDev& ph, int p, 
     }
 }
 
+// ---- Hessian of the Lagrangian (ecuda_eval_hess) ---------------------------------------------------------
+// Node k contributes, with h = (tf - t0)/2, t = h tau_k + m, a = dt/dt0 = (1 - tau_k)/2, b = dt/dtf = (1 + tau_k)/2:
+//   c_i = -lambda~_r sg_r for its defect rows, c_L = sigma sf w_k (negated when maximising), c_q = lambda~_r sg_r
+//   for its path rows;  node block  h (sum_i c_i d2 f_i + c_L d2 L) + sum_q c_q d2 p_q;
+//   (v, t0 | tf) = (-+1/2) (sum_i c_i df_i/dv + c_L dL/dv) + c_q d2p_q/dvdt (a | b)   [moving circles only];
+//   (t0 | tf, t0 | tf) = sum over nodes and moving circles of c_q d2p_q/dt2 (a a | a b | b b).
+// Dynamics and cost are autonomous, so they add nothing to the time-time block. Entries are multiplied by
+// 1/sz of both variables (the solver's variables are z sz). Thread k owns node k; the 3 time-time partial
+// sums per node go through shared memory (m.hf, 3 per node) and thread 0 adds them in node order.
+template <int M>
+ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const HessIO& hio, CtaMem& m, int b, int tid,
+                         int nthr) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NV = NS + NCU;
+    const int N = ph.N, nc = pb.nc, np = ph.npath, nstat = ph.nstat;
+    const PhaseTimes pt = phase_times(pb, ph, m.z);
+    const double* lam = hio.lambda + static_cast<size_t>(b) * pb.ncons;
+    const double* sg = pb.sg;
+    const double* isz = pb.isz + ph.zoff;
+    const double sig = (hio.sigma ? ECUDA_LDG(hio.sigma + b) : hio.sigma0) * pb.sf * (pb.maximize ? -1.0 : 1.0);
+    double* out = hio.vals + static_cast<size_t>(b) * hio.nnz_h + hio.hoff[p];
+    const int Cu = hess_cu(NS, nc), Cx = hess_cx(NS);
+    const int it0 = (NS + nc) * N;
+    const double iszt0 = ECUDA_LDG(isz + it0), iszt1 = ECUDA_LDG(isz + it0 + 1);
+    for (int k = tid; k < N; k += nthr) {
+        const double tau = ECUDA_LDG(ph.tau + k);
+        const double t = pt.h * tau + pt.m, ta = 0.5 * (1.0 - tau), tb = 0.5 * (1.0 + tau);
+        double x[NS], u[NCU], lamf[NS], cdef[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            x[i] = m.z[nc * N + k * NS + i];
+            const int r = ph.goff + k * NS + i;
+            cdef[i] = -(ECUDA_LDG(lam + r) * ECUDA_LDG(sg + r));
+            lamf[i] = cdef[i] * pt.h;
+        }
+#pragma unroll
+        for (int j = 0; j < NCU; ++j) u[j] = m.z[k * nc + j];
+        const double cL = sig * ECUDA_LDG(ph.w + k);
+        double H[NV][NV];
+        Model<M>::hess(x, u, lamf, cL * pt.h, H);
+        // first derivatives for the couplings with t0 / tf
+        double dfdx[NS][NS], dfdu[NS][NCU], dLx[NS], dLu[NCU], gv[NV];
+        Model<M>::jac(x, u, dfdx, dfdu);
+        Model<M>::dcost(x, u, dLx, dLu);
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            double s = cL * dLx[a];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) s = fma(cdef[i], dfdx[i][a], s);
+            gv[a] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < NCU; ++a) {
+            double s = cL * dLu[a];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) s = fma(cdef[i], dfdu[i][a], s);
+            gv[NS + a] = s;
+        }
+        // path rows: static obstacles (position block), moving circles (position block, time couplings)
+        double xt[2] = {0.0, 0.0}, tt = 0.0;
+        const int rp0 = ph.goff + NS * N + pb.ne + k * np;
+        for (int q = 0; q < np; ++q) {
+            const double c = ECUDA_LDG(lam + rp0 + q) * ECUDA_LDG(sg + rp0 + q);
+            if (q < nstat) {
+                double hxx, hxy, hyy;
+                Model<M>::static_row_hess(m.inst + ph.inst_off + q * Model<M>::REC, &hxx, &hxy, &hyy);
+                H[0][0] = fma(c, hxx, H[0][0]);
+                H[0][1] = fma(c, hxy, H[0][1]);
+                H[1][0] = fma(c, hxy, H[1][0]);
+                H[1][1] = fma(c, hyy, H[1][1]);
+            } else {
+                double hxt, hyt, htt;
+                track_row_hess(m.inst + pb.track_off + (q - nstat) * pb.track_size, pb.nway, t, &hxt, &hyt, &htt);
+                H[0][0] = fma(c, -2.0, H[0][0]);
+                H[1][1] = fma(c, -2.0, H[1][1]);
+                xt[0] = fma(c, hxt, xt[0]);
+                xt[1] = fma(c, hyt, xt[1]);
+                tt = fma(c, htt, tt);
+            }
+        }
+        m.hf[3 * k] = (tt * ta) * ta;
+        m.hf[3 * k + 1] = (tt * ta) * tb;
+        m.hf[3 * k + 2] = (tt * tb) * tb;
+        // control columns of the node
+        for (int j = 0; j < nc; ++j) {
+            double* col = out + k * Cu + j * (nc + NS + 2) - j * (j - 1) / 2;
+            const double sj = ECUDA_LDG(isz + k * nc + j);
+            for (int j2 = j; j2 < nc; ++j2) {
+                double v = 0.0;
+#pragma unroll
+                for (int a = 0; a < NCU; ++a)
+#pragma unroll
+                    for (int c2 = 0; c2 < NCU; ++c2)
+                        if (a == j && c2 == j2) v = H[NS + a][NS + c2];
+                col[j2 - j] = (v * sj) * ECUDA_LDG(isz + k * nc + j2);
+            }
+            double gj = 0.0;
+#pragma unroll
+            for (int a = 0; a < NCU; ++a)
+                if (a == j) gj = gv[NS + a];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int a = 0; a < NCU; ++a)
+                    if (a == j) v = H[i][NS + a];
+                col[(nc - j) + i] = (v * sj) * ECUDA_LDG(isz + nc * N + k * NS + i);
+            }
+            col[(nc - j) + NS] = ((-0.5 * gj) * sj) * iszt0;
+            col[(nc - j) + NS + 1] = ((0.5 * gj) * sj) * iszt1;
+        }
+        // state columns of the node
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double* col = out + N * Cu + k * Cx + i * (NS + 2) - i * (i - 1) / 2;
+            const double si = ECUDA_LDG(isz + nc * N + k * NS + i);
+#pragma unroll
+            for (int i2 = i; i2 < NS; ++i2) col[i2 - i] = (H[i][i2] * si) * ECUDA_LDG(isz + nc * N + k * NS + i2);
+            const double xti = i < 2 ? xt[i] : 0.0;
+            col[NS - i] = ((-0.5 * gv[i] + xti * ta) * si) * iszt0;
+            col[NS - i + 1] = ((0.5 * gv[i] + xti * tb) * si) * iszt1;
+        }
+    }
+}
+// after a barrier: the time-time block
+ECUDA_HD void hess_time_block(const ProbDev& pb, const PhaseDev& ph, int p, const HessIO& hio, const CtaMem& m, int b,
+                              int tid) {
+    if (tid != 0) return;
+    const int N = ph.N, it0 = (pb.ns + pb.nc) * N;
+    const double* isz = pb.isz + ph.zoff;
+    double s00 = 0.0, s01 = 0.0, s11 = 0.0;
+    for (int k = 0; k < N; ++k) {
+        s00 = s00 + m.hf[3 * k];
+        s01 = s01 + m.hf[3 * k + 1];
+        s11 = s11 + m.hf[3 * k + 2];
+    }
+    double* out = hio.vals + static_cast<size_t>(b) * hio.nnz_h + hio.hoff[p] + N * (hess_cu(pb.ns, pb.nc) + hess_cx(pb.ns));
+    const double z0 = ECUDA_LDG(isz + it0), z1 = ECUDA_LDG(isz + it0 + 1);
+    out[0] = (s00 * z0) * z0;
+    out[1] = (s01 * z0) * z1;
+    out[2] = (s11 * z1) * z1;
+}
+
 }  // namespace ecuda
 #endif

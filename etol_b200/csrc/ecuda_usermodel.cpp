@@ -43,8 +43,10 @@ bool integral_pow(double e, int* n) {
 // ---- expression pool with the few simplifications that keep derivative code small -------------------
 struct Pool {
     std::vector<ecuda_tape_node>& n;
+    std::vector<unsigned>& deps;  // input slots every node depends on, kept in step with n
     int push(int op, int a, int b = -1, double imm = 0.0) {
         n.push_back(ecuda_tape_node{op, a, b, 0, imm});
+        deps.push_back((a >= 0 ? deps[a] : 0u) | (b >= 0 ? deps[b] : 0u));
         return static_cast<int>(n.size()) - 1;
     }
     bool is_const(int id, double v) const { return id >= 0 && n[id].op == ECUDA_OP_CONST && n[id].imm == v; }
@@ -64,11 +66,18 @@ struct Pool {
 };
 
 // d node[out] / d input[slot] as a node id in the (growing) pool, -1 when identically zero
-int differentiate(Pool& P, int out, int slot, const std::vector<unsigned>& deps) {
-    if (!((deps[out] >> slot) & 1u)) return -1;
+int differentiate(Pool& P, int out, int slot) {
+    if (out < 0 || !((P.deps[out] >> slot) & 1u)) return -1;
     std::vector<int> d(out + 1, -1);
+    std::vector<char> live(out + 1, 0);  // only what `out` is computed from
+    live[out] = 1;
+    for (int k = out; k >= 0; --k) {
+        if (!live[k] || P.n[k].op == ECUDA_OP_INPUT) continue;
+        if (P.n[k].a >= 0) live[P.n[k].a] = 1;
+        if (P.n[k].b >= 0) live[P.n[k].b] = 1;
+    }
     for (int k = 0; k <= out; ++k) {
-        if (!((deps[k] >> slot) & 1u)) continue;
+        if (!live[k] || !((P.deps[k] >> slot) & 1u)) continue;
         const ecuda_tape_node nd = P.n[k];  // by value: the pool grows below
         const int a = nd.a, b = nd.b;
         switch (nd.op) {
@@ -218,11 +227,35 @@ std::string generate_source(const UserModel& m) {
               << (m.dfdu[i][j] < 0 ? std::string("0.0") : "v" + std::to_string(m.dfdu[i][j])) << ";\n";
     }
     o << "    }\n";
+    // hess: H = sum_i lam[i] d2 f_i + lamL d2 L over [x | u]
+    o << "    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,\n"
+         "                              double (*H)[NS + NCU]) {\n";
+    {
+        const int nvn = m.ns + m.nc;
+        outs.assign(m.d2.begin(), m.d2.end());
+        print_body(m, outs, o);
+        for (int a = 0; a < nvn; ++a)
+            for (int b = a; b < nvn; ++b) {
+                std::string sum;
+                for (int k = 0; k <= m.ns; ++k) {
+                    const int id = m.d2[(static_cast<size_t>(k) * nvn + a) * nvn + b];
+                    if (id < 0) continue;
+                    const std::string term =
+                        (k < m.ns ? "lam[" + std::to_string(k) + "]" : std::string("lamL")) + " * v" + std::to_string(id);
+                    sum = sum.empty() ? term : "(" + sum + ") + " + term;
+                }
+                o << "        H[" << a << "][" << b << "] = " << (sum.empty() ? std::string("0.0") : sum) << ";\n";
+                if (b != a) o << "        H[" << b << "][" << a << "] = H[" << a << "][" << b << "];\n";
+            }
+    }
+    o << "    }\n";
     const char* row = m.static_kind == ECUDA_STATIC_EDGE ? "edge_row" : "cylinder_row";
     o << "    ECUDA_HD static double static_row(const double* rec, double x, double y) { return " << row
       << "(rec, x, y); }\n"
       << "    ECUDA_HD static void static_row_dxy(const double* rec, double x, double y, double* a, double* b) {\n"
-      << "        " << row << "_dxy(rec, x, y, a, b);\n    }\n};\n}  // namespace ecuda\n";
+      << "        " << row << "_dxy(rec, x, y, a, b);\n    }\n"
+      << "    ECUDA_HD static void static_row_hess(const double* rec, double* hxx, double* hxy, double* hyy) {\n"
+      << "        " << row << "_hess(rec, hxx, hxy, hyy);\n    }\n};\n}  // namespace ecuda\n";
     return o.str();
 }
 
@@ -378,7 +411,7 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
         m->fu[i] = (deps[m->f_out[i]] >> m->ns) & ((1u << m->nc) - 1u);
     }
     // derivatives, appended to the same node list
-    Pool P{m->nodes};
+    Pool P{m->nodes, deps};
     for (int i = 0; i < ECUDA_MAX_STATES; ++i) {
         for (int j = 0; j < ECUDA_MAX_STATES; ++j) m->dfdx[i][j] = -1;
         for (int j = 0; j < ECUDA_MAX_CONTROLS; ++j) m->dfdu[i][j] = -1;
@@ -386,11 +419,21 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
     }
     for (int j = 0; j < ECUDA_MAX_CONTROLS; ++j) m->dcdu[j] = -1;
     for (int i = 0; i < m->ns; ++i) {
-        for (int j = 0; j < m->ns; ++j) m->dfdx[i][j] = differentiate(P, m->f_out[i], j, deps);
-        for (int j = 0; j < m->nc; ++j) m->dfdu[i][j] = differentiate(P, m->f_out[i], m->ns + j, deps);
-        m->dcdx[i] = differentiate(P, m->cost_out, i, deps);
+        for (int j = 0; j < m->ns; ++j) m->dfdx[i][j] = differentiate(P, m->f_out[i], j);
+        for (int j = 0; j < m->nc; ++j) m->dfdu[i][j] = differentiate(P, m->f_out[i], m->ns + j);
+        m->dcdx[i] = differentiate(P, m->cost_out, i);
     }
-    for (int j = 0; j < m->nc; ++j) m->dcdu[j] = differentiate(P, m->cost_out, m->ns + j, deps);
+    for (int j = 0; j < m->nc; ++j) m->dcdu[j] = differentiate(P, m->cost_out, m->ns + j);
+    // second derivatives over the node variables [x | u] (upper triangle a <= b), for the Lagrangian Hessian
+    const int nvn = m->ns + m->nc;
+    m->d2.assign(static_cast<size_t>(m->ns + 1) * nvn * nvn, -1);
+    for (int o = 0; o <= m->ns; ++o)  // o < ns: f_o, o == ns: the running cost
+        for (int a = 0; a < nvn; ++a) {
+            const int first = o < m->ns ? (a < m->ns ? m->dfdx[o][a] : m->dfdu[o][a - m->ns])
+                                        : (a < m->ns ? m->dcdx[a] : m->dcdu[a - m->ns]);
+            for (int b = a; b < nvn; ++b)
+                m->d2[(static_cast<size_t>(o) * nvn + a) * nvn + b] = differentiate(P, first, b);
+        }
     m->source = generate_source(*m);
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_models.size() >= ECUDA_MAX_USER_MODELS) return bad("too many user models (64 per process)");
@@ -527,6 +570,7 @@ bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, s
     exprs[UserImage::GENERIC] = "ecuda::k_eval<" + M + ", " + NB + ">";
     exprs[UserImage::GRAD] = "ecuda::k_grad<" + M + ">";
     exprs[UserImage::ODE_ERROR] = "ecuda::k_ode_error<" + M + ">";
+    exprs[UserImage::HESS] = "ecuda::k_hess<" + M + ">";
     if (rows) {
         exprs[UserImage::ROWS_FD] = "ecuda::k_eval_rows<" + M + ", " + NB + ", true>";
         exprs[UserImage::ROWS_EXACT] = "ecuda::k_eval_rows<" + M + ", " + NB + ", false>";

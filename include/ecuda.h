@@ -227,6 +227,19 @@ int ecuda_ipopt_eval_g(ecuda_handle h, int n, const double* x, int new_x, int m,
 int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, int m, int nele_jac,
                            int32_t* iRow, int32_t* jCol, double* values);
 int ecuda_set_ipopt_jac_mode(ecuda_handle h, int jac_mode);
+/* TNLP::eval_h; values == NULL: structure query */
+int ecuda_ipopt_eval_h(ecuda_handle h, int n, const double* x, int new_x, double obj_factor, int m, const double* lambda,
+                       int new_lambda, int nele_hess, int32_t* iRow, int32_t* jCol, double* values);
+
+/* ---- Hessian of the Lagrangian (ePSOPT asks PSOPT / IPOPT for hessian = "exact", ePSOPT.cpp:65) -------- */
+/* sigma * f + sum_r lambda_r g_r in the solver's scaled space (f, g as ecuda_eval returns them). Lower
+ * triangle, sorted by (column, row): per phase the dense block of every node's variables [u_k | x_k],
+ * their couplings with t0 / tf and the 3 time-time entries -- everything else is structurally zero.
+ * nnz_h = sum_p N_p * (nc(nc+1)/2 + nc(ns+2) + ns(ns+1)/2 + 2 ns) + 3. */
+int ecuda_get_hess_structure(ecuda_handle h, int32_t* nnz_h, int32_t* iRow, int32_t* jCol); /* any pointer may be NULL */
+/* sigma: [B] objective factors, or NULL to use sigma0 for every instance; lambda: [B][ncons]; vals: [B][nnz_h] */
+int ecuda_eval_hess(ecuda_handle h, const double* x, const double* sigma, double sigma0, const double* lambda,
+                    double* vals, int memkind, void* stream);
 
 /* ---- mesh refinement support (what PSOPT does between NLP solves, ePSOPT.cpp:69-71) ---------------- */
 /* Relative local discretisation error of the collocation solution x on every mesh interval (Betts'
@@ -246,6 +259,7 @@ int ecuda_host_dims(const ecuda_problem_desc* desc, ecuda_dims* out);
 int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t* jCol,
                          int32_t* group_of_col);
 int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double* D);
+int ecuda_host_hess_structure(const ecuda_problem_desc* desc, int32_t* nnz_h, int32_t* iRow, int32_t* jCol);
 /* interpolation data of ecuda_ode_error: quadrature points tq / weights wq [(N-1)*4] inside the mesh
  * intervals, Lagrange basis E and its derivative dE there [(N-1)*4][N]; matrix R [N_to][N_from] of
  * ecuda_resample. Any output may be NULL. */

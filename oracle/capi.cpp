@@ -220,6 +220,39 @@ double oracle_eval_batch(void* hv, int first, int count, const double* x, double
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Hessian of the Lagrangian: structure (nnz returned; arrays may be null) and values [count][nnz_h]
+int oracle_hess_structure(void* hv, int32_t* irow, int32_t* jcol) {
+    Handle* h = static_cast<Handle*>(hv);
+    std::vector<int32_t> ir, jc;
+    h->P->hess_structure(&ir, &jc);
+    for (size_t e = 0; e < ir.size(); ++e) {
+        if (irow) irow[e] = ir[e] + h->P->spec.index_base;
+        if (jcol) jcol[e] = jc[e] + h->P->spec.index_base;
+    }
+    return static_cast<int>(ir.size());
+}
+int oracle_eval_hess(void* hv, int first, int count, const double* x, const double* sigma, const double* lambda,
+                     double* vals) {
+    Handle* h = static_cast<Handle*>(hv);
+    const Problem& P = *h->P;
+    const size_t nnz = oracle_hess_structure(hv, nullptr, nullptr);
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < count; ++b) {
+        try {
+            P.eval_hess(h->inst[first + b], x + b * P.L.nvars, sigma[b], lambda + b * P.L.ncons, vals + b * nnz);
+        } catch (std::exception& e) {
+#pragma omp critical
+            err = e.what();
+        }
+    }
+    if (!err.empty()) {
+        g_err = err;
+        return -1;
+    }
+    return 0;
+}
+
 // mesh refinement support: err[count][sum_p (N_p - 1)]; x_new[count][nvars_new]
 int oracle_ode_error(void* hv, int first, int count, const double* x, double* err) {
     Handle* h = static_cast<Handle*>(hv);

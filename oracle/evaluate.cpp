@@ -185,6 +185,100 @@ std::vector<Callbacks<T>> build_callbacks(const Problem& P, const Instance& I) {
 
 }  // namespace
 
+// Hessian of the Lagrangian sigma*f~ + sum_r lambda_r g~_r (scaled space), lower triangle, entries in the
+// order of make_hess_structure. Every node's contribution is evaluated in second-order forward mode over
+// the directions (x_k, u_k, t0, tf): the time t = h tau_k + m and the factor h = (tf - t0)/2 are themselves
+// dual numbers, so no chain rule is written out by hand here.
+void Problem::eval_hess(const Instance& I, const double* zs, double sigma, const double* lambda, double* vals) const {
+    check_instance(*this, I);
+    auto cbs = build_callbacks<Dual2>(*this, I);
+    std::vector<double> z;
+    unscale(*this, zs, &z);
+    const int ns = L.ns, nc = L.nc, nd = ns + nc + 2;
+    if (nd > MAXD2) throw std::invalid_argument("too many node variables for Dual2");
+    size_t e = 0;
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p], np = L.npath[p];
+        const Collocation& C = col[p];
+        // node Lagrangians
+        std::vector<Dual2> ell(N);
+        for (int k = 0; k < N; ++k) {
+            std::vector<Dual2> x(ns), u(nc), F(ns), path(np > 0 ? np : 1);
+            for (int i = 0; i < ns; ++i) {
+                x[i] = Dual2(z[L.ix(p, k, i)]);
+                x[i].d[i] = 1.0;
+            }
+            for (int j = 0; j < nc; ++j) {
+                u[j] = Dual2(z[L.iu(p, k, j)]);
+                u[j].d[ns + j] = 1.0;
+            }
+            Dual2 t0(z[L.it0(p)]), tf(z[L.itf(p)]);
+            t0.d[ns + nc] = 1.0;
+            tf.d[ns + nc + 1] = 1.0;
+            Dual2 h = Dual2(0.5) * (tf - t0), mid = Dual2(0.5) * (tf + t0);
+            Dual2 t = h * Dual2(C.tau[k]) + mid;
+            node_dae<Dual2>(cbs[p], ns, nc, F.data(), path.data(), x.data(), u.data(), t, 0.0);
+            Dual2 Lk = node_cost<Dual2>(cbs[p], ns, nc, x.data(), u.data(), t, 0.0, spec.maximize);
+            Dual2 acc = Dual2(sigma * sc.sf * C.w[k]) * (h * Lk);
+            for (int i = 0; i < ns; ++i)
+                acc = acc - Dual2(lambda[L.rdef(p, k, i)] * sc.sg[L.rdef(p, k, i)]) * (h * F[i]);
+            for (int q = 0; q < np; ++q) acc = acc + Dual2(lambda[L.rpath(p, k, q)] * sc.sg[L.rpath(p, k, q)]) * path[q];
+            ell[k] = acc;
+        }
+        auto isz = [&](int col) { return sc.isz[col]; };
+        const int it0 = L.it0(p), itf = L.itf(p), T0 = ns + nc, TF = ns + nc + 1;
+        for (int k = 0; k < N; ++k)
+            for (int j = 0; j < nc; ++j) {
+                const int c = L.iu(p, k, j), dj = ns + j;
+                for (int j2 = j; j2 < nc; ++j2) vals[e++] = ell[k].h[dj][ns + j2] * isz(c) * isz(L.iu(p, k, j2));
+                for (int i = 0; i < ns; ++i) vals[e++] = ell[k].h[dj][i] * isz(c) * isz(L.ix(p, k, i));
+                vals[e++] = ell[k].h[dj][T0] * isz(c) * isz(it0);
+                vals[e++] = ell[k].h[dj][TF] * isz(c) * isz(itf);
+            }
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < ns; ++i) {
+                const int c = L.ix(p, k, i);
+                for (int i2 = i; i2 < ns; ++i2) vals[e++] = ell[k].h[i][i2] * isz(c) * isz(L.ix(p, k, i2));
+                vals[e++] = ell[k].h[i][T0] * isz(c) * isz(it0);
+                vals[e++] = ell[k].h[i][TF] * isz(c) * isz(itf);
+            }
+        double s00 = 0.0, s01 = 0.0, s11 = 0.0;
+        for (int k = 0; k < N; ++k) {
+            s00 += ell[k].h[T0][T0];
+            s01 += ell[k].h[T0][TF];
+            s11 += ell[k].h[TF][TF];
+        }
+        vals[e++] = s00 * isz(it0) * isz(it0);
+        vals[e++] = s01 * isz(it0) * isz(itf);
+        vals[e++] = s11 * isz(itf) * isz(itf);
+    }
+}
+
+// pattern of eval_hess: per phase, column by column, rows ascending (lower triangle)
+void Problem::hess_structure(std::vector<int32_t>* irow, std::vector<int32_t>* jcol) const {
+    irow->clear();
+    jcol->clear();
+    for (int p = 0; p < L.nphases; ++p) {
+        const int N = L.N[p];
+        for (int k = 0; k < N; ++k)
+            for (int j = 0; j < L.nc; ++j) {
+                for (int j2 = j; j2 < L.nc; ++j2) irow->push_back(L.iu(p, k, j2)), jcol->push_back(L.iu(p, k, j));
+                for (int i = 0; i < L.ns; ++i) irow->push_back(L.ix(p, k, i)), jcol->push_back(L.iu(p, k, j));
+                irow->push_back(L.it0(p)), jcol->push_back(L.iu(p, k, j));
+                irow->push_back(L.itf(p)), jcol->push_back(L.iu(p, k, j));
+            }
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < L.ns; ++i) {
+                for (int i2 = i; i2 < L.ns; ++i2) irow->push_back(L.ix(p, k, i2)), jcol->push_back(L.ix(p, k, i));
+                irow->push_back(L.it0(p)), jcol->push_back(L.ix(p, k, i));
+                irow->push_back(L.itf(p)), jcol->push_back(L.ix(p, k, i));
+            }
+        irow->push_back(L.it0(p)), jcol->push_back(L.it0(p));
+        irow->push_back(L.itf(p)), jcol->push_back(L.it0(p));
+        irow->push_back(L.itf(p)), jcol->push_back(L.itf(p));
+    }
+}
+
 void Problem::eval_g(const Instance& I, const double* zs, double* g) const {
     check_instance(*this, I);
     auto cbs = build_callbacks<double>(*this, I);

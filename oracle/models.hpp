@@ -93,8 +93,69 @@ inline Dual pow_s(const Dual& a, double e) {
     for (int i = 0; i < MAXD; ++i) r.d[i] = slope * a.d[i];
     return r;
 }
+// ---- second-order forward mode: value, gradient and full Hessian over up to MAXD2 directions ----------
+// (exact second derivatives for the Lagrangian Hessian; the role ADOL-C's sparse_hess plays under PSOPT)
+constexpr int MAXD2 = 18;  // ns + nc + t0 + tf
+struct Dual2 {
+    double v = 0.0;
+    double d[MAXD2] = {0.0};
+    double h[MAXD2][MAXD2] = {{0.0}};
+    Dual2() {}
+    Dual2(double val) : v(val) {}  // NOLINT
+};
+// r = phi(a) with phi' = p1, phi'' = p2 at a.v
+inline Dual2 chain2(const Dual2& a, double val, double p1, double p2) {
+    Dual2 r(val);
+    for (int i = 0; i < MAXD2; ++i) {
+        r.d[i] = p1 * a.d[i];
+        for (int j = 0; j < MAXD2; ++j) r.h[i][j] = p1 * a.h[i][j] + p2 * (a.d[i] * a.d[j]);
+    }
+    return r;
+}
+inline Dual2 operator+(const Dual2& a, const Dual2& b) {
+    Dual2 r(a.v + b.v);
+    for (int i = 0; i < MAXD2; ++i) {
+        r.d[i] = a.d[i] + b.d[i];
+        for (int j = 0; j < MAXD2; ++j) r.h[i][j] = a.h[i][j] + b.h[i][j];
+    }
+    return r;
+}
+inline Dual2 operator-(const Dual2& a) { return chain2(a, -a.v, -1.0, 0.0); }
+inline Dual2 operator-(const Dual2& a, const Dual2& b) { return a + (-b); }
+inline Dual2 operator*(const Dual2& a, const Dual2& b) {
+    Dual2 r(a.v * b.v);
+    for (int i = 0; i < MAXD2; ++i) {
+        r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+        for (int j = 0; j < MAXD2; ++j)
+            r.h[i][j] = a.h[i][j] * b.v + a.d[i] * b.d[j] + a.d[j] * b.d[i] + a.v * b.h[i][j];
+    }
+    return r;
+}
+inline Dual2 operator/(const Dual2& a, const Dual2& b) {
+    return a * chain2(b, 1.0 / b.v, -1.0 / (b.v * b.v), 2.0 / (b.v * b.v * b.v));
+}
+inline void sincos_s(const Dual2& a, Dual2* s, Dual2* c) {
+    double sv, cv;
+    ecuda_sincos(a.v, &sv, &cv);
+    *s = chain2(a, sv, cv, -sv);
+    *c = chain2(a, cv, -sv, -cv);
+}
+inline Dual2 sqrt_s(const Dual2& a) {
+    const double r = std::sqrt(a.v);
+    return chain2(a, r, 0.5 / r, -0.25 / (r * a.v));
+}
+inline Dual2 exp_s(const Dual2& a) {
+    const double e = std::exp(a.v);
+    return chain2(a, e, e, e);
+}
+inline Dual2 pow_s(const Dual2& a, double e) {
+    const double p1 = e == 0.0 ? 0.0 : e * pow_s(a.v, e - 1.0);
+    const double p2 = (e == 0.0 || e == 1.0) ? 0.0 : e * (e - 1.0) * pow_s(a.v, e - 2.0);
+    return chain2(a, pow_s(a.v, e), p1, p2);
+}
 inline double value_of(const double& a) { return a; }
 inline double value_of(const Dual& a) { return a.v; }
+inline double value_of(const Dual2& a) { return a.v; }
 
 // ETOL's own interpolation rule, include/ETOL/TrajectoryOptimizer.hpp:239-257 (interval choice on
 // the value of t, the formula in T so that d/dt flows through).

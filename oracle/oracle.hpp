@@ -140,6 +140,9 @@ class Problem {
     void eval_g_tight(const Instance& I, const double* zs, double* g) const;
     void eval_f_tight(const Instance& I, const double* zs, double* f) const;
     void eval_jac_fd_tight(const Instance& I, const double* zs, double* vals) const;
+    // Hessian of the Lagrangian (evaluate.cpp), lower triangle in the order of hess_structure
+    void eval_hess(const Instance& I, const double* zs, double sigma, const double* lambda, double* vals) const;
+    void hess_structure(std::vector<int32_t>* irow, std::vector<int32_t>* jcol) const;
     // mesh refinement support (tight.cpp): relative local error per mesh interval [sum_p (N_p - 1)];
     // decision vector interpolated onto meshes of nnew[p] nodes (scaled by sz_new when given)
     void ode_error(const Instance& I, const double* zs, double* err) const;

@@ -52,6 +52,8 @@ def lib():
         L.oracle_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                         C.c_int, C.c_int]
         L.oracle_stage_user_tape.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, C.c_int]
+        L.oracle_hess_structure.argtypes = [C.c_void_p, _ip, _ip]
+        L.oracle_eval_hess.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.oracle_ode_error.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
         L.oracle_resample.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _dp, _dp]
         L.oracle_max_threads.restype = C.c_int
@@ -167,6 +169,24 @@ class Oracle:
             raise RuntimeError(lib().oracle_last_error().decode())
         out.update(f=f, g=g, jac=jac, grad=grad, seconds=secs)
         return out
+
+
+def hess_structure(o):
+    n = lib().oracle_hess_structure(o.h, None, None)
+    irow, jcol = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    lib().oracle_hess_structure(o.h, irow.ctypes.data_as(_ip), jcol.ctypes.data_as(_ip))
+    return irow, jcol
+
+
+def eval_hess(o, x, sigma, lam):
+    """Hessian of the Lagrangian sigma*f + lam.g (scaled space), lower triangle, [B][nnz_h]"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    out = np.zeros((x.shape[0], lib().oracle_hess_structure(o.h, None, None)))
+    if lib().oracle_eval_hess(o.h, 0, x.shape[0], _p(x), _p(sigma), _p(lam), _p(out)) != 0:
+        raise RuntimeError(lib().oracle_last_error().decode())
+    return out
 
 
 def ode_error(o, wl, x):

@@ -116,6 +116,37 @@ def test_resample_matches_oracle(evaluators, name):
             assert rel_err(got, ref) <= TOL_VALUE
 
 
+HESS_CASES = ["C0-ocp", "C0-mip", "C0-ocp-cheb-max", "C0-ocp-deps-base1", "C2-pm3d-64", "C2-pm3d-scaled-deps", "C3-fw6",
+              "C3-fw6-small-scaled", "C4-multiphase", "C4-multiphase-ragged", "pm3d-N2", "pm3d-no-obstacles",
+              "user-pm3d", "user-unicycle-tracks", "user-unicycle-cheb-deps", "user-dragmass", "user-dragmass-N70-generic"]
+
+
+@pytest.mark.parametrize("name", HESS_CASES)
+def test_hessian_matches_oracle(evaluators, name):
+    """Hessian of the Lagrangian (lower triangle) against the oracle's second-order forward mode"""
+    ev, orc, wl = _get(evaluators, name)
+    rng = np.random.default_rng(7)
+    lam = rng.normal(size=(wl.batch, ev.ncons))
+    sigma = rng.uniform(0.25, 2.0, size=wl.batch)
+    n = C.c_int32(0)
+    assert capi.lib().ecuda_get_hess_structure(ev.h, C.byref(n), None, None) == 0
+    irow, jcol = np.zeros(n.value, np.int32), np.zeros(n.value, np.int32)
+    assert capi.lib().ecuda_get_hess_structure(ev.h, None, irow.ctypes.data_as(capi._ip), jcol.ctypes.data_as(capi._ip)) == 0
+    oi, oj = ob.hess_structure(orc)
+    assert np.array_equal(irow, oi) and np.array_equal(jcol, oj)
+    ref = ob.eval_hess(orc, wl.x, sigma, lam)
+    got = ev.hess_host(wl.x, sigma, lam)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= TOL_JAC
+    # one objective factor for the whole batch (the IPOPT-shaped call uses this form)
+    if wl.batch == 1:
+        vals = np.zeros(n.value)
+        x0, l0 = np.ascontiguousarray(wl.x[0]), np.ascontiguousarray(lam[0])
+        rc = capi.lib().ecuda_ipopt_eval_h(ev.h, ev.nvars, x0.ctypes.data_as(capi._dp), 1, float(sigma[0]), ev.ncons,
+                                           l0.ctypes.data_as(capi._dp), 1, n.value, None, None, vals.ctypes.data_as(capi._dp))
+        assert rc == 0 and np.array_equal(vals, got[0])
+
+
 def test_resample_round_trip_on_device(evaluators):
     """up-sampling does not change the interpolating polynomial: 40 -> 61 -> 40 nodes returns the decision
     vectors (a size-independent property of the kernel), and the finer mesh sees an error profile of the
