@@ -24,6 +24,9 @@ struct ecuda_alg_t {
     std::string scaling = "automatic";         // "automatic" (PSOPT-like variable scaling) or "none"
     std::string derivatives = "automatic";     // "automatic" = exact Jacobian, "numerical" = index-set FD
     std::string collocation_method = "Legendre";  // or "Chebyshev"
+    std::string hessian = "exact";             // IPOPT driver: "exact" = device Hessian of the Lagrangian (what ePSOPT.cpp:65
+                                               // asks PSOPT for) or "limited-memory"; the built-in driver always uses
+                                               // its own quasi-Newton model
     int nlp_iter_max = 200;
     double nlp_tolerance = 1.e-6;
     // mesh refinement between NLP solves, as ePSOPT configures PSOPT (ePSOPT.cpp:69-71): "automatic" re-solves

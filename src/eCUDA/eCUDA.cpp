@@ -655,6 +655,20 @@ int eCUDA::solveOnce() {
         if (grad && ecuda_eval_grad_f(h, zs, grad, ECUDA_MEM_HOST, nullptr) != ECUDA_OK) return false;
         return true;
     };
+    std::vector<int32_t> hrow, hcol;
+    if (_algorithm.hessian == "exact") {
+        int32_t hn = 0;
+        if (ecuda_get_hess_structure(h, &hn, nullptr, nullptr) != ECUDA_OK) fail("ecuda_get_hess_structure");
+        hrow.resize(hn);
+        hcol.resize(hn);
+        ecuda_get_hess_structure(h, nullptr, hrow.data(), hcol.data());
+        P.hnnz = hn;
+        P.hrow = hrow.data();
+        P.hcol = hcol.data();
+        P.eval_h = [h](const double* zs, double sigma, const double* lambda, double* hv) -> bool {
+            return ecuda_eval_hess(h, zs, nullptr, sigma, lambda, hv, ECUDA_MEM_HOST, nullptr) == ECUDA_OK;
+        };
+    }
     ecuda_nlp::Options opt;
     opt.max_iter = _algorithm.nlp_iter_max;
     opt.tol = _algorithm.nlp_tolerance;

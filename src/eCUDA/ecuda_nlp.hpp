@@ -25,6 +25,14 @@ struct Problem {
     const int32_t* jcol = nullptr;
     // any output may be null. jac in triplet order. Returns false on evaluation failure.
     std::function<bool(const double* z, double* f, double* g, double* jac, double* grad)> eval;
+    // optional exact Hessian of the Lagrangian sigma f + lambda'g: lower triangle in the given pattern (0-based).
+    // Used by solve_ipopt (hessian_approximation = exact). solve_builtin keeps its damped-BFGS model: its
+    // Schur-complement factorisation needs a positive definite Hessian block, and the exact Hessian of an
+    // obstacle-avoidance problem is indefinite (tried: convexifying it with a multiple of I diverges).
+    int hnnz = 0;
+    const int32_t* hrow = nullptr;
+    const int32_t* hcol = nullptr;
+    std::function<bool(const double* z, double sigma, const double* lambda, double* hvals)> eval_h;
 };
 
 struct Options {

@@ -162,6 +162,7 @@ int shim_solve(void* h, int max_iter, int print_level, double* score, int* iters
     *viol = t->getSolution()->max_violation;
     return t->getSolution()->error_flag;
 }
+void shim_set_hessian(void* h, const char* mode) { static_cast<eCUDA*>(h)->getAlgorithm()->hessian = mode; }
 // mesh refinement controls / report (mode "automatic" | "manual")
 void shim_set_mesh(void* h, const char* mode, double ode_tolerance, int max_iterations) {
     eCUDA* t = static_cast<eCUDA*>(h);

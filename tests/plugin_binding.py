@@ -41,6 +41,7 @@ def lib():
         L.shim_evaluate.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
         L.shim_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp]
         L.shim_traj.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.shim_set_hessian.argtypes = [C.c_void_p, C.c_char_p]
         L.shim_set_mesh.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
         L.shim_mesh_history.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), _dp]
         L.shim_next_mesh_size.argtypes = [C.c_int, C.POINTER(C.c_int), _dp, C.c_double, C.c_int, C.c_double]
@@ -148,6 +149,9 @@ class Plugin:
         score, iters, viol = C.c_double(), C.c_int(), C.c_double()
         rc = self.L.shim_solve(self.h, max_iter, print_level, C.byref(score), C.byref(iters), C.byref(viol))
         return rc, score.value, iters.value, viol.value
+
+    def set_hessian(self, mode):
+        self.L.shim_set_hessian(self.h, mode.encode())
 
     def set_mesh(self, mode="automatic", ode_tolerance=1e-4, max_iterations=10):
         self.L.shim_set_mesh(self.h, mode.encode(), ode_tolerance, max_iterations)
