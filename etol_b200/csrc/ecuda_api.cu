@@ -163,6 +163,30 @@ __global__ void k_resample(const __grid_constant__ ProbDev pb, const __grid_cons
     }
 }
 
+// ecuda_upload_bounds: do all instances share "defect bounds 0" and one pair of path-row bounds? (bitwise
+// comparison, so that +-inf are ordinary values). flags[0] is cleared on the first counter-example.
+__global__ void k_bounds_classify(const double* gl, const double* gu, int batch, int ncons, int ndef, int ne, int* flags) {
+    const size_t n = static_cast<size_t>(batch) * ncons;
+    const long long plo = __double_as_longlong(gl[ndef + ne]), phi = __double_as_longlong(gu[ndef + ne]);
+    bool ok = true;
+    for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < n; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(e % ncons);
+        const long long lo = __double_as_longlong(gl[e]), hi = __double_as_longlong(gu[e]);
+        if (r < ndef) ok = ok && lo == 0 && hi == 0;  // +0.0 exactly
+        else if (r >= ndef + ne && r < ncons - 1) ok = ok && lo == plo && hi == phi;
+    }
+    if (!ok) flags[0] = 0;
+}
+__global__ void k_bounds_compact(const double* gl, const double* gu, int batch, int ncons, int ndef, int ne, double* bev) {
+    const int nev = ne + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * nev) return;
+    const int b = i / nev, e = i - b * nev;
+    const size_t src = static_cast<size_t>(b) * ncons + (e < ne ? ndef + e : ncons - 1);
+    bev[static_cast<size_t>(b) * 2 * nev + e] = gl[src];
+    bev[static_cast<size_t>(b) * 2 * nev + nev + e] = gu[src];
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -204,6 +228,10 @@ struct ecuda_ctx {
     cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0, 0, 0};
     DevBuf slam, ssig, shess;  // staging for ecuda_eval_hess with host buffers
+    DevBuf bcls;               // flag word of k_bounds_classify
+    DevBuf bev;                // compact bounds for the fused summary (see EvalIO::bev); valid when bounds_compact
+    bool bounds_compact = false;
+    double plo = 0.0, phi = 0.0;
     // mesh-refinement support (ecuda_ode_error / ecuda_resample), built on first use
     DevBuf mesh[ECUDA_MAX_PHASES];  // E | dE | wq | tq per phase
     bool have_mesh = false;
@@ -579,7 +607,7 @@ int ecuda_destroy(ecuda_handle h) {
         release(*b);
     for (auto& b : h->coll) release(b);
     for (auto& b : h->mesh) release(b);
-    for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew, &h->slam, &h->ssig, &h->shess}) release(*b);
+    for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew, &h->slam, &h->ssig, &h->shess, &h->bev, &h->bcls}) release(*b);
     unload_user_kernels(h);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -746,7 +774,33 @@ int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int 
     auto kind = memkind == ECUDA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CU(cudaMemcpyAsync(h->gl.p, gl, bytes, kind, h->stream));
     CU(cudaMemcpyAsync(h->gu.p, gu, bytes, kind, h->stream));
+    // compact form for the fused summary: single phase with at least one path row, uniform defect / path bounds
+    h->bounds_compact = false;
+    const int B = h->hp.desc.batch, ng = h->pd.ncons, ndef = h->pd.ns * h->pd.ph[0].N, ne = h->pd.ne;
+    if (h->pd.nphases == 1 && h->pd.ph[0].npath > 0 && !std::getenv("ECUDA_DENSE_BOUNDS")) {
+        if ((rc = ensure(h, h->bcls, sizeof(int)))) return rc;
+        int one = 1;
+        int* flag = static_cast<int*>(h->bcls.p);
+        CU(cudaMemcpyAsync(flag, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        k_bounds_classify<<<h->num_sms * 4, 256, 0, h->stream>>>(static_cast<const double*>(h->gl.p),
+                                                                static_cast<const double*>(h->gu.p), B, ng, ndef, ne, flag);
+        double pl[2];
+        CU(cudaMemcpyAsync(&one, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(&pl[0], static_cast<const double*>(h->gl.p) + ndef + ne, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(&pl[1], static_cast<const double*>(h->gu.p) + ndef + ne, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (one == 1) {
+            if ((rc = ensure(h, h->bev, sizeof(double) * B * 2 * (ne + 1)))) return rc;
+            k_bounds_compact<<<(B * (ne + 1) + 255) / 256, 256, 0, h->stream>>>(
+                static_cast<const double*>(h->gl.p), static_cast<const double*>(h->gu.p), B, ng, ndef, ne,
+                static_cast<double*>(h->bev.p));
+            h->plo = pl[0];
+            h->phi = pl[1];
+            h->bounds_compact = true;
+        }
+    }
     CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
     h->have_bounds = true;
     return ECUDA_OK;
 }
@@ -828,6 +882,11 @@ int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, 
     io.bu = static_cast<const double*>(h->gu.p);
     io.nranks = nranks;
     io.rank = rank;
+    if (h->bounds_compact) {
+        io.bev = static_cast<const double*>(h->bev.p);
+        io.plo = h->plo;
+        io.phi = h->phi;
+    }
     for (int r = 0; r < nranks; ++r) {
         if (!peer_out[r] || (reinterpret_cast<uintptr_t>(peer_out[r]) & 15)) return fail(h, ECUDA_ERR_ARG, "peer buffer null or not 16-byte aligned");
         io.peer[r] = static_cast<double*>(peer_out[r]);

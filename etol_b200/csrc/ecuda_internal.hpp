@@ -113,6 +113,10 @@ struct EvalIO {
     // problems, specialised kernels): active when nranks > 0
     const double* bl;    // [B][ncons] constraint bounds
     const double* bu;
+    // compact bounds (single phase; found by ecuda_upload_bounds when every instance has defect bounds 0 and
+    // the same pair of path-row bounds): only the event and duration rows are read per instance
+    const double* bev;   // [B][2 * (ne + 1)]: lower bounds of the ne event rows and the duration row, then upper
+    double plo, phi;     // bounds of every path row
     double* peer[16];    // rank r's gathered buffer [nranks*B][2]
     int nranks, rank;
 };
