@@ -321,6 +321,21 @@ static int upload_collocation(ecuda_ctx* h, int p) {
     return ECUDA_OK;
 }
 
+// CTAs per (instance, phase) of the generic kernel. At least enough for one defect row per thread (the widest
+// phase decides; extra slices of a narrower phase just own fewer nodes). A small batch cannot fill the GPU
+// that way -- a single 200-node instance would run on 5 of 148 SMs -- so the slices are made narrower until the
+// grid covers the SMs (latency of one IPOPT-style evaluation), down to 4 nodes per slice.
+static int slices_for(const ecuda_ctx* h, int grid) {
+    int nslices = 1, nmin = 1 << 30;
+    for (int p = 0; p < h->pd.nphases; ++p) {
+        nslices = std::max(nslices, generic_slices(h->pd.ns, h->pd.ph[p].N, kThreads));
+        nmin = std::min(nmin, h->pd.ph[p].N);
+    }
+    if (const char* e = std::getenv("ECUDA_SLICES")) return std::max(1, std::min(std::atoi(e), nmin));
+    const int fill = h->num_sms / std::max(1, grid);
+    return std::max(nslices, std::min(fill, std::max(1, nmin / 4)));
+}
+
 template <int M, int NB>
 static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     // opt in to more than 48 KB of dynamic shared memory. The attribute is per function and device
@@ -335,8 +350,7 @@ static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int gri
             cur = h->smem_bytes;
         }
     }
-    int nslices = 1;  // the widest phase decides; extra slices of a narrower phase just own fewer nodes
-    for (int p = 0; p < h->pd.nphases; ++p) nslices = std::max(nslices, generic_slices(h->pd.ns, h->pd.ph[p].N, kThreads));
+    const int nslices = slices_for(h, grid);
     k_eval<M, NB><<<dim3(grid, nslices), kThreads, h->smem_bytes, st>>>(h->pd, io);
     return ECUDA_OK;
 }
@@ -519,9 +533,7 @@ static int launch_eval_user(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
             rc = launch_user(h, fd ? UserImage::ROWS_FD : UserImage::ROWS_EXACT, dim3(grid),
                              kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, io, st);
         } else {
-            int nslices = 1;
-            for (int p = 0; p < h->pd.nphases; ++p)
-                nslices = std::max(nslices, generic_slices(h->pd.ns, h->pd.ph[p].N, kThreads));
+            const int nslices = slices_for(h, grid);
             rc = launch_user(h, UserImage::GENERIC, dim3(grid, nslices), kThreads, h->smem_bytes, io, st);
         }
         if (rc) return rc;

@@ -43,7 +43,10 @@ for (addr, txt, cur), r in zip(seq[:n], data[:n]):
     tots += s
 print(f"total warp instructions {tot}, samples {tots}")
 srcs = {}
-for (f, l), c in byline.most_common(top):
+import os
+order = samp.most_common(top) if os.environ.get("SORT") == "samp" else byline.most_common(top)
+for (f, l), _ in order:
+    c = byline[(f, l)]
     if f not in srcs:
         try:
             srcs[f] = open(f"/root/repo/etol_b200/csrc/{f}").read().splitlines()
