@@ -207,6 +207,7 @@ struct ecuda_ctx {
     DevBuf coll[ECUDA_MAX_PHASES];  // D | Dt | tau | w per phase
     DevBuf sx, sf_, sgv, sjac, sgrad, ssum;  // staging for host-memory calls
     size_t smem_bytes = 0, smem_fast_fd = 0, smem_fast_exact = 0;
+    size_t smem_generic_exact = 0;  // generic kernel without the finite-difference arrays
     bool fast_ok = false;  // the specialised kernels (ecuda_fast.cuh) can run this problem
     bool no_fast = false;  // ECUDA_NO_FAST=1 in the environment: never use them (A/B runs and tests)
     bool no_image = true;   // ECUDA_IMAGE=1 opts in to the persistent image kernel (exact mode); measured
@@ -351,7 +352,8 @@ static int launch_keval(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int gri
         }
     }
     const int nslices = slices_for(h, grid);
-    k_eval<M, NB><<<dim3(grid, nslices), kThreads, h->smem_bytes, st>>>(h->pd, io);
+    const bool fd = io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    k_eval<M, NB><<<dim3(grid, nslices), kThreads, fd ? h->smem_bytes : h->smem_generic_exact, st>>>(h->pd, io);
     return ECUDA_OK;
 }
 
@@ -534,7 +536,9 @@ static int launch_eval_user(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
                              kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, io, st);
         } else {
             const int nslices = slices_for(h, grid);
-            rc = launch_user(h, UserImage::GENERIC, dim3(grid, nslices), kThreads, h->smem_bytes, io, st);
+            const bool fdg = io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+            rc = launch_user(h, UserImage::GENERIC, dim3(grid, nslices), kThreads,
+                             fdg ? h->smem_bytes : h->smem_generic_exact, io, st);
         }
         if (rc) return rc;
         if (io.f && h->pd.nphases > 1) {
@@ -653,6 +657,8 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
         smem = std::max(smem, cta_doubles(pd, ph, kThreads) * sizeof(double));
         smem_fd = std::max(smem_fd, cta_doubles(pd, ph, kThreads, CARVE_FD) * sizeof(double));
         smem_ex = std::max(smem_ex, cta_doubles(pd, ph, kThreads, 0) * sizeof(double));
+        h->smem_generic_exact = std::max(p == 0 ? size_t(0) : h->smem_generic_exact,
+                                         cta_doubles(pd, ph, kThreads, CARVE_P) * sizeof(double));
         one_row_per_thread = one_row_per_thread && pd.ns * ph.N <= kThreads &&
                              (2 * ph.npath + pd.nc + 2) * ph.N < 65536;  // fast_div range
     }

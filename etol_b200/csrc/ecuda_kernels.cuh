@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
     const PhaseDev& ph = pb.ph[p];
     const int tid = threadIdx.x, nthr = blockDim.x;
     CtaMem m;
-    carve(m, smem, pb, ph, nthr);
+    // the perturbation arrays exist only when finite differences are asked for (the launch sizes the dynamic
+    // shared memory the same way), so that two exact-mode CTAs of a large phase fit one SM
+    const bool fd = io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    carve(m, smem, pb, ph, nthr, fd ? CARVE_ALL : CARVE_P);
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
     }
-    stage_vars(pb, ph, io, m, b, tid, nthr, io.jac != nullptr && io.jac_mode == ECUDA_JAC_FD_INDEXSET);
+    stage_vars(pb, ph, io, m, b, tid, nthr, fd);
     mbar_wait(&bar, 0);
     __syncthreads();
     // blockIdx.y: slice of the phase (instances whose phases have more defect rows than threads)
