@@ -19,4 +19,8 @@ echo "launch list rc=$?"
 timeout 300 $PROF > gpurun_out/plain2_${TAG}.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_eval -s 4 -c 2 -o gpurun_out/prof_keval_${TAG} -f $PROF > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full capture rc=$?"
+echo "== other configurations / user models / C3 slices"
+timeout 600 python scripts/config_sweep.py > gpurun_out/config_sweep_${TAG}.json 2> gpurun_out/config_sweep_${TAG}.err; tail -3 gpurun_out/config_sweep_${TAG}.err
+timeout 600 python scripts/user_model_time.py > gpurun_out/user_model_time_${TAG}.log 2>&1; tail -3 gpurun_out/user_model_time_${TAG}.log
+timeout 300 python scripts/run_examples.py > gpurun_out/examples_run_${TAG}.txt 2>&1; grep -E "rc |Score|mesh:" gpurun_out/examples_run_${TAG}.txt
 ls -la gpurun_out | tail -20
