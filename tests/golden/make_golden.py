@@ -23,3 +23,19 @@ irow, jcol, grp = o.structure()
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "c0_ocp_golden.npz"), x=wl.x, f=fd["f"], g=fd["g"],
                     jac_fd=fd["jac"], jac_exact=ex["jac"], grad=fd["grad"], irow=irow, jcol=jcol, group_of_col=grp)
 print("wrote c0_ocp_golden.npz", o.nvars, o.ncons, o.nnz)
+
+# ---- second fixture: Hessian of the Lagrangian, discretisation error, resampling (C0) and a user model ------
+rng = np.random.default_rng(20261018)
+lam = rng.normal(size=(1, o.ncons))
+sigma = np.array([1.25])
+hi, hj = ob.hess_structure(o)
+from etol_b200 import tape as T  # noqa: E402
+uw = W.unicycle(batch=1, nnodes=17, ncyl=2, ntracks=1)
+uo = ob.Oracle(uw)
+ufd = uo.eval(uw.x, want=("f", "g", "jac"), jac_mode=1)
+uex = uo.eval(uw.x, want=("jac",), jac_mode=0)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "c0_ext_golden.npz"), x=wl.x, lam=lam, sigma=sigma,
+                    hess=ob.eval_hess(o, wl.x, sigma, lam), hess_irow=hi, hess_jcol=hj,
+                    ode_error=ob.ode_error(o, wl, wl.x), resample_41=ob.resample(o, wl, wl.x, [41]),
+                    user_x=uw.x, user_f=ufd["f"], user_g=ufd["g"], user_jac_fd=ufd["jac"], user_jac_exact=uex["jac"])
+print("wrote c0_ext_golden.npz")

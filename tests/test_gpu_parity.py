@@ -147,6 +147,38 @@ def test_hessian_matches_oracle(evaluators, name):
         assert rc == 0 and np.array_equal(vals, got[0])
 
 
+def test_hessian_error_and_resample_with_device_pointers(evaluators):
+    """the same three entry points with device buffers on a caller's stream (no staging copies)"""
+    import torch
+    ev, orc, wl = _get(evaluators, "C2-pm3d-scaled-deps")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    lam = rng.normal(size=(wl.batch, ev.ncons))
+    sigma = rng.uniform(0.5, 1.5, size=wl.batch)
+    stream = torch.cuda.Stream(device=dev)
+    st = stream.cuda_stream
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(wl.x).to(dev)
+        lam_d, sig_d = torch.from_numpy(lam).to(dev), torch.from_numpy(sigma).to(dev)
+        n = C.c_int32(0)
+        assert capi.lib().ecuda_get_hess_structure(ev.h, C.byref(n), None, None) == 0
+        hv = torch.full((wl.batch, n.value), float("nan"), dtype=torch.float64, device=dev)
+        assert capi.lib().ecuda_eval_hess(ev.h, x.data_ptr(), sig_d.data_ptr(), 0.0, lam_d.data_ptr(), hv.data_ptr(),
+                                          capi.MEM_DEVICE, st) == 0
+        nint = sum(k - 1 for k in wl.nnodes)
+        err = torch.full((wl.batch, nint), float("nan"), dtype=torch.float64, device=dev)
+        assert capi.lib().ecuda_ode_error(ev.h, x.data_ptr(), err.data_ptr(), capi.MEM_DEVICE, st) == 0
+        nn = np.array([n_ + 5 for n_ in wl.nnodes], dtype=np.int32)
+        nv = sum((wl.ns + wl.nc) * int(k) + 2 for k in nn)
+        xn = torch.full((wl.batch, nv), float("nan"), dtype=torch.float64, device=dev)
+        assert capi.lib().ecuda_resample(ev.h, x.data_ptr(), nn.ctypes.data_as(capi._ip), None, xn.data_ptr(),
+                                         capi.MEM_DEVICE, st) == 0
+    stream.synchronize()
+    assert np.array_equal(hv.cpu().numpy(), ev.hess_host(wl.x, sigma, lam))
+    assert np.array_equal(err.cpu().numpy(), ev.ode_error_host(wl.x))
+    assert np.array_equal(xn.cpu().numpy(), ev.resample_host(wl.x, nn))
+
+
 def test_resample_round_trip_on_device(evaluators):
     """up-sampling does not change the interpolating polynomial: 40 -> 61 -> 40 nodes returns the decision
     vectors (a size-independent property of the kernel), and the finer mesh sees an error profile of the
@@ -193,6 +225,26 @@ def test_golden_fixture_c0(evaluators):
     assert np.array_equal(irow, gold["irow"]) and np.array_equal(jcol, gold["jcol"])
     assert np.array_equal(grp, gold["group_of_col"])
     ev.close()
+
+
+def test_extended_golden_fixture(evaluators):
+    """committed oracle outputs: Hessian, discretisation error, resampling on C0; a runtime-compiled user model"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "c0_ext_golden.npz"))
+    wl = W.reference_vgp("ocp")
+    ev = capi.Evaluator(wl)
+    assert rel_err(ev.hess_host(wl.x, gold["sigma"], gold["lam"]), gold["hess"]) <= TOL_JAC
+    assert rel_err(ev.ode_error_host(wl.x), gold["ode_error"]) <= TOL_VALUE
+    assert rel_err(ev.resample_host(wl.x, [41]), gold["resample_41"]) <= TOL_VALUE
+    ev.close()
+    uw = W.unicycle(batch=1, nnodes=17, ncyl=2, ntracks=1)
+    assert np.array_equal(uw.x, gold["user_x"])
+    uev = capi.Evaluator(uw)
+    fd = uev.eval_host(uw.x, jac_mode=W.JAC_FD)
+    ex = uev.eval_host(uw.x, want=("jac",), jac_mode=W.JAC_EXACT)
+    assert rel_err(fd["f"], gold["user_f"]) <= TOL_VALUE and rel_err(fd["g"], gold["user_g"]) <= TOL_VALUE
+    assert np.array_equal(fd["jac"], gold["user_jac_fd"]) and rel_err(ex["jac"], gold["user_jac_exact"]) <= TOL_JAC
+    uev.close()
 
 
 def test_device_pointer_path_and_partial_outputs(evaluators):
