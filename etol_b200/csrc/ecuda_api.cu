@@ -208,6 +208,7 @@ struct ecuda_ctx {
     DevBuf sx, sf_, sgv, sjac, sgrad, ssum;  // staging for host-memory calls
     size_t smem_bytes = 0, smem_fast_fd = 0, smem_fast_exact = 0;
     size_t smem_generic_exact = 0;  // generic kernel without the finite-difference arrays
+    size_t smem_isz = 0;            // extra shared memory of the exact row-owner kernel (CARVE_ISZ)
     bool fast_ok = false;  // the specialised kernels (ecuda_fast.cuh) can run this problem
     bool no_fast = false;  // ECUDA_NO_FAST=1 in the environment: never use them (A/B runs and tests)
     bool no_image = true;   // ECUDA_IMAGE=1 opts in to the persistent image kernel (exact mode); measured
@@ -380,7 +381,7 @@ static int launch_keval_fast(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, in
     // than the column-owner layout; C0 (66 rows) 28 % slower, C4 (180 rows) 5 % slower. Exact mode: always.
     if (!h->no_rows && (!FD || h->rows_fill)) {
         static size_t configured_rows[64] = {0};
-        size_t smem_rows = smem;
+        size_t smem_rows = smem + (FD ? 0 : h->smem_isz);  // exact: 1/sz staged in shared memory (CARVE_ISZ)
         if (io.nranks > 0) {  // staged bounds (fused summary), largest phase
             int ncp = 0;
             for (int p = 0; p < h->pd.nphases; ++p) ncp = std::max(ncp, phase_ncons(h->pd, h->pd.ph[p]));
@@ -534,7 +535,8 @@ static int launch_eval_user(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
             const bool copy_warp = !fd && io.jac != nullptr && !h->no_copy_warp && (h->pd.nnz & 1) == 0 &&
                                    (reinterpret_cast<uintptr_t>(io.jac) & 15) == 0;
             size_t smem = fd ? h->smem_fast_fd
-                             : h->smem_fast_exact + (copy_warp ? (kCopySlots * kCopyChunk + 2) * sizeof(double) : 0);
+                             : h->smem_fast_exact + h->smem_isz +
+                                   (copy_warp ? (kCopySlots * kCopyChunk + 2) * sizeof(double) : 0);
             if (io.nranks > 0) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
             rc = launch_user(h, fd ? UserImage::ROWS_FD : UserImage::ROWS_EXACT, dim3(grid),
                              kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, io, st);
@@ -661,6 +663,8 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
         smem = std::max(smem, cta_doubles(pd, ph, kThreads) * sizeof(double));
         smem_fd = std::max(smem_fd, cta_doubles(pd, ph, kThreads, CARVE_FD) * sizeof(double));
         smem_ex = std::max(smem_ex, cta_doubles(pd, ph, kThreads, 0) * sizeof(double));
+        h->smem_isz = std::max(p == 0 ? size_t(0) : h->smem_isz,
+                               (cta_doubles(pd, ph, kThreads, CARVE_ISZ) - cta_doubles(pd, ph, kThreads, 0)) * sizeof(double));
         h->smem_generic_exact = std::max(p == 0 ? size_t(0) : h->smem_generic_exact,
                                          cta_doubles(pd, ph, kThreads, CARVE_P) * sizeof(double));
         one_row_per_thread = one_row_per_thread && pd.ns * ph.N <= kThreads &&

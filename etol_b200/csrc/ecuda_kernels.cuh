@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     const int tid = threadIdx.x, nthr = kThreads;
     const bool copy_warp = !FD && blockDim.x > kThreads;  // uniform over the CTA
     CtaMem m;
-    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : 0);
+    carve(m, smem, pb, ph, nthr, FD ? CARVE_FD : CARVE_ISZ);
     if (tid == 0) {
         mbar_init(&bar, 1);
         if (copy_warp)
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     __syncthreads();
     // fused summary: this phase's block of the instance's bounds is staged behind the work arrays
     const int nbnd = io.nranks > 0 ? phase_ncons(pb, ph) + (phase_ncons(pb, ph) & 1) : 0;
-    double* bnd = smem + cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0);
+    double* bnd = smem + cta_doubles(pb, ph, nthr, FD ? CARVE_FD : CARVE_ISZ);
     if (!FD && tid >= kThreads) {  // copy warp: template -> triplet array, then the barrier before the triplets
         double* ring = bnd + 2 * nbnd;
         ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         m.bl = bnd;
         m.bu = bnd + nbnd;
     }
-    stage_vars(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
+    stage_vars<!FD>(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
     mbar_wait(&bar, 0);
     if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
     RowState<M, NB> rs;
@@ -317,6 +317,9 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, true);
     } else {
         rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, true, false);
+        // (storing the control / time-column triplets, which lie outside the template's range, before this
+        // barrier was measured: 0.158 vs 0.148 ms -- the second evaluation of the model costs more than the
+        // shorter wait saves)
         __syncthreads();  // all threads: the template has landed before the node-local triplets overwrite it
         rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
         rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, false, true);

@@ -71,7 +71,7 @@ struct CtaMem {
 
 // what a CTA keeps in shared memory: the generic kernels need everything; the fast kernels keep the
 // block sums in registers (no P) and, in exact mode, have no finite-difference data (no xp/xm/rinv)
-enum { CARVE_P = 1, CARVE_FD = 2, CARVE_ALL = 3 };
+enum { CARVE_P = 1, CARVE_FD = 2, CARVE_ALL = 3, CARVE_ISZ = 4 };
 #define ECUDA_STAGE_BATCH 2  // strides of the staging loops whose loads are in flight together
 
 // shared-memory footprint in doubles for one CTA working on phase `ph`
@@ -82,6 +82,7 @@ ECUDA_HD size_t cta_doubles(const ProbDev& pb, const PhaseDev& ph, int nthr, int
     n += static_cast<size_t>(ph.N + (ph.N & 1));
     n += static_cast<size_t>(pb.inst_stride);
     if (what & CARVE_P) n += static_cast<size_t>(ph.nb) * nthr;
+    if (what & CARVE_ISZ) n += static_cast<size_t>(ph.nvars + (ph.nvars & 1));
     n += static_cast<size_t>((ph.nvars + 3) / 2);  // colp (ints), nvars_p + 1 of them
     return n;
 }
@@ -97,6 +98,10 @@ ECUDA_HD void carve(CtaMem& m, double* base, const ProbDev& pb, const PhaseDev& 
         m.xp = base;    base += nv;
         m.xm = base;    base += nv;
         m.rinv = base;  base += nv;
+    }
+    if ((what & CARVE_ISZ) && !(what & CARVE_FD)) {  // exact row-owner kernel: the rinv slot holds 1/sz instead
+        m.rinv = base;
+        base += nv;
     }
     m.hf = base;    base += static_cast<size_t>(ph.N) * pb.ns;
     m.dotv = base;  base += static_cast<size_t>(ph.N) * pb.ns;
@@ -121,6 +126,9 @@ ECUDA_HD PhaseTimes phase_times(const ProbDev& pb, const PhaseDev& ph, const dou
 }
 
 // ---- stage ------------------------------------------------------------------------------------------
+// ISZ: also keep 1/sz in shared memory (in m.rinv, which exact mode does not otherwise use; CARVE_ISZ) -- compile
+// time, so that kernels without it pay nothing
+template <bool ISZ = false>
 ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, CtaMem& m, int b, int tid,
                          int nthr, bool fd) {
     const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
@@ -146,6 +154,7 @@ ECUDA_HD void stage_vars(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io
             if (c < ph.nvars) {
                 m.z[c] = zt[u] * s[u];
                 m.colp[c] = cp[u];
+                if (ISZ) m.rinv[c] = s[u];
                 if (fd) {
                     double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt[u]));
                     m.xp[c] = (zt[u] + delta) * s[u];

@@ -18,6 +18,12 @@
 
 namespace ecuda {
 
+// 1/sz of a variable of the phase in exact mode: the shared-memory copy the exact row-owner kernel staged in the
+// (otherwise unused) rinv slot, else global memory
+ECUDA_HD double isz_of(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int lcol) {
+    return m.rinv ? m.rinv[lcol] : ECUDA_LDG(pb.isz + ph.zoff + lcol);
+}
+
 template <int M, int NB>
 struct RowState {
     double P[NB];  // block sums of (D X)[k][i]
@@ -183,8 +189,7 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
         Model<M>::jac(x, u, dfdx, dfdu);
         Model<M>::f(x, u, t, f);
         const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
-        const int rdef = ph.goff + k * NS + i;
-        const double sgi = ECUDA_LDG(pb.sg + rdef);
+        const double sgi = rs.sgr;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {  // [xcol_local_exact, row i]
             const int rk = pb.xrank[j][i];
@@ -197,7 +202,7 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
                 for (int c2 = 0; c2 < NS; ++c2)
                     if (a == i && c2 == j) d = dfdx[a][c2];
             const double v = ((i == j) ? dkk : 0.0) - pt.h * d;
-            ECUDA_STREAM_STORE(jac + m.colp[lcol] + k + rk, (sgi * v) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+            ECUDA_STREAM_STORE(jac + m.colp[lcol] + k + rk, (sgi * v) * isz_of(pb, ph, m, lcol));
         }
         for (int c = 0; c < nc; ++c) {  // [node_item exact, control columns, row i]
             const int rk = pb.urank[c][i];
@@ -210,7 +215,7 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
                 for (int c2 = 0; c2 < NCU; ++c2)
                     if (a == i && c2 == c) d = dfdu[a][c2];
             const double v = -(pt.h * d);
-            ECUDA_STREAM_STORE(jac + m.colp[lcol] + rk, (sgi * v) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+            ECUDA_STREAM_STORE(jac + m.colp[lcol] + rk, (sgi * v) * isz_of(pb, ph, m, lcol));
         }
         double fi = 0.0;
 #pragma unroll
@@ -220,7 +225,7 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
         for (int which = 0; which < 2; ++which) {  // [node_item exact, time columns, row i]
             const int lcol = tcol + which;
             const double v = which == 0 ? 0.5 * fi : -0.5 * fi;
-            ECUDA_STREAM_STORE(jac + m.colp[lcol] + k * NS + i, (sgi * v) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+            ECUDA_STREAM_STORE(jac + m.colp[lcol] + k * NS + i, (sgi * v) * isz_of(pb, ph, m, lcol));
         }
     }
 }
@@ -313,7 +318,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             for (int j = 0; j < 2; ++j) {
                 const int lcol = lcol0 + j;
                 const double v = (j == 0) ? ddx : ddy;
-                ECUDA_STREAM_STORE(jac + m.colp[lcol] + N - 1 + pb.xcnt[j] + ev + q, (s * v) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+                ECUDA_STREAM_STORE(jac + m.colp[lcol] + N - 1 + pb.xcnt[j] + ev + q, (s * v) * isz_of(pb, ph, m, lcol));
             }
             if (q >= ph.nstat) {
 #pragma unroll
@@ -321,7 +326,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
                     const int lcol = tcol + which;
                     const double dtk = which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau);
                     ECUDA_STREAM_STORE(jac + m.colp[lcol] + NS * N + k * ntr + (q - ph.nstat),
-                                       (s * (ddt * dtk)) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+                                       (s * (ddt * dtk)) * isz_of(pb, ph, m, lcol));
                 }
             }
         }
@@ -344,7 +349,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             if (FD)
                 ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * m.xp[lcol] - s * m.xm[lcol]) * m.rinv[lcol]);
             else
-                ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * 1.0) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+                ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * 1.0) * isz_of(pb, ph, m, lcol));
         }
         return;
     }
@@ -388,7 +393,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
                     ECUDA_STREAM_STORE(jac + at + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
                 }
             } else {
-                const double is = ECUDA_LDG(pb.isz + ph.zoff + lcol);
+                const double is = isz_of(pb, ph, m, lcol);
                 ECUDA_STREAM_STORE(jac + at, (s * (which == 0 ? -1.0 : 1.0)) * is);
                 if (which == 0 && p > 0) {
                     const int rl = pb.linkoff + (p - 1) * (NS + 1) + NS;
@@ -421,7 +426,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             if (FD)
                 ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * (m.xp[lcol] - o) - s * (m.xm[lcol] - o)) * m.rinv[lcol]);
             else
-                ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * 1.0) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+                ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * 1.0) * isz_of(pb, ph, m, lcol));
         }
     } else if (jac) {
         const PhaseDev& pv = pb.ph[p - 1];
@@ -431,7 +436,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             const double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * NS + i);
             ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * (o - m.xp[lcol]) - s * (o - m.xm[lcol])) * m.rinv[lcol]);
         } else {
-            ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * -1.0) * ECUDA_LDG(pb.isz + ph.zoff + lcol));
+            ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * -1.0) * isz_of(pb, ph, m, lcol));
         }
     }
 }

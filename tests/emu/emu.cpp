@@ -39,13 +39,13 @@ static void run_fast(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO&
 // the row-owner kernel (k_eval_rows)
 template <int M, int NB, bool FD>
 static void run_rows(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
-    std::vector<double> smem(cta_doubles(pb, ph, nthr, FD ? CARVE_FD : 0), 0.0);
+    std::vector<double> smem(cta_doubles(pb, ph, nthr, FD ? CARVE_FD : CARVE_ISZ), 0.0);
     CtaMem m;
-    carve(m, smem.data(), pb, ph, nthr, FD ? CARVE_FD : 0);
+    carve(m, smem.data(), pb, ph, nthr, FD ? CARVE_FD : CARVE_ISZ);
     std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
     if (!FD && io.jac)
         for (int t = 0; t < nthr; ++t) fast_copy_template(pb, ph, io, b, t, nthr);
-    for (int t = 0; t < nthr; ++t) stage_vars(pb, ph, io, m, b, t, nthr, FD && io.jac != nullptr);
+    for (int t = 0; t < nthr; ++t) stage_vars<!FD>(pb, ph, io, m, b, t, nthr, FD && io.jac != nullptr);
     std::vector<RowState<M, NB>> rs(nthr);
     for (int t = 0; t < nthr; ++t) {  // no barrier after staging: a thread runs to the end on its own
         rows_values<M, NB, FD>(pb, ph, io, m, b, t, rs[t]);
