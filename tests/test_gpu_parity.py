@@ -179,6 +179,40 @@ def test_hessian_error_and_resample_with_device_pointers(evaluators):
     assert np.array_equal(xn.cpu().numpy(), ev.resample_host(wl.x, nn))
 
 
+@pytest.mark.parametrize("uniform_bounds", [True, False])
+@pytest.mark.parametrize("mode", [W.JAC_FD, W.JAC_EXACT])
+def test_fused_summary_equals_separate_summary(uniform_bounds, mode):
+    """the {f, max bound violation} rows the evaluation kernel's epilogue writes (one rank: into its own buffer)
+    are the bits of the stand-alone summary kernel -- with the compact form of the bounds (every instance has
+    defect bounds 0 and the same path-row bounds) and with dense per-instance bounds"""
+    import torch
+    wl = W.pm3d(batch=37)
+    if not uniform_bounds:  # one instance with its own path-row bound, one with a non-zero defect bound
+        p0 = wl.ns * wl.nnodes[0] + 2 * wl.ns
+        wl.gl[5, p0 + 3] = -2.5
+        wl.gu[9, 4] = 0.125
+    ev = capi.Evaluator(wl, device=0)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    st = stream.cuda_stream
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(wl.x).to(dev)
+        f = torch.empty(wl.batch, dtype=torch.float64, device=dev)
+        g = torch.empty((wl.batch, ev.ncons), dtype=torch.float64, device=dev)
+        jac = torch.empty((wl.batch, ev.nnz), dtype=torch.float64, device=dev)
+        fused = torch.full((wl.batch, 2), float("nan"), dtype=torch.float64, device=dev)
+        sep = torch.full((wl.batch, 2), float("nan"), dtype=torch.float64, device=dev)
+        ev.eval_allgather_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), mode, [fused.data_ptr()], 0, st)
+        ev.summarize_ptr(f.data_ptr(), g.data_ptr(), sep.data_ptr(), st)
+    stream.synchronize()
+    a, b = fused.cpu().numpy(), sep.cpu().numpy()
+    assert np.array_equal(a, b)
+    gv = g.cpu().numpy()
+    want = np.maximum(wl.gl - gv, gv - wl.gu).max(axis=1)   # the definition, on the host
+    assert np.array_equal(a[:, 1], want) and np.array_equal(a[:, 0], f.cpu().numpy())
+    ev.close()
+
+
 def test_resample_round_trip_on_device(evaluators):
     """up-sampling does not change the interpolating polynomial: 40 -> 61 -> 40 nodes returns the decision
     vectors (a size-independent property of the kernel), and the finer mesh sees an error profile of the
