@@ -36,8 +36,17 @@ struct RowRegs {
 };
 
 // bound violation of one constraint value (fused summary; io.nranks > 0)
+// cls: 0 defect row, 1 path row, 2 event row, 3 duration row. With the compact form of the bounds (io.bev: every
+// instance has defect bounds 0 and one pair of path-row bounds) only the event and duration rows read memory.
 ECUDA_HD double row_violation(const EvalIO& io, const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int b, int r,
-                              double val) {
+                              double val, int cls) {
+    if (io.bev) {
+        if (cls == 0) return fabs(val);  // max(0 - val, val - 0)
+        if (cls == 1) return fmax(io.plo - val, val - io.phi);
+        const int nev = pb.ne + 1, e = cls == 2 ? r - ph.goff - pb.ns * ph.N : pb.ne;
+        const double* ev = io.bev + static_cast<size_t>(b) * 2 * nev;
+        return fmax(ECUDA_LDG(ev + e) - val, val - ECUDA_LDG(ev + nev + e));
+    }
     if (m.bl) return fmax(m.bl[r - ph.goff] - val, val - m.bu[r - ph.goff]);
     const size_t o = static_cast<size_t>(b) * pb.ncons + r;
     return fmax(ECUDA_LDG(io.bl + o) - val, val - ECUDA_LDG(io.bu + o));
@@ -244,7 +253,7 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
             const int r = ph.goff + NS * N + pb.ne + it;
             const double val = ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t);
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val, 1));
         }
         for (int e = tid; e < pb.ne; e += nthr) {
             const int r = ph.goff + NS * N + e;
@@ -252,13 +261,13 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
             const int i = (e < NS) ? e : e - NS;
             const double val = ECUDA_LDG(sg + r) * m.z[nc * N + node * NS + i];
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val, 2));
         }
         if (tid == 0) {
             const int r = ph.goff + NS * N + pb.ne + np * N;
             const double val = ECUDA_LDG(sg + r) * (pt.tf - pt.t0);
             ECUDA_STREAM_STORE(g + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val, 3));
         }
         if (p + 1 < pb.nphases) {
             const PhaseDev& nx = pb.ph[p + 1];
@@ -292,7 +301,7 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
         if (io.g) {
             const double val = sgr * (m.dotv[k * NS + j] - hfv);
             ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val));
+            if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val, 0));
         }
         if (jac) {
             if (FD) {

@@ -272,23 +272,7 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     if (io.nranks > 0) {  // coalesced, off the critical path: the values are needed after the barrier
         const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
         const int ncp = phase_ncons(pb, ph);
-        if (io.bev) {  // compact form: defects 0, one pair for all path rows, events + duration per instance
-            const int ndef = pb.ns * ph.N, nev = pb.ne + 1;
-            const double* ev = io.bev + static_cast<size_t>(b) * 2 * nev;
-            for (int c = tid; c < ncp; c += nthr) {
-                double lo = 0.0, hi = 0.0;
-                if (c >= ndef + pb.ne && c < ncp - 1) {
-                    lo = io.plo;
-                    hi = io.phi;
-                } else if (c >= ndef) {
-                    const int e = c < ncp - 1 ? c - ndef : pb.ne;
-                    lo = __ldg(ev + e);
-                    hi = __ldg(ev + nev + e);
-                }
-                bnd[c] = lo;
-                bnd[nbnd + c] = hi;
-            }
-        } else
+        if (!io.bev)  // (compact form of the bounds: nothing to stage, see row_violation)
         for (int c0 = tid; c0 < ncp; c0 += 4 * nthr) {  // loads of four strides in flight together
             double lo[4], hi[4];
 #pragma unroll
@@ -304,8 +288,10 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
                     bnd[nbnd + c0 + u * nthr] = hi[u];
                 }
         }
-        m.bl = bnd;
-        m.bu = bnd + nbnd;
+        if (!io.bev) {
+            m.bl = bnd;
+            m.bu = bnd + nbnd;
+        }
     }
     stage_vars<!FD>(pb, ph, io, m, b, tid, nthr, FD && io.jac != nullptr);
     mbar_wait(&bar, 0);

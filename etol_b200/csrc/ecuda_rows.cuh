@@ -66,7 +66,7 @@ ECUDA_HD void rows_values(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     if (io.g) {
         const double val = rs.sgr * (rs.dv - rs.hfv);
         ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val));
+        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val, 0));
     }
 }
 
@@ -248,8 +248,8 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
     double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
     const int tcol = (NS + nc) * N;
-    auto note = [&](int r, double val) {
-        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val));
+    auto note = [&](int r, double val, int cls) {
+        if (io.nranks > 0) rs.viol = fmax(rs.viol, row_violation(io, pb, ph, m, b, r, val, cls));
     };
 
     if (it == 0) {  // ---- objective: running cost per node and quadrature            [phase_b + objective_phase]
@@ -280,7 +280,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         if (g) {
             const double val = s * path_row<M>(pb, ph, m, q, x0, x1, t);
             ECUDA_STREAM_STORE(g + r, val);
-            note(r, val);
+            note(r, val, 1);
         }
         if (!jac) return;
         const int ev = (k == 0 || k == N - 1) ? 1 : 0;
@@ -342,7 +342,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         if (g) {
             const double val = s * m.z[lcol];
             ECUDA_STREAM_STORE(g + r, val);
-            note(r, val);
+            note(r, val, 2);
         }
         if (jac) {
             const int pos = N - 1 + pb.xcnt[i];
@@ -360,7 +360,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         if (g) {
             const double val = s * (pt.tf - pt.t0);
             ECUDA_STREAM_STORE(g + r, val);
-            note(r, val);
+            note(r, val, 3);
             if (p + 1 < pb.nphases) {  // time continuity with the next phase
                 const PhaseDev& nx = pb.ph[p + 1];
                 const int rl = pb.linkoff + p * (NS + 1) + NS;
