@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(kThreads) k_ode_error(const __grid_constant__ 
     ode_error_dots<M>(pb, ph, m, tid, nthr);
     __syncthreads();
     ode_error_weights<M>(pb, ph, m, tid);
+    ode_error_points<M>(pb, ph, p, mesh, m, tid, nthr);  // writes m.P: the dots above are done with it
     __syncthreads();
     ode_error_intervals<M>(pb, ph, p, mesh, m, b, tid, nthr);
 }

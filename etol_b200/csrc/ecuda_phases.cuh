@@ -917,44 +917,54 @@ ECUDA_HD void ode_error_weights(const ProbDev& pb, const PhaseDev& ph, CtaMem& m
     }
     m.hf[tid] = w;
 }
+// one thread per quadrature point: |dx~/dtau - h f(x~, u~)| of every state into m.P[(k*Q + q)*NS + i]
 template <int M>
-ECUDA_HD void ode_error_intervals(const ProbDev& pb, const PhaseDev& ph, int p, const MeshDev& mesh, const CtaMem& m,
-                                  int b, int tid, int nthr) {
+ECUDA_HD void ode_error_points(const ProbDev& pb, const PhaseDev& ph, int p, const MeshDev& mesh, CtaMem& m, int tid,
+                               int nthr) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
     const int N = ph.N, nc = pb.nc;
     const PhaseTimes pt = phase_times(pb, ph, m.z);
-    for (int k = tid; k < N - 1; k += nthr) {
-        double eta[NS];
+    for (int r = tid; r < (N - 1) * ECUDA_MESH_Q; r += nthr) {
+        const double* E = mesh.E[p] + static_cast<size_t>(r) * N;
+        const double* dE = mesh.dE[p] + static_cast<size_t>(r) * N;
+        double xq[NS], dxq[NS], uq[NCU], f[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) eta[i] = 0.0;
-        for (int q = 0; q < ECUDA_MESH_Q; ++q) {
-            const size_t r = static_cast<size_t>(k) * ECUDA_MESH_Q + q;
-            const double* E = mesh.E[p] + r * N;
-            const double* dE = mesh.dE[p] + r * N;
-            double xq[NS], dxq[NS], uq[NCU], f[NS];
+        for (int i = 0; i < NS; ++i) xq[i] = dxq[i] = 0.0;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) xq[i] = dxq[i] = 0.0;
+        for (int j = 0; j < NCU; ++j) uq[j] = 0.0;
+        for (int l = 0; l < N; ++l) {
+            const double e = ECUDA_LDG(E + l), de = ECUDA_LDG(dE + l);
 #pragma unroll
-            for (int j = 0; j < NCU; ++j) uq[j] = 0.0;
-            for (int l = 0; l < N; ++l) {
-                const double e = ECUDA_LDG(E + l), de = ECUDA_LDG(dE + l);
-#pragma unroll
-                for (int i = 0; i < NS; ++i) {
-                    const double xv = m.z[nc * N + l * NS + i];
-                    xq[i] = fma(e, xv, xq[i]);
-                    dxq[i] = fma(de, xv, dxq[i]);
-                }
-#pragma unroll
-                for (int j = 0; j < NCU; ++j) uq[j] = fma(e, m.z[l * nc + j], uq[j]);
+            for (int i = 0; i < NS; ++i) {
+                const double xv = m.z[nc * N + l * NS + i];
+                xq[i] = fma(e, xv, xq[i]);
+                dxq[i] = fma(de, xv, dxq[i]);
             }
-            Model<M>::f(xq, uq, pt.h * ECUDA_LDG(mesh.tq[p] + r) + pt.m, f);
-            const double w = ECUDA_LDG(mesh.wq[p] + r);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) eta[i] = fma(w, fabs(dxq[i] - pt.h * f[i]), eta[i]);
+            for (int j = 0; j < NCU; ++j) uq[j] = fma(e, m.z[l * nc + j], uq[j]);
         }
+        Model<M>::f(xq, uq, pt.h * ECUDA_LDG(mesh.tq[p] + r) + pt.m, f);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) m.P[static_cast<size_t>(r) * NS + i] = fabs(dxq[i] - pt.h * f[i]);
+    }
+}
+// after a barrier, thread k: the quadrature sums of interval k in point order, then the scaled maximum
+template <int M>
+ECUDA_HD void ode_error_intervals(const ProbDev& pb, const PhaseDev& ph, int p, const MeshDev& mesh, const CtaMem& m,
+                                  int b, int tid, int nthr) {
+    constexpr int NS = Model<M>::NS;
+    const int N = ph.N;
+    for (int k = tid; k < N - 1; k += nthr) {
         double err = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) err = fmax(err, eta[i] / (m.hf[i] + 1.0));
+        for (int i = 0; i < NS; ++i) {
+            double eta = 0.0;
+            for (int q = 0; q < ECUDA_MESH_Q; ++q) {
+                const size_t r = static_cast<size_t>(k) * ECUDA_MESH_Q + q;
+                eta = fma(ECUDA_LDG(mesh.wq[p] + r), m.P[r * NS + i], eta);
+            }
+            err = fmax(err, eta / (m.hf[i] + 1.0));
+        }
         mesh.out[static_cast<size_t>(b) * mesh.nint + mesh.eoff[p] + k] = err;
     }
 }
