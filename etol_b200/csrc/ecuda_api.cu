@@ -223,6 +223,7 @@ struct ecuda_ctx {
     int64_t launches = 0;
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
+    int rowsn_N = 0;     // node count shared by all phases when the N-specialised kernels may run (else 0)
     int nb_uniform = 0;  // summation-block count if all phases share it and it is <= 8, else 0
     std::vector<double> h_sz, h_sg;
     // user model (ecuda_register_user_model): kernels compiled with NVRTC, loaded per handle
@@ -424,6 +425,49 @@ static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     return ECUDA_OK;
 }
 
+// N-specialised row-owner kernels (ecuda_rowsn.cuh): instantiated ahead of time for the node counts of the
+// BASELINE configurations; other shapes take the kernels above
+template <int M, int N, bool TRK, bool SUM>
+static int launch_rows_n_fd_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    size_t smem = rn_doubles<M>(h->pd, N, true) * sizeof(double);
+    if (io.nranks > 0 && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < smem) {
+            CU(cudaFuncSetAttribute(k_rows_n_fd<M, N, TRK, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    k_rows_n_fd<M, N, TRK, SUM><<<grid, kThreads, smem, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
+// TRK: instantiated with track rows (moving zones) or without; a problem whose model is only instantiated without
+// them and has tracks falls back (returns 1)
+template <int M, int N, bool TRK>
+static int launch_rows_n_fd(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    if (!TRK && h->pd.ntracks > 0) return 1;
+    return io.nranks > 0 ? launch_rows_n_fd_t<M, N, TRK, true>(h, io, st, grid)
+                         : launch_rows_n_fd_t<M, N, TRK, false>(h, io, st, grid);
+}
+// returns 1 when no instantiation matches (the caller falls back)
+template <int M>
+static int launch_rows_n(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    if (!fd) return 1;
+    if (M == ECUDA_MODEL_PM3D) {
+        if (h->rowsn_N == 40) return launch_rows_n_fd<M, 40, false>(h, io, st, grid);
+        if (h->rowsn_N == 30) return launch_rows_n_fd<M, 30, false>(h, io, st, grid);
+    }
+    if (M == ECUDA_MODEL_SI2D) {
+        if (h->rowsn_N == 33) return launch_rows_n_fd<M, 33, true>(h, io, st, grid);
+        if (h->rowsn_N == 17) return launch_rows_n_fd<M, 17, true>(h, io, st, grid);
+    }
+    return 1;
+}
+
 template <int M, int NB>
 static int launch_keval_fast_mode(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     if (io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET) return launch_keval_fast<M, NB, true>(h, io, st, grid);
@@ -449,20 +493,24 @@ static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
         ++h->launches;
     }
     if (io.f || io.g || io.jac) {
-        int rc = ECUDA_OK;
-        if (h->fast_ok) {
+        int rc = h->rowsn_N > 0 ? launch_rows_n<M>(h, io, st, grid) : 1;
+        if (rc <= 0) {
+        } else if (h->fast_ok) {
+            rc = ECUDA_OK;
             switch (h->nb_uniform) {
                 case 3: rc = launch_keval_fast_mode<M, 3>(h, io, st, grid); break;
                 case 4: rc = launch_keval_fast_mode<M, 4>(h, io, st, grid); break;
                 default: rc = launch_keval_fast_mode<M, 5>(h, io, st, grid); break;
             }
-        } else
+        } else {
+        rc = ECUDA_OK;
         switch (h->nb_uniform) {  // block count shared by all phases, or 0
             // specialised for the node counts of the BASELINE configs: 17 -> 3, 30 -> 4, 33 / 40 -> 5
             case 3: rc = launch_keval<M, 3>(h, io, st, grid); break;
             case 4: rc = launch_keval<M, 4>(h, io, st, grid); break;
             case 5: rc = launch_keval<M, 5>(h, io, st, grid); break;
             default: rc = launch_keval<M, 0>(h, io, st, grid); break;
+        }
         }
         if (rc) return rc;
         ++h->launches;
@@ -690,6 +738,12 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     // the specialised kernels: block counts of the BASELINE configs, one defect row per thread
     h->fast_ok = !h->no_fast && !h->force_generic && h->nb_uniform >= 3 && h->nb_uniform <= 5 && one_row_per_thread;
     h->image_ok = h->fast_ok && !h->no_image && (pd.nnz & 1) == 0 && smem_img <= 227 * 1024 - 1024;
+    h->rowsn_N = 0;
+    if (h->fast_ok && !std::getenv("ECUDA_NO_ROWSN")) {
+        h->rowsn_N = pd.ph[0].N;
+        for (int p = 1; p < hp.nphases; ++p)
+            if (pd.ph[p].N != h->rowsn_N) h->rowsn_N = 0;
+    }
     h->rows_fill = true;
     for (int p = 0; p < hp.nphases; ++p) h->rows_fill = h->rows_fill && 8 * pd.ns * pd.ph[p].N >= 7 * kThreads;
     if (std::getenv("ECUDA_ROWS_ALWAYS")) h->rows_fill = true;

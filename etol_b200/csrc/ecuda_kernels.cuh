@@ -14,7 +14,7 @@
 #ifndef ECUDA_KERNELS_CUH_
 #define ECUDA_KERNELS_CUH_
 
-#include "ecuda_rows.cuh"
+#include "ecuda_rowsn.cuh"
 
 namespace ecuda {
 
@@ -317,6 +317,67 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         if ((tid & 31) == 0) red[tid >> 5] = v;
         if (tid == nthr - 1) red[kThreads / 32] = rs.fval;
         named_barrier(2, kThreads);
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
+}
+
+// N-specialised row-owner kernel, finite differences (ecuda_rowsn.cuh): the node count is a template argument.
+// One CTA per (instance, phase); every phase of the problem has N nodes (checked by the launcher).
+#ifndef ECUDA_MIN_CTAS_ROWSN_FD
+#define ECUDA_MIN_CTAS_ROWSN_FD 3
+#endif
+// TRK: the problem has moving zones (track rows); SUM: fused per-instance summary + all-gather (io.nranks > 0)
+template <int M, int N, bool TRK, bool SUM>
+__global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
+    k_rows_n_fd(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = kThreads;
+    RnMem m;
+    rn_carve<M>(m, smem, pb, N, true);
+    CtaMem cm{};
+    cm.inst = m.inst;
+    cm.z = m.z;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the records
+        const int ncp = phase_ncons(pb, ph), nbnd = ncp + (ncp & 1);
+        double* bnd = smem + rn_doubles<M>(pb, N, true);
+        const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
+        for (int c = tid; c < ncp; c += nthr) {
+            bnd[c] = __ldg(io.bl + o + c);
+            bnd[nbnd + c] = __ldg(io.bu + o + c);
+        }
+        cm.bl = bnd;
+        cm.bu = bnd + nbnd;
+    }
+    rn_stage<M, N, true>(pb, ph, io, m, b, tid, nthr);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    double viol, fval;
+    rn_thread_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
+    if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
+        __shared__ double red[kThreads / 32 + 1];
+        double v = viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = fval;
+        __syncthreads();
         if (tid < 32) {
             double w = tid < kThreads / 32 ? red[tid] : 0.0;
             for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));

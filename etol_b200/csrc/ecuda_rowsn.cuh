@@ -1,0 +1,612 @@
+// ecuda_rowsn.cuh -- row-owner evaluation with the node count N as a COMPILE-TIME constant.
+//
+// Same arithmetic as ecuda_rows.cuh / ecuda_phases.cuh (every value is produced by the same FP64 operation
+// sequence, so results are bit-identical to the generic kernels and to the oracle); what changes is what the
+// instruction stream spends its issue slots on. The round-1 kernel (k_eval_rows<M,NB,FD>, N a kernel
+// parameter) executed 3000 warp instructions per warp of which only 1068 were FP64: every D[k][l] load
+// needed a 64-bit multiply-add for its address, every triplet two compares, two selects and a four-instruction
+// 64-bit address computation, and the per-column finite-difference data came from five separate shared arrays.
+// Here
+//   * N, the block count and every offset derived from them are constants: D[k][l], X(l,i) and the
+//     per-column records are addressed as  per-thread base + immediate;
+//   * the finite-difference data of a column live in ONE 32-byte shared-memory record {z+d, z-d, 1/(2d),
+//     first triplet}, fetched with two 128-bit loads;
+//   * triplet addresses are  (jac + k) + 8 * (record.cp + select) : one compare, one select, one add, one
+//     wide multiply-add.
+// Reference counterparts: PSOPT's defect assembly and index-set finite differences entered at
+// src/ePSOPT/ePSOPT.cpp:84 (mode chosen at :64), callbacks src/ePSOPT/ePSOPT.cpp:186-306.
+#ifndef ECUDA_ROWSN_CUH_
+#define ECUDA_ROWSN_CUH_
+
+#include "ecuda_rows.cuh"
+
+namespace ecuda {
+
+// finite-difference data of one decision variable (one Jacobian column), staged per instance
+struct alignas(16) FdRec {
+    double xp;  // (z~ + delta) / sz
+    double xm;  // (z~ - delta) / sz
+    double ri;  // 1 / (2 delta)
+    int cp;     // first triplet of the column
+    int pad_;
+};
+// the two halves of a record as 128-bit shared-memory loads
+struct FdVals {
+    double xp, xm, ri;
+    unsigned cp;
+};
+ECUDA_HD FdVals rn_load(const FdRec* r) {
+    FdVals v;
+#if defined(__CUDA_ARCH__)
+    const double2 a = *reinterpret_cast<const double2*>(r);
+    const double2 c = *(reinterpret_cast<const double2*>(r) + 1);
+    v.xp = a.x;
+    v.xm = a.y;
+    v.ri = c.x;
+    v.cp = static_cast<unsigned>(__double2loint(c.y));
+#else
+    v.xp = r->xp;
+    v.xm = r->xm;
+    v.ri = r->ri;
+    v.cp = static_cast<unsigned>(r->cp);
+#endif
+    return v;
+}
+// byte a (0..3) of w
+ECUDA_HD unsigned rn_byte(unsigned w, int a) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + static_cast<unsigned>(a));
+#else
+    return (w >> (8 * a)) & 0xffu;
+#endif
+}
+
+// shared memory of one CTA of the N-specialised kernels
+struct RnMem {
+    double* inst;  // [inst_stride] obstacle / track records (bulk-copied)
+    double* z;     // [nv]          unscaled variables of the phase
+    FdRec* rec;    // [nv]          FD mode
+    double* isz;   // [nv]          exact mode: 1 / sz
+    int* colp;     // [nv + 1]      exact mode: first triplet of each column
+};
+
+template <int M>
+ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N + 2; }
+
+// doubles of shared memory, without the exact-mode ring and the fused-summary bounds
+template <int M>
+ECUDA_HD size_t rn_doubles(const ProbDev& pb, int N, bool fd) {
+    const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
+    size_t n = static_cast<size_t>(pb.inst_stride) + nve;
+    n += fd ? 4 * nv : nve + (nv + 2) / 2;
+    return n + (n & 1);
+}
+
+template <int M>
+ECUDA_HD void rn_carve(RnMem& m, double* base, const ProbDev& pb, int N, bool fd) {
+    const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
+    m.inst = base;  // first: 16-byte aligned destination of the bulk copy (inst_stride is even)
+    base += pb.inst_stride;
+    m.z = base;
+    base += nve;
+    m.rec = nullptr;
+    m.isz = nullptr;
+    m.colp = nullptr;
+    if (fd) {
+        m.rec = reinterpret_cast<FdRec*>(base);
+    } else {
+        m.isz = base;
+        base += nve;
+        m.colp = reinterpret_cast<int*>(base);
+    }
+}
+
+// ---- stage: same arithmetic as stage_vars ----------------------------------------------------------------------
+template <int M, int N, bool FD>
+ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, int tid, int nthr) {
+    const int nv = rn_nv<M>(pb, N);
+    const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
+    const double* is = pb.isz + ph.zoff;
+    const int* cpg = pb.colptr + ph.zoff;
+    if (!FD && tid == 0) m.colp[nv] = ECUDA_LDG(cpg + nv);
+    for (int c0 = tid; c0 < nv; c0 += 2 * nthr) {
+        double zt[2], s[2];
+        int cp[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = c0 + u * nthr;
+            if (c < nv) {
+                zt[u] = ECUDA_LDG(xs + c);
+                s[u] = ECUDA_LDG(is + c);
+                cp[u] = ECUDA_LDG(cpg + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = c0 + u * nthr;
+            if (c < nv) {
+                m.z[c] = zt[u] * s[u];
+                if (FD) {
+                    const double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt[u]));
+                    FdRec r;
+                    r.xp = (zt[u] + delta) * s[u];
+                    r.xm = (zt[u] - delta) * s[u];
+                    r.ri = 1.0 / (2.0 * delta);
+                    r.cp = cp[u];
+                    r.pad_ = 0;
+                    m.rec[c] = r;
+                } else {
+                    m.isz[c] = s[u];
+                    m.colp[c] = cp[u];
+                }
+            }
+        }
+    }
+}
+
+// ---- D X: block sums and total (canonical blocked order, see dot_row) ----------------------------------------
+template <int NS, int N>
+ECUDA_HD double rn_dot(const double* __restrict__ Dtk, const double* __restrict__ Xi, double (&P)[(N + 7) / 8]) {
+    constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL;
+    double total = 0.0;
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi) {
+        double p = 0.0;
+#pragma unroll
+        for (int a = 0; a < BL; ++a)
+            if (bi * BL + a < N) p = fma(ECUDA_LDG(Dtk + (bi * BL + a) * N), Xi[(bi * BL + a) * NS], p);
+        P[bi] = p;
+        total = (bi == 0) ? p : total + p;
+    }
+    return total;
+}
+
+// perturbed dots of the row's own diagonal column (models whose f_i reads x_i): sequence of fast_diag
+template <int NS, int N>
+ECUDA_HD void rn_diag(const double* __restrict__ Dtk, const double* __restrict__ Xi, double xpk, double xmk, int k,
+                      const double (&P)[(N + 7) / 8], double& dp, double& dm) {
+    constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL;
+    const int bk = k / BL, l0 = bk * BL, krel = k - l0;
+    double q = 0.0, sp = 0.0, sm = 0.0;
+#pragma unroll
+    for (int a = 0; a < BL; ++a) {
+        if (l0 + a < N) {
+            const double di = ECUDA_LDG(Dtk + (l0 + a) * N);
+            const double xi = Xi[(l0 + a) * NS];
+            if (a < krel) {
+                q = fma(di, xi, q);
+            } else if (a == krel) {
+                sp = fma(di, xpk, q);
+                sm = fma(di, xmk, q);
+            } else {
+                sp = fma(di, xi, sp);
+                sm = fma(di, xi, sm);
+            }
+        }
+    }
+    double pre = 0.0;
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        if (t < bk) pre = pre + P[t];
+    double tp = pre + sp, tm = pre + sm;
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        if (t > bk) {
+            tp = tp + P[t];
+            tm = tm + P[t];
+        }
+    dp = tp;
+    dm = tm;
+}
+
+// D-coupled triplets of defect row (k,i) in the state columns of summation block BI, by index-set central
+// differences, row-restricted (operation sequence of fast_fd_block). jk = jac + k. Triplet of row k in column
+// X(l,i): rows k < l sit at position k of the column; rows k > l come after its node-local block, dlt = (number of
+// node-local defect rows of column X(.,i)) - 1 places further; l == k is the row's own diagonal triplet at
+// kdo = its rank among the node-local rows (final for DIAG_FREE models, otherwise overwritten by the caller
+// afterwards). These offsets are one byte per node of the block, packed in w0 (nodes 0..3) and w1 (4..7).
+template <int NS, int N, int BI>
+ECUDA_HD void rn_fd_block(const double* __restrict__ Dtk, const double* __restrict__ Xi, const FdRec* __restrict__ Ri,
+                          const double (&P)[(N + 7) / 8], double sgr, double hfv, unsigned w0, unsigned w1,
+                          double* __restrict__ jk) {
+    constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL, l0 = BI * BL;
+    constexpr int nin = (N - l0) < BL ? (N - l0) : BL;
+    double d[nin], xv[nin];
+#pragma unroll
+    for (int a = 0; a < nin; ++a) {
+        d[a] = ECUDA_LDG(Dtk + (l0 + a) * N);
+        xv[a] = Xi[(l0 + a) * NS];
+    }
+    double pre = 0.0;
+#pragma unroll
+    for (int t = 0; t < BI; ++t) pre = (t == 0) ? P[0] : pre + P[t];
+    double q = 0.0;  // unperturbed in-block prefix
+#pragma unroll
+    for (int a = 0; a < nin; ++a) {
+        const FdVals rc = rn_load(Ri + (l0 + a) * NS);
+        double sp = fma(d[a], rc.xp, q);
+        double sm = fma(d[a], rc.xm, q);
+#pragma unroll
+        for (int e = a + 1; e < nin; ++e) {
+            sp = fma(d[e], xv[e], sp);
+            sm = fma(d[e], xv[e], sm);
+        }
+        double tp = (BI > 0) ? pre + sp : sp;
+        double tm = (BI > 0) ? pre + sm : sm;
+#pragma unroll
+        for (int t = BI + 1; t < NB; ++t) {
+            tp = tp + P[t];
+            tm = tm + P[t];
+        }
+        const double gp = sgr * (tp - hfv);
+        const double gm = sgr * (tm - hfv);
+        const double v = (gp - gm) * rc.ri;
+        ECUDA_STREAM_STORE(jk + (rc.cp + rn_byte(a < 4 ? w0 : w1, a & 3)), v);
+        q = fma(d[a], xv[a], q);
+    }
+}
+template <int NS, int N, int BI>
+struct RnFdBlocks {
+    ECUDA_HD static void run(const double* Dtk, const double* Xi, const FdRec* Ri, const double (&P)[(N + 7) / 8],
+                             double sgr, double hfv, int kb, unsigned all, unsigned m0, unsigned m1, double* jk) {
+        // offsets of this block's nodes: all `dlt` below the row's own block, the mixed pattern inside it, 0 above
+        const unsigned w0 = BI < kb ? all : (BI == kb ? m0 : 0u);
+        const unsigned w1 = BI < kb ? all : (BI == kb ? m1 : 0u);
+        rn_fd_block<NS, N, BI>(Dtk, Xi, Ri, P, sgr, hfv, w0, w1, jk);
+        RnFdBlocks<NS, N, BI + 1>::run(Dtk, Xi, Ri, P, sgr, hfv, kb, all, m0, m1, jk);
+    }
+};
+template <int NS, int N>
+struct RnFdBlocks<NS, N, (N + 7) / 8> {
+    ECUDA_HD static void run(const double*, const double*, const FdRec*, const double (&)[(N + 7) / 8], double, double,
+                             int, unsigned, unsigned, unsigned, double*) {}
+};
+
+// ---- defect row (k,i), finite differences: value, D-coupled triplets, node-local triplets -------------------------
+// [rows_values + rows_jacobian<FD>]
+template <int M, int N, bool SUM>
+ECUDA_HD void rn_row_fd(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                        int tid, double& viol) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
+    if (tid >= NS * N) return;
+    const int nc = pb.nc;
+    const int i = tid / N, k = tid - i * N;
+    const double* zx = m.z + nc * N;  // X(l,j) = zx[l*NS + j]
+    const double* Dtk = ph.Dt + k;
+    const double* Xi = zx + i;
+    const int r = ph.goff + k * NS + i;
+    const double sgr = ECUDA_LDG(pb.sg + r);
+    double hfv, P[NB];
+    {
+        const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+        const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+        const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+        double x[NS], u[NCU], f[NS];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+        for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+        Model<M>::f(x, u, t, f);
+        double fi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) fi = f[a];
+        hfv = h * fi;
+        const double dv = rn_dot<NS, N>(Dtk, Xi, P);
+        if (io.g) {
+            const double val = sgr * (dv - hfv);
+            ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+            if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
+        }
+    }
+    if (!io.jac) return;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    constexpr bool DS = Model<M>::DIAG_FREE;
+    const FdRec* rx = m.rec + nc * N;  // record of X(l,j) = rx[l*NS + j]
+    {
+        // packed triplet offsets of the row's own summation block (see rn_fd_block)
+        const int kb = k >> 3, kr = k & 7;
+        const unsigned dlt = static_cast<unsigned>(pb.xcnt[i] - 1), kdo = static_cast<unsigned>(pb.xrank[i][i]);
+        const unsigned all = dlt * 0x01010101u;
+        const unsigned lowmask = (1u << (8 * (kr & 3))) - 1u;  // bytes below kr & 3
+        const unsigned own = kdo << (8 * (kr & 3));
+        const unsigned m0 = kr < 4 ? ((all & lowmask) | own) : all;
+        const unsigned m1 = kr < 4 ? 0u : ((all & lowmask) | own);
+        double* jk = jac + k;
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+l"(jk));  // keep jac + k in a register pair: every triplet address is one wide multiply-add
+#endif
+        RnFdBlocks<NS, N, 0>::run(Dtk, Xi, rx + i, P, sgr, hfv, kb, all, m0, m1, jk);
+    }
+    // node-local triplets. Everything they need is re-read (shared memory, L1) or recomputed from the block sums
+    // here, so that it does not occupy registers across the D-coupled loop above
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");
+#endif
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double tau = ECUDA_LDG(ph.tau + k);
+    const double t = h * tau + mid;
+    double dv = P[0];
+#pragma unroll
+    for (int bi = 1; bi < NB; ++bi) dv = dv + P[bi];
+    double x[NS], u[NCU];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+    for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+    double dpk = 0.0, dmk = 0.0;
+    if (!DS) {
+        const FdRec& rc = rx[k * NS + i];
+        rn_diag<NS, N>(Dtk, Xi, rc.xp, rc.xm, k, P, dpk, dmk);
+    }
+    // the node's state columns X(k,j)                                   [xcol_local_fd, row i]
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int rk = pb.xrank[j][i];
+        if (rk < 0 || (DS && j == i)) continue;
+        const FdRec& rc = rx[k * NS + j];
+        if (j != i && !reads_state<M>(i, j)) {  // f_i does not read x_j: g+ == g- bit for bit
+            ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), 0.0);
+            continue;
+        }
+        double xq[NS], xr[NS], fp[NS], fm[NS];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            xq[a] = (a == j) ? rc.xp : x[a];
+            xr[a] = (a == j) ? rc.xm : x[a];
+        }
+        Model<M>::f(xq, u, t, fp);
+        Model<M>::f(xr, u, t, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (((i == j) ? dpk : dv) - h * fpi);
+        const double gm = sgr * (((i == j) ? dmk : dv) - h * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
+    }
+    // the node's control columns U(k,c)                                 [node_item, c < nc, row i]
+    for (int c = 0; c < nc; ++c) {
+        const int rk = pb.urank[c][i];
+        if (rk < 0) continue;
+        const FdRec& rc = m.rec[k * nc + c];
+        if (c >= NCU || !reads_control<M>(i, c)) {  // unused or unread control: exactly +0.0
+            ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+            continue;
+        }
+        double up[NCU], um[NCU], fp[NS], fm[NS];
+#pragma unroll
+        for (int a = 0; a < NCU; ++a) {
+            up[a] = (a == c) ? rc.xp : u[a];
+            um[a] = (a == c) ? rc.xm : u[a];
+        }
+        Model<M>::f(x, up, t, fp);
+        Model<M>::f(x, um, t, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (dv - h * fpi);
+        const double gm = sgr * (dv - h * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
+    }
+    // t0 / tf columns                                                    [node_item, time columns, row i]
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const FdRec& rc = m.rec[(NS + nc) * N + which];
+        const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
+        const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
+        const double hp = 0.5 * (tfp - t0p), mp = 0.5 * (tfp + t0p);
+        const double hm = 0.5 * (tfm - t0m), mm = 0.5 * (tfm + t0m);
+        const double tp = hp * tau + mp, tm = hm * tau + mm;
+        double fp[NS], fm[NS];
+        Model<M>::f(x, u, tp, fp);
+        Model<M>::f(x, u, tm, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (dv - hp * fpi);
+        const double gm = sgr * (dv - hm * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
+    }
+}
+
+// path row q at (x, y, t); TRK = false: the problem has no moving zones, every path row is a static record
+template <int M, bool TRK>
+ECUDA_HD double rn_path_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& cm, int q, double x, double y, double t) {
+    if (!TRK) return Model<M>::static_row(cm.inst + ph.inst_off + q * Model<M>::REC, x, y);
+    return path_row<M>(pb, ph, cm, q, x, y, t);
+}
+
+// ---- the other rows, finite differences: one item each [other_item<FD = true>] -----------------------------------
+// item numbering: 0 objective | path rows (k,q) | event rows | duration row | linkage state rows towards the next
+// phase | linkage triplets of the previous phase's rows in this phase
+template <int M, int N>
+ECUDA_HD int rn_items(const ProbDev& pb, const PhaseDev& ph, int p) {
+    return 1 + ph.npath * N + pb.ne + 1 + (p + 1 < pb.nphases ? pb.ns : 0) + (p > 0 ? pb.ns : 0);
+}
+
+template <int M, int N, bool TRK, bool SUM>
+ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
+                         int b, int it, double& viol, double& fval) {
+    constexpr int NS = Model<M>::NS;
+    const int nc = pb.nc, np = ph.npath, ntr = np - ph.nstat;
+    const double* zx = m.z + nc * N;
+    const FdRec* rx = m.rec + nc * N;
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double* sg = pb.sg;
+    double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
+    double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
+    const int tcol = (NS + nc) * N;
+    auto note = [&](int r, double val, int cls) {
+        if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, cls));
+    };
+
+    if (it == 0) {  // ---- objective: running cost per node and quadrature
+        if (!io.f) return;
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) {
+            const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+            const double L = Model<M>::cost(zx + k * NS, m.z + k * nc, t);
+            acc = fma(ECUDA_LDG(ph.w + k), pb.maximize ? -1.0 * L : L, acc);
+        }
+        const double fp = h * acc;
+        if (pb.nphases == 1)
+            io.f[b] = pb.sf * fp;
+        else
+            io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
+        fval = pb.sf * fp;
+        return;
+    }
+    it -= 1;
+    if (it < np * N) {  // ---- path row (k,q)
+        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        const double tau = ECUDA_LDG(ph.tau + k);
+        const double t = h * tau + mid;
+        const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
+        const int r = ph.goff + NS * N + pb.ne + it;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 1);
+        }
+        if (!jac) return;
+        const int ev = (k == 0 || k == N - 1) ? 1 : 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const FdRec& rc = rx[k * NS + j];
+            const double vp = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xp : x0, j == 1 ? rc.xp : x1, t);
+            const double vm = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xm : x0, j == 1 ? rc.xm : x1, t);
+            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[j] + ev + q), (s * vp - s * vm) * rc.ri);
+        }
+        if (TRK && q >= ph.nstat) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const FdRec& rc = m.rec[tcol + which];
+                const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
+                const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
+                const double hp = 0.5 * (tfp - t0p), mp = 0.5 * (tfp + t0p);
+                const double hm = 0.5 * (tfm - t0m), mm = 0.5 * (tfm + t0m);
+                const double tp = hp * tau + mp, tm = hm * tau + mm;
+                const double vp = rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, tp);
+                const double vm = rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, tm);
+                ECUDA_STREAM_STORE(jac + (rc.cp + NS * N + k * ntr + (q - ph.nstat)), (s * vp - s * vm) * rc.ri);
+            }
+        }
+        return;
+    }
+    it -= np * N;
+    if (it < pb.ne) {  // ---- event row: x(t0) or x(tf)
+        const int e = it;
+        const int node = (e < NS) ? 0 : N - 1, i = (e < NS) ? e : e - NS;
+        const int r = ph.goff + NS * N + e;
+        const int lx = node * NS + i;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * zx[lx];
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 2);
+        }
+        if (jac) {
+            const FdRec& rc = rx[lx];
+            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[i]), (s * rc.xp - s * rc.xm) * rc.ri);
+        }
+        return;
+    }
+    it -= pb.ne;
+    if (it == 0) {  // ---- duration row tf - t0, and the time linkage
+        const int r = ph.goff + NS * N + pb.ne + np * N;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * (tf - t0);
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 3);
+            if (p + 1 < pb.nphases) {  // time continuity with the next phase
+                const PhaseDev& nx = pb.ph[p + 1];
+                const int rl = pb.linkoff + p * (NS + 1) + NS;
+                const double other = other_phase_value(pb, io, b, nx.zoff + (NS + nc) * nx.N);
+                ECUDA_STREAM_STORE(g + rl, ECUDA_LDG(sg + rl) * (tf - other));
+            }
+        }
+        if (!jac) return;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const FdRec& rc = m.rec[tcol + which];
+            const int at = rc.cp + NS * N + N * ntr;
+            const double ri = rc.ri;
+            const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
+            const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
+            ECUDA_STREAM_STORE(jac + at, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
+            if (which == 0 && p > 0) {
+                const PhaseDev& pv = pb.ph[p - 1];
+                const int rl = pb.linkoff + (p - 1) * (NS + 1) + NS;
+                const double sl = ECUDA_LDG(sg + rl);
+                const double o = other_phase_value(pb, io, b, pv.zoff + (NS + nc) * pv.N + 1);
+                ECUDA_STREAM_STORE(jac + at + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
+            }
+            if (which == 1 && p + 1 < pb.nphases) {
+                const PhaseDev& nx = pb.ph[p + 1];
+                const int rl = pb.linkoff + p * (NS + 1) + NS;
+                const double sl = ECUDA_LDG(sg + rl);
+                const double o = other_phase_value(pb, io, b, nx.zoff + (NS + nc) * nx.N);
+                ECUDA_STREAM_STORE(jac + at + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
+            }
+        }
+        return;
+    }
+    it -= 1;
+    // ---- state linkage with the next phase (row owned by this phase) / with the previous phase (triplet of its
+    // row in this phase's first node)
+    const bool to_next = (p + 1 < pb.nphases) && it < NS;
+    const int i = to_next ? it : it - (p + 1 < pb.nphases ? NS : 0);
+    const int k = to_next ? N - 1 : 0;
+    const int lx = k * NS + i;
+    int pos = N - 1 + pb.xcnt[i] + 1;  // after the event triplet of a boundary node
+    if (i < 2) pos += np;
+    if (to_next) {
+        const PhaseDev& nx = pb.ph[p + 1];
+        const int r = pb.linkoff + p * (NS + 1) + i;
+        const double s = ECUDA_LDG(sg + r);
+        const double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + i);
+        if (g) ECUDA_STREAM_STORE(g + r, s * (zx[lx] - o));
+        if (jac) {
+            const FdRec& rc = rx[lx];
+            ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * (rc.xp - o) - s * (rc.xm - o)) * rc.ri);
+        }
+    } else if (jac) {
+        const PhaseDev& pv = pb.ph[p - 1];
+        const int r = pb.linkoff + (p - 1) * (NS + 1) + i;
+        const double s = ECUDA_LDG(sg + r);
+        const double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * NS + i);
+        const FdRec& rc = rx[lx];
+        ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * (o - rc.xp) - s * (o - rc.xm)) * rc.ri);
+    }
+}
+
+// whole thread program after the staging barrier, finite differences
+template <int M, int N, bool TRK, bool SUM>
+ECUDA_HD void rn_thread_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
+                           int b, int tid, int nthr, double& viol, double& fval) {
+    viol = 0.0;
+    fval = 0.0;
+    rn_row_fd<M, N, SUM>(pb, ph, io, m, cm, b, tid, viol);
+    const int nitems = rn_items<M, N>(pb, ph, p);
+    for (int it = nthr - 1 - tid; it < nitems; it += nthr)
+        rn_item_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
+}
+
+}  // namespace ecuda
+#endif

@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../etol_b200/csrc/ecuda_rows.cuh"
+#include "../../etol_b200/csrc/ecuda_rowsn.cuh"
 
 using namespace ecuda;
 
@@ -64,6 +64,48 @@ static void run_rows(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO&
 }
 static int g_use_rows = 1;
 extern "C" void emu_use_rows(int on) { g_use_rows = on; }
+static int g_use_rowsn = 0;
+extern "C" void emu_use_rowsn(int on) { g_use_rowsn = on; }
+static long g_rowsn_runs = 0;
+extern "C" long emu_rowsn_runs() { return g_rowsn_runs; }
+
+// the N-specialised row-owner kernel (k_rows_n_fd): one pass of every thread after staging
+template <int M, int N, bool TRK>
+static void run_rowsn_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    std::vector<double> smem(rn_doubles<M>(pb, N, true) + 2, 0.0);
+    RnMem m;
+    rn_carve<M>(m, smem.data(), pb, N, true);
+    CtaMem cm{};
+    cm.inst = m.inst;
+    cm.z = m.z;
+    std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
+    for (int t = 0; t < nthr; ++t) rn_stage<M, N, true>(pb, ph, io, m, b, t, nthr);
+    for (int t = 0; t < nthr; ++t) {
+        double viol, fval;
+        rn_thread_fd<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
+    }
+    ++g_rowsn_runs;
+}
+// same instantiation list as launch_rows_n (ecuda_api.cu); false: no instantiation, the caller falls back
+template <int M>
+static bool run_rowsn(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    if (!fd || nthr < pb.ns * ph.N) return false;
+    for (int q = 0; q < pb.nphases; ++q)
+        if (pb.ph[q].N != ph.N) return false;
+#ifndef ECUDA_USER_MODEL_HEADER
+    if constexpr (M == ECUDA_MODEL_PM3D) {
+        if (pb.ntracks > 0) return false;
+        if (ph.N == 40) return run_rowsn_fd<M, 40, false>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 30) return run_rowsn_fd<M, 30, false>(pb, ph, p, io, b, nthr), true;
+    }
+    if constexpr (M == ECUDA_MODEL_SI2D) {
+        if (ph.N == 33) return run_rowsn_fd<M, 33, true>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 17) return run_rowsn_fd<M, 17, true>(pb, ph, p, io, b, nthr), true;
+    }
+#endif
+    return false;
+}
 
 template <int M, int NB>
 static void run_fast_mode(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
@@ -144,6 +186,7 @@ static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
                     for (int t = 0; t < nthr; ++t) cost_nodes<M>(pb, ph, m, t, nthr);
                     for (int t = 0; t < nthr; ++t) gradient_phase<M>(pb, ph, io, m, b, t, nthr);
                 }
+                if (g_use_rowsn && run_rowsn<M>(pb, ph, p, io, b, nthr)) continue;
                 switch (ph.nb) {
                     case 3: run_fast_mode<M, 3>(pb, ph, p, io, b, nthr); break;
                     case 4: run_fast_mode<M, 4>(pb, ph, p, io, b, nthr); break;

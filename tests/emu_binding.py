@@ -82,9 +82,11 @@ def lib():
 
 def emu_eval(wl, x, want=("f", "g", "jac"), jac_mode=1, nthr=64, generic=False, variant="rows"):
     """variant: which specialised kernel the emulator steps when the problem qualifies -- "rows"
-    (k_eval_rows, the default), "columns" (k_eval_fast) or "image" (k_eval_image, exact mode)"""
+    (k_eval_rows), "rowsn" (the N-specialised k_rows_n_* where an instantiation exists, the product's default),
+    "columns" (k_eval_fast) or "image" (k_eval_image, exact mode)"""
     L, model = (lib(), wl.model) if getattr(wl, "tape", None) is None else user_lib(wl.tape)
-    L.emu_use_rows(1 if variant == "rows" else 0)
+    L.emu_use_rows(1 if variant in ("rows", "rowsn") else 0)
+    L.emu_use_rowsn(1 if variant == "rowsn" else 0)
     L.emu_use_image(1 if variant == "image" else 0)
     dims = capi.host_dims(wl)
     inst = capi.pack_instances(wl, dims)

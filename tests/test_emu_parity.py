@@ -30,13 +30,14 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("nthr,generic,variant", [(32, False, "rows"), (256, False, "rows"), (256, False, "columns"),
+@pytest.mark.parametrize("nthr,generic,variant", [(32, False, "rows"), (256, False, "rows"), (256, False, "rowsn"),
+                                                  (256, False, "columns"),
                                                   (256, False, "image"), (256, True, "rows")])
 def test_phases_match_oracle(name, nthr, generic, variant):
     wl = CASES[name]()
     if name == "C3-fw6-N200" and (nthr == 32 or generic or variant != "rows"):
         pytest.skip("one thread count is enough for the large case")
-    if name.startswith("user-") and variant != "rows":
+    if name.startswith("user-") and variant not in ("rows", "rowsn"):
         pytest.skip("user models are compiled for the row-owner and the generic kernels only")
     o = ob.Oracle(wl)
     style = 1 if name == "C3-fw6-N200" else 0
