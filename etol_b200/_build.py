@@ -2,6 +2,7 @@
 
   etol_b200/csrc/libecuda.so   CUDA kernels + C ABI, nvcc -gencode arch=compute_100a,code=sm_100a
   oracle/_build/liboracle.so   CPU oracle (test infrastructure), g++
+  oracle/_ref/libetol_ref.so   the reference's ePSOPT.cpp + example, unmodified, against a stub psopt.h (test infrastructure)
   tests/emu/libecuda_emu.so    test-only host stepping of the kernel phases, g++
   build/libetol_ecuda.so       C++ plugin layer (TrajectoryOptimizer core-lite + eCUDA), g++ (when present)
 """
@@ -57,6 +58,10 @@ def build_libecuda(force=False, verbose=False):
 
 def build_oracle():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    # oracle/_ref: the reference's own ePSOPT.cpp + example compiled unmodified against oracle/refstub/psopt.h.
+    # Only where the reference tree exists (this container); the GPU box uses the built file that travelled.
+    if os.path.isdir("/root/reference/src/ePSOPT"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
 
 
 def build_emu():

@@ -39,3 +39,21 @@ np.savez_compressed(os.path.join(ROOT, "tests", "golden", "c0_ext_golden.npz"), 
                     ode_error=ob.ode_error(o, wl, wl.x), resample_41=ob.resample(o, wl, wl.x, [41]),
                     user_x=uw.x, user_f=ufd["f"], user_g=ufd["g"], user_jac_fd=ufd["jac"], user_jac_exact=uex["jac"])
 print("wrote c0_ext_golden.npz")
+
+# ---- third fixture: outputs of the REFERENCE'S OWN callbacks (oracle/_ref, `make -C oracle ref`) ----------------
+# /root/reference/src/ePSOPT/ePSOPT.cpp + src/Examples/PSOPT/etol_psopt_example1.cpp compiled unmodified against
+# oracle/refstub/psopt.h, run at every node of the seeded C0 decision vector. Needs /root/reference (this container).
+import ref_binding as rb  # noqa: E402
+if rb.available():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_vs_reference import _run_reference  # noqa: E402
+    ref = rb.Reference(rb.REF_XML)
+    out = _run_reference(ref, wl, wl.x)
+    bd = ref.bounds()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "c0_ref_pernode.npz"), x=wl.x, t=out["t"], f=out["f"],
+                        path=out["path"], df=out["df"], dpath=out["dpath"], L=out["L"], events=out["events"],
+                        endpoint=out["endpoint"], bounds_events=bd["events"], bounds_path=bd["path"],
+                        bounds_states=bd["states"], bounds_controls=bd["controls"])
+    print("wrote c0_ref_pernode.npz from oracle/_ref (reference callbacks)")
+else:
+    print("oracle/_ref not available: c0_ref_pernode.npz left as committed")
