@@ -427,43 +427,45 @@ static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
 
 // N-specialised row-owner kernels (ecuda_rowsn.cuh): instantiated ahead of time for the node counts of the
 // BASELINE configurations; other shapes take the kernels above
-template <int M, int N, bool TRK, bool SUM>
-static int launch_rows_n_fd_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+template <int M, int N, bool FD, bool TRK, bool SUM>
+static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     static std::mutex mu;
     static size_t configured[64] = {0};
-    size_t smem = rn_doubles<M>(h->pd, N, true) * sizeof(double);
-    if (io.nranks > 0 && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
+    size_t smem = rn_doubles<M>(h->pd, N, FD) * sizeof(double);
+    if (SUM && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
     if (smem > 48 * 1024) {
         std::lock_guard<std::mutex> lock(mu);
         size_t& cur = configured[h->device & 63];
         if (cur < smem) {
-            CU(cudaFuncSetAttribute(k_rows_n_fd<M, N, TRK, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(k_rows_n<M, N, FD, TRK, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cur = smem;
         }
     }
-    k_rows_n_fd<M, N, TRK, SUM><<<grid, kThreads, smem, st>>>(h->pd, io);
+    k_rows_n<M, N, FD, TRK, SUM><<<grid, kThreads, smem, st>>>(h->pd, io);
     return ECUDA_OK;
 }
 // TRK: instantiated with track rows (moving zones) or without; a problem whose model is only instantiated without
 // them and has tracks falls back (returns 1)
 template <int M, int N, bool TRK>
-static int launch_rows_n_fd(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     if (!TRK && h->pd.ntracks > 0) return 1;
-    return io.nranks > 0 ? launch_rows_n_fd_t<M, N, TRK, true>(h, io, st, grid)
-                         : launch_rows_n_fd_t<M, N, TRK, false>(h, io, st, grid);
+    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    if (fd)
+        return io.nranks > 0 ? launch_rows_n_t<M, N, true, TRK, true>(h, io, st, grid)
+                             : launch_rows_n_t<M, N, true, TRK, false>(h, io, st, grid);
+    return io.nranks > 0 ? launch_rows_n_t<M, N, false, TRK, true>(h, io, st, grid)
+                         : launch_rows_n_t<M, N, false, TRK, false>(h, io, st, grid);
 }
 // returns 1 when no instantiation matches (the caller falls back)
 template <int M>
 static int launch_rows_n(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
-    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
-    if (!fd) return 1;
     if (M == ECUDA_MODEL_PM3D) {
-        if (h->rowsn_N == 40) return launch_rows_n_fd<M, 40, false>(h, io, st, grid);
-        if (h->rowsn_N == 30) return launch_rows_n_fd<M, 30, false>(h, io, st, grid);
+        if (h->rowsn_N == 40) return launch_rows_n_mn<M, 40, false>(h, io, st, grid);
+        if (h->rowsn_N == 30) return launch_rows_n_mn<M, 30, false>(h, io, st, grid);
     }
     if (M == ECUDA_MODEL_SI2D) {
-        if (h->rowsn_N == 33) return launch_rows_n_fd<M, 33, true>(h, io, st, grid);
-        if (h->rowsn_N == 17) return launch_rows_n_fd<M, 17, true>(h, io, st, grid);
+        if (h->rowsn_N == 33) return launch_rows_n_mn<M, 33, true>(h, io, st, grid);
+        if (h->rowsn_N == 17) return launch_rows_n_mn<M, 17, true>(h, io, st, grid);
     }
     return 1;
 }

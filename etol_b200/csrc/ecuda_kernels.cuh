@@ -328,15 +328,19 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
     }
 }
 
-// N-specialised row-owner kernel, finite differences (ecuda_rowsn.cuh): the node count is a template argument.
-// One CTA per (instance, phase); every phase of the problem has N nodes (checked by the launcher).
+// N-specialised row-owner kernels (ecuda_rowsn.cuh): the node count is a template argument. One CTA per
+// (instance, phase); every phase of the problem has N nodes (checked by the launcher). FD: index-set finite
+// differences; otherwise the exact Jacobian (also the instantiation that runs when no Jacobian is asked for).
+// TRK: the problem has moving zones (track rows); SUM: fused per-instance summary + all-gather (io.nranks > 0).
 #ifndef ECUDA_MIN_CTAS_ROWSN_FD
 #define ECUDA_MIN_CTAS_ROWSN_FD 3
 #endif
-// TRK: the problem has moving zones (track rows); SUM: fused per-instance summary + all-gather (io.nranks > 0)
-template <int M, int N, bool TRK, bool SUM>
-__global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
-    k_rows_n_fd(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+#ifndef ECUDA_MIN_CTAS_ROWSN_EXACT
+#define ECUDA_MIN_CTAS_ROWSN_EXACT 5
+#endif
+template <int M, int N, bool FD, bool TRK, bool SUM>
+__global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA_MIN_CTAS_ROWSN_EXACT)
+    k_rows_n(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     const int b = blockIdx.x / pb.nphases;
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
     const PhaseDev& ph = pb.ph[p];
     const int tid = threadIdx.x, nthr = kThreads;
     RnMem m;
-    rn_carve<M>(m, smem, pb, N, true);
+    rn_carve<M>(m, smem, pb, N, FD);
     CtaMem cm{};
     cm.inst = m.inst;
     cm.z = m.z;
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
     }
     if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the records
         const int ncp = phase_ncons(pb, ph), nbnd = ncp + (ncp & 1);
-        double* bnd = smem + rn_doubles<M>(pb, N, true);
+        double* bnd = smem + rn_doubles<M>(pb, N, FD);
         const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
         for (int c = tid; c < ncp; c += nthr) {
             bnd[c] = __ldg(io.bl + o + c);
@@ -366,11 +370,14 @@ __global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
         cm.bl = bnd;
         cm.bu = bnd + nbnd;
     }
-    rn_stage<M, N, true>(pb, ph, io, m, b, tid, nthr);
+    rn_stage<M, N, FD>(pb, ph, io, m, b, tid, nthr);
     mbar_wait(&bar, 0);
     __syncthreads();
     double viol, fval;
-    rn_thread_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
+    if (FD)
+        rn_thread_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
+    else
+        rn_thread_exact<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
     if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
         __shared__ double red[kThreads / 32 + 1];
         double v = viol;

@@ -61,13 +61,35 @@ ECUDA_HD unsigned rn_byte(unsigned w, int a) {
 #endif
 }
 
+// exact mode: what a triplet of a column needs -- 1 / sz of the variable and the column's first triplet
+struct alignas(16) ExRec {
+    double isz;
+    int cp;
+    int pad_;
+};
+struct ExVals {
+    double isz;
+    unsigned cp;
+};
+ECUDA_HD ExVals rn_load(const ExRec* r) {
+    ExVals v;
+#if defined(__CUDA_ARCH__)
+    const double2 a = *reinterpret_cast<const double2*>(r);
+    v.isz = a.x;
+    v.cp = static_cast<unsigned>(__double2loint(a.y));
+#else
+    v.isz = r->isz;
+    v.cp = static_cast<unsigned>(r->cp);
+#endif
+    return v;
+}
+
 // shared memory of one CTA of the N-specialised kernels
 struct RnMem {
     double* inst;  // [inst_stride] obstacle / track records (bulk-copied)
     double* z;     // [nv]          unscaled variables of the phase
     FdRec* rec;    // [nv]          FD mode
-    double* isz;   // [nv]          exact mode: 1 / sz
-    int* colp;     // [nv + 1]      exact mode: first triplet of each column
+    ExRec* erec;   // [nv]          exact mode
 };
 
 template <int M>
@@ -78,7 +100,7 @@ template <int M>
 ECUDA_HD size_t rn_doubles(const ProbDev& pb, int N, bool fd) {
     const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
     size_t n = static_cast<size_t>(pb.inst_stride) + nve;
-    n += fd ? 4 * nv : nve + (nv + 2) / 2;
+    n += fd ? 4 * nv : 2 * nv;
     return n + (n & 1);
 }
 
@@ -90,15 +112,11 @@ ECUDA_HD void rn_carve(RnMem& m, double* base, const ProbDev& pb, int N, bool fd
     m.z = base;
     base += nve;
     m.rec = nullptr;
-    m.isz = nullptr;
-    m.colp = nullptr;
-    if (fd) {
+    m.erec = nullptr;
+    if (fd)
         m.rec = reinterpret_cast<FdRec*>(base);
-    } else {
-        m.isz = base;
-        base += nve;
-        m.colp = reinterpret_cast<int*>(base);
-    }
+    else
+        m.erec = reinterpret_cast<ExRec*>(base);
 }
 
 // ---- stage: same arithmetic as stage_vars ----------------------------------------------------------------------
@@ -108,7 +126,6 @@ ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
     const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
     const double* is = pb.isz + ph.zoff;
     const int* cpg = pb.colptr + ph.zoff;
-    if (!FD && tid == 0) m.colp[nv] = ECUDA_LDG(cpg + nv);
     for (int c0 = tid; c0 < nv; c0 += 2 * nthr) {
         double zt[2], s[2];
         int cp[2];
@@ -136,8 +153,11 @@ ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
                     r.pad_ = 0;
                     m.rec[c] = r;
                 } else {
-                    m.isz[c] = s[u];
-                    m.colp[c] = cp[u];
+                    ExRec r;
+                    r.isz = s[u];
+                    r.cp = cp[u];
+                    r.pad_ = 0;
+                    m.erec[c] = r;
                 }
             }
         }
@@ -606,6 +626,284 @@ ECUDA_HD void rn_thread_fd(const ProbDev& pb, const PhaseDev& ph, int p, const E
     const int nitems = rn_items<M, N>(pb, ph, p);
     for (int it = nthr - 1 - tid; it < nitems; it += nthr)
         rn_item_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
+}
+
+// ---- exact mode --------------------------------------------------------------------------------------------------
+// D-coupled triplets of defect row (k,i), block BI: (sg_r * D[k][l]) / sz(X(l,i)) -- the expression of
+// build_jac_template, so the values equal the round-1 template copy bit for bit. They are COMPUTED here (two
+// multiplications per triplet, D from L1, the column's record with one 128-bit shared load) instead of being
+// streamed from a per-problem template through a shared-memory ring: with N a compile-time constant a triplet
+// costs 8 instructions, the kernel has no second barrier, no copy warp and no L2 -> SM template traffic.
+template <int NS, int N, int BI>
+ECUDA_HD void rn_ex_block(const double* __restrict__ Dtk, const ExRec* __restrict__ Ri, double sgr, unsigned w0,
+                          unsigned w1, double* __restrict__ jk) {
+    constexpr int BL = ECUDA_DOT_BLOCK, l0 = BI * BL;
+    constexpr int nin = (N - l0) < BL ? (N - l0) : BL;
+#pragma unroll
+    for (int a = 0; a < nin; ++a) {
+        const ExVals rc = rn_load(Ri + (l0 + a) * NS);
+        const double v = (sgr * ECUDA_LDG(Dtk + (l0 + a) * N)) * rc.isz;
+        ECUDA_STREAM_STORE(jk + (rc.cp + rn_byte(a < 4 ? w0 : w1, a & 3)), v);
+    }
+}
+template <int NS, int N, int BI>
+struct RnExBlocks {
+    ECUDA_HD static void run(const double* Dtk, const ExRec* Ri, double sgr, int kb, unsigned all, unsigned m0, unsigned m1,
+                             double* jk) {
+        const unsigned w0 = BI < kb ? all : (BI == kb ? m0 : 0u);
+        const unsigned w1 = BI < kb ? all : (BI == kb ? m1 : 0u);
+        rn_ex_block<NS, N, BI>(Dtk, Ri, sgr, w0, w1, jk);
+        RnExBlocks<NS, N, BI + 1>::run(Dtk, Ri, sgr, kb, all, m0, m1, jk);
+    }
+};
+template <int NS, int N>
+struct RnExBlocks<NS, N, (N + 7) / 8> {
+    ECUDA_HD static void run(const double*, const ExRec*, double, int, unsigned, unsigned, unsigned, double*) {}
+};
+
+// defect row (k,i), exact: value, D-coupled triplets, node-local triplets   [rows_values + rows_jacobian<exact>]
+template <int M, int N, bool SUM>
+ECUDA_HD void rn_row_exact(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                           int tid, double& viol) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
+    if (tid >= NS * N) return;
+    const int nc = pb.nc;
+    const int i = tid / N, k = tid - i * N;
+    const double* zx = m.z + nc * N;
+    const double* Dtk = ph.Dt + k;
+    const int r = ph.goff + k * NS + i;
+    const double sgr = ECUDA_LDG(pb.sg + r);
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+    double x[NS], u[NCU], f[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+    for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+    Model<M>::f(x, u, t, f);
+    double fi = 0.0;
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+        if (a == i) fi = f[a];
+    if (io.g) {
+        double P[NB];
+        const double dv = rn_dot<NS, N>(Dtk, zx + i, P);
+        const double val = sgr * (dv - h * fi);
+        ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+        if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
+    }
+    if (!io.jac) return;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    const ExRec* rx = m.erec + nc * N;
+    {
+        const int kb = k >> 3, kr = k & 7;
+        const unsigned dlt = static_cast<unsigned>(pb.xcnt[i] - 1), kdo = static_cast<unsigned>(pb.xrank[i][i]);
+        const unsigned all = dlt * 0x01010101u;
+        const unsigned lowmask = (1u << (8 * (kr & 3))) - 1u;
+        const unsigned own = kdo << (8 * (kr & 3));
+        const unsigned m0 = kr < 4 ? ((all & lowmask) | own) : all;
+        const unsigned m1 = kr < 4 ? 0u : ((all & lowmask) | own);
+        double* jk = jac + k;
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+l"(jk));
+#endif
+        // the l == k store puts (sg D_kk) / sz into the row's diagonal slot; the node-local pass below overwrites it
+        // (same thread, program order) with the full diagonal entry
+        RnExBlocks<NS, N, 0>::run(Dtk, rx + i, sgr, kb, all, m0, m1, jk);
+    }
+    double dfdx[NS][NS], dfdu[NS][NCU];
+    Model<M>::jac(x, u, dfdx, dfdu);
+    const double dkk = ECUDA_LDG(Dtk + k * N);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {  // [xcol_local_exact, row i]
+        const int rk = pb.xrank[j][i];
+        if (rk < 0) continue;
+        const ExVals rc = rn_load(rx + k * NS + j);
+        double d = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) d = dfdx[a][j];
+        const double v = ((i == j) ? dkk : 0.0) - h * d;
+        ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (sgr * v) * rc.isz);
+    }
+    for (int c = 0; c < nc; ++c) {  // [node_item exact, control columns, row i]
+        const int rk = pb.urank[c][i];
+        if (rk < 0) continue;
+        const ExVals rc = rn_load(m.erec + k * nc + c);
+        double d = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int c2 = 0; c2 < NCU; ++c2)
+                if (a == i && c2 == c) d = dfdu[a][c2];
+        const double v = -(h * d);
+        ECUDA_STREAM_STORE(jac + (rc.cp + rk), (sgr * v) * rc.isz);
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // [node_item exact, time columns, row i]
+        const ExVals rc = rn_load(m.erec + (NS + nc) * N + which);
+        const double v = which == 0 ? 0.5 * fi : -0.5 * fi;
+        ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (sgr * v) * rc.isz);
+    }
+}
+
+// the other rows, exact   [other_item<FD = false>]
+template <int M, int N, bool TRK, bool SUM>
+ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
+                            int b, int it, double& viol, double& fval) {
+    constexpr int NS = Model<M>::NS;
+    const int nc = pb.nc, np = ph.npath, ntr = np - ph.nstat;
+    const double* zx = m.z + nc * N;
+    const ExRec* rx = m.erec + nc * N;
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double* sg = pb.sg;
+    double* g = io.g ? io.g + static_cast<size_t>(b) * pb.ncons : nullptr;
+    double* jac = io.jac ? io.jac + static_cast<size_t>(b) * pb.nnz : nullptr;
+    const int tcol = (NS + nc) * N;
+    auto note = [&](int r, double val, int cls) {
+        if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, cls));
+    };
+
+    if (it == 0) {  // ---- objective
+        if (!io.f) return;
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) {
+            const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+            const double L = Model<M>::cost(zx + k * NS, m.z + k * nc, t);
+            acc = fma(ECUDA_LDG(ph.w + k), pb.maximize ? -1.0 * L : L, acc);
+        }
+        const double fp = h * acc;
+        if (pb.nphases == 1)
+            io.f[b] = pb.sf * fp;
+        else
+            io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
+        fval = pb.sf * fp;
+        return;
+    }
+    it -= 1;
+    if (it < np * N) {  // ---- path row (k,q)
+        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        const double tau = ECUDA_LDG(ph.tau + k);
+        const double t = h * tau + mid;
+        const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
+        const int r = ph.goff + NS * N + pb.ne + it;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 1);
+        }
+        if (!jac) return;
+        const int ev = (k == 0 || k == N - 1) ? 1 : 0;
+        double ddx, ddy, ddt = 0.0;
+        if (!TRK || q < ph.nstat)
+            Model<M>::static_row_dxy(cm.inst + ph.inst_off + q * Model<M>::REC, x0, x1, &ddx, &ddy);
+        else
+            track_row_partials(cm.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x0, x1, t, &ddx, &ddy, &ddt);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const ExVals rc = rn_load(rx + k * NS + j);
+            const double v = (j == 0) ? ddx : ddy;
+            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[j] + ev + q), (s * v) * rc.isz);
+        }
+        if (TRK && q >= ph.nstat) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const ExVals rc = rn_load(m.erec + tcol + which);
+                const double dtk = which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau);
+                ECUDA_STREAM_STORE(jac + (rc.cp + NS * N + k * ntr + (q - ph.nstat)), (s * (ddt * dtk)) * rc.isz);
+            }
+        }
+        return;
+    }
+    it -= np * N;
+    if (it < pb.ne) {  // ---- event row
+        const int e = it;
+        const int node = (e < NS) ? 0 : N - 1, i = (e < NS) ? e : e - NS;
+        const int r = ph.goff + NS * N + e;
+        const int lx = node * NS + i;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * zx[lx];
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 2);
+        }
+        if (jac) {
+            const ExVals rc = rn_load(rx + lx);
+            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[i]), (s * 1.0) * rc.isz);
+        }
+        return;
+    }
+    it -= pb.ne;
+    if (it == 0) {  // ---- duration row tf - t0, and the time linkage
+        const int r = ph.goff + NS * N + pb.ne + np * N;
+        const double s = ECUDA_LDG(sg + r);
+        if (g) {
+            const double val = s * (tf - t0);
+            ECUDA_STREAM_STORE(g + r, val);
+            note(r, val, 3);
+            if (p + 1 < pb.nphases) {
+                const PhaseDev& nx = pb.ph[p + 1];
+                const int rl = pb.linkoff + p * (NS + 1) + NS;
+                const double other = other_phase_value(pb, io, b, nx.zoff + (NS + nc) * nx.N);
+                ECUDA_STREAM_STORE(g + rl, ECUDA_LDG(sg + rl) * (tf - other));
+            }
+        }
+        if (!jac) return;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const ExVals rc = rn_load(m.erec + tcol + which);
+            const int at = rc.cp + NS * N + N * ntr;
+            ECUDA_STREAM_STORE(jac + at, (s * (which == 0 ? -1.0 : 1.0)) * rc.isz);
+            if (which == 0 && p > 0) {
+                const int rl = pb.linkoff + (p - 1) * (NS + 1) + NS;
+                ECUDA_STREAM_STORE(jac + at + 1, (ECUDA_LDG(sg + rl) * -1.0) * rc.isz);
+            }
+            if (which == 1 && p + 1 < pb.nphases) {
+                const int rl = pb.linkoff + p * (NS + 1) + NS;
+                ECUDA_STREAM_STORE(jac + at + 1, (ECUDA_LDG(sg + rl) * 1.0) * rc.isz);
+            }
+        }
+        return;
+    }
+    it -= 1;
+    // ---- state linkage rows
+    const bool to_next = (p + 1 < pb.nphases) && it < NS;
+    const int i = to_next ? it : it - (p + 1 < pb.nphases ? NS : 0);
+    const int k = to_next ? N - 1 : 0;
+    const int lx = k * NS + i;
+    int pos = N - 1 + pb.xcnt[i] + 1;
+    if (i < 2) pos += np;
+    if (to_next) {
+        const PhaseDev& nx = pb.ph[p + 1];
+        const int r = pb.linkoff + p * (NS + 1) + i;
+        const double s = ECUDA_LDG(sg + r);
+        const double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + i);
+        if (g) ECUDA_STREAM_STORE(g + r, s * (zx[lx] - o));
+        if (jac) {
+            const ExVals rc = rn_load(rx + lx);
+            ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * 1.0) * rc.isz);
+        }
+    } else if (jac) {
+        const int r = pb.linkoff + (p - 1) * (NS + 1) + i;
+        const double s = ECUDA_LDG(sg + r);
+        const ExVals rc = rn_load(rx + lx);
+        ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * -1.0) * rc.isz);
+    }
+}
+
+// whole thread program after the staging barrier, exact Jacobian (also used when no Jacobian is asked for)
+template <int M, int N, bool TRK, bool SUM>
+ECUDA_HD void rn_thread_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
+                              int b, int tid, int nthr, double& viol, double& fval) {
+    viol = 0.0;
+    fval = 0.0;
+    rn_row_exact<M, N, SUM>(pb, ph, io, m, cm, b, tid, viol);
+    const int nitems = rn_items<M, N>(pb, ph, p);
+    for (int it = nthr - 1 - tid; it < nitems; it += nthr)
+        rn_item_exact<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
 }
 
 }  // namespace ecuda

@@ -72,25 +72,30 @@ extern "C" long emu_rowsn_runs() { return g_rowsn_runs; }
 // the N-specialised row-owner kernel (k_rows_n_fd): one pass of every thread after staging
 template <int M, int N, bool TRK>
 static void run_rowsn_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
-    std::vector<double> smem(rn_doubles<M>(pb, N, true) + 2, 0.0);
+    const bool FD = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    std::vector<double> smem(rn_doubles<M>(pb, N, FD) + 2, 0.0);
     RnMem m;
-    rn_carve<M>(m, smem.data(), pb, N, true);
+    rn_carve<M>(m, smem.data(), pb, N, FD);
     CtaMem cm{};
     cm.inst = m.inst;
     cm.z = m.z;
     std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
-    for (int t = 0; t < nthr; ++t) rn_stage<M, N, true>(pb, ph, io, m, b, t, nthr);
+    for (int t = 0; t < nthr; ++t) {
+        if (FD) rn_stage<M, N, true>(pb, ph, io, m, b, t, nthr); else rn_stage<M, N, false>(pb, ph, io, m, b, t, nthr);
+    }
     for (int t = 0; t < nthr; ++t) {
         double viol, fval;
-        rn_thread_fd<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
+        if (FD)
+            rn_thread_fd<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
+        else
+            rn_thread_exact<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
     }
     ++g_rowsn_runs;
 }
 // same instantiation list as launch_rows_n (ecuda_api.cu); false: no instantiation, the caller falls back
 template <int M>
 static bool run_rowsn(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
-    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
-    if (!fd || nthr < pb.ns * ph.N) return false;
+    if (nthr < pb.ns * ph.N) return false;
     for (int q = 0; q < pb.nphases; ++q)
         if (pb.ph[q].N != ph.N) return false;
 #ifndef ECUDA_USER_MODEL_HEADER
