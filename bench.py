@@ -8,10 +8,12 @@ finite differences, triplet layout) at one fixed decision vector.
   python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path (this repo)
   python bench.py --impl reference [...]                       the CPU path on the host cores
 
-Workload at N=1: BASELINE.json configs[1] -- the 3-D point-mass UAS VGP (8 cylinders, 40 LGL nodes)
-batched to 4096 random instances. N>1 (torchrun, one process per GPU): every rank evaluates its own
-4096 instances (weak scaling) and the ranks exchange per-instance summaries {f, max violation}
-with one NCCL all-gather per step.
+Workload at N=1: BASELINE.json configs[1] (C2) -- the 3-D point-mass UAS VGP (8 cylinders, 40 LGL nodes)
+batched to 4096 random instances. N>1 (torchrun, one process per GPU): BASELINE.json configs[4] (C5) -- the
+scenario sweep of 65 536 instances of the same VGP, sharded in contiguous ranges of 65536/N instances per GPU;
+every step the ranks exchange per-instance summaries {f, max violation} (fused into the evaluation kernel, P2P
+stores over NVLink) and, measured separately on the same line ("gather_full"), all-gather the full per-instance
+results [g | Jvals] with NCCL.
 
 The `--impl reference` arm times the reference's CPU algorithm for the same path. The reference's
 own binaries (PSOPT 5.0.0 + ADOL-C + IPOPT) cannot be built in this image,
@@ -36,7 +38,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "nlp_constraint_jacobian_evals_per_sec"
 UNIT = "evals/s"
-BATCH_PER_GPU = 4096
+BATCH_PER_GPU = 4096   # C2, the N=1 workload
+C5_INSTANCES = 65536   # C5, sharded over the ranks when N > 1
 
 
 def parse():
@@ -45,7 +48,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ecuda", choices=["ecuda", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="instances per GPU (default: 4096 at N=1 = C2; 65536/N at N>1 = C5)")
     ap.add_argument("--jac", default="fd", choices=["fd", "exact"])
     ap.add_argument("--gather", default="summary", choices=["summary", "full", "none"])
     ap.add_argument("--nccl-gather", action="store_true",
@@ -53,17 +57,41 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the exact-mode line, the other BASELINE configurations, the D2H probe and gather_full")
+    args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = BATCH_PER_GPU if args.gpus <= 1 else C5_INSTANCES // args.gpus
+    return args
 
 
 def workload_config(wl, args, n_gpus):
-    return {"workload": "C2: pm3d UAS VGP (6 states, 3 controls, 8 cylinders, 40 Legendre nodes), "
-                        f"{wl.batch} random instances per GPU, evaluation only at fixed decision vectors",
-            "instances_per_gpu": wl.batch, "n_instances": wl.batch * n_gpus, "nvars": wl.nvars, "ncons": wl.ncons,
+    """identical in both arms (the driver compares the dicts)"""
+    total = wl.batch * n_gpus
+    name = ("C2: pm3d UAS VGP (6 states, 3 controls, 8 cylinders, 40 Legendre nodes), 4096 random instances"
+            if n_gpus == 1 and wl.batch == BATCH_PER_GPU else
+            f"C5: scenario sweep of {total} pm3d UAS VGP instances (6 states, 3 controls, 8 cylinders, 40 Legendre "
+            f"nodes) sharded over {n_gpus} GPU(s) in contiguous ranges of {wl.batch}" if total == C5_INSTANCES else
+            f"pm3d UAS VGP (C2 shape), {wl.batch} random instances per GPU on {n_gpus} GPU(s)")
+    return {"workload": name + ", evaluation only at fixed decision vectors",
+            "instances_per_gpu": wl.batch, "n_instances": total, "nvars": wl.nvars, "ncons": wl.ncons,
             "jacobian": "fd_indexset" if args.jac == "fd" else "exact", "pattern": "dense_node",
             "l2": "flushed between timed steps: 256 MiB write, then a 256 MiB read sweep so the flush buffer's "
-                  "dirty lines are written back before the timed region; outputs per step (446 MB) exceed L2",
-            "parallelism": f"instances sharded over {n_gpus} GPU(s), gather={args.gather if n_gpus > 1 else 'n/a'}"}
+                  "dirty lines are written back before the timed region; outputs per step exceed L2",
+            "parallelism": f"instances sharded over {n_gpus} GPU(s), gather={args.gather if n_gpus > 1 else 'n/a'}",
+            "timing": "before every timed step the ranks are aligned by an untimed in-stream barrier, so that the skew "
+                      "of the untimed L2-flush kernels is not charged to the step's exchange" if n_gpus > 1 else
+                      "CUDA events on the launching stream around each step"}
+
+
+def shard_workload(args, world, rank):
+    """N=1: C2 (4096 instances, seed W.SEED). N>1: rank r owns the contiguous range [r*B, (r+1)*B) of the sweep."""
+    from etol_b200 import shard, workloads as W
+    if world == 1:
+        return W.pm3d(batch=args.batch)
+    full = W.pm3d(batch=args.batch * world)
+    lo, hi = shard.shard_range(full.batch, world, rank)  # SURVEY 8(e): [r*B/G, (r+1)*B/G)
+    return full.slice_batch(lo, hi)
 
 
 
@@ -149,12 +177,41 @@ def cpu_sample(wl, seconds_budget, jac_mode, style=0):
             "seconds": r["seconds"], "n": n}
 
 
+def cpu_rowrestricted_sample(wl, seconds_budget):
+    """tight loops + row-restricted finite differences on all host threads: the kernel logic of etol_b200/csrc stepped
+    on the CPU (tests/emu, the N-specialised row-owner variant), one instance range per thread"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu_binding as eb
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        nthr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthr = os.cpu_count() or 1
+    eb.lib()
+    per = 4
+
+    def work(i):
+        sub = wl.slice_batch(i * per, (i + 1) * per)
+        eb.emu_eval(sub, sub.x, want=("f", "g", "jac"), jac_mode=1, nthr=256, variant="rowsn")
+        return per
+
+    t0 = time.time()
+    work(0)
+    one = max(time.time() - t0, 1e-4)
+    chunks = int(max(nthr, min(seconds_budget / one * nthr, wl.batch // per)))
+    t0 = time.time()
+    with ThreadPoolExecutor(max_workers=nthr) as pool:
+        n = sum(pool.map(work, range(chunks)))
+    dt = time.time() - t0
+    return {"value": n / dt, "sample": f"{n} of {wl.batch} instances, f+g+J(fd_indexset, row-restricted), kernel logic "
+                                        f"stepped on the CPU, {nthr} threads, {dt:.2f} s"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from etol_b200 import workloads as W
-    wl = W.pm3d(batch=args.batch)
+    wl = shard_workload(args, max(1, args.gpus), 0)
     jac_mode = 1 if args.jac == "fd" else 0
     per_step_budget = max(0.5, min(8.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
@@ -167,8 +224,9 @@ def run_reference(args):
     value = tot_n / tot_s
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(wl, args, args.gpus),
+            "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(wl, args, max(1, args.gpus)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
                              "sample": f"each step: {last['sample']}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,8 +257,8 @@ def run_ecuda(args):
         dist.init_process_group("nccl", device_id=dev)
 
     jac_mode = capi.JAC_FD if args.jac == "fd" else capi.JAC_EXACT
-    # every rank draws its own 4096 instances (weak scaling): seed offset by rank
-    wl = W.pm3d(batch=args.batch, seed=W.SEED + rank)
+    # N=1: C2. N>1: this rank's contiguous range of the C5 sweep
+    wl = shard_workload(args, world, rank)
     ev = capi.Evaluator(wl, device=local)
     B, nv, ng, nz = wl.batch, ev.nvars, ev.ncons, ev.nnz
     torch.cuda.synchronize()
@@ -239,6 +297,7 @@ def run_ecuda(args):
                 peers, hdls = None, None
                 gather_impl = f"nccl all_gather_into_tensor (symmetric memory unavailable: {type(exc).__name__})"
     step_no = [0]
+    gather_parity = None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     sweep = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
@@ -290,6 +349,7 @@ def run_ecuda(args):
         last = sym_bufs[(step_no[0] - 1) & 1]
         if not torch.equal(last, gathered):
             raise SystemExit("bench.py: fused P2P all-gather disagrees with NCCL all_gather")
+        gather_parity = "bit-equal (fused P2P exchange == summary kernel + NCCL all_gather, all rows, this run)"
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -345,12 +405,13 @@ def run_ecuda(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     achieved = alg_bytes_unit * B / (kern_avg_ms / 1e3) / 1e9
-    traffic, fp64 = None, None
+    traffic, fp64, tsrc = None, None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and B == BATCH_PER_GPU:  # the ncu captures were taken at the default batch
         try:
             tj = json.load(open(tpath))
             traffic = tj.get(f"k_eval_{args.jac}_C2_bytes_per_launch")
+            tsrc = tj.get("source", "ncu capture (profiles/traffic.json), not a measurement of this run")
             ops = tj.get(f"k_eval_{args.jac}_C2_fp64_thread_instr_per_launch")
             if ops:
                 # second roof of the finite-difference kernel: FP64 pipe. Peak measured now with a
@@ -365,10 +426,95 @@ def run_ecuda(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"k_eval_rows<pm3d> ({args.jac})", "kernel_ms": kern_avg_ms,
-                "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B, "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": tsrc, "kernel": f"k_rows_n<pm3d,40> ({args.jac})",
+                "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B,
+                "peak_source": peak_src}
     if fp64:
         roofline["fp64"] = fp64
+
+    def kernel_only(mode, n):
+        ts = []
+        for i in range(n):
+            flush_l2(i)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), mode, capi.MEM_DEVICE, sp)
+            e.record(stream)
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.mean(ts))
+
+    # ---- the reference's default derivative mode (derivatives = "automatic", ePSOPT.cpp:64): exact Jacobian,
+    # same workload, same flush, kernel-only like the roofline above
+    extras = {}
+    if not args.no_extras:
+        other = capi.JAC_EXACT if args.jac == "fd" else capi.JAC_FD
+        oms = kernel_only(other, max(5, min(args.steps, 20)))
+        och = alg_bytes_unit * B / (oms / 1e3) / 1e9
+        extras["exact" if args.jac == "fd" else "fd"] = {
+            "kernel_ms": oms, "achieved": och, "unit": "GB/s", "frac": och / peak, "evals_per_s": B / (oms / 1e3),
+            "what": "same workload and flush, Jacobian mode " + ("exact (the reference's default)" if args.jac == "fd" else "fd")}
+        # bare pinned device -> host copy of one step's Jacobian values on the same stream: the roof of the e2e number
+        hprobe = torch.empty((B, nz), dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            hprobe.copy_(jac, non_blocking=True)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(3):
+            hprobe.copy_(jac, non_blocking=True)
+        e.record(stream)
+        barrier()
+        tp = torch.tensor([s.elapsed_time(e) / 3.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        extras["d2h_probe"] = {"bytes": int(8 * B * nz), "ms": float(tp.item()),
+                               "GBps_per_gpu": 8 * B * nz / (float(tp.item()) / 1e3) / 1e9,
+                               "what": "cudaMemcpyAsync device -> pinned host of one step's Jacobian values, all ranks "
+                                       "at once, max over ranks"}
+        del hprobe
+
+    # ---- C5: all-gather of the full per-instance results [g | Jvals] over NVLink (NCCL), timed on its own ----
+    if world > 1 and not args.no_extras:
+        try:
+            big_g = torch.empty((world * B, ng), dtype=torch.float64, device=dev)
+            big_j = torch.empty((world * B, nz), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                dist.all_gather_into_tensor(big_g, g)
+                dist.all_gather_into_tensor(big_j, jac)
+            gts = []
+            for i in range(3):
+                barrier()
+                align()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                dist.all_gather_into_tensor(big_g, g)
+                dist.all_gather_into_tensor(big_j, jac)
+                e.record(stream)
+                torch.cuda.synchronize()
+                gts.append(s.elapsed_time(e))
+            tg = torch.tensor([float(np.mean(gts))], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            gms = float(tg.item())
+            recv = 8.0 * (world - 1) * B * (ng + nz)
+            ok = bool(torch.equal(big_j[rank * B:(rank + 1) * B], jac) and torch.equal(big_g[rank * B:(rank + 1) * B], g))
+            chk = torch.stack([big_j.view(torch.int64).sum(), big_g.view(torch.int64).sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ok = ok and bool(torch.equal(lo, hi))
+            extras["gather_full"] = {
+                "ms": gms, "recv_bytes_per_rank": int(recv), "GBps_per_rank": recv / (gms / 1e3) / 1e9,
+                "frac_of_nvlink_900GBps": recv / (gms / 1e3) / 1e9 / 900.0,
+                "ms_per_step_with_full_gather": total_ms_max / args.steps + gms,
+                "evals_per_s_with_full_gather": world * B / ((total_ms_max / args.steps + gms) / 1e3),
+                "parity": "bit-equal (own rows == local results; 64-bit checksum of the gathered arrays identical on "
+                          "all ranks)" if ok else "MISMATCH",
+                "what": f"NCCL all_gather_into_tensor of g[{B}x{ng}] and Jvals[{B}x{nz}] per rank into "
+                        f"[{world * B} x ...] on every rank"}
+            del big_g, big_j
+        except Exception as exc:  # noqa: BLE001
+            extras["gather_full"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -406,14 +552,31 @@ def run_ecuda(args):
         cpu_baseline.pop("seconds"), cpu_baseline.pop("n")
         cpu_baseline["tight_loops_value"] = tight["value"]
         cpu_baseline["note"] = ("oracle port (restatement, not PSOPT/ADOL-C binaries); value = reference-style "
-                                "callbacks on all host threads; tight_loops_value = same arithmetic, plain loops")
+                                "callbacks on all host threads; tight_loops_value = same arithmetic, plain loops; "
+                                "tight_rowrestricted_value = plain loops with the row-restricted finite differences "
+                                "the GPU kernels use (bit-identical Jacobian, O(nnz) instead of O(groups x ncons) work)")
+        if args.jac == "fd" and not args.no_extras:
+            try:
+                rr = cpu_rowrestricted_sample(wl, max(2.0, args.cpu_seconds / 4))
+                cpu_baseline["tight_rowrestricted_value"] = rr["value"]
+                cpu_baseline["tight_rowrestricted_sample"] = rr["sample"]
+            except Exception as exc:  # noqa: BLE001
+                cpu_baseline["tight_rowrestricted_value"] = None
+                cpu_baseline["tight_rowrestricted_sample"] = f"unavailable: {type(exc).__name__}: {exc}"
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(wl, args, world), gather_impl=gather_impl), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline}
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(wl, args, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "exchange": gather_impl}
+        if gather_parity:
+            line["gather_parity"] = gather_parity
+        line.update(extras)
+        if e2e and "d2h_probe" in extras:
+            # achieved device -> host rate per GPU inside the e2e step against the bare copy measured above
+            e2e["frac_of_d2h_probe"] = (e2e["d2h_bytes_per_step"] / (B * world / e2e["value"]) / 1e9) / \
+                extras["d2h_probe"]["GBps_per_gpu"]
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         emit(line)

@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
-    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
+    "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_peer_barrier_status", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
     "ecuda_host_path_eval", "ecuda_get_hess_structure", "ecuda_eval_hess", "ecuda_ipopt_eval_h", "ecuda_host_hess_structure",
@@ -94,6 +94,8 @@ def lib():
     L.ecuda_eval_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
     L.ecuda_peer_barrier.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+    L.ecuda_peer_barrier_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_int32), C.c_int]
     L.ecuda_sync.argtypes = [C.c_void_p]
     L.ecuda_launch_count.restype = C.c_int64
     L.ecuda_launch_count.argtypes = [C.c_void_p]
@@ -376,6 +378,17 @@ class Evaluator:
     def peer_barrier_ptr(self, flag_ptrs, rank, step, stream=None):
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         self._check(self.L.ecuda_peer_barrier(self.h, arr, len(flag_ptrs), rank, step, stream))
+
+    def peer_barrier_status(self, stream=None, reset=False):
+        """(timed_out, step, late_rank) of the peer barriers issued through this handle (sticky until reset)"""
+        to, st, lr = C.c_int32(0), C.c_uint64(0), C.c_int32(-1)
+        self._check(self.L.ecuda_peer_barrier_status(self.h, stream, C.byref(to), C.byref(st), C.byref(lr), int(reset)))
+        return bool(to.value), int(st.value), int(lr.value)
+
+    def sync_status(self):
+        """ecuda_sync return code (0, or ECUDA_ERR_PEER after a peer barrier timed out) and the error text"""
+        rc = self.L.ecuda_sync(self.h)
+        return rc, (self.L.ecuda_last_error(self.h) or b"").decode()
 
     def hess_host(self, x, sigma, lam):
         """Hessian of the Lagrangian per instance (host buffers): sigma [B], lam [B][ncons] -> [B][nnz_h]"""

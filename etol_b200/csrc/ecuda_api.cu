@@ -89,22 +89,33 @@ __global__ void k_summary_scatter(const double* f, const double* g, const double
 // of counters in peer-visible memory; "I have finished step s" is a store of s into my slot of every
 // peer's array, after a system-scope fence that orders this GPU's earlier peer stores (the gathered
 // rows of the kernel before) ahead of it; then every thread waits until its peer's slot in the local
-// array has reached s. Counters only grow, so nothing is ever reset. The wait is bounded (about 0.1 s
-// of SM clocks): a lost peer turns into a wrong result the caller can detect, not into a hung GPU.
+// array has reached s. Counters only grow, so nothing is ever reset. The wait is bounded (timeout_ns of the
+// global timer; default 10 s, ECUDA_PEER_TIMEOUT_MS): a lost peer does not hang the GPU. When it expires the kernel
+// records {1, step, first late rank + 1} in the handle's status words, which are STICKY: every later ecuda_sync /
+// ecuda_peer_barrier_status on the handle reports the failure until the status is read with reset.
 struct PeerFlags {
     unsigned long long* p[16];
 };
-__global__ void k_peer_barrier(PeerFlags flags, int nranks, int rank, unsigned long long step, int* timed_out) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_peer_barrier(PeerFlags flags, int nranks, int rank, unsigned long long step,
+                               unsigned long long timeout_ns, unsigned long long* status) {
     const int r = threadIdx.x;
     if (r >= nranks) return;
     __threadfence_system();
     volatile unsigned long long* theirs = flags.p[r] + rank;  // my slot in rank r's array
     *theirs = step;
     volatile unsigned long long* mine = flags.p[rank] + r;    // rank r's slot in my array
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
     while (*mine < step) {
-        if (clock64() - t0 > 200000000ll) {
-            if (timed_out) *timed_out = 1;
+        if (global_timer_ns() - t0 > timeout_ns) {
+            if (atomicCAS(&status[0], 0ull, 1ull) == 0ull) {  // first failure wins, later ones keep it
+                status[1] = step;
+                status[2] = static_cast<unsigned long long>(r) + 1ull;
+            }
             break;
         }
     }
@@ -221,6 +232,7 @@ struct ecuda_ctx {
     bool no_rows = false;   // ECUDA_NO_ROWS=1: use the column-owner kernels (k_eval_fast) instead of k_eval_rows
     bool no_copy_warp = false;  // ECUDA_NO_COPY_WARP=1: exact mode copies the template with plain loads/stores
     int64_t launches = 0;
+    bool barrier_used = false;  // ecuda_peer_barrier has been issued: ecuda_sync also reports its sticky status
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
     int rowsn_N = 0;     // node count shared by all phases when the N-specialised kernels may run (else 0)
@@ -431,7 +443,9 @@ template <int M, int N, bool FD, bool TRK, bool SUM>
 static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     static std::mutex mu;
     static size_t configured[64] = {0};
-    size_t smem = rn_doubles<M>(h->pd, N, FD) * sizeof(double);
+    size_t ring = 0;  // the store ring: three buffers of the largest node group of any phase
+    for (int p = 0; p < h->pd.nphases; ++p) ring = std::max(ring, kRnBufs * rn_group_cap<M>(h->pd, h->pd.ph[p], N));
+    size_t smem = (rn_doubles<M>(h->pd, N, FD) + ring) * sizeof(double);
     if (SUM && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
     if (smem > 48 * 1024) {
         std::lock_guard<std::mutex> lock(mu);
@@ -1315,10 +1329,47 @@ int ecuda_peer_barrier(ecuda_handle h, void* const* peer_flags, int nranks, int 
         pf.p[r] = static_cast<unsigned long long*>(peer_flags[r]);
     }
     int rc;
-    if ((rc = ensure(h, h->bflag, sizeof(int)))) return rc;
-    k_peer_barrier<<<1, 32, 0, st>>>(pf, nranks, rank, static_cast<unsigned long long>(step), static_cast<int*>(h->bflag.p));
+    if (!h->bflag.p) {  // status words {timed out, step, late rank + 1}: zeroed once, when they are allocated
+        if ((rc = ensure(h, h->bflag, 4 * sizeof(unsigned long long)))) return rc;
+        CU(cudaMemsetAsync(h->bflag.p, 0, 4 * sizeof(unsigned long long), st));
+    }
+    unsigned long long timeout_ms = 10000;
+    if (const char* e = std::getenv("ECUDA_PEER_TIMEOUT_MS")) {
+        const long long v = std::atoll(e);
+        if (v > 0) timeout_ms = static_cast<unsigned long long>(v);
+    }
+    k_peer_barrier<<<1, 32, 0, st>>>(pf, nranks, rank, static_cast<unsigned long long>(step), timeout_ms * 1000000ull,
+                                     static_cast<unsigned long long*>(h->bflag.p));
+    h->barrier_used = true;
     ++h->launches;
     CU(cudaGetLastError());
+    return ECUDA_OK;
+}
+
+// reads the sticky status of the peer barriers issued through this handle (after the work on `stream` has finished)
+static int read_barrier_status(ecuda_ctx* h, cudaStream_t st, unsigned long long out[3], bool reset) {
+    out[0] = out[1] = out[2] = 0;
+    if (!h->barrier_used || !h->bflag.p) return ECUDA_OK;
+    CU(cudaMemcpyAsync(out, h->bflag.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (reset && out[0]) {
+        CU(cudaMemsetAsync(h->bflag.p, 0, 4 * sizeof(unsigned long long), st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_peer_barrier_status(ecuda_handle h, void* stream, int32_t* timed_out, uint64_t* step, int32_t* late_rank, int reset) {
+    if (!h) return ECUDA_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long w[3];
+    int rc = read_barrier_status(h, st, w, reset != 0);
+    if (rc) return rc;
+    if (timed_out) *timed_out = w[0] ? 1 : 0;
+    if (step) *step = w[1];
+    if (late_rank) *late_rank = w[0] ? static_cast<int32_t>(w[2]) - 1 : -1;
     return ECUDA_OK;
 }
 
@@ -1326,6 +1377,14 @@ int ecuda_sync(ecuda_handle h) {
     if (!h) return ECUDA_ERR_ARG;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    unsigned long long w[3];
+    int rc = read_barrier_status(h, h->stream, w, false);
+    if (rc) return rc;
+    if (w[0])
+        return fail(h, ECUDA_ERR_PEER, "ecuda_peer_barrier timed out at step " + std::to_string(w[1]) + " waiting for rank " +
+                                           std::to_string(static_cast<long long>(w[2]) - 1) +
+                                           ": the gathered rows of that step are incomplete (read and clear with "
+                                           "ecuda_peer_barrier_status)");
     return ECUDA_OK;
 }
 

@@ -70,6 +70,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
+// element index of the first one, so that shared and global addresses are 16-byte aligned together)
+// to dst[0..n): the aligned interior by one bulk copy issued by thread `lead`, the at most two
+// boundary elements by plain stores from the next two threads.
+__device__ __forceinline__ void flush_range(double* dst, const double* src, int par, int n, int tid, int lead) {
+    const int start = par;             // par == 1: element 0 sits at an odd global index
+    const int nal = (n - start) & ~1;  // doubles in the 16-byte aligned interior
+    if (tid == lead) {
+        if (nal > 0) bulk_s2g(dst + start, src + par + start, static_cast<uint32_t>(nal) * 8u);
+        bulk_commit();
+    } else if (tid == lead + 1) {
+        if (start == 1 && n > 0) __stcs(dst, src[par]);
+    } else if (tid == lead + 2) {
+        if (start + nal < n) __stcs(dst + n - 1, src[par + n - 1]);
+    }
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- kernels ------------------------------------------------------------------------------------------
 // NB > 0: every phase has exactly NB summation blocks (block sums in registers); NB == 0: generic
 template <int M, int NB>
@@ -338,6 +357,33 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
 #ifndef ECUDA_MIN_CTAS_ROWSN_EXACT
 #define ECUDA_MIN_CTAS_ROWSN_EXACT 5
 #endif
+// the node groups of a phase, unrolled: compute group G into its ring buffer, hand it to the TMA, go on with G + 1.
+// Buffer G % 3 is free when group G starts: its previous user, group G - 3, was read out of shared memory before
+// thread 0 arrived at the barrier of group G - 1 (it waits for "all but the newest bulk group have been read" right
+// after issuing a store), so one CTA barrier per group is enough with three buffers.
+template <int M, int N, bool FD, int G>
+struct RnGroups {
+    __device__ __forceinline__ static void run(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st,
+                                               double* ring, int cap, double* jac, int tid) {
+        double* buf = ring + (G % kRnBufs) * cap;
+        int c0, c1;
+        rn_group_range<M, N, FD>(pb, m, G, c0, c1);
+        // shared and global addresses must agree modulo 16 bytes: triplet e sits at buf[par + e - c0]
+        const int par = static_cast<int>((reinterpret_cast<uintptr_t>(jac + c0) >> 3) & 1);
+        rn_group<M, N, FD, G>(pb, ph, m, st, buf + par - c0);
+        fence_async_smem();  // generic-proxy writes to the buffer -> visible to the bulk copy
+        __syncthreads();
+        flush_range(jac + c0, buf, par, c1 - c0, tid, 0);
+        if (tid == 0) bulk_wait_read_but_one();
+        RnGroups<M, N, FD, G + 1>::run(pb, ph, m, st, ring, cap, jac, tid);
+    }
+};
+template <int M, int N, bool FD>
+struct RnGroups<M, N, FD, (N + kRnGroup - 1) / kRnGroup> {
+    __device__ __forceinline__ static void run(const ProbDev&, const PhaseDev&, const RnMem&, RnRow<N>&, double*, int, double*,
+                                               int) {}
+};
+
 template <int M, int N, bool FD, bool TRK, bool SUM>
 __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA_MIN_CTAS_ROWSN_EXACT)
     k_rows_n(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
@@ -352,6 +398,8 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     CtaMem cm{};
     cm.inst = m.inst;
     cm.z = m.z;
+    const int cap = static_cast<int>(rn_group_cap<M>(pb, ph, N));
+    double* ring = smem + rn_doubles<M>(pb, N, FD);
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -359,9 +407,9 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
     }
-    if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the records
+    if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the store ring
         const int ncp = phase_ncons(pb, ph), nbnd = ncp + (ncp & 1);
-        double* bnd = smem + rn_doubles<M>(pb, N, FD);
+        double* bnd = ring + kRnBufs * cap;
         const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
         for (int c = tid; c < ncp; c += nthr) {
             bnd[c] = __ldg(io.bl + o + c);
@@ -373,11 +421,15 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     rn_stage<M, N, FD>(pb, ph, io, m, b, tid, nthr);
     mbar_wait(&bar, 0);
     __syncthreads();
+    RnRow<N> st;
     double viol, fval;
-    if (FD)
-        rn_thread_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
-    else
-        rn_thread_exact<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
+    rn_begin<M, N, FD, SUM>(pb, ph, io, m, cm, b, tid, st, viol, fval);
+    if (io.jac) {  // uniform over the CTA
+        RnGroups<M, N, FD, 0>::run(pb, ph, m, st, ring, cap, io.jac + static_cast<size_t>(b) * pb.nnz, tid);
+        if (tid == 0) bulk_wait_all();  // the groups' global writes are performed ...
+        __syncthreads();                // ... before any thread writes a node-local triplet inside their ranges
+    }
+    rn_end<M, N, FD, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, st, viol, fval);
     if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
         __shared__ double red[kThreads / 32 + 1];
         double v = viol;
@@ -395,25 +447,6 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
         }
     }
 }
-
-// Write n doubles from the shared image `src` (element i at src[par + i], par = parity of the global
-// element index of the first one, so that shared and global addresses are 16-byte aligned together)
-// to dst[0..n): the aligned interior by one bulk copy issued by thread `lead`, the at most two
-// boundary elements by plain stores from the next two threads.
-__device__ __forceinline__ void flush_range(double* dst, const double* src, int par, int n, int tid, int lead) {
-    const int start = par;             // par == 1: element 0 sits at an odd global index
-    const int nal = (n - start) & ~1;  // doubles in the 16-byte aligned interior
-    if (tid == lead) {
-        if (nal > 0) bulk_s2g(dst + start, src + par + start, static_cast<uint32_t>(nal) * 8u);
-        bulk_commit();
-    } else if (tid == lead + 1) {
-        if (start == 1 && n > 0) __stcs(dst, src[par]);
-    } else if (tid == lead + 2) {
-        if (start + nal < n) __stcs(dst + n - 1, src[par + n - 1]);
-    }
-}
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Exact mode, persistent: a CTA keeps a shared-memory IMAGE of its phase's whole triplet range. The
 // instance-independent D-coupled triplets are loaded into it once from the per-problem template;

@@ -35,7 +35,19 @@ namespace ecuda {
 
 #if defined(__CUDA_ARCH__)
 #define ECUDA_LDG(p) __ldg(p)
+// result stores. ECUDA_STORE_MODE 0: st.global.cs (streaming, evict first); 1: plain write-back stores (lines stay in
+// L2 until they are complete, so the node-local triplets written later merge with the D-coupled ones of the same
+// sectors before anything goes to HBM); 2: st.global.cg
+#ifndef ECUDA_STORE_MODE
+#define ECUDA_STORE_MODE 0
+#endif
+#if ECUDA_STORE_MODE == 1
+#define ECUDA_STREAM_STORE(p, v) (*(p) = (v))
+#elif ECUDA_STORE_MODE == 2
+#define ECUDA_STREAM_STORE(p, v) __stcg((p), (v))
+#else
 #define ECUDA_STREAM_STORE(p, v) __stcs((p), (v))
+#endif
 #else
 #define ECUDA_LDG(p) (*(p))
 #define ECUDA_STREAM_STORE(p, v) (*(p) = (v))

@@ -13,6 +13,14 @@
 //     first triplet}, fetched with two 128-bit loads;
 //   * triplet addresses are  (jac + k) + 8 * (record.cp + select) : one compare, one select, one add, one
 //     wide multiply-add.
+//   * STORES: the D-coupled triplets (74 % of the Jacobian) are not stored from registers. A store-only kernel with
+//     the row-owner pattern (every warp instruction writes one 256-byte piece, consecutive instructions advance by a
+//     column) reaches 2.2 TB/s on a B200; 8 KB bulk stores from shared memory reach 5.9 TB/s (scripts/wroof.cu,
+//     profiles/r2). So the threads write their D-coupled values into a shared-memory ring -- one buffer per group of
+//     ECUDA_RN_GROUP nodes, whose state columns are one contiguous range of the (col,row)-sorted triplet array --
+//     and every finished group leaves with one cp.async.bulk shared -> global (TMA) while the next one is computed.
+//     The few node-local triplets inside those ranges are written afterwards, into lines the bulk stores have
+//     just put into L2.
 // Reference counterparts: PSOPT's defect assembly and index-set finite differences entered at
 // src/ePSOPT/ePSOPT.cpp:84 (mode chosen at :64), callbacks src/ePSOPT/ePSOPT.cpp:186-306.
 #ifndef ECUDA_ROWSN_CUH_
@@ -94,6 +102,19 @@ struct RnMem {
 
 template <int M>
 ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N + 2; }
+
+// store ring: kRnBufs buffers, each holds the triplets of the state columns of kRnGroup consecutive nodes
+constexpr int kRnGroup = 4;  // nodes per group (half a summation block)
+constexpr int kRnBufs = 3;   // one barrier per group needs three buffers (see k_rows_n)
+// doubles of one ring buffer: upper bound of a group's triplet range (+ 2: parity pad, even size)
+template <int M>
+ECUDA_HD size_t rn_group_cap(const ProbDev& pb, const PhaseDev& ph, int N) {
+    constexpr int NS = Model<M>::NS;
+    int per_node = NS * (N - 1) + 2 * ph.npath + 2 * NS;  // D-coupled + path rows (states 0, 1) + event + linkage
+    for (int j = 0; j < NS; ++j) per_node += pb.xcnt[j];
+    const size_t n = static_cast<size_t>(kRnGroup) * per_node + 2;
+    return n + (n & 1);
+}
 
 // doubles of shared memory, without the exact-mode ring and the fused-summary bounds
 template <int M>
@@ -219,130 +240,134 @@ ECUDA_HD void rn_diag(const double* __restrict__ Dtk, const double* __restrict__
     dm = tm;
 }
 
-// D-coupled triplets of defect row (k,i) in the state columns of summation block BI, by index-set central
-// differences, row-restricted (operation sequence of fast_fd_block). jk = jac + k. Triplet of row k in column
-// X(l,i): rows k < l sit at position k of the column; rows k > l come after its node-local block, dlt = (number of
-// node-local defect rows of column X(.,i)) - 1 places further; l == k is the row's own diagonal triplet at
-// kdo = its rank among the node-local rows (final for DIAG_FREE models, otherwise overwritten by the caller
-// afterwards). These offsets are one byte per node of the block, packed in w0 (nodes 0..3) and w1 (4..7).
-template <int NS, int N, int BI>
-ECUDA_HD void rn_fd_block(const double* __restrict__ Dtk, const double* __restrict__ Xi, const FdRec* __restrict__ Ri,
-                          const double (&P)[(N + 7) / 8], double sgr, double hfv, unsigned w0, unsigned w1,
-                          double* __restrict__ jk) {
-    constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL, l0 = BI * BL;
-    constexpr int nin = (N - l0) < BL ? (N - l0) : BL;
-    double d[nin], xv[nin];
-#pragma unroll
-    for (int a = 0; a < nin; ++a) {
-        d[a] = ECUDA_LDG(Dtk + (l0 + a) * N);
-        xv[a] = Xi[(l0 + a) * NS];
-    }
-    double pre = 0.0;
-#pragma unroll
-    for (int t = 0; t < BI; ++t) pre = (t == 0) ? P[0] : pre + P[t];
-    double q = 0.0;  // unperturbed in-block prefix
-#pragma unroll
-    for (int a = 0; a < nin; ++a) {
-        const FdVals rc = rn_load(Ri + (l0 + a) * NS);
-        double sp = fma(d[a], rc.xp, q);
-        double sm = fma(d[a], rc.xm, q);
-#pragma unroll
-        for (int e = a + 1; e < nin; ++e) {
-            sp = fma(d[e], xv[e], sp);
-            sm = fma(d[e], xv[e], sm);
-        }
-        double tp = (BI > 0) ? pre + sp : sp;
-        double tm = (BI > 0) ? pre + sm : sm;
-#pragma unroll
-        for (int t = BI + 1; t < NB; ++t) {
-            tp = tp + P[t];
-            tm = tm + P[t];
-        }
-        const double gp = sgr * (tp - hfv);
-        const double gm = sgr * (tm - hfv);
-        const double v = (gp - gm) * rc.ri;
-        ECUDA_STREAM_STORE(jk + (rc.cp + rn_byte(a < 4 ? w0 : w1, a & 3)), v);
-        q = fma(d[a], xv[a], q);
-    }
+// ---- per-thread state of a defect row between the phases of the kernel (registers) ----------------------------------
+// Triplet of row k in column X(l,i): rows k < l sit at position k of the column; rows k > l come after its
+// node-local block, dlt = (number of node-local defect rows of column X(.,i)) - 1 places further; l == k is the
+// row's own diagonal triplet at kdo = its rank among the node-local rows (final for DIAG_FREE models, otherwise
+// overwritten afterwards). For one group of kRnGroup nodes these offsets are one byte per node: `all` (dlt in every
+// byte) for the groups below the row's own, `mix` inside it, 0 above.
+template <int N>
+struct RnRow {
+    double P[(N + 7) / 8];  // block sums of (D X)[k][i]
+    double d[8], xv[8];     // FD: D[k][l] and X(l,i) of the current summation block
+    double pre, q;          // FD: sum of the earlier block sums, unperturbed in-block prefix
+    double sgr, hfv;        // row scale, h * f_i(node k)
+    int i, k, kg;           // state, node, group of the node
+    unsigned all, mix;
+    bool row;               // this thread owns a defect row
+};
+template <int N>
+ECUDA_HD void rn_row_offsets(const ProbDev& pb, RnRow<N>& st) {
+    const int kr = st.k & (kRnGroup - 1);
+    const unsigned dlt = static_cast<unsigned>(pb.xcnt[st.i] - 1), kdo = static_cast<unsigned>(pb.xrank[st.i][st.i]);
+    st.kg = st.k / kRnGroup;
+    st.all = dlt * 0x01010101u;
+    st.mix = (st.all & ((1u << (8 * kr)) - 1u)) | (kdo << (8 * kr));
 }
-template <int NS, int N, int BI>
-struct RnFdBlocks {
-    ECUDA_HD static void run(const double* Dtk, const double* Xi, const FdRec* Ri, const double (&P)[(N + 7) / 8],
-                             double sgr, double hfv, int kb, unsigned all, unsigned m0, unsigned m1, double* jk) {
-        // offsets of this block's nodes: all `dlt` below the row's own block, the mixed pattern inside it, 0 above
-        const unsigned w0 = BI < kb ? all : (BI == kb ? m0 : 0u);
-        const unsigned w1 = BI < kb ? all : (BI == kb ? m1 : 0u);
-        rn_fd_block<NS, N, BI>(Dtk, Xi, Ri, P, sgr, hfv, w0, w1, jk);
-        RnFdBlocks<NS, N, BI + 1>::run(Dtk, Xi, Ri, P, sgr, hfv, kb, all, m0, m1, jk);
-    }
-};
-template <int NS, int N>
-struct RnFdBlocks<NS, N, (N + 7) / 8> {
-    ECUDA_HD static void run(const double*, const double*, const FdRec*, const double (&)[(N + 7) / 8], double, double,
-                             int, unsigned, unsigned, unsigned, double*) {}
-};
 
-// ---- defect row (k,i), finite differences: value, D-coupled triplets, node-local triplets -------------------------
-// [rows_values + rows_jacobian<FD>]
+// ---- finite differences, part 1: value of defect row (k,i)                     [rows_values]
 template <int M, int N, bool SUM>
-ECUDA_HD void rn_row_fd(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
-                        int tid, double& viol) {
-    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
-    if (tid >= NS * N) return;
+ECUDA_HD void rn_fd_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                          int tid, RnRow<N>& st, double& viol) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    st.row = tid < NS * N;
+    if (!st.row) return;
     const int nc = pb.nc;
     const int i = tid / N, k = tid - i * N;
+    st.i = i;
+    st.k = k;
+    rn_row_offsets<N>(pb, st);
     const double* zx = m.z + nc * N;  // X(l,j) = zx[l*NS + j]
+    const int r = ph.goff + k * NS + i;
+    st.sgr = ECUDA_LDG(pb.sg + r);
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+    double x[NS], u[NCU], f[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+    for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+    Model<M>::f(x, u, t, f);
+    double fi = 0.0;
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+        if (a == i) fi = f[a];
+    st.hfv = h * fi;
+    const double dv = rn_dot<NS, N>(ph.Dt + k, zx + i, st.P);
+    if (io.g) {
+        const double val = st.sgr * (dv - st.hfv);
+        ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+        if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
+    }
+}
+
+// ---- finite differences, part 2: the D-coupled triplets of row (k,i) in the state columns of node group G (nodes
+// kRnGroup*G ...), by index-set central differences, row-restricted (operation sequence of fast_fd_block).
+// out[e] is the slot of triplet e of the instance (a shared-memory ring buffer, or the global array).
+template <int NS, int N, int G>
+ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* __restrict__ out) {
+    constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL, BI = (G * kRnGroup) / BL, l0 = BI * BL;
+    constexpr int a0 = G * kRnGroup - l0;                  // first node of the group inside its summation block
+    constexpr int nin = (N - l0) < BL ? (N - l0) : BL;     // nodes of the block
+    constexpr int a1 = (a0 + kRnGroup) < nin ? (a0 + kRnGroup) : nin;
+    if (!st.row) return;
+    const double* Dtk = ph.Dt + st.k;
+    const double* Xi = m.z + pb.nc * N + st.i;
+    const FdRec* Ri = m.rec + pb.nc * N + st.i;
+    if (a0 == 0) {  // first group of a summation block: its D entries and node values, the prefix of block sums
+#pragma unroll
+        for (int a = 0; a < nin; ++a) {
+            st.d[a] = ECUDA_LDG(Dtk + (l0 + a) * N);
+            st.xv[a] = Xi[(l0 + a) * NS];
+        }
+        st.pre = 0.0;
+#pragma unroll
+        for (int t = 0; t < BI; ++t) st.pre = (t == 0) ? st.P[0] : st.pre + st.P[t];
+        st.q = 0.0;
+    }
+    const unsigned w = G < st.kg ? st.all : (G == st.kg ? st.mix : 0u);
+    double* ok = out + st.k;
+#pragma unroll
+    for (int a = a0; a < a1; ++a) {
+        const FdVals rc = rn_load(Ri + (l0 + a) * NS);
+        double sp = fma(st.d[a], rc.xp, st.q);
+        double sm = fma(st.d[a], rc.xm, st.q);
+#pragma unroll
+        for (int e = a + 1; e < nin; ++e) {
+            sp = fma(st.d[e], st.xv[e], sp);
+            sm = fma(st.d[e], st.xv[e], sm);
+        }
+        double tp = (BI > 0) ? st.pre + sp : sp;
+        double tm = (BI > 0) ? st.pre + sm : sm;
+#pragma unroll
+        for (int t = BI + 1; t < NB; ++t) {
+            tp = tp + st.P[t];
+            tm = tm + st.P[t];
+        }
+        const double gp = st.sgr * (tp - st.hfv);
+        const double gm = st.sgr * (tm - st.hfv);
+        ok[rc.cp + rn_byte(w, a - a0)] = (gp - gm) * rc.ri;
+        st.q = fma(st.d[a], st.xv[a], st.q);
+    }
+}
+
+// ---- finite differences, part 3: the node-local triplets of row (k,i)          [rows_jacobian<FD>, node-local part]
+// Runs after every D-coupled group has been stored (the bulk stores are complete): a slot inside a group's range that
+// this part writes overwrites what the ring buffer held there.
+template <int M, int N>
+ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
+    if (!st.row || !io.jac) return;
+    const int nc = pb.nc, i = st.i, k = st.k;
+    const double sgr = st.sgr;
+    const double (&P)[NB] = st.P;
+    const double* zx = m.z + nc * N;
     const double* Dtk = ph.Dt + k;
     const double* Xi = zx + i;
-    const int r = ph.goff + k * NS + i;
-    const double sgr = ECUDA_LDG(pb.sg + r);
-    double hfv, P[NB];
-    {
-        const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
-        const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
-        const double t = h * ECUDA_LDG(ph.tau + k) + mid;
-        double x[NS], u[NCU], f[NS];
-#pragma unroll
-        for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
-#pragma unroll
-        for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
-        Model<M>::f(x, u, t, f);
-        double fi = 0.0;
-#pragma unroll
-        for (int a = 0; a < NS; ++a)
-            if (a == i) fi = f[a];
-        hfv = h * fi;
-        const double dv = rn_dot<NS, N>(Dtk, Xi, P);
-        if (io.g) {
-            const double val = sgr * (dv - hfv);
-            ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-            if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
-        }
-    }
-    if (!io.jac) return;
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
     constexpr bool DS = Model<M>::DIAG_FREE;
     const FdRec* rx = m.rec + nc * N;  // record of X(l,j) = rx[l*NS + j]
-    {
-        // packed triplet offsets of the row's own summation block (see rn_fd_block)
-        const int kb = k >> 3, kr = k & 7;
-        const unsigned dlt = static_cast<unsigned>(pb.xcnt[i] - 1), kdo = static_cast<unsigned>(pb.xrank[i][i]);
-        const unsigned all = dlt * 0x01010101u;
-        const unsigned lowmask = (1u << (8 * (kr & 3))) - 1u;  // bytes below kr & 3
-        const unsigned own = kdo << (8 * (kr & 3));
-        const unsigned m0 = kr < 4 ? ((all & lowmask) | own) : all;
-        const unsigned m1 = kr < 4 ? 0u : ((all & lowmask) | own);
-        double* jk = jac + k;
-#if defined(__CUDA_ARCH__)
-        asm volatile("" : "+l"(jk));  // keep jac + k in a register pair: every triplet address is one wide multiply-add
-#endif
-        RnFdBlocks<NS, N, 0>::run(Dtk, Xi, rx + i, P, sgr, hfv, kb, all, m0, m1, jk);
-    }
-    // node-local triplets. Everything they need is re-read (shared memory, L1) or recomputed from the block sums
-    // here, so that it does not occupy registers across the D-coupled loop above
-#if defined(__CUDA_ARCH__)
-    asm volatile("" ::: "memory");
-#endif
     const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
     const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
     const double tau = ECUDA_LDG(ph.tau + k);
@@ -616,63 +641,27 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     }
 }
 
-// whole thread program after the staging barrier, finite differences
-template <int M, int N, bool TRK, bool SUM>
-ECUDA_HD void rn_thread_fd(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
-                           int b, int tid, int nthr, double& viol, double& fval) {
-    viol = 0.0;
-    fval = 0.0;
-    rn_row_fd<M, N, SUM>(pb, ph, io, m, cm, b, tid, viol);
-    const int nitems = rn_items<M, N>(pb, ph, p);
-    for (int it = nthr - 1 - tid; it < nitems; it += nthr)
-        rn_item_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
-}
-
 // ---- exact mode --------------------------------------------------------------------------------------------------
-// D-coupled triplets of defect row (k,i), block BI: (sg_r * D[k][l]) / sz(X(l,i)) -- the expression of
-// build_jac_template, so the values equal the round-1 template copy bit for bit. They are COMPUTED here (two
-// multiplications per triplet, D from L1, the column's record with one 128-bit shared load) instead of being
-// streamed from a per-problem template through a shared-memory ring: with N a compile-time constant a triplet
-// costs 8 instructions, the kernel has no second barrier, no copy warp and no L2 -> SM template traffic.
-template <int NS, int N, int BI>
-ECUDA_HD void rn_ex_block(const double* __restrict__ Dtk, const ExRec* __restrict__ Ri, double sgr, unsigned w0,
-                          unsigned w1, double* __restrict__ jk) {
-    constexpr int BL = ECUDA_DOT_BLOCK, l0 = BI * BL;
-    constexpr int nin = (N - l0) < BL ? (N - l0) : BL;
-#pragma unroll
-    for (int a = 0; a < nin; ++a) {
-        const ExVals rc = rn_load(Ri + (l0 + a) * NS);
-        const double v = (sgr * ECUDA_LDG(Dtk + (l0 + a) * N)) * rc.isz;
-        ECUDA_STREAM_STORE(jk + (rc.cp + rn_byte(a < 4 ? w0 : w1, a & 3)), v);
-    }
-}
-template <int NS, int N, int BI>
-struct RnExBlocks {
-    ECUDA_HD static void run(const double* Dtk, const ExRec* Ri, double sgr, int kb, unsigned all, unsigned m0, unsigned m1,
-                             double* jk) {
-        const unsigned w0 = BI < kb ? all : (BI == kb ? m0 : 0u);
-        const unsigned w1 = BI < kb ? all : (BI == kb ? m1 : 0u);
-        rn_ex_block<NS, N, BI>(Dtk, Ri, sgr, w0, w1, jk);
-        RnExBlocks<NS, N, BI + 1>::run(Dtk, Ri, sgr, kb, all, m0, m1, jk);
-    }
-};
-template <int NS, int N>
-struct RnExBlocks<NS, N, (N + 7) / 8> {
-    ECUDA_HD static void run(const double*, const ExRec*, double, int, unsigned, unsigned, unsigned, double*) {}
-};
-
-// defect row (k,i), exact: value, D-coupled triplets, node-local triplets   [rows_values + rows_jacobian<exact>]
+// D-coupled triplets of defect row (k,i): (sg_r * D[k][l]) / sz(X(l,i)) -- the expression of build_jac_template, so
+// the values equal the round-1 template copy bit for bit. They are COMPUTED here (two multiplications per triplet, D
+// from L1, the column's record with one 128-bit shared load) instead of being streamed from a per-problem template:
+// no copy warp and no L2 -> SM template traffic; they leave through the same shared-memory store ring as in FD mode.
+// part 1: value of defect row (k,i)
 template <int M, int N, bool SUM>
-ECUDA_HD void rn_row_exact(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
-                           int tid, double& viol) {
-    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
-    if (tid >= NS * N) return;
+ECUDA_HD void rn_ex_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                          int tid, RnRow<N>& st, double& viol) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    st.row = tid < NS * N;
+    if (!st.row) return;
     const int nc = pb.nc;
     const int i = tid / N, k = tid - i * N;
+    st.i = i;
+    st.k = k;
+    rn_row_offsets<N>(pb, st);
     const double* zx = m.z + nc * N;
-    const double* Dtk = ph.Dt + k;
     const int r = ph.goff + k * NS + i;
-    const double sgr = ECUDA_LDG(pb.sg + r);
+    st.sgr = ECUDA_LDG(pb.sg + r);
+    if (!io.g) return;
     const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
     const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
     const double t = h * ECUDA_LDG(ph.tau + k) + mid;
@@ -686,32 +675,54 @@ ECUDA_HD void rn_row_exact(const ProbDev& pb, const PhaseDev& ph, const EvalIO& 
 #pragma unroll
     for (int a = 0; a < NS; ++a)
         if (a == i) fi = f[a];
-    if (io.g) {
-        double P[NB];
-        const double dv = rn_dot<NS, N>(Dtk, zx + i, P);
-        const double val = sgr * (dv - h * fi);
-        ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
-        if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
+    const double dv = rn_dot<NS, N>(ph.Dt + k, zx + i, st.P);
+    const double val = st.sgr * (dv - h * fi);
+    ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+    if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
+}
+
+// D-coupled triplets of row (k,i) in the state columns of node group G (see rn_fd_group for `out`)
+template <int NS, int N, int G>
+ECUDA_HD void rn_ex_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, const RnRow<N>& st, double* __restrict__ out) {
+    constexpr int l0 = G * kRnGroup;
+    constexpr int nin = (N - l0) < kRnGroup ? (N - l0) : kRnGroup;
+    if (!st.row) return;
+    const double* Dtk = ph.Dt + st.k;
+    const ExRec* Ri = m.erec + pb.nc * N + st.i;
+    const unsigned w = G < st.kg ? st.all : (G == st.kg ? st.mix : 0u);
+    double* ok = out + st.k;
+#pragma unroll
+    for (int a = 0; a < nin; ++a) {
+        const ExVals rc = rn_load(Ri + (l0 + a) * NS);
+        // the l == k value, (sg D_kk) / sz, lands in the row's diagonal slot; rn_ex_end overwrites it with the full entry
+        ok[rc.cp + rn_byte(w, a)] = (st.sgr * ECUDA_LDG(Dtk + (l0 + a) * N)) * rc.isz;
     }
-    if (!io.jac) return;
+}
+
+// node-local triplets of row (k,i), exact                                   [rows_jacobian<exact>]
+template <int M, int N>
+ECUDA_HD void rn_ex_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU;
+    if (!st.row || !io.jac) return;
+    const int nc = pb.nc, i = st.i, k = st.k;
+    const double sgr = st.sgr;
+    const double* zx = m.z + nc * N;
+    const double* Dtk = ph.Dt + k;
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
     const ExRec* rx = m.erec + nc * N;
-    {
-        const int kb = k >> 3, kr = k & 7;
-        const unsigned dlt = static_cast<unsigned>(pb.xcnt[i] - 1), kdo = static_cast<unsigned>(pb.xrank[i][i]);
-        const unsigned all = dlt * 0x01010101u;
-        const unsigned lowmask = (1u << (8 * (kr & 3))) - 1u;
-        const unsigned own = kdo << (8 * (kr & 3));
-        const unsigned m0 = kr < 4 ? ((all & lowmask) | own) : all;
-        const unsigned m1 = kr < 4 ? 0u : ((all & lowmask) | own);
-        double* jk = jac + k;
-#if defined(__CUDA_ARCH__)
-        asm volatile("" : "+l"(jk));
-#endif
-        // the l == k store puts (sg D_kk) / sz into the row's diagonal slot; the node-local pass below overwrites it
-        // (same thread, program order) with the full diagonal entry
-        RnExBlocks<NS, N, 0>::run(Dtk, rx + i, sgr, kb, all, m0, m1, jk);
-    }
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+    double x[NS], u[NCU], f[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+    for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+    Model<M>::f(x, u, t, f);
+    double fi = 0.0;
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+        if (a == i) fi = f[a];
     double dfdx[NS][NS], dfdu[NS][NCU];
     Model<M>::jac(x, u, dfdx, dfdu);
     const double dkk = ECUDA_LDG(Dtk + k * N);
@@ -894,17 +905,68 @@ ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const 
     }
 }
 
-// whole thread program after the staging barrier, exact Jacobian (also used when no Jacobian is asked for)
-template <int M, int N, bool TRK, bool SUM>
-ECUDA_HD void rn_thread_exact(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm,
-                              int b, int tid, int nthr, double& viol, double& fval) {
+// ---- the three parts of a thread's program after the staging barrier -------------------------------------------------
+//   rn_begin   defect-row value (+ the per-row state kept in registers)
+//   rn_group   D-coupled triplets of node group G into `out` (k_rows_n: a ring buffer that leaves by bulk store)
+//   rn_end     node-local triplets of the row, then the other rows (objective, path, event, duration, linkage)
+template <int M, int N, bool FD, bool SUM>
+ECUDA_HD void rn_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                       int tid, RnRow<N>& st, double& viol, double& fval) {
     viol = 0.0;
     fval = 0.0;
-    rn_row_exact<M, N, SUM>(pb, ph, io, m, cm, b, tid, viol);
-    const int nitems = rn_items<M, N>(pb, ph, p);
-    for (int it = nthr - 1 - tid; it < nitems; it += nthr)
-        rn_item_exact<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
+    if (FD)
+        rn_fd_begin<M, N, SUM>(pb, ph, io, m, cm, b, tid, st, viol);
+    else
+        rn_ex_begin<M, N, SUM>(pb, ph, io, m, cm, b, tid, st, viol);
 }
+template <int M, int N, bool FD, int G>
+ECUDA_HD void rn_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
+    if (FD)
+        rn_fd_group<Model<M>::NS, N, G>(pb, ph, m, st, out);
+    else
+        rn_ex_group<Model<M>::NS, N, G>(pb, ph, m, st, out);
+}
+template <int N>
+ECUDA_HD constexpr int rn_ngroups() { return (N + kRnGroup - 1) / kRnGroup; }
+// triplet range [c0, c1) of the state columns of node group g: from the first state column of its first node to the
+// first state column of the node after its last (the t0 column after the last node)
+template <int M, int N, bool FD>
+ECUDA_HD void rn_group_range(const ProbDev& pb, const RnMem& m, int g, int& c0, int& c1) {
+    constexpr int NS = Model<M>::NS;
+    const int l0 = g * kRnGroup, l1 = (l0 + kRnGroup) < N ? (l0 + kRnGroup) : N;
+    const int a = pb.nc * N + l0 * NS, e = pb.nc * N + l1 * NS;
+    c0 = FD ? m.rec[a].cp : m.erec[a].cp;
+    c1 = FD ? m.rec[e].cp : m.erec[e].cp;
+}
+template <int M, int N, bool FD, bool TRK, bool SUM>
+ECUDA_HD void rn_end(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
+                     int tid, int nthr, const RnRow<N>& st, double& viol, double& fval) {
+    if (FD)
+        rn_fd_end<M, N>(pb, ph, io, m, b, st);
+    else
+        rn_ex_end<M, N>(pb, ph, io, m, b, st);
+    const int nitems = rn_items<M, N>(pb, ph, p);
+    for (int it = nthr - 1 - tid; it < nitems; it += nthr) {
+        if (FD)
+            rn_item_fd<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
+        else
+            rn_item_exact<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
+    }
+}
+// node group by run-time index (the kernel-logic emulator of the test-suite; the kernel unrolls the groups)
+template <int M, int N, bool FD, int G = 0>
+struct RnGroupRt {
+    ECUDA_HD static void run(int g, const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
+        if (g == G)
+            rn_group<M, N, FD, G>(pb, ph, m, st, out);
+        else
+            RnGroupRt<M, N, FD, G + 1>::run(g, pb, ph, m, st, out);
+    }
+};
+template <int M, int N, bool FD>
+struct RnGroupRt<M, N, FD, (N + kRnGroup - 1) / kRnGroup> {
+    ECUDA_HD static void run(int, const ProbDev&, const PhaseDev&, const RnMem&, RnRow<N>&, double*) {}
+};
 
 }  // namespace ecuda
 #endif

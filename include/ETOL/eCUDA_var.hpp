@@ -10,8 +10,10 @@
 #ifndef INCLUDE_ETOL_ECUDA_VAR_HPP_
 #define INCLUDE_ETOL_ECUDA_VAR_HPP_
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <stdexcept>
 #include <vector>
 
 namespace ecuda {
@@ -28,6 +30,20 @@ struct Node {
 class Tape {
  public:
     std::vector<Node> nodes;
+    // every recording has its own serial number: a var remembers which recording its node id belongs to, so a
+    // constant kept across recordings (captured by a callback, static, global) is materialised again on the new tape
+    // instead of pointing at an unrelated node of it
+    const uint64_t serial;
+    Tape() : serial(next_serial()) {}
+    Tape(const Tape& o) : nodes(o.nodes), serial(next_serial()) {}
+    Tape& operator=(const Tape& o) {
+        nodes = o.nodes;
+        return *this;
+    }
+    static uint64_t next_serial() {
+        static std::atomic<uint64_t> n{1};
+        return n.fetch_add(1);
+    }
     int push(Op op, int a = -1, int b = -1, double imm = 0.0) {
         nodes.push_back(Node{op, a, b, imm});
         return static_cast<int>(nodes.size()) - 1;
@@ -62,30 +78,51 @@ class Tape {
 
 class var {
  public:
-    var() : id_(-1), value_(0.0) {}
-    var(double c) : id_(-1), value_(c) {}  // NOLINT: constants convert implicitly, like adouble
+    var() : id_(-1), tape_(0), constant_(true), value_(0.0) {}
+    var(double c) : id_(-1), tape_(0), constant_(true), value_(c) {}  // NOLINT: constants convert implicitly, like adouble
     static var input(int slot) {
         var v;
+        v.constant_ = false;
         v.id_ = Tape::active()->push(Op::INPUT, slot);
+        v.tape_ = Tape::active()->serial;
         return v;
     }
-    int id() const {  // node id, materialising a constant on first use
-        if (id_ < 0) id_ = Tape::active()->push(Op::CONST, -1, -1, value_);
+    // node id on the ACTIVE tape. A constant is materialised on first use per recording; a recorded value that
+    // belongs to another recording cannot be used (its id would name an unrelated node).
+    int id() const {
+        Tape* t = Tape::active();
+        if (!t) throw std::logic_error("ecuda::var used outside a recording");
+        if (constant_) {
+            if (id_ < 0 || tape_ != t->serial) {
+                id_ = t->push(Op::CONST, -1, -1, value_);
+                tape_ = t->serial;
+            }
+            return id_;
+        }
+        if (tape_ != t->serial) throw std::logic_error("ecuda::var recorded on another tape (kept across transcriptions?)");
         return id_;
     }
     static var make(Op op, const var& a, const var& b) {
         var r;
-        r.id_ = Tape::active()->push(op, a.id(), b.id());
+        r.constant_ = false;
+        const int ia = a.id(), ib = b.id();
+        r.id_ = Tape::active()->push(op, ia, ib);
+        r.tape_ = Tape::active()->serial;
         return r;
     }
     static var make1(Op op, const var& a, double imm = 0.0) {
         var r;
-        r.id_ = Tape::active()->push(op, a.id(), -1, imm);
+        r.constant_ = false;
+        const int ia = a.id();
+        r.id_ = Tape::active()->push(op, ia, -1, imm);
+        r.tape_ = Tape::active()->serial;
         return r;
     }
 
  private:
     mutable int id_;
+    mutable uint64_t tape_;  // serial of the recording id_ belongs to
+    bool constant_;
     double value_;
 };
 

@@ -65,6 +65,7 @@ extern "C" {
 #define ECUDA_ERR_STATE (-2)   /* call order violated (e.g. eval before set_problem) */
 #define ECUDA_ERR_CUDA (-3)    /* CUDA runtime failure or no usable device */
 #define ECUDA_ERR_ALLOC (-4)   /* host or device allocation failed */
+#define ECUDA_ERR_PEER (-5)    /* a cross-GPU barrier timed out: a peer did not arrive (gathered rows incomplete) */
 
 /* device models of the VGP callbacks (dynamics, running cost, path constraints) */
 enum ecuda_model {
@@ -210,8 +211,17 @@ int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, 
 /* cross-GPU barrier for the fused exchanges above: peer_flags[r] is rank r's array of nranks 64-bit
  * counters in peer-visible memory (zero-initialised once, e.g. a symmetric-memory buffer); step must
  * grow by one per call (first call: 1). Enqueued on `stream` after the kernel whose peer stores it
- * publishes; when it completes on every rank, every rank's rows of this step are visible everywhere. */
+ * publishes; when it completes on every rank, every rank's rows of this step are visible everywhere.
+ * The wait is bounded (10 s, or ECUDA_PEER_TIMEOUT_MS in the environment): a peer that never arrives does not hang
+ * the GPU; the failure is recorded in the handle (sticky) and reported by ecuda_sync (ECUDA_ERR_PEER) and by
+ * ecuda_peer_barrier_status. */
 int ecuda_peer_barrier(ecuda_handle h, void* const* peer_flags, int nranks, int rank, uint64_t step, void* stream);
+/* synchronises `stream` (NULL: the handle's own) and reports whether any peer barrier issued through this handle has
+ * timed out since the status was last cleared: *timed_out 0/1, *step the first failed step, *late_rank the first
+ * rank that had not arrived (-1: none). reset != 0 clears the status. There is no reference counterpart (the
+ * reference has no parallelism, src/ePSOPT/CMakeLists.txt:10,25-27). */
+int ecuda_peer_barrier_status(ecuda_handle h, void* stream, int32_t* timed_out, uint64_t* step, int32_t* late_rank, int reset);
+/* waits for the handle's own stream; ECUDA_ERR_PEER when a peer barrier of this handle has timed out (sticky) */
 int ecuda_sync(ecuda_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches evidence) */
 int64_t ecuda_launch_count(ecuda_handle h);

@@ -83,12 +83,24 @@ static void run_rowsn_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     for (int t = 0; t < nthr; ++t) {
         if (FD) rn_stage<M, N, true>(pb, ph, io, m, b, t, nthr); else rn_stage<M, N, false>(pb, ph, io, m, b, t, nthr);
     }
+    // begin | node groups (the kernel stages each group in a shared-memory ring buffer and stores it with one bulk
+    // copy behind a CTA barrier; here the slots are those of the global array itself) | end
+    std::vector<RnRow<N>> st(nthr);
+    std::vector<double> viol(nthr), fval(nthr);
     for (int t = 0; t < nthr; ++t) {
-        double viol, fval;
-        if (FD)
-            rn_thread_fd<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
-        else
-            rn_thread_exact<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
+        if (FD) rn_begin<M, N, true, false>(pb, ph, io, m, cm, b, t, st[t], viol[t], fval[t]);
+        else rn_begin<M, N, false, false>(pb, ph, io, m, cm, b, t, st[t], viol[t], fval[t]);
+    }
+    if (io.jac) {
+        double* out = io.jac + static_cast<size_t>(b) * pb.nnz;
+        for (int g = 0; g < rn_ngroups<N>(); ++g)
+            for (int t = 0; t < nthr; ++t) {
+                if (FD) RnGroupRt<M, N, true>::run(g, pb, ph, m, st[t], out); else RnGroupRt<M, N, false>::run(g, pb, ph, m, st[t], out);
+            }
+    }
+    for (int t = 0; t < nthr; ++t) {
+        if (FD) rn_end<M, N, true, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, st[t], viol[t], fval[t]);
+        else rn_end<M, N, false, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, st[t], viol[t], fval[t]);
     }
     ++g_rowsn_runs;
 }

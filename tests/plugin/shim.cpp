@@ -36,7 +36,7 @@ int shim_load(void* h, const char* xml, int model, int flags, int batch, const c
 // load + register USER CALLBACKS (ecuda::var) like the reference example does, then try to match them.
 // variant 0: the example's callbacks; 1: a different objective; 2: exclusion zones only; 3: zones
 // registered in the opposite order (moving zones first); 4: dynamics no built-in model has (wind field
-// depending on the position) -> user model. Returns 1 when matched; *model, *flags
+// depending on the position) -> user model; 5: an objective holding a static ecuda::var constant. Returns 1 when matched; *model, *flags
 // (bit0 obstacles, bit1 tracks) report what was recognised, why (<= 255 chars) the reason otherwise.
 int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* flags, char* why) {
     eCUDA* t = static_cast<eCUDA*>(h);
@@ -51,7 +51,14 @@ int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* 
         ecuda::var a = vgp_si2d::at(u, 0), b = vgp_si2d::at(u, 1);
         return a * a + 2.0 * (b * b);
     };
-    t->setObjective(hold(variant == 1 ? other : ETOL::f_t(&vgp_si2d::effort)));
+    // variant 5: the example's objective written with a constant that OUTLIVES one recording (static ecuda::var):
+    // every transcription records the callback on a fresh tape, the constant must be materialised again on each
+    ETOL::f_t kept_constant = [](F_ARGS) -> ETOL::scalar_t {
+        static const ecuda::var one(1.0);
+        ecuda::var a = vgp_si2d::at(u, 0), b = vgp_si2d::at(u, 1);
+        return one * (a * a) + one * (b * b);
+    };
+    t->setObjective(hold(variant == 1 ? other : variant == 5 ? kept_constant : ETOL::f_t(&vgp_si2d::effort)));
     if (variant == 4)
         t->setGradient({hold(&vgp_si2d::windyXdot), hold(&vgp_si2d::windyYdot)});
     else

@@ -20,7 +20,8 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 B = 33
-wl = W.pm3d(batch=B, nnodes=17, ncyl=3, seed=W.SEED + rank)   # every rank its own shard
+NN = int(sys.argv[3])
+wl = W.pm3d(batch=B, nnodes=NN, ncyl=3, seed=W.SEED + rank)   # every rank its own shard
 ev = capi.Evaluator(wl, device=local)
 x = torch.from_numpy(wl.x).to(dev)
 f = torch.empty(B, dtype=torch.float64, device=dev)
@@ -79,14 +80,19 @@ dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_fused_allgather_matches_nccl(tmp_path):
+@pytest.mark.parametrize("nnodes", [17, 40])  # 17: round-1 kernels (k_eval_rows); 40: the N-specialised k_rows_n
+def test_fused_allgather_matches_nccl(tmp_path, nnodes):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip(f"multi-GPU parity of the fused exchange needs 2 GPUs; this box exposes {ngpu} "
+                    "(the same check runs inside `bench.py --gpus N`, field gather_parity, and on one GPU in "
+                    "test_gpu_parity.py::test_fused_summary_equals_separate_summary)")
     script, out = tmp_path / "worker.py", tmp_path / "result.txt"
     script.write_text(WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                    "--master-addr", "127.0.0.1", "--master-port", "29547", str(script), ROOT, str(out)],
+                    "--master-addr", "127.0.0.1", "--master-port", str(29547 + nnodes), str(script), ROOT, str(out),
+                    str(nnodes)],
                    check=True, env=env, timeout=600)
     assert out.read_text() == "ok"

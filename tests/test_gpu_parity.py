@@ -436,3 +436,35 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
             assert np.array_equal(out["fast-ldst"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["fast-image"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["columns"][m][key], out["generic"][m][key]), (name, m, key)
+
+
+def test_peer_barrier_reports_an_absent_peer(monkeypatch):
+    """a peer that never arrives must be detectable through the ABI. One GPU plays rank 0 of 2; rank 1's
+    flag slot is never written, so the bounded wait expires: ecuda_peer_barrier_status says so (step, late rank),
+    ecuda_sync returns ECUDA_ERR_PEER, and the status is sticky until it is read with reset."""
+    import torch
+    monkeypatch.setenv("ECUDA_PEER_TIMEOUT_MS", "20")
+    wl = W.pm3d(batch=2, nnodes=9, ncyl=1)
+    ev = capi.Evaluator(wl, device=0)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    st = stream.cuda_stream
+    flags = torch.zeros(64, dtype=torch.int64, device=dev)
+    ghost = torch.zeros(64, dtype=torch.int64, device=dev)  # stands for the absent rank's array
+    torch.cuda.synchronize()
+    # a barrier every rank reaches: one rank, completes at once
+    ev.peer_barrier_ptr([flags.data_ptr()], 0, 1, st)
+    assert ev.peer_barrier_status(st) == (False, 0, -1)
+    assert ev.sync_status()[0] == 0
+    # two ranks, the second never shows up
+    ev.peer_barrier_ptr([flags.data_ptr(), ghost.data_ptr()], 0, 2, st)
+    timed_out, step, late = ev.peer_barrier_status(st)
+    assert (timed_out, step, late) == (True, 2, 1)
+    rc, msg = ev.sync_status()
+    assert rc == -5 and "timed out at step 2" in msg
+    assert ev.peer_barrier_status(st)[0] is True                       # sticky
+    assert ev.peer_barrier_status(st, reset=True) == (True, 2, 1)      # read and clear
+    assert ev.peer_barrier_status(st) == (False, 0, -1)
+    assert ev.sync_status()[0] == 0
+    assert int(ghost[0].item()) == 2  # this rank did publish its arrival to the peer's array
+    ev.close()

@@ -158,6 +158,20 @@ def test_user_callbacks_are_recognised(xml):
     p.close(), q.close()
 
 
+
+def test_constant_kept_across_recordings_is_rematerialised(tmp_path):
+    """a callback that keeps an ecuda::var constant alive between transcriptions (static / captured) is recorded on
+    a fresh tape every time: the second and third recordings must still be the example's model (the
+    constant's cached node id used to point into the previous tape)"""
+    xml = pb.write_reference_xml(str(tmp_path / "vgp.xml"))
+    p = pb.Plugin()
+    for _ in range(3):
+        ok, model, flags, why = p.load_callbacks(xml, 5)
+        assert ok, why
+        assert model == W.SI2D and flags == 3
+    p.close()
+
+
 def test_user_callbacks_zones_only(xml):
     p = pb.Plugin()
     ok, model, flags, why = p.load_callbacks(xml, 2)
