@@ -235,6 +235,8 @@ struct ecuda_ctx {
     bool barrier_used = false;  // ecuda_peer_barrier has been issued: ecuda_sync also reports its sticky status
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
+    bool rows_exact = false;  // ECUDA_ROWS_EXACT=1: exact mode on k_rows_n instead of the streaming kernel
+    DevBuf desc;              // exact-mode triplet descriptors
     int rowsn_N = 0;     // node count shared by all phases when the N-specialised kernels may run (else 0)
     int nb_uniform = 0;  // summation-block count if all phases share it and it is <= 8, else 0
     std::vector<double> h_sz, h_sg;
@@ -441,21 +443,41 @@ static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
 // BASELINE configurations; other shapes take the kernels above
 template <int M, int N, bool FD, bool TRK, bool SUM>
 static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    constexpr bool RING = !FD;  // see k_rows_n
     static std::mutex mu;
     static size_t configured[64] = {0};
     size_t ring = 0;  // the store ring: three buffers of the largest node group of any phase
-    for (int p = 0; p < h->pd.nphases; ++p) ring = std::max(ring, kRnBufs * rn_group_cap<M>(h->pd, h->pd.ph[p], N));
+    for (int p = 0; RING && p < h->pd.nphases; ++p) ring = std::max(ring, kRnBufs * rn_group_cap<M>(h->pd, h->pd.ph[p], N));
     size_t smem = (rn_doubles<M>(h->pd, N, FD) + ring) * sizeof(double);
     if (SUM && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
     if (smem > 48 * 1024) {
         std::lock_guard<std::mutex> lock(mu);
         size_t& cur = configured[h->device & 63];
         if (cur < smem) {
-            CU(cudaFuncSetAttribute(k_rows_n<M, N, FD, TRK, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(k_rows_n<M, N, FD, TRK, SUM, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cur = smem;
         }
     }
-    k_rows_n<M, N, FD, TRK, SUM><<<grid, kThreads, smem, st>>>(h->pd, io);
+    k_rows_n<M, N, FD, TRK, SUM, RING><<<grid, kThreads, smem, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
+// exact Jacobian / values only: the streaming kernel (ecuda_stream.cuh)
+template <int M, int N, bool TRK, bool SUM>
+static int launch_stream_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    size_t smem = 0;
+    for (int p = 0; p < h->pd.nphases; ++p) smem = std::max(smem, st_doubles<M>(h->pd, h->pd.ph[p], N) * sizeof(double));
+    if (SUM && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < smem) {
+            CU(cudaFuncSetAttribute(k_stream_exact<M, N, TRK, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    k_stream_exact<M, N, TRK, SUM><<<grid, kThreads, smem, st>>>(h->pd, io);
     return ECUDA_OK;
 }
 // TRK: instantiated with track rows (moving zones) or without; a problem whose model is only instantiated without
@@ -467,8 +489,10 @@ static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int
     if (fd)
         return io.nranks > 0 ? launch_rows_n_t<M, N, true, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, true, TRK, false>(h, io, st, grid);
-    return io.nranks > 0 ? launch_rows_n_t<M, N, false, TRK, true>(h, io, st, grid)
-                         : launch_rows_n_t<M, N, false, TRK, false>(h, io, st, grid);
+    if (h->rows_exact)  // ECUDA_ROWS_EXACT=1: the row-owner exact kernel (A/B)
+        return io.nranks > 0 ? launch_rows_n_t<M, N, false, TRK, true>(h, io, st, grid)
+                             : launch_rows_n_t<M, N, false, TRK, false>(h, io, st, grid);
+    return io.nranks > 0 ? launch_stream_t<M, N, TRK, true>(h, io, st, grid) : launch_stream_t<M, N, TRK, false>(h, io, st, grid);
 }
 // returns 1 when no instantiation matches (the caller falls back)
 template <int M>
@@ -688,7 +712,7 @@ int ecuda_destroy(ecuda_handle h) {
     if (!h) return ECUDA_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->bflag, &h->sx, &h->sf_, &h->sgv,
+    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->bflag, &h->desc, &h->sx, &h->sf_, &h->sgv,
                       &h->sjac, &h->sgrad, &h->ssum})
         release(*b);
     for (auto& b : h->coll) release(b);
@@ -775,6 +799,10 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
     CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));
     pd.colptr = static_cast<const int*>(h->colptr.p);
+    if ((rc = ensure(h, h->desc, sizeof(uint64_t) * std::max<size_t>(1, hp.tdesc.size())))) return rc;
+    CU(cudaMemcpy(h->desc.p, hp.tdesc.data(), sizeof(uint64_t) * hp.tdesc.size(), cudaMemcpyHostToDevice));
+    pd.desc = static_cast<const unsigned long long*>(h->desc.p);
+    h->rows_exact = std::getenv("ECUDA_ROWS_EXACT") != nullptr;
     h->h_sz.assign(pd.nvars, 1.0);
     h->h_sg.assign(pd.ncons, 1.0);
     if ((rc = upload_scaling(h))) return rc;

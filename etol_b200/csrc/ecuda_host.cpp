@@ -247,6 +247,12 @@ void build_structure(HostProblem* hp) {
     hp->jcol.clear();
     hp->colptr.assign(1, 0);
     auto& R = hp->irow;
+    // T[e]: where the exact value of triplet e comes from (desc_pack: D entry or per-instance table entry)
+    std::vector<unsigned> T;
+    auto add = [&](int row, unsigned tab) {
+        R.push_back(row);
+        T.push_back(tab);
+    };
     auto close_col = [&]() {
         int c = static_cast<int>(hp->colptr.size()) - 1;
         for (size_t e = hp->colptr.back(); e < R.size(); ++e) hp->jcol.push_back(c);
@@ -256,41 +262,47 @@ void build_structure(HostProblem* hp) {
     for (int p = 0; p < P; ++p) {
         const int N = hp->N[p], np = hp->npath[p], nstat = hp->nstat[p], g0 = hp->goff[p];
         const int r_ev = g0 + ns * N, r_path = r_ev + ne, r_last = r_path + np * N;
+        const unsigned W = desc_rowtab_width(ns, nc), TP = desc_path_off(ns, nc, N), ONE = 0u, MINUS = 1u;
+        auto rowtab = [&](int k, int i, int j) { return 2u + static_cast<unsigned>(k * ns + i) * W + static_cast<unsigned>(j); };
         for (int k = 0; k < N; ++k)  // control columns, node-major
             for (int j = 0; j < nc; ++j) {
                 for (int i = 0; i < ns; ++i)
-                    if (hp->urank[j][i] >= 0) R.push_back(g0 + k * ns + i);
+                    if (hp->urank[j][i] >= 0) add(g0 + k * ns + i, rowtab(k, i, ns + j));
                 close_col();
             }
         for (int l = 0; l < N; ++l)  // state columns, node-major
             for (int j = 0; j < ns; ++j) {
                 for (int k = 0; k < N; ++k) {
                     if (k != l) {
-                        R.push_back(g0 + k * ns + j);
+                        add(g0 + k * ns + j, ECUDA_DESC_DFLAG | static_cast<unsigned>(l * N + k));
                     } else {
                         for (int i = 0; i < ns; ++i)
-                            if (hp->xrank[j][i] >= 0) R.push_back(g0 + k * ns + i);
+                            if (hp->xrank[j][i] >= 0) add(g0 + k * ns + i, rowtab(k, i, j));
                     }
                 }
-                if (l == 0) R.push_back(r_ev + j);
-                if (l == N - 1) R.push_back(r_ev + ns + j);
+                if (l == 0) add(r_ev + j, ONE);
+                if (l == N - 1) add(r_ev + ns + j, ONE);
                 if (hp->mi.path_x >> j & 1u)
-                    for (int q = 0; q < np; ++q) R.push_back(r_path + l * np + q);
-                if (l == N - 1 && p + 1 < P) R.push_back(link_row(p, j));
-                if (l == 0 && p > 0) R.push_back(link_row(p - 1, j));
+                    for (int q = 0; q < np; ++q) add(r_path + l * np + q, TP + static_cast<unsigned>((l * np + q) * 4 + j));
+                if (l == N - 1 && p + 1 < P) add(link_row(p, j), ONE);
+                if (l == 0 && p > 0) add(link_row(p - 1, j), MINUS);
                 close_col();
             }
         for (int which = 0; which < 2; ++which) {  // t0 then tf
-            for (int r = 0; r < ns * N; ++r) R.push_back(g0 + r);
+            for (int r = 0; r < ns * N; ++r) add(g0 + r, 2u + static_cast<unsigned>(r) * W + static_cast<unsigned>(ns + nc + which));
             for (int k = 0; k < N; ++k)
-                for (int q = nstat; q < np; ++q) R.push_back(r_path + k * np + q);  // track rows read t
-            R.push_back(r_last);
-            if (which == 0 && p > 0) R.push_back(link_row(p - 1, ns));
-            if (which == 1 && p + 1 < P) R.push_back(link_row(p, ns));
+                for (int q = nstat; q < np; ++q)  // track rows read t
+                    add(r_path + k * np + q, TP + static_cast<unsigned>((k * np + q) * 4 + 2 + which));
+            add(r_last, which == 0 ? MINUS : ONE);
+            if (which == 0 && p > 0) add(link_row(p - 1, ns), MINUS);
+            if (which == 1 && p + 1 < P) add(link_row(p, ns), ONE);
             close_col();
         }
     }
     hp->dims.nnz = static_cast<int32_t>(R.size());
+    hp->tdesc.resize(R.size());
+    for (size_t e = 0; e < R.size(); ++e)
+        hp->tdesc[e] = desc_pack(T[e], static_cast<unsigned>(R[e]), static_cast<unsigned>(hp->jcol[e]));
     // Curtis-Powell-Reid first-fit in natural column order; group row sets kept as 64-bit masks
     const int words = (ncons + 63) / 64;
     std::vector<std::vector<uint64_t>> cover;

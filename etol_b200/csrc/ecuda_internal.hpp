@@ -58,6 +58,9 @@ struct ProbDev {
     const double* jtmpl;  // [nnz] exact-mode template: the instance-independent D-coupled entries
                           //       sg[row] * D[k][l] / sz[col]; other slots are 0
     const double* isz;    // [nvars]  1/sz
+    // [nnz] exact-mode triplet descriptors (ecuda_stream.cuh): every exact triplet is (sg[row] * T) / sz[col] with T
+    // either an entry of D or an entry of a small per-instance table; desc packs {T index, row, col}
+    const unsigned long long* desc;
     const double* sg;     // [ncons]
     // position of defect row (k,i) inside the node-local part of column X(k,j) / U(k,j); -1 = absent
     signed char xrank[ECUDA_MAX_STATES][ECUDA_MAX_STATES];
@@ -66,6 +69,22 @@ struct ProbDev {
     int ucnt[ECUDA_MAX_CONTROLS];
     PhaseDev ph[ECUDA_MAX_PHASES];
 };
+
+// ---- exact-mode triplet descriptors ----------------------------------------------------------------------------------
+// bits 0..22 table index, bit 23 set: the index addresses D^T of the phase (Dt[l*N + k] = D[k][l]) instead of the
+// per-instance table, bits 24..43 constraint row, bits 44..63 decision variable. Per-instance table of a phase:
+//   [0] = 1.0, [1] = -1.0,
+//   [2 + (k*ns + i)*W + j]            j < ns: d zeta_ki / d x_kj (unscaled, includes D_kk for j == i); ns <= j < ns+nc:
+//                                     d zeta_ki / d u_k(j-ns); j = ns+nc, ns+nc+1: d zeta_ki / d t0, d tf;  W = ns+nc+2
+//   [2 + ns*N*W + (k*np + q)*4 + j]   path row (k,q): d/dx_0, d/dx_1, d/dt0, d/dtf
+#define ECUDA_DESC_DFLAG (1u << 23)
+ECUDA_HD unsigned long long desc_pack(unsigned tab, unsigned row, unsigned col) {
+    return static_cast<unsigned long long>(tab) | (static_cast<unsigned long long>(row) << 24) |
+           (static_cast<unsigned long long>(col) << 44);
+}
+ECUDA_HD int desc_rowtab_width(int ns, int nc) { return ns + nc + 2; }
+ECUDA_HD int desc_path_off(int ns, int nc, int N) { return 2 + ns * N * desc_rowtab_width(ns, nc); }
+ECUDA_HD int desc_table_size(int ns, int nc, int N, int np) { return desc_path_off(ns, nc, N) + np * N * 4; }
 
 // constraint rows of one phase: defects, events, path rows, duration
 ECUDA_HD int phase_ncons(const ProbDev& pb, const PhaseDev& ph) { return (pb.ns + ph.npath) * ph.N + pb.ne + 1; }
@@ -182,6 +201,7 @@ struct HostProblem {
     std::vector<int> N, npath, nstat, zoff, goff, nvars_p, inst_off;
     int track_off = 0;
     std::vector<int32_t> irow, jcol, colptr, group_of_col;
+    std::vector<uint64_t> tdesc;  // exact-mode triplet descriptors (see desc_pack), built with the pattern
     std::vector<Collocation> col;
     signed char xrank[ECUDA_MAX_STATES][ECUDA_MAX_STATES];
     signed char urank[ECUDA_MAX_CONTROLS][ECUDA_MAX_STATES];

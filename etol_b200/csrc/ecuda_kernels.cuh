@@ -14,7 +14,7 @@
 #ifndef ECUDA_KERNELS_CUH_
 #define ECUDA_KERNELS_CUH_
 
-#include "ecuda_rowsn.cuh"
+#include "ecuda_stream.cuh"
 
 namespace ecuda {
 
@@ -361,30 +361,44 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
 // Buffer G % 3 is free when group G starts: its previous user, group G - 3, was read out of shared memory before
 // thread 0 arrived at the barrier of group G - 1 (it waits for "all but the newest bulk group have been read" right
 // after issuing a store), so one CTA barrier per group is enough with three buffers.
-template <int M, int N, bool FD, int G>
+template <int M, int N, bool FD, int G, bool RING>
 struct RnGroups {
     __device__ __forceinline__ static void run(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st,
-                                               double* ring, int cap, double* jac, int tid) {
+                                               double* ring, int cap, double* jac, int jpar, int tid) {
+        constexpr int NS = Model<M>::NS;
+        if (!RING) {  // straight into the global triplet array, no barrier
+            rn_group<M, N, FD, G, false>(pb, ph, m, st, jac);
+            RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, m, st, ring, cap, jac, jpar, tid);
+            return;
+        }
         double* buf = ring + (G % kRnBufs) * cap;
-        int c0, c1;
-        rn_group_range<M, N, FD>(pb, m, G, c0, c1);
+        const int ca = pb.nc * N + G * kRnGroup * NS;  // first state column of the group's first node
+        const int c0 = FD ? m.rec[ca].cp : m.erec[ca].cp;
         // shared and global addresses must agree modulo 16 bytes: triplet e sits at buf[par + e - c0]
-        const int par = static_cast<int>((reinterpret_cast<uintptr_t>(jac + c0) >> 3) & 1);
-        rn_group<M, N, FD, G>(pb, ph, m, st, buf + par - c0);
+        const int par = (jpar + c0) & 1;
+        rn_group<M, N, FD, G, true>(pb, ph, m, st, buf + par - c0);
         fence_async_smem();  // generic-proxy writes to the buffer -> visible to the bulk copy
         __syncthreads();
-        flush_range(jac + c0, buf, par, c1 - c0, tid, 0);
-        if (tid == 0) bulk_wait_read_but_one();
-        RnGroups<M, N, FD, G + 1>::run(pb, ph, m, st, ring, cap, jac, tid);
+        if (tid < 3) {  // thread 0: the bulk store; 1, 2: an unaligned first / last element
+            int d0, c1;
+            rn_group_range<M, N, FD>(pb, m, G, d0, c1);
+            flush_range(jac + c0, buf, par, c1 - c0, tid, 0);
+            if (tid == 0) bulk_wait_read_but_one();
+        }
+        RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, m, st, ring, cap, jac, jpar, tid);
     }
 };
-template <int M, int N, bool FD>
-struct RnGroups<M, N, FD, (N + kRnGroup - 1) / kRnGroup> {
+template <int M, int N, bool FD, bool RING>
+struct RnGroups<M, N, FD, (N + kRnGroup - 1) / kRnGroup, RING> {
     __device__ __forceinline__ static void run(const ProbDev&, const PhaseDev&, const RnMem&, RnRow<N>&, double*, int, double*,
-                                               int) {}
+                                               int, int) {}
 };
 
-template <int M, int N, bool FD, bool TRK, bool SUM>
+// RING: the D-coupled triplets leave through the shared-memory store ring (TMA bulk stores per node group) instead
+// of being stored from registers. Measured on C2 (profiles/r2): exact 0.199 -> 0.154 ms with the ring, finite
+// differences 0.171 -> 0.183 ms (their stores are spread over a long computation and the ten extra barriers cost
+// more than the store pattern), so FD runs without it and exact mode runs on k_stream_exact.
+template <int M, int N, bool FD, bool TRK, bool SUM, bool RING>
 __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA_MIN_CTAS_ROWSN_EXACT)
     k_rows_n(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
     extern __shared__ __align__(16) double smem[];
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     }
     if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the store ring
         const int ncp = phase_ncons(pb, ph), nbnd = ncp + (ncp & 1);
-        double* bnd = ring + kRnBufs * cap;
+        double* bnd = ring + (RING ? kRnBufs * cap : 0);
         const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
         for (int c = tid; c < ncp; c += nthr) {
             bnd[c] = __ldg(io.bl + o + c);
@@ -425,11 +439,76 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     double viol, fval;
     rn_begin<M, N, FD, SUM>(pb, ph, io, m, cm, b, tid, st, viol, fval);
     if (io.jac) {  // uniform over the CTA
-        RnGroups<M, N, FD, 0>::run(pb, ph, m, st, ring, cap, io.jac + static_cast<size_t>(b) * pb.nnz, tid);
-        if (tid == 0) bulk_wait_all();  // the groups' global writes are performed ...
-        __syncthreads();                // ... before any thread writes a node-local triplet inside their ranges
+        double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+        RnGroups<M, N, FD, 0, RING>::run(pb, ph, m, st, ring, cap, jac, static_cast<int>((reinterpret_cast<uintptr_t>(jac) >> 3) & 1), tid);
+        if (RING) {
+            if (tid == 0) bulk_wait_all();  // the groups' global writes are performed ...
+            __syncthreads();                // ... before any thread writes a node-local triplet inside their ranges
+        }
     }
     rn_end<M, N, FD, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, st, viol, fval);
+    if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
+        __shared__ double red[kThreads / 32 + 1];
+        double v = viol;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (tid == nthr - 1) red[kThreads / 32] = fval;
+        __syncthreads();
+        if (tid < 32) {
+            double w = tid < kThreads / 32 ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (tid < io.nranks) {
+                double2* dst = reinterpret_cast<double2*>(io.peer[tid] + (static_cast<size_t>(io.rank) * io.batch + b) * 2);
+                *dst = make_double2(red[kThreads / 32], w);
+            }
+        }
+    }
+}
+
+// Exact Jacobian (and plain f / g evaluation) as a stream (ecuda_stream.cuh): phase 1 fills the instance's table and
+// constraint values in shared memory, one barrier, phase 2 writes every triplet in address order.
+#ifndef ECUDA_MIN_CTAS_STREAM
+#define ECUDA_MIN_CTAS_STREAM 6
+#endif
+template <int M, int N, bool TRK, bool SUM>
+__global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_STREAM)
+    k_stream_exact(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x / pb.nphases;
+    const int p = blockIdx.x - b * pb.nphases;
+    const PhaseDev& ph = pb.ph[p];
+    const int tid = threadIdx.x, nthr = kThreads;
+    StMem m;
+    st_carve<M>(m, smem, pb, ph, N);
+    CtaMem cm{};
+    cm.inst = m.inst;
+    cm.z = m.z;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
+    }
+    if (SUM && !io.bev) {  // fused summary with general bounds: this phase's block, staged behind the tables
+        const int ncp = phase_ncons(pb, ph), nbnd = ncp + (ncp & 1);
+        double* bnd = smem + st_doubles<M>(pb, ph, N);
+        const size_t o = static_cast<size_t>(b) * pb.ncons + ph.goff;
+        for (int c = tid; c < ncp; c += nthr) {
+            bnd[c] = __ldg(io.bl + o + c);
+            bnd[nbnd + c] = __ldg(io.bu + o + c);
+        }
+        cm.bl = bnd;
+        cm.bu = bnd + nbnd;
+    }
+    st_stage<M, N>(pb, ph, io, m, b, tid, nthr);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    double viol, fval;
+    st_phase1<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, viol, fval);
+    __syncthreads();
+    st_phase2<M, N>(pb, ph, io, m, b, tid, nthr);
     if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
         __shared__ double red[kThreads / 32 + 1];
         double v = viol;

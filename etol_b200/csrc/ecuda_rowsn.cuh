@@ -305,7 +305,8 @@ ECUDA_HD void rn_fd_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
 // ---- finite differences, part 2: the D-coupled triplets of row (k,i) in the state columns of node group G (nodes
 // kRnGroup*G ...), by index-set central differences, row-restricted (operation sequence of fast_fd_block).
 // out[e] is the slot of triplet e of the instance (a shared-memory ring buffer, or the global array).
-template <int NS, int N, int G>
+// RING: `out` is a shared-memory ring buffer (plain stores); otherwise the global triplet array (streaming stores)
+template <int NS, int N, int G, bool RING>
 ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* __restrict__ out) {
     constexpr int BL = ECUDA_DOT_BLOCK, NB = (N + BL - 1) / BL, BI = (G * kRnGroup) / BL, l0 = BI * BL;
     constexpr int a0 = G * kRnGroup - l0;                  // first node of the group inside its summation block
@@ -347,7 +348,10 @@ ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m,
         }
         const double gp = st.sgr * (tp - st.hfv);
         const double gm = st.sgr * (tm - st.hfv);
-        ok[rc.cp + rn_byte(w, a - a0)] = (gp - gm) * rc.ri;
+        if (RING)
+            ok[rc.cp + rn_byte(w, a - a0)] = (gp - gm) * rc.ri;
+        else
+            ECUDA_STREAM_STORE(ok + (rc.cp + rn_byte(w, a - a0)), (gp - gm) * rc.ri);
         st.q = fma(st.d[a], st.xv[a], st.q);
     }
 }
@@ -682,7 +686,7 @@ ECUDA_HD void rn_ex_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
 }
 
 // D-coupled triplets of row (k,i) in the state columns of node group G (see rn_fd_group for `out`)
-template <int NS, int N, int G>
+template <int NS, int N, int G, bool RING>
 ECUDA_HD void rn_ex_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, const RnRow<N>& st, double* __restrict__ out) {
     constexpr int l0 = G * kRnGroup;
     constexpr int nin = (N - l0) < kRnGroup ? (N - l0) : kRnGroup;
@@ -695,7 +699,11 @@ ECUDA_HD void rn_ex_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m,
     for (int a = 0; a < nin; ++a) {
         const ExVals rc = rn_load(Ri + (l0 + a) * NS);
         // the l == k value, (sg D_kk) / sz, lands in the row's diagonal slot; rn_ex_end overwrites it with the full entry
-        ok[rc.cp + rn_byte(w, a)] = (st.sgr * ECUDA_LDG(Dtk + (l0 + a) * N)) * rc.isz;
+        const double v = (st.sgr * ECUDA_LDG(Dtk + (l0 + a) * N)) * rc.isz;
+        if (RING)
+            ok[rc.cp + rn_byte(w, a)] = v;
+        else
+            ECUDA_STREAM_STORE(ok + (rc.cp + rn_byte(w, a)), v);
     }
 }
 
@@ -919,12 +927,12 @@ ECUDA_HD void rn_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
     else
         rn_ex_begin<M, N, SUM>(pb, ph, io, m, cm, b, tid, st, viol);
 }
-template <int M, int N, bool FD, int G>
+template <int M, int N, bool FD, int G, bool RING>
 ECUDA_HD void rn_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
     if (FD)
-        rn_fd_group<Model<M>::NS, N, G>(pb, ph, m, st, out);
+        rn_fd_group<Model<M>::NS, N, G, RING>(pb, ph, m, st, out);
     else
-        rn_ex_group<Model<M>::NS, N, G>(pb, ph, m, st, out);
+        rn_ex_group<Model<M>::NS, N, G, RING>(pb, ph, m, st, out);
 }
 template <int N>
 ECUDA_HD constexpr int rn_ngroups() { return (N + kRnGroup - 1) / kRnGroup; }
@@ -958,7 +966,7 @@ template <int M, int N, bool FD, int G = 0>
 struct RnGroupRt {
     ECUDA_HD static void run(int g, const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
         if (g == G)
-            rn_group<M, N, FD, G>(pb, ph, m, st, out);
+            rn_group<M, N, FD, G, false>(pb, ph, m, st, out);
         else
             RnGroupRt<M, N, FD, G + 1>::run(g, pb, ph, m, st, out);
     }

@@ -496,7 +496,7 @@ bool load_nvrtc(Nvrtc* nv, std::string* err) {
 }
 
 // the kernel sources as NVRTC in-memory headers, under the names the #include directives use
-const char* const kHeaderNames[] = {"ecuda_kernels.cuh", "ecuda_rowsn.cuh", "ecuda_rows.cuh", "ecuda_fast.cuh", "ecuda_phases.cuh",
+const char* const kHeaderNames[] = {"ecuda_kernels.cuh", "ecuda_stream.cuh", "ecuda_rowsn.cuh", "ecuda_rows.cuh", "ecuda_fast.cuh", "ecuda_phases.cuh",
                                     "ecuda_models.cuh", "ecuda_internal.hpp", "../../include/ecuda.h",
                                     "../../include/ecuda_detmath.h"};
 constexpr int kNumHeaders = sizeof(kHeaderNames) / sizeof(kHeaderNames[0]);
@@ -510,7 +510,7 @@ bool read_file(const std::string& path, std::string* out) {
     return true;
 }
 
-// ECUDA_KERNEL_SOURCE_DIR (flat directory with the nine files) or the in-tree layout next to libecuda.so
+// ECUDA_KERNEL_SOURCE_DIR (flat directory with the ten files) or the in-tree layout next to libecuda.so
 bool load_kernel_sources(std::vector<std::string>* texts, std::string* err) {
     static std::vector<std::string> cached;
     static std::mutex mu;

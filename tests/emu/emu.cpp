@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../etol_b200/csrc/ecuda_rowsn.cuh"
+#include "../../etol_b200/csrc/ecuda_stream.cuh"
 
 using namespace ecuda;
 
@@ -104,21 +104,49 @@ static void run_rowsn_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     }
     ++g_rowsn_runs;
 }
+// the streaming exact kernel (k_stream_exact): phase 1 of every thread, (barrier), phase 2 of every thread
+template <int M, int N, bool TRK>
+static void run_stream(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    std::vector<double> smem(st_doubles<M>(pb, ph, N) + 2, 0.0);
+    StMem m;
+    st_carve<M>(m, smem.data(), pb, ph, N);
+    CtaMem cm{};
+    cm.inst = m.inst;
+    cm.z = m.z;
+    std::memcpy(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, sizeof(double) * pb.inst_stride);
+    for (int t = 0; t < nthr; ++t) st_stage<M, N>(pb, ph, io, m, b, t, nthr);
+    for (int t = 0; t < nthr; ++t) {
+        double viol, fval;
+        st_phase1<M, N, TRK, false>(pb, ph, p, io, m, cm, b, t, nthr, viol, fval);
+    }
+    for (int t = 0; t < nthr; ++t) st_phase2<M, N>(pb, ph, io, m, b, t, nthr);
+    ++g_rowsn_runs;
+}
+static int g_rows_exact = 0;  // exact mode on the row-owner kernel instead of the streaming one (ECUDA_ROWS_EXACT)
+extern "C" void emu_rows_exact(int on) { g_rows_exact = on; }
+template <int M, int N, bool TRK>
+static void run_rowsn(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+    const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
+    if (fd || g_rows_exact)
+        run_rowsn_fd<M, N, TRK>(pb, ph, p, io, b, nthr);
+    else
+        run_stream<M, N, TRK>(pb, ph, p, io, b, nthr);
+}
 // same instantiation list as launch_rows_n (ecuda_api.cu); false: no instantiation, the caller falls back
 template <int M>
-static bool run_rowsn(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
+static bool run_rowsn_any(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, int b, int nthr) {
     if (nthr < pb.ns * ph.N) return false;
     for (int q = 0; q < pb.nphases; ++q)
         if (pb.ph[q].N != ph.N) return false;
 #ifndef ECUDA_USER_MODEL_HEADER
     if constexpr (M == ECUDA_MODEL_PM3D) {
         if (pb.ntracks > 0) return false;
-        if (ph.N == 40) return run_rowsn_fd<M, 40, false>(pb, ph, p, io, b, nthr), true;
-        if (ph.N == 30) return run_rowsn_fd<M, 30, false>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 40) return run_rowsn<M, 40, false>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 30) return run_rowsn<M, 30, false>(pb, ph, p, io, b, nthr), true;
     }
     if constexpr (M == ECUDA_MODEL_SI2D) {
-        if (ph.N == 33) return run_rowsn_fd<M, 33, true>(pb, ph, p, io, b, nthr), true;
-        if (ph.N == 17) return run_rowsn_fd<M, 17, true>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 33) return run_rowsn<M, 33, true>(pb, ph, p, io, b, nthr), true;
+        if (ph.N == 17) return run_rowsn<M, 17, true>(pb, ph, p, io, b, nthr), true;
     }
 #endif
     return false;
@@ -203,7 +231,7 @@ static void run(const ProbDev& pb, const EvalIO& io, int nthr, bool generic) {
                     for (int t = 0; t < nthr; ++t) cost_nodes<M>(pb, ph, m, t, nthr);
                     for (int t = 0; t < nthr; ++t) gradient_phase<M>(pb, ph, io, m, b, t, nthr);
                 }
-                if (g_use_rowsn && run_rowsn<M>(pb, ph, p, io, b, nthr)) continue;
+                if (g_use_rowsn && run_rowsn_any<M>(pb, ph, p, io, b, nthr)) continue;
                 switch (ph.nb) {
                     case 3: run_fast_mode<M, 3>(pb, ph, p, io, b, nthr); break;
                     case 4: run_fast_mode<M, 4>(pb, ph, p, io, b, nthr); break;
@@ -277,7 +305,7 @@ extern "C" int emu_eval(const ecuda_problem_desc* desc, const double* sz, const 
     pd.sf = sf;
     std::vector<double> tmpl;
     build_jac_template(hp, isz.data(), sgv.data(), &tmpl);
-    pd.colptr = hp.colptr.data(); pd.isz = isz.data(); pd.sg = sgv.data(); pd.jtmpl = tmpl.data();
+    pd.colptr = hp.colptr.data(); pd.desc = reinterpret_cast<const unsigned long long*>(hp.tdesc.data()); pd.isz = isz.data(); pd.sg = sgv.data(); pd.jtmpl = tmpl.data();
     for (int p = 0; p < hp.nphases; ++p) {
         PhaseDev& ph = pd.ph[p];
         ph.D = hp.col[p].D.data(); ph.Dt = Dt[p].data(); ph.tau = hp.col[p].tau.data(); ph.w = hp.col[p].w.data();
