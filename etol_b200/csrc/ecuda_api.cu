@@ -489,7 +489,7 @@ static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int
     if (fd)
         return io.nranks > 0 ? launch_rows_n_t<M, N, true, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, true, TRK, false>(h, io, st, grid);
-    if (h->rows_exact)  // ECUDA_ROWS_EXACT=1: the row-owner exact kernel (A/B)
+    if (h->rows_exact || h->pd.ncons > 65535 || h->pd.nvars > 65535)  // ECUDA_ROWS_EXACT=1 (A/B), or 16-bit descriptors too narrow
         return io.nranks > 0 ? launch_rows_n_t<M, N, false, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, false, TRK, false>(h, io, st, grid);
     return io.nranks > 0 ? launch_stream_t<M, N, TRK, true>(h, io, st, grid) : launch_stream_t<M, N, TRK, false>(h, io, st, grid);

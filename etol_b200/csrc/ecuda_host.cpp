@@ -262,7 +262,8 @@ void build_structure(HostProblem* hp) {
     for (int p = 0; p < P; ++p) {
         const int N = hp->N[p], np = hp->npath[p], nstat = hp->nstat[p], g0 = hp->goff[p];
         const int r_ev = g0 + ns * N, r_path = r_ev + ne, r_last = r_path + np * N;
-        const unsigned W = desc_rowtab_width(ns, nc), TP = desc_path_off(ns, nc, N), ONE = 0u, MINUS = 1u;
+        const unsigned W = desc_rowtab_width(ns, nc), TP = desc_path_off(ns, nc, N), TD = desc_d_off(ns, nc, N, np);
+        const unsigned ONE = 0u, MINUS = 1u;
         auto rowtab = [&](int k, int i, int j) { return 2u + static_cast<unsigned>(k * ns + i) * W + static_cast<unsigned>(j); };
         for (int k = 0; k < N; ++k)  // control columns, node-major
             for (int j = 0; j < nc; ++j) {
@@ -274,7 +275,7 @@ void build_structure(HostProblem* hp) {
             for (int j = 0; j < ns; ++j) {
                 for (int k = 0; k < N; ++k) {
                     if (k != l) {
-                        add(g0 + k * ns + j, ECUDA_DESC_DFLAG | static_cast<unsigned>(l * N + k));
+                        add(g0 + k * ns + j, TD + static_cast<unsigned>(l * N + k));
                     } else {
                         for (int i = 0; i < ns; ++i)
                             if (hp->xrank[j][i] >= 0) add(g0 + k * ns + i, rowtab(k, i, j));
@@ -300,9 +301,12 @@ void build_structure(HostProblem* hp) {
         }
     }
     hp->dims.nnz = static_cast<int32_t>(R.size());
+    // 16-bit rows / phase-local columns (ecuda_set_problem does not use the streaming kernel beyond that)
     hp->tdesc.resize(R.size());
-    for (size_t e = 0; e < R.size(); ++e)
-        hp->tdesc[e] = desc_pack(T[e], static_cast<unsigned>(R[e]), static_cast<unsigned>(hp->jcol[e]));
+    for (int p = 0; p < P; ++p)
+        for (int c = hp->zoff[p]; c < hp->zoff[p] + hp->nvars_p[p]; ++c)
+            for (int e = hp->colptr[c]; e < hp->colptr[c + 1]; ++e)
+                hp->tdesc[e] = desc_pack(T[e], static_cast<unsigned>(R[e]) & 0xffffu, static_cast<unsigned>(c - hp->zoff[p]) & 0xffffu);
     // Curtis-Powell-Reid first-fit in natural column order; group row sets kept as 64-bit masks
     const int words = (ncons + 63) / 64;
     std::vector<std::vector<uint64_t>> cover;

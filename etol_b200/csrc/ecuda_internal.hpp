@@ -71,20 +71,21 @@ struct ProbDev {
 };
 
 // ---- exact-mode triplet descriptors ----------------------------------------------------------------------------------
-// bits 0..22 table index, bit 23 set: the index addresses D^T of the phase (Dt[l*N + k] = D[k][l]) instead of the
-// per-instance table, bits 24..43 constraint row, bits 44..63 decision variable. Per-instance table of a phase:
+// One 64-bit word per triplet: low 32 bits = index into the instance's table, bits 32..47 = constraint row (global),
+// bits 48..63 = decision variable (phase-local). Table of a phase (ns states, nc controls, N nodes, np path rows):
 //   [0] = 1.0, [1] = -1.0,
 //   [2 + (k*ns + i)*W + j]            j < ns: d zeta_ki / d x_kj (unscaled, includes D_kk for j == i); ns <= j < ns+nc:
 //                                     d zeta_ki / d u_k(j-ns); j = ns+nc, ns+nc+1: d zeta_ki / d t0, d tf;  W = ns+nc+2
-//   [2 + ns*N*W + (k*np + q)*4 + j]   path row (k,q): d/dx_0, d/dx_1, d/dt0, d/dtf
-#define ECUDA_DESC_DFLAG (1u << 23)
-ECUDA_HD unsigned long long desc_pack(unsigned tab, unsigned row, unsigned col) {
-    return static_cast<unsigned long long>(tab) | (static_cast<unsigned long long>(row) << 24) |
-           (static_cast<unsigned long long>(col) << 44);
+//   [TP + (k*np + q)*4 + j]           path row (k,q): d/dx_0, d/dx_1, d/dt0, d/dtf
+//   [TD + l*N + k]                    D[k][l] (instance independent, copied in by every CTA)
+ECUDA_HD unsigned long long desc_pack(unsigned tab, unsigned row, unsigned lcol) {
+    return static_cast<unsigned long long>(tab) | (static_cast<unsigned long long>(row) << 32) |
+           (static_cast<unsigned long long>(lcol) << 48);
 }
 ECUDA_HD int desc_rowtab_width(int ns, int nc) { return ns + nc + 2; }
 ECUDA_HD int desc_path_off(int ns, int nc, int N) { return 2 + ns * N * desc_rowtab_width(ns, nc); }
-ECUDA_HD int desc_table_size(int ns, int nc, int N, int np) { return desc_path_off(ns, nc, N) + np * N * 4; }
+ECUDA_HD int desc_d_off(int ns, int nc, int N, int np) { return desc_path_off(ns, nc, N) + np * N * 4; }
+ECUDA_HD int desc_table_size(int ns, int nc, int N, int np) { return desc_d_off(ns, nc, N, np) + N * N; }
 
 // constraint rows of one phase: defects, events, path rows, duration
 ECUDA_HD int phase_ncons(const ProbDev& pb, const PhaseDev& ph) { return (pb.ns + ph.npath) * ph.N + pb.ne + 1; }

@@ -77,6 +77,10 @@ ECUDA_HD void st_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
         m.tab[0] = 1.0;
         m.tab[1] = -1.0;
     }
+    // D^T of the phase behind the per-instance entries: phase 2 reads every T from one shared-memory table
+    double* td = m.tab + desc_d_off(Model<M>::NS, pb.nc, N, ph.npath);
+    if (io.jac)
+        for (int e = tid; e < N * N; e += nthr) td[e] = ECUDA_LDG(ph.Dt + e);
 }
 
 // phase 1, defect row (k,i): value and the row of the table           [rows_values + rows_jacobian<exact>]
@@ -241,32 +245,34 @@ ECUDA_HD void st_phase1(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
     for (int it = nthr - 1 - tid; it < nitems; it += nthr) st_item<M, N, TRK, SUM>(pb, ph, p, io, m, cm, b, it, viol, fval);
 }
 
-// phase 2: the triplets of the phase in address order, then its constraint values
+// phase 2: the triplets of the phase in address order, then its constraint values. Per triplet: descriptor (one
+// coalesced 64-bit load), T and 1/sz from shared memory, sg[row] from L1, two multiplications, one streaming store.
 template <int M, int N>
 ECUDA_HD void st_phase2(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const StMem& m, int b, int tid, int nthr) {
-    constexpr int UNR = 4;
+    constexpr int UNR = 8;
     const int nv = rn_nv<M>(pb, N);
     if (io.jac) {
         const int e0 = ECUDA_LDG(pb.colptr + ph.zoff), e1 = ECUDA_LDG(pb.colptr + ph.zoff + nv);
-        double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-        const double* isz = m.isz - ph.zoff;  // indexed by the global column
-        for (int e = e0 + tid; e < e1; e += UNR * nthr) {
+        double* __restrict__ jac = io.jac + static_cast<size_t>(b) * pb.nnz + e0;
+        const unsigned long long* __restrict__ desc = pb.desc + e0;
+        const double* __restrict__ sg = pb.sg;
+        const int n = e1 - e0, nfull = n - n % (UNR * nthr);
+        int e = tid;
+        for (; e < nfull; e += UNR * nthr) {  // full batches: no bounds tests, UNR descriptor loads in flight
             unsigned long long d[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (e + u * nthr < e1) d[u] = ECUDA_LDG(pb.desc + e + u * nthr);
-            double T[UNR], s[UNR];
+            for (int u = 0; u < UNR; ++u) d[u] = ECUDA_LDG(desc + e + u * nthr);
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (e + u * nthr < e1) {
-                    const unsigned tb = static_cast<unsigned>(d[u]) & 0xffffffu;
-                    T[u] = (tb & ECUDA_DESC_DFLAG) ? ECUDA_LDG(ph.Dt + (tb & (ECUDA_DESC_DFLAG - 1u))) : m.tab[tb];
-                    s[u] = ECUDA_LDG(pb.sg + static_cast<unsigned>((d[u] >> 24) & 0xfffffu));
-                }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (e + u * nthr < e1)
-                    ECUDA_STREAM_STORE(jac + e + u * nthr, (s[u] * T[u]) * isz[static_cast<unsigned>(d[u] >> 44)]);
+            for (int u = 0; u < UNR; ++u) {
+                const unsigned hi = static_cast<unsigned>(d[u] >> 32);
+                const double v = (ECUDA_LDG(sg + (hi & 0xffffu)) * m.tab[static_cast<unsigned>(d[u])]) * m.isz[hi >> 16];
+                ECUDA_STREAM_STORE(jac + e + u * nthr, v);
+            }
+        }
+        for (; e < n; e += nthr) {
+            const unsigned long long d = ECUDA_LDG(desc + e);
+            const unsigned hi = static_cast<unsigned>(d >> 32);
+            ECUDA_STREAM_STORE(jac + e, (ECUDA_LDG(sg + (hi & 0xffffu)) * m.tab[static_cast<unsigned>(d)]) * m.isz[hi >> 16]);
         }
     }
     if (io.g) {

@@ -316,6 +316,13 @@ void eCUDA::deviceSetup() {
 
 // host half of setup(): VGP -> NLP description (no device needed)
 void eCUDA::transcribe() {
+    // delayed states / controls: ePSOPT::dae appends x(t - i dt) for 1 <= i < xrhorizon and u(t - i dt) for
+    // 1 <= i <= urhorizon to the callback arguments (src/ePSOPT/ePSOPT.cpp:231-248). The device kernels have no
+    // delayed terms, so a VGP that asks for them must not be evaluated without them: fail, loudly.
+    if (getXrhorizon() >= 2 || getUrhorizon() >= 1)
+        fail("delayed states / controls (states rhorizon " + std::to_string(getXrhorizon()) + ", controls rhorizon " +
+             std::to_string(getUrhorizon()) + ") are not supported by the eCUDA evaluator: ePSOPT would pass x(t - i dt), "
+             "u(t - i dt) to the callbacks (ePSOPT.cpp:231-248)");
     if (_objective || !_gradient.empty() || !_constraints.empty()) {
         std::string why;
         if (!matchCallbacks(&why)) fail("the registered callbacks match no device model: " + why);

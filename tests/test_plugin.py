@@ -317,3 +317,30 @@ def test_plugin_solves_reference_vgp(xml, callbacks):
     assert X[0, 0] == 0.0 and abs(X[-1, 0] - 16.0) < 1e-12
     assert abs(score - 1.51287) < 1e-3
     p.close()
+
+
+def test_delayed_states_fail_loudly(tmp_path):
+    """a VGP with rhorizon >= 2 (states) or >= 1 (controls) gets delayed arguments in ePSOPT::dae (ePSOPT.cpp:231-248);
+    eCUDA has no delayed terms and must refuse the VGP (ETOL's convention: message + exit) instead of evaluating it
+    without them. The shipped files (0 and 1 on the states, 0 on the controls) add nothing and load."""
+    import subprocess
+    import sys
+    xml = pb.write_reference_xml(str(tmp_path / "vgp.xml"))
+    text = open(xml).read()
+    assert 'rhorizon="0"' in text
+    bad_x = str(tmp_path / "delayed_x.xml")
+    open(bad_x, "w").write(text.replace('<states nstates="2" rhorizon="0">', '<states nstates="2" rhorizon="2">'))
+    bad_u = str(tmp_path / "delayed_u.xml")
+    open(bad_u, "w").write(text.replace('<controls ncontrols="2" rhorizon="0">', '<controls ncontrols="2" rhorizon="1">'))
+    ok_x1 = str(tmp_path / "x1.xml")
+    open(ok_x1, "w").write(text.replace('<states nstates="2" rhorizon="0">', '<states nstates="2" rhorizon="1">'))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import plugin_binding as pb; "
+            "pb.Plugin().load(sys.argv[1]); print('loaded')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path, should_load in ((bad_x, False), (bad_u, False), (ok_x1, True)):
+        r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests")), path], capture_output=True,
+                           text=True, timeout=300)
+        if should_load:
+            assert r.returncode == 0 and "loaded" in r.stdout, r.stderr
+        else:
+            assert r.returncode != 0 and "delayed states / controls" in r.stderr and "loaded" not in r.stdout
