@@ -195,13 +195,12 @@ def cpu_rowrestricted_sample(wl, seconds_budget):
         eb.emu_eval(sub, sub.x, want=("f", "g", "jac"), jac_mode=1, nthr=256, variant="rowsn")
         return per
 
-    t0 = time.time()
     work(0)
-    one = max(time.time() - t0, 1e-4)
-    chunks = int(max(nthr, min(seconds_budget / one * nthr, wl.batch // per)))
-    t0 = time.time()
+    nchunks = wl.batch // per
+    n, t0 = 0, time.time()
     with ThreadPoolExecutor(max_workers=nthr) as pool:
-        n = sum(pool.map(work, range(chunks)))
+        while time.time() - t0 < seconds_budget:  # whole passes over the batch until the budget is used
+            n += sum(pool.map(lambda i: work(i % nchunks), range(nchunks)))
     dt = time.time() - t0
     return {"value": n / dt, "sample": f"{n} of {wl.batch} instances, f+g+J(fd_indexset, row-restricted), kernel logic "
                                         f"stepped on the CPU, {nthr} threads, {dt:.2f} s"}
@@ -473,6 +472,45 @@ def run_ecuda(args):
                                "what": "cudaMemcpyAsync device -> pinned host of one step's Jacobian values, all ranks "
                                        "at once, max over ranks"}
         del hprobe
+
+    # ---- the other BASELINE configurations (parity-test cases): kernel time per batch in the same run, same clocks ----
+    if world == 1 and not args.no_extras:
+        others = {}
+        cfgs = (("C0 reference VGP (si2d, 33 nodes, ocp_2d_ex1 shape), B=4096", lambda: W.reference_vgp("ocp", batch=4096, jitter=0.02)),
+                ("C3 fw6 200 nodes 64 cylinders, B=64", lambda: W.fw6(batch=64)),
+                ("C4 pm3d 3 phases x 30 nodes, B=1024", lambda: W.pm3d_multiphase(batch=1024)))
+        for name, mk in cfgs:
+            try:
+                w2 = mk()
+                e2 = capi.Evaluator(w2, device=local)
+                x2 = torch.from_numpy(w2.x).to(dev)
+                f2 = torch.empty(w2.batch, dtype=torch.float64, device=dev)
+                g2 = torch.empty((w2.batch, e2.ncons), dtype=torch.float64, device=dev)
+                j2 = torch.empty((w2.batch, e2.nnz), dtype=torch.float64, device=dev)
+                unit = 8 * (e2.nvars + 1 + e2.ncons + e2.nnz) + 8 * e2.dims.inst_stride
+                row = {"nvars": e2.nvars, "ncons": e2.ncons, "nnz": e2.nnz, "batch": w2.batch,
+                       "algorithmic_bytes_per_unit": unit}
+                for mode, tag in ((capi.JAC_FD, "fd"), (capi.JAC_EXACT, "exact")):
+                    for _ in range(2):
+                        e2.eval_ptr(x2.data_ptr(), f2.data_ptr(), g2.data_ptr(), j2.data_ptr(), mode, capi.MEM_DEVICE, sp)
+                    ts = []
+                    for i in range(5):
+                        flush_l2(i)
+                        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        s.record(stream)
+                        e2.eval_ptr(x2.data_ptr(), f2.data_ptr(), g2.data_ptr(), j2.data_ptr(), mode, capi.MEM_DEVICE, sp)
+                        e.record(stream)
+                        torch.cuda.synchronize()
+                        ts.append(s.elapsed_time(e))
+                    ms = float(np.median(ts))
+                    row[tag] = {"ms_per_batch": ms, "evals_per_s": w2.batch / (ms / 1e3),
+                                "frac_of_hbm_peak": unit * w2.batch / (ms / 1e3) / 1e9 / peak}
+                others[name] = row
+                e2.close()
+                del x2, f2, g2, j2
+            except Exception as exc:  # noqa: BLE001
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        extras["other_configs"] = others
 
     # ---- C5: all-gather of the full per-instance results [g | Jvals] over NVLink (NCCL), timed on its own ----
     if world > 1 and not args.no_extras:

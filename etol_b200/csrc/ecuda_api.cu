@@ -235,7 +235,7 @@ struct ecuda_ctx {
     bool barrier_used = false;  // ecuda_peer_barrier has been issued: ecuda_sync also reports its sticky status
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
-    bool rows_exact = false;  // ECUDA_ROWS_EXACT=1: exact mode on k_rows_n instead of the streaming kernel
+    int exact_kernel = 0;     // ECUDA_EXACT_KERNEL: 0 k_eval_rows (default), 1 "ring" k_rows_n, 2 "stream" k_stream_exact
     DevBuf desc;              // exact-mode triplet descriptors
     int rowsn_N = 0;     // node count shared by all phases when the N-specialised kernels may run (else 0)
     int nb_uniform = 0;  // summation-block count if all phases share it and it is <= 8, else 0
@@ -486,13 +486,24 @@ template <int M, int N, bool TRK>
 static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
     if (!TRK && h->pd.ntracks > 0) return 1;
     const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
-    if (fd)
+    if (fd) {
+        // the row-owner layout gives the D-coupled work to the threads that own a defect row: it pays when those are
+        // at least half of the CTA (C2 240 and C4 180 of 256: 0.158 vs 0.179 ms, 0.089 vs 0.116 ms); a phase with few
+        // rows (C0: 66) is faster on the column-owner kernel, which spreads that work over all threads (0.164 vs 0.207)
+        if (2 * Model<M>::NS * N < kThreads && !std::getenv("ECUDA_ROWS_ALWAYS")) return 1;
         return io.nranks > 0 ? launch_rows_n_t<M, N, true, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, true, TRK, false>(h, io, st, grid);
-    if (h->rows_exact || h->pd.ncons > 65535 || h->pd.nvars > 65535)  // ECUDA_ROWS_EXACT=1 (A/B), or 16-bit descriptors too narrow
+    }
+    // Exact mode. Measured on C2 (B200, same box, profiles/r2/README.md): round-1 k_eval_rows (TMA copy of the
+    // template + node-local overwrite) 0.144 ms, k_rows_n with the store ring 0.154 ms, k_stream_exact 0.165 ms. The
+    // fastest one stays the default; the other two are selected with ECUDA_EXACT_KERNEL=ring | stream (A/B, tests).
+    if (h->exact_kernel == 1)
         return io.nranks > 0 ? launch_rows_n_t<M, N, false, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, false, TRK, false>(h, io, st, grid);
-    return io.nranks > 0 ? launch_stream_t<M, N, TRK, true>(h, io, st, grid) : launch_stream_t<M, N, TRK, false>(h, io, st, grid);
+    if (h->exact_kernel == 2 && h->pd.ncons <= 65535 && h->pd.nvars <= 65535)  // 16-bit descriptor fields
+        return io.nranks > 0 ? launch_stream_t<M, N, TRK, true>(h, io, st, grid)
+                             : launch_stream_t<M, N, TRK, false>(h, io, st, grid);
+    return 1;  // the caller falls back to k_eval_rows
 }
 // returns 1 when no instantiation matches (the caller falls back)
 template <int M>
@@ -802,7 +813,9 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if ((rc = ensure(h, h->desc, sizeof(uint64_t) * std::max<size_t>(1, hp.tdesc.size())))) return rc;
     CU(cudaMemcpy(h->desc.p, hp.tdesc.data(), sizeof(uint64_t) * hp.tdesc.size(), cudaMemcpyHostToDevice));
     pd.desc = static_cast<const unsigned long long*>(h->desc.p);
-    h->rows_exact = std::getenv("ECUDA_ROWS_EXACT") != nullptr;
+    h->exact_kernel = 0;
+    if (const char* ek = std::getenv("ECUDA_EXACT_KERNEL"))
+        h->exact_kernel = std::strcmp(ek, "ring") == 0 ? 1 : std::strcmp(ek, "stream") == 0 ? 2 : 0;
     h->h_sz.assign(pd.nvars, 1.0);
     h->h_sg.assign(pd.ncons, 1.0);
     if ((rc = upload_scaling(h))) return rc;

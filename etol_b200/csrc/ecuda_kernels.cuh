@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     RnRow<N> st;
     double viol, fval;
     rn_begin<M, N, FD, SUM>(pb, ph, io, m, cm, b, tid, st, viol, fval);
+    if (tid >= nthr - 32) rn_objective_warp<M, N>(pb, p, io, m, b, tid & 31, fval);  // the last warp, converged here
     if (io.jac) {  // uniform over the CTA
         double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
         RnGroups<M, N, FD, 0, RING>::run(pb, ph, m, st, ring, cap, jac, static_cast<int>((reinterpret_cast<uintptr_t>(jac) >> 3) & 1), tid);
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
 // Exact Jacobian (and plain f / g evaluation) as a stream (ecuda_stream.cuh): phase 1 fills the instance's table and
 // constraint values in shared memory, one barrier, phase 2 writes every triplet in address order.
 #ifndef ECUDA_MIN_CTAS_STREAM
-#define ECUDA_MIN_CTAS_STREAM 6
+#define ECUDA_MIN_CTAS_STREAM 4
 #endif
 template <int M, int N, bool TRK, bool SUM>
 __global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_STREAM)

@@ -98,6 +98,12 @@ struct RnMem {
     double* z;     // [nv]          unscaled variables of the phase
     FdRec* rec;    // [nv]          FD mode
     ExRec* erec;   // [nv]          exact mode
+    // collocation data of the phase, copied into shared memory while the decision vector is on its way (FD mode):
+    // after the staging barrier the threads read nothing from global memory -- under the kernel's own write traffic
+    // even an L1 hit queues behind the stores, and a miss costs thousands of cycles
+    const double* dt;   // [N*N] D^T (dt[l*N + k] = D[k][l]); exact mode: the global array
+    const double* tau;  // [N]
+    const double* w;    // [N]
 };
 
 template <int M>
@@ -122,6 +128,7 @@ ECUDA_HD size_t rn_doubles(const ProbDev& pb, int N, bool fd) {
     const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
     size_t n = static_cast<size_t>(pb.inst_stride) + nve;
     n += fd ? 4 * nv : 2 * nv;
+    if (fd) n += static_cast<size_t>(N) * N + 2 * static_cast<size_t>(N + (N & 1));
     return n + (n & 1);
 }
 
@@ -134,16 +141,37 @@ ECUDA_HD void rn_carve(RnMem& m, double* base, const ProbDev& pb, int N, bool fd
     base += nve;
     m.rec = nullptr;
     m.erec = nullptr;
-    if (fd)
+    m.dt = m.tau = m.w = nullptr;  // exact mode: rn_stage points them at the global arrays
+    if (fd) {
         m.rec = reinterpret_cast<FdRec*>(base);
-    else
+        base += 4 * nv;
+        m.dt = base;
+        base += static_cast<size_t>(N) * N;
+        m.tau = base;
+        base += N + (N & 1);
+        m.w = base;
+    } else {
         m.erec = reinterpret_cast<ExRec*>(base);
+    }
 }
 
 // ---- stage: same arithmetic as stage_vars ----------------------------------------------------------------------
 template <int M, int N, bool FD>
-ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, int tid, int nthr) {
+ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, RnMem& m, int b, int tid, int nthr) {
     const int nv = rn_nv<M>(pb, N);
+    if (FD) {
+        double* dt = const_cast<double*>(m.dt);
+        double* tw = const_cast<double*>(m.tau);
+        for (int e = tid; e < N * N; e += nthr) dt[e] = ECUDA_LDG(ph.Dt + e);
+        if (tid < N) {
+            tw[tid] = ECUDA_LDG(ph.tau + tid);
+            const_cast<double*>(m.w)[tid] = ECUDA_LDG(ph.w + tid);
+        }
+    } else {
+        m.dt = ph.Dt;
+        m.tau = ph.tau;
+        m.w = ph.w;
+    }
     const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
     const double* is = pb.isz + ph.zoff;
     const int* cpg = pb.colptr + ph.zoff;
@@ -195,7 +223,7 @@ ECUDA_HD double rn_dot(const double* __restrict__ Dtk, const double* __restrict_
         double p = 0.0;
 #pragma unroll
         for (int a = 0; a < BL; ++a)
-            if (bi * BL + a < N) p = fma(ECUDA_LDG(Dtk + (bi * BL + a) * N), Xi[(bi * BL + a) * NS], p);
+            if (bi * BL + a < N) p = fma(Dtk[(bi * BL + a) * N], Xi[(bi * BL + a) * NS], p);
         P[bi] = p;
         total = (bi == 0) ? p : total + p;
     }
@@ -212,7 +240,7 @@ ECUDA_HD void rn_diag(const double* __restrict__ Dtk, const double* __restrict__
 #pragma unroll
     for (int a = 0; a < BL; ++a) {
         if (l0 + a < N) {
-            const double di = ECUDA_LDG(Dtk + (l0 + a) * N);
+            const double di = Dtk[(l0 + a) * N];
             const double xi = Xi[(l0 + a) * NS];
             if (a < krel) {
                 q = fma(di, xi, q);
@@ -282,7 +310,7 @@ ECUDA_HD void rn_fd_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     st.sgr = ECUDA_LDG(pb.sg + r);
     const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
     const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
-    const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+    const double t = h * m.tau[k] + mid;
     double x[NS], u[NCU], f[NS];
 #pragma unroll
     for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
@@ -294,7 +322,7 @@ ECUDA_HD void rn_fd_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     for (int a = 0; a < NS; ++a)
         if (a == i) fi = f[a];
     st.hfv = h * fi;
-    const double dv = rn_dot<NS, N>(ph.Dt + k, zx + i, st.P);
+    const double dv = rn_dot<NS, N>(m.dt + k, zx + i, st.P);
     if (io.g) {
         const double val = st.sgr * (dv - st.hfv);
         ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
@@ -313,13 +341,13 @@ ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m,
     constexpr int nin = (N - l0) < BL ? (N - l0) : BL;     // nodes of the block
     constexpr int a1 = (a0 + kRnGroup) < nin ? (a0 + kRnGroup) : nin;
     if (!st.row) return;
-    const double* Dtk = ph.Dt + st.k;
+    const double* Dtk = m.dt + st.k;
     const double* Xi = m.z + pb.nc * N + st.i;
     const FdRec* Ri = m.rec + pb.nc * N + st.i;
     if (a0 == 0) {  // first group of a summation block: its D entries and node values, the prefix of block sums
 #pragma unroll
         for (int a = 0; a < nin; ++a) {
-            st.d[a] = ECUDA_LDG(Dtk + (l0 + a) * N);
+            st.d[a] = Dtk[(l0 + a) * N];
             st.xv[a] = Xi[(l0 + a) * NS];
         }
         st.pre = 0.0;
@@ -367,14 +395,14 @@ ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
     const double sgr = st.sgr;
     const double (&P)[NB] = st.P;
     const double* zx = m.z + nc * N;
-    const double* Dtk = ph.Dt + k;
+    const double* Dtk = m.dt + k;
     const double* Xi = zx + i;
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
     constexpr bool DS = Model<M>::DIAG_FREE;
     const FdRec* rx = m.rec + nc * N;  // record of X(l,j) = rx[l*NS + j]
     const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
     const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
-    const double tau = ECUDA_LDG(ph.tau + k);
+    const double tau = m.tau[k];
     const double t = h * tau + mid;
     double dv = P[0];
 #pragma unroll
@@ -504,12 +532,15 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     };
 
     if (it == 0) {  // ---- objective: running cost per node and quadrature
+#if defined(__CUDA_ARCH__)
+        return;  // the kernel's last warp has computed it cooperatively (rn_objective_warp)
+#endif
         if (!io.f) return;
         double acc = 0.0;
         for (int k = 0; k < N; ++k) {
-            const double t = h * ECUDA_LDG(ph.tau + k) + mid;
+            const double t = h * m.tau[k] + mid;
             const double L = Model<M>::cost(zx + k * NS, m.z + k * nc, t);
-            acc = fma(ECUDA_LDG(ph.w + k), pb.maximize ? -1.0 * L : L, acc);
+            acc = fma(m.w[k], pb.maximize ? -1.0 * L : L, acc);
         }
         const double fp = h * acc;
         if (pb.nphases == 1)
@@ -522,7 +553,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     it -= 1;
     if (it < np * N) {  // ---- path row (k,q)
         const int k = fast_div(it, ph.mnp), q = it - k * np;
-        const double tau = ECUDA_LDG(ph.tau + k);
+        const double tau = m.tau[k];
         const double t = h * tau + mid;
         const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
         const int r = ph.goff + NS * N + pb.ne + it;
@@ -786,6 +817,9 @@ ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const 
     };
 
     if (it == 0) {  // ---- objective
+#if defined(__CUDA_ARCH__)
+        return;  // the kernel's last warp has computed it cooperatively (rn_objective_warp)
+#endif
         if (!io.f) return;
         double acc = 0.0;
         for (int k = 0; k < N; ++k) {
@@ -912,6 +946,47 @@ ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const 
         ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * -1.0) * rc.isz);
     }
 }
+
+// Objective of the phase by ONE WARP: lane j evaluates the running cost at nodes j, j + 32, ...; the quadrature is
+// the same serial ascending fma chain as everywhere else (objective_phase), its operands arriving by shuffle. As a
+// single thread's item it was a 40-iteration loop of dependent loads on the CTA's critical path (the last warp
+// finished ~4000 cycles after the others).
+#if defined(__CUDA_ARCH__)
+template <int M, int N>
+__device__ __forceinline__ void rn_objective_warp(const ProbDev& pb, int p, const EvalIO& io, const RnMem& m, int b, int lane,
+                                                  double& fval) {
+    constexpr int NS = Model<M>::NS, NC32 = (N + 31) / 32;
+    if (!io.f) return;
+    const int nc = pb.nc;
+    const double* zx = m.z + nc * N;
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    double Lw[NC32], ww[NC32];
+#pragma unroll
+    for (int c = 0; c < NC32; ++c) {
+        const int k = c * 32 + lane;
+        Lw[c] = 0.0;
+        ww[c] = 0.0;
+        if (k < N) {
+            const double L = Model<M>::cost(zx + k * NS, m.z + k * nc, h * m.tau[k] + mid);
+            Lw[c] = pb.maximize ? -1.0 * L : L;
+            ww[c] = m.w[k];
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        acc = fma(__shfl_sync(0xffffffffu, ww[k >> 5], k & 31), __shfl_sync(0xffffffffu, Lw[k >> 5], k & 31), acc);
+    const double fp = h * acc;
+    if (lane == 31) {
+        if (pb.nphases == 1)
+            io.f[b] = pb.sf * fp;
+        else
+            io.fpart[static_cast<size_t>(b) * pb.nphases + p] = fp;
+        fval = pb.sf * fp;
+    }
+}
+#endif
 
 // ---- the three parts of a thread's program after the staging barrier -------------------------------------------------
 //   rn_begin   defect-row value (+ the per-row state kept in registers)

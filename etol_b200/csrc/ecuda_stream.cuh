@@ -28,6 +28,7 @@ struct StMem {
     double* isz;   // [nv]   1 / sz
     double* tab;   // [desc_table_size] per-instance table T
     double* gbuf;  // [phase_ncons]     scaled constraint values of the phase
+    double* sg;    // [ncons]           row scales (all rows: a phase's triplets also sit in linkage rows)
 };
 
 template <int M>
@@ -35,7 +36,8 @@ ECUDA_HD size_t st_doubles(const ProbDev& pb, const PhaseDev& ph, int N) {
     const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
     const size_t nt = static_cast<size_t>(desc_table_size(Model<M>::NS, pb.nc, N, ph.npath));
     const size_t ng = static_cast<size_t>(phase_ncons(pb, ph));
-    return static_cast<size_t>(pb.inst_stride) + 2 * nve + (nt + (nt & 1)) + (ng + (ng & 1));
+    const size_t nr = static_cast<size_t>(pb.ncons);
+    return static_cast<size_t>(pb.inst_stride) + 2 * nve + (nt + (nt & 1)) + (ng + (ng & 1)) + (nr + (nr & 1));
 }
 template <int M>
 ECUDA_HD void st_carve(StMem& m, double* base, const ProbDev& pb, const PhaseDev& ph, int N) {
@@ -50,6 +52,9 @@ ECUDA_HD void st_carve(StMem& m, double* base, const ProbDev& pb, const PhaseDev
     m.tab = base;
     base += nt + (nt & 1);
     m.gbuf = base;
+    const size_t ng = static_cast<size_t>(phase_ncons(pb, ph));
+    base += ng + (ng & 1);
+    m.sg = base;
 }
 
 // stage: z = z~ / sz and 1 / sz
@@ -79,8 +84,10 @@ ECUDA_HD void st_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
     }
     // D^T of the phase behind the per-instance entries: phase 2 reads every T from one shared-memory table
     double* td = m.tab + desc_d_off(Model<M>::NS, pb.nc, N, ph.npath);
-    if (io.jac)
+    if (io.jac) {
         for (int e = tid; e < N * N; e += nthr) td[e] = ECUDA_LDG(ph.Dt + e);
+        for (int r = tid; r < pb.ncons; r += nthr) m.sg[r] = ECUDA_LDG(pb.sg + r);
+    }
 }
 
 // phase 1, defect row (k,i): value and the row of the table           [rows_values + rows_jacobian<exact>]
@@ -255,24 +262,37 @@ ECUDA_HD void st_phase2(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
         const int e0 = ECUDA_LDG(pb.colptr + ph.zoff), e1 = ECUDA_LDG(pb.colptr + ph.zoff + nv);
         double* __restrict__ jac = io.jac + static_cast<size_t>(b) * pb.nnz + e0;
         const unsigned long long* __restrict__ desc = pb.desc + e0;
-        const double* __restrict__ sg = pb.sg;
         const int n = e1 - e0, nfull = n - n % (UNR * nthr);
+        // Software pipeline: the descriptors of the next batch are in flight while this one is computed and stored --
+        // the descriptor read is the only global load of the loop, and under the kernel's own write traffic a load
+        // takes thousands of cycles.
+        unsigned long long d[UNR], dn[UNR];
         int e = tid;
-        for (; e < nfull; e += UNR * nthr) {  // full batches: no bounds tests, UNR descriptor loads in flight
-            unsigned long long d[UNR];
+        if (e < nfull) {
 #pragma unroll
             for (int u = 0; u < UNR; ++u) d[u] = ECUDA_LDG(desc + e + u * nthr);
+        }
+        for (; e < nfull; e += UNR * nthr) {
+            const bool more = e + UNR * nthr < nfull;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) dn[u] = ECUDA_LDG(desc + e + (UNR + u) * nthr);
+            }
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 const unsigned hi = static_cast<unsigned>(d[u] >> 32);
-                const double v = (ECUDA_LDG(sg + (hi & 0xffffu)) * m.tab[static_cast<unsigned>(d[u])]) * m.isz[hi >> 16];
+                const double v = (m.sg[hi & 0xffffu] * m.tab[static_cast<unsigned>(d[u])]) * m.isz[hi >> 16];
                 ECUDA_STREAM_STORE(jac + e + u * nthr, v);
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) d[u] = dn[u];
             }
         }
         for (; e < n; e += nthr) {
-            const unsigned long long d = ECUDA_LDG(desc + e);
-            const unsigned hi = static_cast<unsigned>(d >> 32);
-            ECUDA_STREAM_STORE(jac + e, (ECUDA_LDG(sg + (hi & 0xffffu)) * m.tab[static_cast<unsigned>(d)]) * m.isz[hi >> 16]);
+            const unsigned long long dd = ECUDA_LDG(desc + e);
+            const unsigned hi = static_cast<unsigned>(dd >> 32);
+            ECUDA_STREAM_STORE(jac + e, (m.sg[hi & 0xffffu] * m.tab[static_cast<unsigned>(dd)]) * m.isz[hi >> 16]);
         }
     }
     if (io.g) {

@@ -420,8 +420,13 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
     # "fast-image": exact through the persistent k_eval_image (shared-memory image + bulk stores);
     # "fast-ldst": template copied with plain loads/stores; "generic": k_eval
     # ("fast" is k_eval_rows, the row-owner kernel; "columns" the column-owner k_eval_fast)
+    # round 2: "fast" now means the N-specialised k_rows_n for finite differences wherever an instantiation exists
+    # (all five cases); "rows-r1" switches it off (round-1 k_eval_rows); "ring" / "stream" select the two other
+    # exact-mode kernels (k_rows_n with the shared-memory store ring, k_stream_exact)
     for tag, env in (("fast", {}), ("fast-image", {"ECUDA_IMAGE": "1"}), ("fast-ldst", {"ECUDA_NO_COPY_WARP": "1"}),
-                     ("columns", {"ECUDA_NO_ROWS": "1"}), ("generic", {"ECUDA_NO_FAST": "1"})):
+                     ("columns", {"ECUDA_NO_ROWS": "1"}), ("generic", {"ECUDA_NO_FAST": "1"}),
+                     ("rows-r1", {"ECUDA_NO_ROWSN": "1"}), ("ring", {"ECUDA_EXACT_KERNEL": "ring"}),
+                     ("stream", {"ECUDA_EXACT_KERNEL": "stream"})):
         os.environ.update(env)  # read by ecuda_create
         try:
             ev = capi.Evaluator(wl, device=0)
@@ -436,6 +441,8 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
             assert np.array_equal(out["fast-ldst"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["fast-image"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["columns"][m][key], out["generic"][m][key]), (name, m, key)
+            for tag in ("rows-r1", "ring", "stream"):
+                assert np.array_equal(out[tag][m][key], out["generic"][m][key]), (name, m, key, tag)
 
 
 def test_peer_barrier_reports_an_absent_peer(monkeypatch):
