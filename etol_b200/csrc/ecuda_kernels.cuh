@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     RnRow<N> st;
     double viol, fval;
     rn_begin<M, N, FD, SUM>(pb, ph, io, m, cm, b, tid, st, viol, fval);
+#if defined(__CUDA_ARCH__)
     if (tid >= nthr - 32) rn_objective_warp<M, N>(pb, p, io, m, b, tid & 31, fval);  // the last warp, converged here
+#endif
     if (io.jac) {  // uniform over the CTA
         double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
         RnGroups<M, N, FD, 0, RING>::run(pb, ph, m, st, ring, cap, jac, static_cast<int>((reinterpret_cast<uintptr_t>(jac) >> 3) & 1), tid);
