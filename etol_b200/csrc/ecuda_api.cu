@@ -235,6 +235,7 @@ struct ecuda_ctx {
     bool barrier_used = false;  // ecuda_peer_barrier has been issued: ecuda_sync also reports its sticky status
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
+    bool persist = false;     // ECUDA_PERSIST=1: finite differences on the persistent kernel (k_rows_n_fd_persist)
     int exact_kernel = 0;     // ECUDA_EXACT_KERNEL: 0 k_eval_rows (default), 1 "ring" k_rows_n, 2 "stream" k_stream_exact
     DevBuf desc;              // exact-mode triplet descriptors
     int rowsn_N = 0;     // node count shared by all phases when the N-specialised kernels may run (else 0)
@@ -461,6 +462,26 @@ static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int 
     k_rows_n<M, N, FD, TRK, SUM, RING><<<grid, kThreads, smem, st>>>(h->pd, io);
     return ECUDA_OK;
 }
+// finite differences, persistent CTAs with TMA prefetch of the next instance (k_rows_n_fd_persist)
+template <int M, int N, bool TRK>
+static int launch_rows_n_persist(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    const size_t nv = static_cast<size_t>(rn_nv<M>(h->pd, N)), nve = nv + (nv & 1);
+    const size_t smem = (4 * nve + 2 * static_cast<size_t>(h->pd.inst_stride) + 4 * nv + static_cast<size_t>(N) * N +
+                         2 * static_cast<size_t>(N + (N & 1))) * sizeof(double);
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = configured[h->device & 63];
+        if (cur < smem) {
+            CU(cudaFuncSetAttribute(k_rows_n_fd_persist<M, N, TRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    const int grid = std::min(io.batch, h->num_sms * ECUDA_MIN_CTAS_ROWSN_FD);
+    k_rows_n_fd_persist<M, N, TRK><<<grid, kThreads, smem, st>>>(h->pd, io);
+    return ECUDA_OK;
+}
 // exact Jacobian / values only: the streaming kernel (ecuda_stream.cuh)
 template <int M, int N, bool TRK, bool SUM>
 static int launch_stream_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
@@ -491,6 +512,9 @@ static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int
         // at least half of the CTA (C2 240 and C4 180 of 256: 0.158 vs 0.179 ms, 0.089 vs 0.116 ms); a phase with few
         // rows (C0: 66) is faster on the column-owner kernel, which spreads that work over all threads (0.164 vs 0.207)
         if (2 * Model<M>::NS * N < kThreads && !std::getenv("ECUDA_ROWS_ALWAYS")) return 1;
+        if (h->persist && io.nranks == 0 && h->pd.nphases == 1 && (h->pd.nvars & 1) == 0 && (h->pd.inst_stride & 1) == 0 &&
+            (reinterpret_cast<uintptr_t>(io.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(io.inst) & 15) == 0)
+            return launch_rows_n_persist<M, N, TRK>(h, io, st);
         return io.nranks > 0 ? launch_rows_n_t<M, N, true, TRK, true>(h, io, st, grid)
                              : launch_rows_n_t<M, N, true, TRK, false>(h, io, st, grid);
     }
@@ -813,6 +837,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if ((rc = ensure(h, h->desc, sizeof(uint64_t) * std::max<size_t>(1, hp.tdesc.size())))) return rc;
     CU(cudaMemcpy(h->desc.p, hp.tdesc.data(), sizeof(uint64_t) * hp.tdesc.size(), cudaMemcpyHostToDevice));
     pd.desc = static_cast<const unsigned long long*>(h->desc.p);
+    h->persist = std::getenv("ECUDA_PERSIST") != nullptr;
     h->exact_kernel = 0;
     if (const char* ek = std::getenv("ECUDA_EXACT_KERNEL"))
         h->exact_kernel = std::strcmp(ek, "ring") == 0 ? 1 : std::strcmp(ek, "stream") == 0 ? 2 : 0;

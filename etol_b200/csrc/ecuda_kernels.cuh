@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     RnRow<N> st;
     double viol, fval;
     rn_begin<M, N, FD, SUM>(pb, ph, io, m, cm, b, tid, st, viol, fval);
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && ECUDA_RN_OBJWARP
     if (tid >= nthr - 32) rn_objective_warp<M, N>(pb, p, io, m, b, tid & 31, fval);  // the last warp, converged here
 #endif
     if (io.jac) {  // uniform over the CTA
@@ -465,6 +465,93 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
                 *dst = make_double2(red[kThreads / 32], w);
             }
         }
+    }
+}
+
+// Finite differences, PERSISTENT: 3 CTAs per SM loop over the instances. What a one-shot CTA spends a quarter of its
+// life on -- waiting for its decision vector to arrive from HBM under the kernel's own write traffic, and re-reading
+// data that is the same for every instance (1 / sz, column starts, D^T, tau, w) -- is taken off the critical path:
+// the next instance's decision vector and obstacle records are fetched by TMA (cp.async.bulk + mbarrier, double
+// buffered) while the current one is evaluated, and the per-problem data are staged once per CTA.
+// Single-phase problems with an even number of variables (16-byte granularity of the bulk copies).
+template <int M, int N, bool TRK>
+__global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
+    k_rows_n_fd_persist(const __grid_constant__ ProbDev pb, const __grid_constant__ EvalIO io) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const PhaseDev& ph = pb.ph[0];
+    const int tid = threadIdx.x, nthr = kThreads;
+    const int nv = rn_nv<M>(pb, N), nve = nv + (nv & 1);
+    // layout: raw x (2 buffers) | obstacle records (2 buffers) | 1/sz | z | records | D^T | tau | w
+    double* xin = smem;
+    double* instb = xin + 2 * nve;
+    double* iszs = instb + 2 * pb.inst_stride;
+    RnMem m;
+    m.inst = instb;
+    m.z = iszs + nve;
+    m.rec = reinterpret_cast<FdRec*>(m.z + nve);
+    m.erec = nullptr;
+    double* dt = reinterpret_cast<double*>(m.rec + nv);
+    double* tw = dt + N * N;
+    m.dt = dt;
+    m.tau = tw;
+    m.w = tw + N + (N & 1);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    // once per CTA: everything that does not depend on the instance
+    for (int c = tid; c < nv; c += nthr) {
+        iszs[c] = __ldg(pb.isz + c);
+        m.rec[c].cp = __ldg(pb.colptr + c);
+        m.rec[c].pad_ = 0;
+    }
+    for (int e = tid; e < N * N; e += nthr) dt[e] = __ldg(ph.Dt + e);
+    if (tid < N) {
+        tw[tid] = __ldg(ph.tau + tid);
+        const_cast<double*>(m.w)[tid] = __ldg(ph.w + tid);
+    }
+    __syncthreads();
+    const uint32_t xbytes = static_cast<uint32_t>(nv) * 8u, ibytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+    auto fetch = [&](int b, int buf) {  // thread 0
+        mbar_expect_tx(&bars[buf], xbytes + ibytes);
+        bulk_g2s(xin + buf * nve, io.x + static_cast<size_t>(b) * pb.nvars, xbytes, &bars[buf]);
+        if (ibytes) bulk_g2s(instb + buf * pb.inst_stride, io.inst + static_cast<size_t>(b) * pb.inst_stride, ibytes, &bars[buf]);
+    };
+    int b = blockIdx.x;
+    if (tid == 0 && b < io.batch) fetch(b, 0);
+    uint32_t par0 = 0, par1 = 0;
+    for (int cur = 0; b < io.batch; b += gridDim.x, cur ^= 1) {
+        mbar_wait(&bars[cur], cur ? par1 : par0);
+        if (cur) par1 ^= 1; else par0 ^= 1;
+        const double* xs = xin + cur * nve;
+        for (int c = tid; c < nv; c += nthr) {  // rn_stage<FD>, inputs from shared memory
+            const double zt = xs[c], sc = iszs[c];
+            m.z[c] = zt * sc;
+            const double delta = ECUDA_SQRT_EPS * (1.0 + fabs(zt));
+            FdRec* r = m.rec + c;
+            r->xp = (zt + delta) * sc;
+            r->xm = (zt - delta) * sc;
+            r->ri = 1.0 / (2.0 * delta);
+        }
+        CtaMem cm{};
+        cm.inst = instb + cur * pb.inst_stride;
+        cm.z = m.z;
+        m.inst = cm.inst;
+        __syncthreads();  // z and the records are complete; the other buffer's previous contents are no longer needed
+        if (tid == 0 && b + static_cast<int>(gridDim.x) < io.batch) fetch(b + gridDim.x, cur ^ 1);
+        RnRow<N> st;
+        double viol, fval;
+        rn_begin<M, N, true, false>(pb, ph, io, m, cm, b, tid, st, viol, fval);
+#if defined(__CUDA_ARCH__) && ECUDA_RN_OBJWARP
+        if (tid >= nthr - 32) rn_objective_warp<M, N>(pb, 0, io, m, b, tid & 31, fval);
+#endif
+        if (io.jac) {
+            double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+            RnGroups<M, N, true, 0, false>::run(pb, ph, m, st, nullptr, 0, jac, 0, tid);
+        }
+        rn_end<M, N, true, TRK, false>(pb, ph, 0, io, m, cm, b, tid, nthr, st, viol, fval);
+        __syncthreads();  // everyone is done with z / records / this instance's obstacle records
     }
 }
 

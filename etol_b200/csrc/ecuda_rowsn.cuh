@@ -109,6 +109,15 @@ struct RnMem {
 template <int M>
 ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N + 2; }
 
+// ECUDA_RN_DSMEM: the one-shot FD kernel copies D^T, tau and w into shared memory per CTA. Measured on C2: 0.165 ms
+// with the copy, 0.159 ms reading them through L1 (the copy costs more than the shorter load latency saves), so it is
+// off; the persistent kernel, which copies once per CTA lifetime, always has them in shared memory.
+#ifndef ECUDA_RN_DSMEM
+#define ECUDA_RN_DSMEM 0
+#endif
+#ifndef ECUDA_RN_OBJWARP
+#define ECUDA_RN_OBJWARP 1
+#endif
 // store ring: kRnBufs buffers, each holds the triplets of the state columns of kRnGroup consecutive nodes
 constexpr int kRnGroup = 4;  // nodes per group (half a summation block)
 constexpr int kRnBufs = 3;   // one barrier per group needs three buffers (see k_rows_n)
@@ -128,7 +137,7 @@ ECUDA_HD size_t rn_doubles(const ProbDev& pb, int N, bool fd) {
     const size_t nv = static_cast<size_t>(rn_nv<M>(pb, N)), nve = nv + (nv & 1);
     size_t n = static_cast<size_t>(pb.inst_stride) + nve;
     n += fd ? 4 * nv : 2 * nv;
-    if (fd) n += static_cast<size_t>(N) * N + 2 * static_cast<size_t>(N + (N & 1));
+    if (fd && ECUDA_RN_DSMEM) n += static_cast<size_t>(N) * N + 2 * static_cast<size_t>(N + (N & 1));
     return n + (n & 1);
 }
 
@@ -159,32 +168,48 @@ ECUDA_HD void rn_carve(RnMem& m, double* base, const ProbDev& pb, int N, bool fd
 template <int M, int N, bool FD>
 ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, RnMem& m, int b, int tid, int nthr) {
     const int nv = rn_nv<M>(pb, N);
-    if (FD) {
-        double* dt = const_cast<double*>(m.dt);
-        double* tw = const_cast<double*>(m.tau);
-        for (int e = tid; e < N * N; e += nthr) dt[e] = ECUDA_LDG(ph.Dt + e);
+    const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
+    const double* is = pb.isz + ph.zoff;
+    const int* cpg = pb.colptr + ph.zoff;
+    // Every global load of the thread is issued before the first dependent store: the decision vector comes from HBM
+    // (thousands of cycles under the kernel's own write traffic), the rest from L2 -- one wait for all of them.
+    double zt[2], s[2];
+    int cp[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int c = tid + u * nthr;
+        if (c < nv) {
+            zt[u] = ECUDA_LDG(xs + c);
+            s[u] = ECUDA_LDG(is + c);
+            cp[u] = ECUDA_LDG(cpg + c);
+        }
+    }
+    constexpr bool DSM = FD && ECUDA_RN_DSMEM;
+    constexpr int ND = DSM ? (N * N + 255) / 256 : 1;
+    double dv[ND], tv = 0.0, wv = 0.0;
+    if (DSM) {
+#pragma unroll
+        for (int u = 0; u < ND; ++u)
+            if (tid + u * nthr < N * N) dv[u] = ECUDA_LDG(ph.Dt + tid + u * nthr);
         if (tid < N) {
-            tw[tid] = ECUDA_LDG(ph.tau + tid);
-            const_cast<double*>(m.w)[tid] = ECUDA_LDG(ph.w + tid);
+            tv = ECUDA_LDG(ph.tau + tid);
+            wv = ECUDA_LDG(ph.w + tid);
         }
     } else {
         m.dt = ph.Dt;
         m.tau = ph.tau;
         m.w = ph.w;
     }
-    const double* xs = io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff;
-    const double* is = pb.isz + ph.zoff;
-    const int* cpg = pb.colptr + ph.zoff;
     for (int c0 = tid; c0 < nv; c0 += 2 * nthr) {
-        double zt[2], s[2];
-        int cp[2];
+        if (c0 != tid) {  // further batches (more than 2 * nthr variables)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int c = c0 + u * nthr;
-            if (c < nv) {
-                zt[u] = ECUDA_LDG(xs + c);
-                s[u] = ECUDA_LDG(is + c);
-                cp[u] = ECUDA_LDG(cpg + c);
+            for (int u = 0; u < 2; ++u) {
+                const int c = c0 + u * nthr;
+                if (c < nv) {
+                    zt[u] = ECUDA_LDG(xs + c);
+                    s[u] = ECUDA_LDG(is + c);
+                    cp[u] = ECUDA_LDG(cpg + c);
+                }
             }
         }
 #pragma unroll
@@ -209,6 +234,16 @@ ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
                     m.erec[c] = r;
                 }
             }
+        }
+    }
+    if (DSM) {  // collocation data of the phase into shared memory
+        double* dt = const_cast<double*>(m.dt);
+#pragma unroll
+        for (int u = 0; u < ND; ++u)
+            if (tid + u * nthr < N * N) dt[tid + u * nthr] = dv[u];
+        if (tid < N) {
+            const_cast<double*>(m.tau)[tid] = tv;
+            const_cast<double*>(m.w)[tid] = wv;
         }
     }
 }
@@ -532,7 +567,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     };
 
     if (it == 0) {  // ---- objective: running cost per node and quadrature
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && ECUDA_RN_OBJWARP
         return;  // the kernel's last warp has computed it cooperatively (rn_objective_warp)
 #endif
         if (!io.f) return;
@@ -817,7 +852,7 @@ ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const 
     };
 
     if (it == 0) {  // ---- objective
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && ECUDA_RN_OBJWARP
         return;  // the kernel's last warp has computed it cooperatively (rn_objective_warp)
 #endif
         if (!io.f) return;

@@ -11,8 +11,9 @@
  *
  * Method: Cody-Waite reduction by pi/2 with a two-term (hi/lo) constant applied through fma, then
  * degree-13 / degree-14 minimax kernels on [-pi/4, pi/4] (the classic fdlibm coefficient sets).
- * Accuracy: < 1.5 ulp for |x| < 1e5 (tests/test_detmath.py checks it against libm and mpmath-free
- * long-double references). Not intended for huge arguments.
+ * Accuracy: < 2 ulp on [-7, 7], the range the fw6 model can feed it (measured maxima over a 2.4-million-point sweep
+ * against long-double libm: sin 1.56 ulp, cos 1.38 ulp, both at the edge of a reduction interval); < 1.5 ulp on
+ * random samples of |x| < 100 (tests/test_detmath.py). Not intended for huge arguments.
  */
 #ifndef ECUDA_DETMATH_H_
 #define ECUDA_DETMATH_H_
