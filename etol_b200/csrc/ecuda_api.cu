@@ -451,6 +451,7 @@ static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int 
     for (int p = 0; RING && p < h->pd.nphases; ++p) ring = std::max(ring, kRnBufs * rn_group_cap<M>(h->pd, h->pd.ph[p], N));
     size_t smem = (rn_doubles<M>(h->pd, N, FD) + ring) * sizeof(double);
     if (SUM && !io.bev) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
+    if (smem > 227 * 1024 - 1024) return 1;  // does not fit one CTA: the caller falls back
     if (smem > 48 * 1024) {
         std::lock_guard<std::mutex> lock(mu);
         size_t& cur = configured[h->device & 63];
@@ -812,6 +813,18 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     if (h->force_generic) h->nb_uniform = 0;
     // the specialised kernels: block counts of the BASELINE configs, one defect row per thread
     h->fast_ok = !h->no_fast && !h->force_generic && h->nb_uniform >= 3 && h->nb_uniform <= 5 && one_row_per_thread;
+    if (h->fast_ok) {
+        // every launch variant of the specialised kernels must fit one CTA's shared memory, not only the generic
+        // footprint checked above: exact mode adds the 1/sz copy, the template ring and (fused summary) the staged
+        // bounds. A problem that does not fit (many obstacle records per instance) runs on the generic kernel instead
+        // of failing at its first evaluation.
+        int ncp = 0;
+        for (int p = 0; p < hp.nphases; ++p) ncp = std::max(ncp, phase_ncons(pd, pd.ph[p]));
+        const size_t bounds = 2 * static_cast<size_t>(ncp + 2) * sizeof(double);
+        const size_t worst_exact = smem_ex + h->smem_isz + (kCopySlots * kCopyChunk + 2) * sizeof(double) + bounds;
+        const size_t worst_fd = smem_fd + bounds;
+        if (std::max(worst_exact, worst_fd) > 227 * 1024 - 1024) h->fast_ok = false;
+    }
     h->image_ok = h->fast_ok && !h->no_image && (pd.nnz & 1) == 0 && smem_img <= 227 * 1024 - 1024;
     h->rowsn_N = 0;
     if (h->fast_ok && !std::getenv("ECUDA_NO_ROWSN")) {

@@ -116,7 +116,7 @@ ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N
 #define ECUDA_RN_DSMEM 0
 #endif
 #ifndef ECUDA_RN_OBJWARP
-#define ECUDA_RN_OBJWARP 1
+#define ECUDA_RN_OBJWARP 0
 #endif
 // store ring: kRnBufs buffers, each holds the triplets of the state columns of kRnGroup consecutive nodes
 constexpr int kRnGroup = 4;  // nodes per group (half a summation block)

@@ -422,11 +422,12 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
     # ("fast" is k_eval_rows, the row-owner kernel; "columns" the column-owner k_eval_fast)
     # round 2: "fast" now means the N-specialised k_rows_n for finite differences wherever an instantiation exists
     # (all five cases); "rows-r1" switches it off (round-1 k_eval_rows); "ring" / "stream" select the two other
-    # exact-mode kernels (k_rows_n with the shared-memory store ring, k_stream_exact)
+    # exact-mode kernels (k_rows_n with the shared-memory store ring, k_stream_exact); "persist" the persistent
+    # finite-difference kernel with TMA prefetch of the next instance (k_rows_n_fd_persist)
     for tag, env in (("fast", {}), ("fast-image", {"ECUDA_IMAGE": "1"}), ("fast-ldst", {"ECUDA_NO_COPY_WARP": "1"}),
                      ("columns", {"ECUDA_NO_ROWS": "1"}), ("generic", {"ECUDA_NO_FAST": "1"}),
                      ("rows-r1", {"ECUDA_NO_ROWSN": "1"}), ("ring", {"ECUDA_EXACT_KERNEL": "ring"}),
-                     ("stream", {"ECUDA_EXACT_KERNEL": "stream"})):
+                     ("stream", {"ECUDA_EXACT_KERNEL": "stream"}), ("persist", {"ECUDA_PERSIST": "1"})):
         os.environ.update(env)  # read by ecuda_create
         try:
             ev = capi.Evaluator(wl, device=0)
@@ -441,7 +442,7 @@ def test_fast_and_generic_kernels_agree_bitwise(name):
             assert np.array_equal(out["fast-ldst"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["fast-image"][m][key], out["generic"][m][key]), (name, m, key)
             assert np.array_equal(out["columns"][m][key], out["generic"][m][key]), (name, m, key)
-            for tag in ("rows-r1", "ring", "stream"):
+            for tag in ("rows-r1", "ring", "stream", "persist"):
                 assert np.array_equal(out[tag][m][key], out["generic"][m][key]), (name, m, key, tag)
 
 
