@@ -1,14 +1,18 @@
 // oracle.hpp -- CPU oracle for the eCUDA hot path.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
-// PARITY UNPINNED: the reference (olasanni1/ETOL) ships no tests, golden vectors or expected outputs
-// for this path, and the arithmetic lives in PSOPT 5.0.0 / ADOL-C / IPOPT, which
-// are not vendored and cannot be built here. This oracle therefore restates
+// PARITY: the reference (olasanni1/ETOL) ships no tests, golden vectors or expected outputs for this path
+// (SURVEY.md section 4), and part of the arithmetic lives in PSOPT 5.0.0 / ADOL-C / IPOPT, which are not
+// vendored and cannot be built here. This oracle restates
 //   * the ETOL side from the in-tree sources it cites (src/ePSOPT/ePSOPT.cpp,
-//     src/Examples/PSOPT/etol_psopt_example1.cpp, include/ETOL/TrajectoryOptimizer.hpp), and
-//   * the PSOPT side from its published algorithm (Legendre/Chebyshev pseudospectral transcription,
-//     SURVEY.md Appendix A),
-// and is pinned only by the known answers derivable by hand from the in-tree formulas
-// (tests/golden/) and by closed-form identities of the method.
+//     src/Examples/PSOPT/etol_psopt_example1.cpp, include/ETOL/TrajectoryOptimizer.hpp). PINNED: those two
+//     reference files are compiled unmodified against a stub psopt.h (oracle/refstub, `make ref` ->
+//     oracle/_ref/libetol_ref.so) and their dae / integrand_cost / events / endpoint_cost / addBounds and the
+//     obs / saa lambdas are compared with this oracle at every node (tests/test_oracle_vs_reference.py; the same
+//     outputs are committed as tests/golden/c0_ref_pernode.npz);
+//   * the PSOPT side from its published algorithm (Legendre/Chebyshev pseudospectral transcription, layout,
+//     scaling, colouring, finite-difference step: SURVEY.md Appendix A). PARITY UNPINNED for this part: it is
+//     checked only against the known answers derivable by hand from the in-tree formulas (SURVEY.md Appendix B;
+//     tests/golden/) and closed-form identities of the method.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use
 // anything under oracle/. The product (etol_b200/, src/) never includes, links or calls it.
