@@ -363,12 +363,12 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
 // after issuing a store), so one CTA barrier per group is enough with three buffers.
 template <int M, int N, bool FD, int G, bool RING>
 struct RnGroups {
-    __device__ __forceinline__ static void run(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st,
-                                               double* ring, int cap, double* jac, int jpar, int tid) {
+    __device__ __forceinline__ static void run(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b,
+                                               RnRow<N>& st, double* ring, int cap, double* jac, int jpar, int tid) {
         constexpr int NS = Model<M>::NS;
         if (!RING) {  // straight into the global triplet array, no barrier
-            rn_group<M, N, FD, G, false>(pb, ph, m, st, jac);
-            RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, m, st, ring, cap, jac, jpar, tid);
+            rn_group<M, N, FD, G, false>(pb, ph, io, m, b, st, jac);
+            RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, io, m, b, st, ring, cap, jac, jpar, tid);
             return;
         }
         double* buf = ring + (G % kRnBufs) * cap;
@@ -376,7 +376,7 @@ struct RnGroups {
         const int c0 = FD ? m.rec[ca].cp : m.erec[ca].cp;
         // shared and global addresses must agree modulo 16 bytes: triplet e sits at buf[par + e - c0]
         const int par = (jpar + c0) & 1;
-        rn_group<M, N, FD, G, true>(pb, ph, m, st, buf + par - c0);
+        rn_group<M, N, FD, G, true>(pb, ph, io, m, b, st, buf + par - c0);
         fence_async_smem();  // generic-proxy writes to the buffer -> visible to the bulk copy
         __syncthreads();
         if (tid < 3) {  // thread 0: the bulk store; 1, 2: an unaligned first / last element
@@ -385,13 +385,13 @@ struct RnGroups {
             flush_range(jac + c0, buf, par, c1 - c0, tid, 0);
             if (tid == 0) bulk_wait_read_but_one();
         }
-        RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, m, st, ring, cap, jac, jpar, tid);
+        RnGroups<M, N, FD, G + 1, RING>::run(pb, ph, io, m, b, st, ring, cap, jac, jpar, tid);
     }
 };
 template <int M, int N, bool FD, bool RING>
 struct RnGroups<M, N, FD, (N + kRnGroup - 1) / kRnGroup, RING> {
-    __device__ __forceinline__ static void run(const ProbDev&, const PhaseDev&, const RnMem&, RnRow<N>&, double*, int, double*,
-                                               int, int) {}
+    __device__ __forceinline__ static void run(const ProbDev&, const PhaseDev&, const EvalIO&, const RnMem&, int, RnRow<N>&,
+                                               double*, int, double*, int, int) {}
 };
 
 // RING: the D-coupled triplets leave through the shared-memory store ring (TMA bulk stores per node group) instead
@@ -443,13 +443,14 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
 #endif
     if (io.jac) {  // uniform over the CTA
         double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-        RnGroups<M, N, FD, 0, RING>::run(pb, ph, m, st, ring, cap, jac, static_cast<int>((reinterpret_cast<uintptr_t>(jac) >> 3) & 1), tid);
+        RnGroups<M, N, FD, 0, RING>::run(pb, ph, io, m, b, st, ring, cap, jac,
+                                         static_cast<int>((reinterpret_cast<uintptr_t>(jac) >> 3) & 1), tid);
         if (RING) {
             if (tid == 0) bulk_wait_all();  // the groups' global writes are performed ...
             __syncthreads();                // ... before any thread writes a node-local triplet inside their ranges
         }
     }
-    rn_end<M, N, FD, TRK, SUM>(pb, ph, p, io, m, cm, b, tid, nthr, st, viol, fval);
+    rn_end<M, N, FD, TRK, SUM, RING>(pb, ph, p, io, m, cm, b, tid, nthr, st, viol, fval);
     if (SUM) {  // fused summary + all-gather epilogue (see k_eval_fast)
         __shared__ double red[kThreads / 32 + 1];
         double v = viol;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, ECUDA_MIN_CTAS_ROWSN_FD)
 #endif
         if (io.jac) {
             double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-            RnGroups<M, N, true, 0, false>::run(pb, ph, m, st, nullptr, 0, jac, 0, tid);
+            RnGroups<M, N, true, 0, false>::run(pb, ph, io, m, b, st, nullptr, 0, jac, 0, tid);
         }
         rn_end<M, N, true, TRK, false>(pb, ph, 0, io, m, cm, b, tid, nthr, st, viol, fval);
         __syncthreads();  // everyone is done with z / records / this instance's obstacle records

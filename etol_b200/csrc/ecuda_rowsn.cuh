@@ -118,6 +118,12 @@ ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N
 #ifndef ECUDA_RN_OBJWARP
 #define ECUDA_RN_OBJWARP 0
 #endif
+// ECUDA_RN_INTERLEAVE: run the node-local pieces of a defect row between the D-coupled node groups instead of after
+// the last one. Measured on C2: 0.167 ms interleaved, 0.159 ms at the end (the longer live ranges cost more than the
+// hidden latency saves), so it is off.
+#ifndef ECUDA_RN_INTERLEAVE
+#define ECUDA_RN_INTERLEAVE 0
+#endif
 // store ring: kRnBufs buffers, each holds the triplets of the state columns of kRnGroup consecutive nodes
 constexpr int kRnGroup = 4;  // nodes per group (half a summation block)
 constexpr int kRnBufs = 3;   // one barrier per group needs three buffers (see k_rows_n)
@@ -420,48 +426,52 @@ ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m,
 }
 
 // ---- finite differences, part 3: the node-local triplets of row (k,i)          [rows_jacobian<FD>, node-local part]
-// Runs after every D-coupled group has been stored (the bulk stores are complete): a slot inside a group's range that
-// this part writes overwrites what the ring buffer held there.
-template <int M, int N>
-ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
+// One PIECE per column of the node: P < NS the state column X(k,P), NS <= P < NS + 8 the control column U(k,P-NS),
+// then t0 and tf. A piece is straight-line code (loads, two evaluations of the dynamics, one store), independent of
+// the D-coupled groups. They run after the last group; ECUDA_RN_INTERLEAVE runs piece P right after node group
+// P % ngroups instead (tried to hide their dependent loads behind the groups' FP64 work: slower, see the macro).
+// For models whose f_i reads x_i the row's own state column needs the perturbed diagonal dots and must be written
+// after the group that stores the provisional diagonal value: rn_fd_end does it.
+constexpr int kRnPieces = ECUDA_MAX_STATES + ECUDA_MAX_CONTROLS + 2;
+template <int M, int N, int P>
+ECUDA_HD void rn_fd_piece(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st,
+                          bool own_diag) {
     constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
+    constexpr bool DS = Model<M>::DIAG_FREE;
+    constexpr bool IS_X = P < NS, IS_U = P >= ECUDA_MAX_STATES && P < ECUDA_MAX_STATES + ECUDA_MAX_CONTROLS,
+                   IS_T = P >= ECUDA_MAX_STATES + ECUDA_MAX_CONTROLS;
+    if (!(IS_X || IS_U || IS_T)) return;  // state slots beyond the model's states
     if (!st.row || !io.jac) return;
     const int nc = pb.nc, i = st.i, k = st.k;
+    if (IS_U && P - ECUDA_MAX_STATES >= nc) return;  // uniform over the CTA
+    if (IS_X && !own_diag && !DS && P == i) return;  // the row's own column: see rn_fd_end
+    if (IS_X && own_diag && P != i) return;
     const double sgr = st.sgr;
-    const double (&P)[NB] = st.P;
     const double* zx = m.z + nc * N;
-    const double* Dtk = m.dt + k;
-    const double* Xi = zx + i;
     double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
-    constexpr bool DS = Model<M>::DIAG_FREE;
-    const FdRec* rx = m.rec + nc * N;  // record of X(l,j) = rx[l*NS + j]
     const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
     const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
     const double tau = m.tau[k];
     const double t = h * tau + mid;
-    double dv = P[0];
+    double dv = st.P[0];
 #pragma unroll
-    for (int bi = 1; bi < NB; ++bi) dv = dv + P[bi];
+    for (int bi = 1; bi < NB; ++bi) dv = dv + st.P[bi];
     double x[NS], u[NCU];
 #pragma unroll
     for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
 #pragma unroll
     for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
-    double dpk = 0.0, dmk = 0.0;
-    if (!DS) {
-        const FdRec& rc = rx[k * NS + i];
-        rn_diag<NS, N>(Dtk, Xi, rc.xp, rc.xm, k, P, dpk, dmk);
-    }
-    // the node's state columns X(k,j)                                   [xcol_local_fd, row i]
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
+    if (IS_X) {  // the node's state column X(k,j)                          [xcol_local_fd, row i]
+        constexpr int j = IS_X ? P : 0;
         const int rk = pb.xrank[j][i];
-        if (rk < 0 || (DS && j == i)) continue;
-        const FdRec& rc = rx[k * NS + j];
+        if (rk < 0 || (DS && j == i)) return;
+        const FdRec& rc = m.rec[nc * N + k * NS + j];
         if (j != i && !reads_state<M>(i, j)) {  // f_i does not read x_j: g+ == g- bit for bit
             ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), 0.0);
-            continue;
+            return;
         }
+        double dpk = 0.0, dmk = 0.0;
+        if (!DS && j == i) rn_diag<NS, N>(m.dt + k, zx + i, rc.xp, rc.xm, k, st.P, dpk, dmk);
         double xq[NS], xr[NS], fp[NS], fm[NS];
 #pragma unroll
         for (int a = 0; a < NS; ++a) {
@@ -480,38 +490,39 @@ ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
         const double gp = sgr * (((i == j) ? dpk : dv) - h * fpi);
         const double gm = sgr * (((i == j) ? dmk : dv) - h * fmi);
         ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
-    }
-    // the node's control columns U(k,c)                                 [node_item, c < nc, row i]
-    for (int c = 0; c < nc; ++c) {
+    } else if (IS_U) {  // the node's control column U(k,c)                 [node_item, c < nc, row i]
+        constexpr int c = IS_U ? P - ECUDA_MAX_STATES : 0;
         const int rk = pb.urank[c][i];
-        if (rk < 0) continue;
+        if (rk < 0) return;
         const FdRec& rc = m.rec[k * nc + c];
-        if (c >= NCU || !reads_control<M>(i, c)) {  // unused or unread control: exactly +0.0
+        if constexpr (c >= NCU) {  // a control the model does not use: exactly +0.0
             ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
-            continue;
-        }
-        double up[NCU], um[NCU], fp[NS], fm[NS];
-#pragma unroll
-        for (int a = 0; a < NCU; ++a) {
-            up[a] = (a == c) ? rc.xp : u[a];
-            um[a] = (a == c) ? rc.xm : u[a];
-        }
-        Model<M>::f(x, up, t, fp);
-        Model<M>::f(x, um, t, fm);
-        double fpi = 0.0, fmi = 0.0;
-#pragma unroll
-        for (int a = 0; a < NS; ++a)
-            if (a == i) {
-                fpi = fp[a];
-                fmi = fm[a];
+        } else {
+            if (!reads_control<M>(i, c)) {  // unread control: exactly +0.0
+                ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+                return;
             }
-        const double gp = sgr * (dv - h * fpi);
-        const double gm = sgr * (dv - h * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
-    }
-    // t0 / tf columns                                                    [node_item, time columns, row i]
+            double up[NCU], um[NCU], fp[NS], fm[NS];
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
+            for (int a = 0; a < NCU; ++a) {
+                up[a] = (a == c) ? rc.xp : u[a];
+                um[a] = (a == c) ? rc.xm : u[a];
+            }
+            Model<M>::f(x, up, t, fp);
+            Model<M>::f(x, um, t, fm);
+            double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+                if (a == i) {
+                    fpi = fp[a];
+                    fmi = fm[a];
+                }
+            const double gp = sgr * (dv - h * fpi);
+            const double gm = sgr * (dv - h * fmi);
+            ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
+        }
+    } else {  // t0 / tf column                                            [node_item, time columns, row i]
+        constexpr int which = IS_T ? P - ECUDA_MAX_STATES - ECUDA_MAX_CONTROLS : 0;
         const FdRec& rc = m.rec[(NS + nc) * N + which];
         const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
         const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
@@ -532,6 +543,37 @@ ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
         const double gm = sgr * (dv - hm * fmi);
         ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
     }
+}
+// the pieces that run after node group G: P = G, G + ngroups, ...
+template <int M, int N, int G, int P = G>
+struct RnPiecesAfter {
+    ECUDA_HD static void run(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b,
+                             const RnRow<N>& st) {
+        rn_fd_piece<M, N, P>(pb, ph, io, m, b, st, false);
+        RnPiecesAfter<M, N, G, (P + (N + kRnGroup - 1) / kRnGroup < kRnPieces) ? P + (N + kRnGroup - 1) / kRnGroup : -1>::run(
+            pb, ph, io, m, b, st);
+    }
+};
+template <int M, int N, int G>
+struct RnPiecesAfter<M, N, G, -1> {
+    ECUDA_HD static void run(const ProbDev&, const PhaseDev&, const EvalIO&, const RnMem&, int, const RnRow<N>&) {}
+};
+// what is left after the last group: the row's own state column for models whose f_i reads x_i
+template <int M, int N, int J = 0>
+struct RnOwnDiag {
+    ECUDA_HD static void run(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b,
+                             const RnRow<N>& st) {
+        rn_fd_piece<M, N, J>(pb, ph, io, m, b, st, true);
+        RnOwnDiag<M, N, J + 1>::run(pb, ph, io, m, b, st);
+    }
+};
+template <int M, int N>
+struct RnOwnDiag<M, N, Model<M>::NS> {
+    ECUDA_HD static void run(const ProbDev&, const PhaseDev&, const EvalIO&, const RnMem&, int, const RnRow<N>&) {}
+};
+template <int M, int N>
+ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
+    if (!Model<M>::DIAG_FREE) RnOwnDiag<M, N>::run(pb, ph, io, m, b, st);
 }
 
 // path row q at (x, y, t); TRK = false: the problem has no moving zones, every path row is a static record
@@ -1038,12 +1080,30 @@ ECUDA_HD void rn_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
         rn_ex_begin<M, N, SUM>(pb, ph, io, m, cm, b, tid, st, viol);
 }
 template <int M, int N, bool FD, int G, bool RING>
-ECUDA_HD void rn_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
-    if (FD)
+ECUDA_HD void rn_group(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, RnRow<N>& st,
+                       double* out) {
+    if (FD) {
         rn_fd_group<Model<M>::NS, N, G, RING>(pb, ph, m, st, out);
-    else
+        // node-local pieces interleaved with the groups (direct stores; with the store ring they would have to wait
+        // for the bulk stores, so the ring variant keeps them for the end)
+        if (!RING && ECUDA_RN_INTERLEAVE) RnPiecesAfter<M, N, G>::run(pb, ph, io, m, b, st);
+    } else {
         rn_ex_group<Model<M>::NS, N, G, RING>(pb, ph, m, st, out);
+    }
 }
+// every piece at once (the store-ring variant, after its bulk stores are complete)
+template <int M, int N, int G = 0>
+struct RnAllPieces {
+    ECUDA_HD static void run(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b,
+                             const RnRow<N>& st) {
+        RnPiecesAfter<M, N, G>::run(pb, ph, io, m, b, st);
+        RnAllPieces<M, N, G + 1>::run(pb, ph, io, m, b, st);
+    }
+};
+template <int M, int N>
+struct RnAllPieces<M, N, (N + kRnGroup - 1) / kRnGroup> {
+    ECUDA_HD static void run(const ProbDev&, const PhaseDev&, const EvalIO&, const RnMem&, int, const RnRow<N>&) {}
+};
 template <int N>
 ECUDA_HD constexpr int rn_ngroups() { return (N + kRnGroup - 1) / kRnGroup; }
 // triplet range [c0, c1) of the state columns of node group g: from the first state column of its first node to the
@@ -1056,13 +1116,16 @@ ECUDA_HD void rn_group_range(const ProbDev& pb, const RnMem& m, int g, int& c0, 
     c0 = FD ? m.rec[a].cp : m.erec[a].cp;
     c1 = FD ? m.rec[e].cp : m.erec[e].cp;
 }
-template <int M, int N, bool FD, bool TRK, bool SUM>
+// RING: the FD node-local pieces have not run yet (see rn_group)
+template <int M, int N, bool FD, bool TRK, bool SUM, bool RING = false>
 ECUDA_HD void rn_end(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
                      int tid, int nthr, const RnRow<N>& st, double& viol, double& fval) {
-    if (FD)
+    if (FD) {
+        if (RING || !ECUDA_RN_INTERLEAVE) RnAllPieces<M, N>::run(pb, ph, io, m, b, st);
         rn_fd_end<M, N>(pb, ph, io, m, b, st);
-    else
+    } else {
         rn_ex_end<M, N>(pb, ph, io, m, b, st);
+    }
     const int nitems = rn_items<M, N>(pb, ph, p);
     for (int it = nthr - 1 - tid; it < nitems; it += nthr) {
         if (FD)
@@ -1074,16 +1137,17 @@ ECUDA_HD void rn_end(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO&
 // node group by run-time index (the kernel-logic emulator of the test-suite; the kernel unrolls the groups)
 template <int M, int N, bool FD, int G = 0>
 struct RnGroupRt {
-    ECUDA_HD static void run(int g, const ProbDev& pb, const PhaseDev& ph, const RnMem& m, RnRow<N>& st, double* out) {
+    ECUDA_HD static void run(int g, const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b,
+                             RnRow<N>& st, double* out) {
         if (g == G)
-            rn_group<M, N, FD, G, false>(pb, ph, m, st, out);
+            rn_group<M, N, FD, G, false>(pb, ph, io, m, b, st, out);
         else
-            RnGroupRt<M, N, FD, G + 1>::run(g, pb, ph, m, st, out);
+            RnGroupRt<M, N, FD, G + 1>::run(g, pb, ph, io, m, b, st, out);
     }
 };
 template <int M, int N, bool FD>
 struct RnGroupRt<M, N, FD, (N + kRnGroup - 1) / kRnGroup> {
-    ECUDA_HD static void run(int, const ProbDev&, const PhaseDev&, const RnMem&, RnRow<N>&, double*) {}
+    ECUDA_HD static void run(int, const ProbDev&, const PhaseDev&, const EvalIO&, const RnMem&, int, RnRow<N>&, double*) {}
 };
 
 }  // namespace ecuda

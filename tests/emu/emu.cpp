@@ -95,7 +95,8 @@ static void run_rowsn_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         double* out = io.jac + static_cast<size_t>(b) * pb.nnz;
         for (int g = 0; g < rn_ngroups<N>(); ++g)
             for (int t = 0; t < nthr; ++t) {
-                if (FD) RnGroupRt<M, N, true>::run(g, pb, ph, m, st[t], out); else RnGroupRt<M, N, false>::run(g, pb, ph, m, st[t], out);
+                if (FD) RnGroupRt<M, N, true>::run(g, pb, ph, io, m, b, st[t], out);
+                else RnGroupRt<M, N, false>::run(g, pb, ph, io, m, b, st[t], out);
             }
     }
     for (int t = 0; t < nthr; ++t) {
