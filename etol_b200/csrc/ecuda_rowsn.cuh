@@ -118,9 +118,9 @@ ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N
 #ifndef ECUDA_RN_OBJWARP
 #define ECUDA_RN_OBJWARP 0
 #endif
-// ECUDA_RN_INTERLEAVE: run the node-local pieces of a defect row between the D-coupled node groups instead of after
-// the last one. Measured on C2: 0.167 ms interleaved, 0.159 ms at the end (the longer live ranges cost more than the
-// hidden latency saves), so it is off.
+// ECUDA_RN_INTERLEAVE: the node-local triplets of a defect row as separate pieces that run between the D-coupled node
+// groups instead of as one function after the last one. Measured on C2: 0.167 ms as pieces (interleaved or all at
+// the end: each piece reloads the node's variables), 0.159 ms as one function, so it is off.
 #ifndef ECUDA_RN_INTERLEAVE
 #define ECUDA_RN_INTERLEAVE 0
 #endif
@@ -425,7 +425,123 @@ ECUDA_HD void rn_fd_group(const ProbDev& pb, const PhaseDev& ph, const RnMem& m,
     }
 }
 
-// ---- finite differences, part 3: the node-local triplets of row (k,i)          [rows_jacobian<FD>, node-local part]
+// ---- finite differences, part 3: the node-local triplets of row (k,i), all columns in one function
+// [rows_jacobian<FD>, node-local part]
+// Runs after every D-coupled group has been stored (the bulk stores are complete): a slot inside a group's range that
+// this part writes overwrites what the ring buffer held there.
+template <int M, int N>
+ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
+    constexpr int NS = Model<M>::NS, NCU = Model<M>::NCU, NB = (N + 7) / 8;
+    if (!st.row || !io.jac) return;
+    const int nc = pb.nc, i = st.i, k = st.k;
+    const double sgr = st.sgr;
+    const double (&P)[NB] = st.P;
+    const double* zx = m.z + nc * N;
+    const double* Dtk = m.dt + k;
+    const double* Xi = zx + i;
+    double* jac = io.jac + static_cast<size_t>(b) * pb.nnz;
+    constexpr bool DS = Model<M>::DIAG_FREE;
+    const FdRec* rx = m.rec + nc * N;  // record of X(l,j) = rx[l*NS + j]
+    const double t0 = m.z[(NS + nc) * N], tf = m.z[(NS + nc) * N + 1];
+    const double h = 0.5 * (tf - t0), mid = 0.5 * (tf + t0);
+    const double tau = m.tau[k];
+    const double t = h * tau + mid;
+    double dv = P[0];
+#pragma unroll
+    for (int bi = 1; bi < NB; ++bi) dv = dv + P[bi];
+    double x[NS], u[NCU];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) x[a] = zx[k * NS + a];
+#pragma unroll
+    for (int a = 0; a < NCU; ++a) u[a] = m.z[k * nc + a];
+    double dpk = 0.0, dmk = 0.0;
+    if (!DS) {
+        const FdRec& rc = rx[k * NS + i];
+        rn_diag<NS, N>(Dtk, Xi, rc.xp, rc.xm, k, P, dpk, dmk);
+    }
+    // the node's state columns X(k,j)                                   [xcol_local_fd, row i]
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int rk = pb.xrank[j][i];
+        if (rk < 0 || (DS && j == i)) continue;
+        const FdRec& rc = rx[k * NS + j];
+        if (j != i && !reads_state<M>(i, j)) {  // f_i does not read x_j: g+ == g- bit for bit
+            ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), 0.0);
+            continue;
+        }
+        double xq[NS], xr[NS], fp[NS], fm[NS];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            xq[a] = (a == j) ? rc.xp : x[a];
+            xr[a] = (a == j) ? rc.xm : x[a];
+        }
+        Model<M>::f(xq, u, t, fp);
+        Model<M>::f(xr, u, t, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (((i == j) ? dpk : dv) - h * fpi);
+        const double gm = sgr * (((i == j) ? dmk : dv) - h * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
+    }
+    // the node's control columns U(k,c)                                 [node_item, c < nc, row i]
+    for (int c = 0; c < nc; ++c) {
+        const int rk = pb.urank[c][i];
+        if (rk < 0) continue;
+        const FdRec& rc = m.rec[k * nc + c];
+        if (c >= NCU || !reads_control<M>(i, c)) {  // unused or unread control: exactly +0.0
+            ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+            continue;
+        }
+        double up[NCU], um[NCU], fp[NS], fm[NS];
+#pragma unroll
+        for (int a = 0; a < NCU; ++a) {
+            up[a] = (a == c) ? rc.xp : u[a];
+            um[a] = (a == c) ? rc.xm : u[a];
+        }
+        Model<M>::f(x, up, t, fp);
+        Model<M>::f(x, um, t, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (dv - h * fpi);
+        const double gm = sgr * (dv - h * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
+    }
+    // t0 / tf columns                                                    [node_item, time columns, row i]
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const FdRec& rc = m.rec[(NS + nc) * N + which];
+        const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
+        const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
+        const double hp = 0.5 * (tfp - t0p), mp = 0.5 * (tfp + t0p);
+        const double hm = 0.5 * (tfm - t0m), mm = 0.5 * (tfm + t0m);
+        const double tp = hp * tau + mp, tm = hm * tau + mm;
+        double fp[NS], fm[NS];
+        Model<M>::f(x, u, tp, fp);
+        Model<M>::f(x, u, tm, fm);
+        double fpi = 0.0, fmi = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) {
+                fpi = fp[a];
+                fmi = fm[a];
+            }
+        const double gp = sgr * (dv - hp * fpi);
+        const double gm = sgr * (dv - hm * fmi);
+        ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
+    }
+}
+
+// ---- the same triplets as separate PIECES (ECUDA_RN_INTERLEAVE and the store-ring variant)
 // One PIECE per column of the node: P < NS the state column X(k,P), NS <= P < NS + 8 the control column U(k,P-NS),
 // then t0 and tf. A piece is straight-line code (loads, two evaluations of the dynamics, one store), independent of
 // the D-coupled groups. They run after the last group; ECUDA_RN_INTERLEAVE runs piece P right after node group
@@ -573,7 +689,11 @@ struct RnOwnDiag<M, N, Model<M>::NS> {
 };
 template <int M, int N>
 ECUDA_HD void rn_fd_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, const RnMem& m, int b, const RnRow<N>& st) {
-    if (!Model<M>::DIAG_FREE) RnOwnDiag<M, N>::run(pb, ph, io, m, b, st);
+    if (ECUDA_RN_INTERLEAVE) {
+        if (!Model<M>::DIAG_FREE) RnOwnDiag<M, N>::run(pb, ph, io, m, b, st);
+    } else {
+        rn_fd_local_all<M, N>(pb, ph, io, m, b, st);  // one function: 0.159 ms on C2; as pieces run at the end 0.167 ms
+    }
 }
 
 // path row q at (x, y, t); TRK = false: the problem has no moving zones, every path row is a static record
@@ -1121,7 +1241,7 @@ template <int M, int N, bool FD, bool TRK, bool SUM, bool RING = false>
 ECUDA_HD void rn_end(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO& io, const RnMem& m, const CtaMem& cm, int b,
                      int tid, int nthr, const RnRow<N>& st, double& viol, double& fval) {
     if (FD) {
-        if (RING || !ECUDA_RN_INTERLEAVE) RnAllPieces<M, N>::run(pb, ph, io, m, b, st);
+        if (RING && ECUDA_RN_INTERLEAVE) RnAllPieces<M, N>::run(pb, ph, io, m, b, st);
         rn_fd_end<M, N>(pb, ph, io, m, b, st);
     } else {
         rn_ex_end<M, N>(pb, ph, io, m, b, st);
