@@ -410,7 +410,7 @@ def run_ecuda(args):
         try:
             tj = json.load(open(tpath))
             traffic = tj.get(f"k_eval_{args.jac}_C2_bytes_per_launch")
-            tsrc = tj.get("source", "ncu capture (profiles/traffic.json), not a measurement of this run")
+            tsrc = tj.get(f"k_eval_{args.jac}_C2_source", "ncu capture") + " -- an ncu capture recorded in profiles/traffic.json, not a measurement of this run"
             ops = tj.get(f"k_eval_{args.jac}_C2_fp64_thread_instr_per_launch")
             if ops:
                 # second roof of the finite-difference kernel: FP64 pipe. Peak measured now with a
@@ -425,7 +425,7 @@ def run_ecuda(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": tsrc, "kernel": f"k_rows_n<pm3d,40> ({args.jac})",
+                "traffic": traffic, "traffic_source": tsrc, "kernel": "k_rows_n<pm3d,40,FD>" if args.jac == "fd" else "k_eval_rows<pm3d,5,exact>",
                 "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_unit": alg_bytes_unit, "units_per_launch": B,
                 "peak_source": peak_src}
     if fp64:
