@@ -52,9 +52,10 @@ ABI_SYMBOLS = [
     "ecuda_abi_version", "ecuda_create", "ecuda_destroy", "ecuda_last_error", "ecuda_set_problem",
     "ecuda_get_dims", "ecuda_get_structure", "ecuda_get_collocation", "ecuda_set_collocation",
     "ecuda_set_scaling", "ecuda_upload_instances", "ecuda_upload_bounds", "ecuda_eval", "ecuda_eval_grad_f",
+    "ecuda_get_compact_structure", "ecuda_eval_compact", "ecuda_splice_jacobian",
     "ecuda_summary", "ecuda_summarize", "ecuda_summarize_allgather", "ecuda_eval_allgather", "ecuda_peer_barrier", "ecuda_peer_barrier_status", "ecuda_sync", "ecuda_launch_count", "ecuda_fp64_peak", "ecuda_ipopt_eval_f", "ecuda_ipopt_eval_grad_f",
     "ecuda_ipopt_eval_g", "ecuda_ipopt_eval_jac_g", "ecuda_set_ipopt_jac_mode", "ecuda_si2d_edge_records",
-    "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
+    "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_compact_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
     "ecuda_host_path_eval", "ecuda_get_hess_structure", "ecuda_eval_hess", "ecuda_ipopt_eval_h", "ecuda_host_hess_structure",
     "ecuda_ode_error", "ecuda_resample", "ecuda_host_error_mesh", "ecuda_host_resample_matrix",
     "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
@@ -86,6 +87,9 @@ def lib():
     L.ecuda_upload_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ecuda_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                              C.c_void_p]
+    L.ecuda_get_compact_structure.argtypes = [C.c_void_p, _ip, _ip, _dp]
+    L.ecuda_eval_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ecuda_splice_jacobian.argtypes = [_dp, _ip, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     L.ecuda_eval_grad_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_summarize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -108,6 +112,7 @@ def lib():
     L.ecuda_si2d_edge_records.argtypes = [_dp, C.c_int, _dp]
     L.ecuda_host_dims.argtypes = [C.POINTER(ProblemDesc), C.POINTER(Dims)]
     L.ecuda_host_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip, _ip]
+    L.ecuda_host_compact_structure.argtypes = [C.POINTER(ProblemDesc), _ip, _ip]
     L.ecuda_host_collocation.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
     L.ecuda_host_model_eval.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, _dp]
     L.ecuda_get_hess_structure.argtypes = [C.c_void_p, _ip, _ip, _ip]
@@ -211,6 +216,29 @@ def host_structure(wl):
     if rc != 0:
         raise EcudaError("ecuda_host_structure failed")
     return irow, jcol, grp
+
+
+def host_compact_structure(wl):
+    """ascending triplet indices of the per-instance part of an exact Jacobian (ecuda_eval_compact)"""
+    d = make_desc(wl)
+    n = C.c_int32(0)
+    if lib().ecuda_host_compact_structure(C.byref(d), C.byref(n), None):
+        raise EcudaError("ecuda_host_compact_structure failed")
+    idx = np.zeros(n.value, dtype=np.int32)
+    lib().ecuda_host_compact_structure(C.byref(d), None, idx.ctypes.data_as(_ip))
+    return idx
+
+
+def splice_jacobian(shared, idx, jac_local, nnz):
+    jac_local = np.ascontiguousarray(jac_local, dtype=np.float64)
+    shared = np.ascontiguousarray(shared, dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    full = np.empty((jac_local.shape[0], nnz))
+    rc = lib().ecuda_splice_jacobian(_p(shared), idx.ctypes.data_as(_ip), nnz, len(idx), jac_local.ctypes.data,
+                                     jac_local.shape[0], full.ctypes.data)
+    if rc:
+        raise EcudaError(f"ecuda_splice_jacobian: {rc}")
+    return full
 
 
 def host_hess_structure(wl):
@@ -355,6 +383,28 @@ class Evaluator:
             self._check(self.L.ecuda_eval_grad_f(self.h, x.ctypes.data, grad.ctypes.data, MEM_HOST, None))
             out["grad"] = grad
         return out
+
+    # ---- compact exact Jacobian: per-instance triplets only (ecuda.h "compact exact Jacobian") ---------
+    def compact_structure(self):
+        """(local_index [nlocal] int32, shared_vals [nnz])"""
+        n = C.c_int32(0)
+        self._check(self.L.ecuda_get_compact_structure(self.h, C.byref(n), None, None))
+        idx = np.zeros(n.value, dtype=np.int32)
+        shared = np.zeros(self.nnz)
+        self._check(self.L.ecuda_get_compact_structure(self.h, None, idx.ctypes.data_as(_ip), _p(shared)))
+        return idx, shared
+
+    def eval_compact_host(self, x, nlocal):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.batch, self.nvars)
+        f, g, jl = np.zeros(self.batch), np.zeros((self.batch, self.ncons)), np.zeros((self.batch, nlocal))
+        self._check(self.L.ecuda_eval_compact(self.h, x.ctypes.data, f.ctypes.data, g.ctypes.data, jl.ctypes.data, MEM_HOST, None))
+        return dict(f=f, g=g, jac_local=jl)
+
+    def eval_compact_ptr(self, x_ptr, f_ptr, g_ptr, jl_ptr, memkind, stream=None):
+        self._check(self.L.ecuda_eval_compact(self.h, x_ptr, f_ptr, g_ptr, jl_ptr, memkind, stream))
+
+    def splice(self, shared, idx, jac_local):
+        return splice_jacobian(shared, idx, jac_local, self.nnz)
 
     # ---- raw-pointer evaluation (device tensors or pinned host tensors from torch) -----------------
     def eval_ptr(self, x_ptr, f_ptr, g_ptr, jac_ptr, jac_mode, memkind, stream=None):

@@ -198,6 +198,18 @@ __global__ void k_bounds_compact(const double* gl, const double* gu, int batch, 
     bev[static_cast<size_t>(b) * 2 * nev + nev + e] = gu[src];
 }
 
+// ecuda_eval_compact: the per-instance triplets of an exact Jacobian gathered out of the full array.
+// One CTA row per instance (grid.y) so the index list is read once per CTA column and stays in L1/L2;
+// loads are streaming (the full array is scratch), stores are coalesced.
+__global__ void __launch_bounds__(256) k_gather_local(const double* __restrict__ jac, const int32_t* __restrict__ idx,
+                                                      double* __restrict__ out, int nnz, int nlocal) {
+    const size_t b = blockIdx.y;
+    const double* src = jac + b * static_cast<size_t>(nnz);
+    double* dst = out + b * static_cast<size_t>(nlocal);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x)
+        __stcs(dst + i, __ldcs(src + __ldg(idx + i)));
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -206,6 +218,8 @@ struct DevBuf {
 }  // namespace ecuda
 
 using namespace ecuda;
+
+constexpr int kMaxHostChunks = 8;
 
 struct ecuda_ctx {
     int device = 0;
@@ -255,6 +269,13 @@ struct ecuda_ctx {
     DevBuf mesh[ECUDA_MAX_PHASES];  // E | dE | wq | tq per phase
     bool have_mesh = false;
     DevBuf serr, resmat, sxnew, ssznew;
+    // compact exact output (ecuda_eval_compact): indices of the per-instance triplets, built on first use
+    std::vector<int32_t> local_index;
+    DevBuf lidx, sjl;
+    // HOST-buffer calls are pipelined over instance chunks (eval_host): copy streams and their events
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_entry = nullptr, ev_done = nullptr, ev_x[kMaxHostChunks] = {}, ev_k[kMaxHostChunks] = {};
+    int host_chunks = 0;  // ECUDA_HOST_CHUNKS=1..8 in the environment; 0 = automatic (4 when the results exceed 16 MB)
 };
 
 static std::string g_create_err;
@@ -734,8 +755,24 @@ int ecuda_create(int device, ecuda_handle* out) {
         const char* nw = std::getenv("ECUDA_NO_COPY_WARP");
         h->no_copy_warp = nw && nw[0] == '1';
     }
+    {
+        const char* hc = std::getenv("ECUDA_HOST_CHUNKS");
+        const int v = hc ? std::atoi(hc) : 0;
+        h->host_chunks = v >= 1 && v <= kMaxHostChunks ? v : 0;
+    }
+    auto make_events = [&]() {
+        cudaError_t r = cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming);
+        if (r == cudaSuccess) r = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+        for (int c = 0; c < kMaxHostChunks && r == cudaSuccess; ++c) {
+            r = cudaEventCreateWithFlags(&h->ev_x[c], cudaEventDisableTiming);
+            if (r == cudaSuccess) r = cudaEventCreateWithFlags(&h->ev_k[c], cudaEventDisableTiming);
+        }
+        return r;
+    };
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess || (e = make_events()) != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
         delete h;
         return fail(nullptr, ECUDA_ERR_CUDA, msg);
@@ -748,7 +785,7 @@ int ecuda_destroy(ecuda_handle h) {
     if (!h) return ECUDA_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->bflag, &h->desc, &h->sx, &h->sf_, &h->sgv,
+    for (DevBuf* b : {&h->colptr, &h->isz, &h->sg, &h->inst, &h->gl, &h->gu, &h->fpart, &h->jtmpl, &h->bflag, &h->desc, &h->lidx, &h->sjl, &h->sx, &h->sf_, &h->sgv,
                       &h->sjac, &h->sgrad, &h->ssum})
         release(*b);
     for (auto& b : h->coll) release(b);
@@ -756,6 +793,14 @@ int ecuda_destroy(ecuda_handle h) {
     for (DevBuf* b : {&h->serr, &h->resmat, &h->sxnew, &h->ssznew, &h->slam, &h->ssig, &h->shess, &h->bev, &h->bcls}) release(*b);
     unload_user_kernels(h);
     cudaStreamDestroy(h->stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->ev_entry) cudaEventDestroy(h->ev_entry);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int c = 0; c < kMaxHostChunks; ++c) {
+        if (h->ev_x[c]) cudaEventDestroy(h->ev_x[c]);
+        if (h->ev_k[c]) cudaEventDestroy(h->ev_k[c]);
+    }
     delete h;
     return ECUDA_OK;
 }
@@ -772,6 +817,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     for (int p = 0; p < hp.nphases; ++p)
         if (!build_collocation(desc->collocation, hp.N[p], &hp.col[p], &err)) return fail(h, ECUDA_ERR_ARG, err);
     h->hp = hp;
+    h->local_index.clear();
     h->have_problem = false;
     h->have_inst = false;
     h->have_bounds = false;
@@ -983,6 +1029,77 @@ int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int 
     return ECUDA_OK;
 }
 
+// HOST-buffer evaluation: the batch goes through the device in chunks of instances on three streams -- host->device
+// copies of x on h->s_h2d, kernels on the caller's stream, device->host copies on h->s_d2h -- so that the upload
+// of chunk c+1 and the kernels of chunk c+1 overlap the download of chunk c (the download is > 95 % of the call:
+// 106 KB of results per instance against 2.9 KB of input). jac_local != null: exact mode, the full triplet array
+// stays in device scratch and only the per-instance triplets (k_gather_local) are downloaded.
+static int eval_host(ecuda_ctx* h, const double* x, double* f, double* g, double* jac, double* grad, double* jac_local,
+                     int jac_mode, cudaStream_t st) {
+    const size_t B = h->hp.desc.batch, nv = h->pd.nvars, ng = h->pd.ncons, nz = h->pd.nnz;
+    const size_t nl = jac_local ? h->local_index.size() : 0;
+    const bool want_full = jac || jac_local;
+    int rc;
+    if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
+    if (f && (rc = ensure(h, h->sf_, sizeof(double) * B))) return rc;
+    if (g && (rc = ensure(h, h->sgv, sizeof(double) * B * ng))) return rc;
+    if (want_full && (rc = ensure(h, h->sjac, sizeof(double) * B * nz))) return rc;
+    if (jac_local && (rc = ensure(h, h->sjl, sizeof(double) * B * nl))) return rc;
+    if (grad && (rc = ensure(h, h->sgrad, sizeof(double) * B * nv))) return rc;
+    const size_t out_bytes = 8 * B * ((f ? 1 : 0) + (g ? ng : 0) + (jac ? nz : 0) + nl + (grad ? nv : 0));
+    int K = h->host_chunks > 0 ? h->host_chunks : (out_bytes >= (size_t(16) << 20) ? 4 : 1);
+    if (static_cast<size_t>(K) > B) K = static_cast<int>(B);
+    if (K > kMaxHostChunks) K = kMaxHostChunks;
+    double* dx = static_cast<double*>(h->sx.p);
+    double* df = f ? static_cast<double*>(h->sf_.p) : nullptr;
+    double* dg = g ? static_cast<double*>(h->sgv.p) : nullptr;
+    double* dj = want_full ? static_cast<double*>(h->sjac.p) : nullptr;
+    double* djl = jac_local ? static_cast<double*>(h->sjl.p) : nullptr;
+    double* dgr = grad ? static_cast<double*>(h->sgrad.p) : nullptr;
+    // the copy streams start behind whatever the caller has queued on st
+    CU(cudaEventRecord(h->ev_entry, st));
+    CU(cudaStreamWaitEvent(h->s_h2d, h->ev_entry, 0));
+    CU(cudaStreamWaitEvent(h->s_d2h, h->ev_entry, 0));
+    for (int c = 0; c < K; ++c) {
+        const size_t b0 = B * c / K, nb = B * (c + 1) / K - b0;
+        CU(cudaMemcpyAsync(dx + b0 * nv, x + b0 * nv, sizeof(double) * nb * nv, cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaEventRecord(h->ev_x[c], h->s_h2d));
+    }
+    for (int c = 0; c < K; ++c) {
+        const size_t b0 = B * c / K, nb = B * (c + 1) / K - b0;
+        CU(cudaStreamWaitEvent(st, h->ev_x[c], 0));
+        EvalIO io{};
+        io.inst = static_cast<const double*>(h->inst.p) + b0 * h->pd.inst_stride;
+        io.fpart = static_cast<double*>(h->fpart.p) + b0 * h->pd.nphases;
+        io.jac_mode = jac_mode;
+        io.batch = static_cast<int>(nb);
+        io.x = dx + b0 * nv;
+        io.f = df ? df + b0 : nullptr;
+        io.g = dg ? dg + b0 * ng : nullptr;
+        io.jac = dj ? dj + b0 * nz : nullptr;
+        io.grad = dgr ? dgr + b0 * nv : nullptr;
+        if ((rc = launch_eval(h, io, st))) return rc;
+        if (jac_local) {
+            const dim3 grid(static_cast<unsigned>((nl + 255) / 256), static_cast<unsigned>(nb));
+            k_gather_local<<<grid, 256, 0, st>>>(io.jac, static_cast<const int32_t*>(h->lidx.p), djl + b0 * nl, (int)nz, (int)nl);
+            ++h->launches;
+        }
+        CU(cudaEventRecord(h->ev_k[c], st));
+        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_k[c], 0));
+        if (f) CU(cudaMemcpyAsync(f + b0, df + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (g) CU(cudaMemcpyAsync(g + b0 * ng, dg + b0 * ng, sizeof(double) * nb * ng, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (jac) CU(cudaMemcpyAsync(jac + b0 * nz, dj + b0 * nz, sizeof(double) * nb * nz, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (jac_local) CU(cudaMemcpyAsync(jac_local + b0 * nl, djl + b0 * nl, sizeof(double) * nb * nl, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (grad) CU(cudaMemcpyAsync(grad + b0 * nv, dgr + b0 * nv, sizeof(double) * nb * nv, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    // the caller's stream continues only after the results have landed; so does the host
+    CU(cudaEventRecord(h->ev_done, h->s_d2h));
+    CU(cudaStreamWaitEvent(st, h->ev_done, 0));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return ECUDA_OK;
+}
+
 static int eval_common(ecuda_handle h, const double* x, double* f, double* g, double* jac, double* grad,
                        int jac_mode, int memkind, void* stream) {
     if (!h) return ECUDA_ERR_ARG;
@@ -993,13 +1110,12 @@ static int eval_common(ecuda_handle h, const double* x, double* f, double* g, do
     if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-    const size_t B = h->hp.desc.batch, nv = h->pd.nvars, ng = h->pd.ncons, nz = h->pd.nnz;
-    EvalIO io{};
-    io.inst = static_cast<const double*>(h->inst.p);
-    io.fpart = static_cast<double*>(h->fpart.p);
-    io.jac_mode = jac_mode;
-    io.batch = static_cast<int>(B);
     if (memkind == ECUDA_MEM_DEVICE) {
+        EvalIO io{};
+        io.inst = static_cast<const double*>(h->inst.p);
+        io.fpart = static_cast<double*>(h->fpart.p);
+        io.jac_mode = jac_mode;
+        io.batch = h->hp.desc.batch;
         io.x = x;
         io.f = f;
         io.g = g;
@@ -1007,30 +1123,83 @@ static int eval_common(ecuda_handle h, const double* x, double* f, double* g, do
         io.grad = grad;
         return launch_eval(h, io, st);
     }
-    int rc;
-    if ((rc = ensure(h, h->sx, sizeof(double) * B * nv))) return rc;
-    if (f && (rc = ensure(h, h->sf_, sizeof(double) * B))) return rc;
-    if (g && (rc = ensure(h, h->sgv, sizeof(double) * B * ng))) return rc;
-    if (jac && (rc = ensure(h, h->sjac, sizeof(double) * B * nz))) return rc;
-    if (grad && (rc = ensure(h, h->sgrad, sizeof(double) * B * nv))) return rc;
-    CU(cudaMemcpyAsync(h->sx.p, x, sizeof(double) * B * nv, cudaMemcpyHostToDevice, st));
-    io.x = static_cast<const double*>(h->sx.p);
-    io.f = f ? static_cast<double*>(h->sf_.p) : nullptr;
-    io.g = g ? static_cast<double*>(h->sgv.p) : nullptr;
-    io.jac = jac ? static_cast<double*>(h->sjac.p) : nullptr;
-    io.grad = grad ? static_cast<double*>(h->sgrad.p) : nullptr;
-    if ((rc = launch_eval(h, io, st))) return rc;
-    if (f) CU(cudaMemcpyAsync(f, io.f, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    if (g) CU(cudaMemcpyAsync(g, io.g, sizeof(double) * B * ng, cudaMemcpyDeviceToHost, st));
-    if (jac) CU(cudaMemcpyAsync(jac, io.jac, sizeof(double) * B * nz, cudaMemcpyDeviceToHost, st));
-    if (grad) CU(cudaMemcpyAsync(grad, io.grad, sizeof(double) * B * nv, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return ECUDA_OK;
+    return eval_host(h, x, f, g, jac, grad, nullptr, jac_mode, st);
 }
 
 int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode, int memkind,
                void* stream) {
     return eval_common(h, x, f, g, jac, nullptr, jac_mode, memkind, stream);
+}
+
+static int ensure_compact(ecuda_ctx* h) {
+    if (!h->local_index.empty()) return ECUDA_OK;
+    build_local_index(h->hp, &h->local_index);
+    int rc;
+    if ((rc = ensure(h, h->lidx, sizeof(int32_t) * h->local_index.size()))) return rc;
+    CU(cudaMemcpy(h->lidx.p, h->local_index.data(), sizeof(int32_t) * h->local_index.size(), cudaMemcpyHostToDevice));
+    return ECUDA_OK;
+}
+
+int ecuda_get_compact_structure(ecuda_handle h, int32_t* nlocal, int32_t* local_index, double* shared_vals) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    std::vector<int32_t> tmp;
+    const std::vector<int32_t>* li = &h->local_index;
+    if (li->empty()) {
+        build_local_index(h->hp, &tmp);
+        li = &tmp;
+    }
+    if (nlocal) *nlocal = static_cast<int32_t>(li->size());
+    if (local_index) std::memcpy(local_index, li->data(), sizeof(int32_t) * li->size());
+    if (shared_vals) {
+        std::vector<double> isz(h->hp.dims.nvars), tmpl;
+        for (int c = 0; c < h->hp.dims.nvars; ++c) isz[c] = 1.0 / h->h_sz[c];
+        build_jac_template(h->hp, isz.data(), h->h_sg.data(), &tmpl);
+        std::memcpy(shared_vals, tmpl.data(), sizeof(double) * h->hp.dims.nnz);
+    }
+    return ECUDA_OK;
+}
+
+int ecuda_eval_compact(ecuda_handle h, const double* x, double* f, double* g, double* jac_local, int memkind, void* stream) {
+    if (!h) return ECUDA_ERR_ARG;
+    if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
+    if (!jac_local) return fail(h, ECUDA_ERR_ARG, "jac_local is required (use ecuda_eval for values only)");
+    if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_compact(h))) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const size_t B = h->hp.desc.batch, nz = h->pd.nnz, nl = h->local_index.size();
+    // the full triplet array is handle-owned scratch on the device; only the per-instance part leaves it
+    if ((rc = ensure(h, h->sjac, sizeof(double) * B * nz))) return rc;
+    double* full = static_cast<double*>(h->sjac.p);
+    const dim3 grid(static_cast<unsigned>((nl + 255) / 256), static_cast<unsigned>(B));
+    if (B > 65535) return fail(h, ECUDA_ERR_ARG, "ecuda_eval_compact: batch > 65535");
+    if (memkind == ECUDA_MEM_DEVICE) {
+        if ((rc = eval_common(h, x, f, g, full, nullptr, ECUDA_JAC_EXACT, ECUDA_MEM_DEVICE, stream))) return rc;
+        k_gather_local<<<grid, 256, 0, st>>>(full, static_cast<const int32_t*>(h->lidx.p), jac_local, (int)nz, (int)nl);
+        ++h->launches;
+        CU(cudaGetLastError());
+        return ECUDA_OK;
+    }
+    if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
+    if (!x) return fail(h, ECUDA_ERR_ARG, "null decision vector");
+    return eval_host(h, x, f, g, nullptr, nullptr, jac_local, ECUDA_JAC_EXACT, st);
+}
+
+int ecuda_splice_jacobian(const double* shared_vals, const int32_t* local_index, int32_t nnz, int32_t nlocal,
+                          const double* jac_local, int32_t batch, double* jac_full) {
+    if (!shared_vals || !local_index || !jac_local || !jac_full || nnz < 0 || nlocal < 0 || nlocal > nnz || batch < 0)
+        return ECUDA_ERR_ARG;
+    for (int32_t i = 0; i < nlocal; ++i)
+        if (local_index[i] < 0 || local_index[i] >= nnz) return ECUDA_ERR_ARG;
+    for (int32_t b = 0; b < batch; ++b) {
+        double* dst = jac_full + static_cast<size_t>(b) * nnz;
+        const double* src = jac_local + static_cast<size_t>(b) * nlocal;
+        std::memcpy(dst, shared_vals, sizeof(double) * nnz);
+        for (int32_t i = 0; i < nlocal; ++i) dst[local_index[i]] = src[i];
+    }
+    return ECUDA_OK;
 }
 
 int ecuda_eval_allgather(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,

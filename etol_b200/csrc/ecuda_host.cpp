@@ -396,6 +396,25 @@ void build_jac_template(const HostProblem& hp, const double* isz, const double* 
     }
 }
 
+// Triplets that are NOT covered by the exact-mode template (everything but the D-coupled off-diagonal entries):
+// the per-instance part of an exact Jacobian, in ascending triplet order. See ecuda_eval_compact.
+void build_local_index(const HostProblem& hp, std::vector<int32_t>* local) {
+    std::vector<char> shared(static_cast<size_t>(hp.dims.nnz), 0);
+    const int ns = hp.ns, nc = hp.nc;
+    for (int p = 0; p < hp.nphases; ++p) {
+        const int N = hp.N[p];
+        for (int l = 0; l < N; ++l)
+            for (int j = 0; j < ns; ++j) {
+                const int base = hp.colptr[hp.zoff[p] + nc * N + l * ns + j];
+                for (int k = 0; k < N; ++k)
+                    if (k != l) shared[base + (k < l ? k : k + hp.xcnt[j] - 1)] = 1;
+            }
+    }
+    local->clear();
+    for (int e = 0; e < hp.dims.nnz; ++e)
+        if (!shared[e]) local->push_back(e);
+}
+
 }  // namespace ecuda
 
 // ---- extern "C" host helpers ---------------------------------------------------------------------------
@@ -496,6 +515,19 @@ int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t*
         if (jCol) jCol[e] = hp.jcol[e] + base;
     }
     if (group_of_col) std::memcpy(group_of_col, hp.group_of_col.data(), sizeof(int32_t) * hp.dims.nvars);
+    return ECUDA_OK;
+}
+
+int ecuda_host_compact_structure(const ecuda_problem_desc* desc, int32_t* nlocal, int32_t* local_index) {
+    if (!desc) return ECUDA_ERR_ARG;
+    HostProblem hp;
+    std::string err;
+    if (!build_layout(*desc, &hp, &err)) return ECUDA_ERR_ARG;
+    build_structure(&hp);
+    std::vector<int32_t> li;
+    build_local_index(hp, &li);
+    if (nlocal) *nlocal = static_cast<int32_t>(li.size());
+    if (local_index) std::memcpy(local_index, li.data(), sizeof(int32_t) * li.size());
     return ECUDA_OK;
 }
 

@@ -221,6 +221,8 @@ void fill_probdev(const HostProblem& hp, ProbDev* pd);
 // exact-mode Jacobian template: tmpl[e] = (sg[row] * D[k][l]) * isz[col] for every D-coupled triplet
 // (defect row (k,j) x state column X(l,j), k != l), 0 elsewhere. Needs the collocation data in hp.col.
 void build_jac_template(const HostProblem& hp, const double* isz, const double* sg, std::vector<double>* tmpl);
+// ascending indices of the triplets the template does not cover (the per-instance part of an exact Jacobian)
+void build_local_index(const HostProblem& hp, std::vector<int32_t>* local);
 
 #endif  // !__CUDACC_RTC__
 

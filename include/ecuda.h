@@ -189,6 +189,22 @@ int ecuda_upload_bounds(ecuda_handle h, const double* gl, const double* gu, int 
  * have landed. */
 int ecuda_eval(ecuda_handle h, const double* x, double* f, double* g, double* jac, int jac_mode,
                int memkind, void* stream);
+/* ---- compact exact Jacobian -----------------------------------------------------------------------
+ * In ECUDA_JAC_EXACT mode the D-coupled off-diagonal triplets (defect row (k,j) x state column X(l,j), k != l:
+ * 74 % of the triplets of the benchmark shape) are (sg*D[k][l])*(1/sz): the same for every instance. A host
+ * consumer does not need them B times over PCIe. ecuda_get_compact_structure returns the split:
+ * local_index [nlocal] = ascending triplet indices of the per-instance part; shared_vals [nnz] = the shared
+ * values (0 at the per-instance positions; they depend on the scaling and on D: fetch again after
+ * ecuda_set_scaling / ecuda_set_collocation). Any pointer may be NULL. No reference counterpart: PSOPT hands
+ * IPOPT one instance at a time (src/ePSOPT/ePSOPT.cpp:84). */
+int ecuda_get_compact_structure(ecuda_handle h, int32_t* nlocal, int32_t* local_index, double* shared_vals);
+/* as ecuda_eval(..., ECUDA_JAC_EXACT, ...), but the Jacobian output is jac_local [B][nlocal]: the per-instance
+ * triplets in the order of local_index. The full array is written to handle-owned device scratch by the same
+ * evaluation kernel and gathered on the device. batch <= 65535. */
+int ecuda_eval_compact(ecuda_handle h, const double* x, double* f, double* g, double* jac_local, int memkind, void* stream);
+/* host helper (no GPU): jac_full [batch][nnz] from the compact form; bit-identical to what ecuda_eval returns */
+int ecuda_splice_jacobian(const double* shared_vals, const int32_t* local_index, int32_t nnz, int32_t nlocal,
+                          const double* jac_local, int32_t batch, double* jac_full);
 /* gradient of the (scaled) objective, [B][nvars]; exact. */
 int ecuda_eval_grad_f(ecuda_handle h, const double* x, double* grad, int memkind, void* stream);
 /* per-instance summary [B][2] = { f, max bound violation of g } (needs ecuda_upload_bounds) */
@@ -269,6 +285,8 @@ int ecuda_host_dims(const ecuda_problem_desc* desc, ecuda_dims* out);
 int ecuda_host_structure(const ecuda_problem_desc* desc, int32_t* iRow, int32_t* jCol,
                          int32_t* group_of_col);
 int ecuda_host_collocation(int kind, int nnodes, double* tau, double* w, double* D);
+/* the index part of ecuda_get_compact_structure without a device (local_index may be NULL to query nlocal) */
+int ecuda_host_compact_structure(const ecuda_problem_desc* desc, int32_t* nlocal, int32_t* local_index);
 int ecuda_host_hess_structure(const ecuda_problem_desc* desc, int32_t* nnz_h, int32_t* iRow, int32_t* jCol);
 /* interpolation data of ecuda_ode_error: quadrature points tq / weights wq [(N-1)*4] inside the mesh
  * intervals, Lagrange basis E and its derivative dE there [(N-1)*4][N]; matrix R [N_to][N_from] of

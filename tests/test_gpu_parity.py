@@ -305,6 +305,32 @@ def test_device_pointer_path_and_partial_outputs(evaluators):
     assert torch.equal(g2, g)
 
 
+@pytest.mark.parametrize("name", ["C0-ocp", "C2-pm3d-64", "C2-pm3d-scaled-deps", "C4-multiphase", "C3-fw6-small-scaled",
+                                  "pm3d-N2", "user-dragmass"])
+def test_compact_exact_jacobian_splices_to_the_full_one(evaluators, name):
+    """ecuda_eval_compact returns only the per-instance triplets of the exact Jacobian (26 % of them at the benchmark
+    shape); shared values + splice must reproduce ecuda_eval's full array bit for bit, through host buffers and
+    through device pointers, and f / g must be the same as ecuda_eval's."""
+    import torch
+    ev, orc, wl = _get(evaluators, name)
+    full = ev.eval_host(wl.x, want=("f", "g", "jac"), jac_mode=W.JAC_EXACT)
+    idx, shared = ev.compact_structure()
+    assert np.array_equal(idx, capi.host_compact_structure(wl))
+    assert 0 < idx.size < ev.nnz or min(wl.nnodes) < 2
+    out = ev.eval_compact_host(wl.x, idx.size)
+    assert np.array_equal(out["f"], full["f"]) and np.array_equal(out["g"], full["g"])
+    assert np.array_equal(out["jac_local"], full["jac"][:, idx])
+    assert np.array_equal(ev.splice(shared, idx, out["jac_local"]), full["jac"])
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(wl.x).to(dev)
+    f = torch.empty(wl.batch, dtype=torch.float64, device=dev)
+    g = torch.empty((wl.batch, ev.ncons), dtype=torch.float64, device=dev)
+    jl = torch.full((wl.batch, idx.size), float("nan"), dtype=torch.float64, device=dev)
+    ev.eval_compact_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jl.data_ptr(), capi.MEM_DEVICE, None)
+    ev.sync()
+    assert np.array_equal(jl.cpu().numpy(), out["jac_local"]) and np.array_equal(g.cpu().numpy(), full["g"])
+
+
 def test_full_size_batch_properties():
     """BASELINE config C2 at full size (4096 instances): properties that need no 4096-instance oracle run."""
     import torch

@@ -82,3 +82,33 @@ def test_pack_instances_layout():
     inst = capi.pack_instances(wl, d)
     assert d.rec_size == 4 and inst.shape == (3, 24)
     assert np.array_equal(inst[:, 2::4], wl.cylinders[:, :, 2] ** 2)
+
+
+@pytest.mark.parametrize("mk", [lambda: W.reference_vgp("ocp", batch=3, jitter=0.02), lambda: W.pm3d(batch=4),
+                                lambda: W.pm3d(batch=3, scaled=True, pattern_mode=W.MODEL_DEPS),
+                                lambda: W.pm3d_multiphase(batch=3, scaled=True), lambda: W.fw6(batch=2, nnodes=21, ncyl=5),
+                                lambda: W.pm3d(batch=2, nnodes=2, ncyl=1)])
+def test_compact_split_of_the_exact_jacobian(mk):
+    """ecuda_eval_compact's split: the triplets outside local_index are the D-coupled
+    off-diagonal entries; in the oracle's exact Jacobian they are the same for every instance (different x, different
+    obstacles), and splicing the per-instance part back with ecuda_splice_jacobian gives the full array bit for bit."""
+    wl = mk()
+    o = ob.Oracle(wl)
+    idx = capi.host_compact_structure(wl)
+    d = capi.host_dims(wl)
+    irow, jcol, _ = capi.host_structure(wl)
+    nshared = sum(N * (N - 1) * d.nstates for N in wl.nnodes)
+    assert idx.size == d.nnz - nshared and np.all(np.diff(idx) > 0)
+    jac = o.eval(wl.x, want=("jac",), jac_mode=W.JAC_EXACT)["jac"]
+    shared_mask = np.ones(d.nnz, dtype=bool)
+    shared_mask[idx] = False
+    assert np.all(jac[:, shared_mask] == jac[0, shared_mask])      # instance-independent
+    assert np.all(jac[0, shared_mask] != 0.0)                      # and structurally non-zero (D has no zeros off the diagonal)
+    shared = np.where(shared_mask, jac[0], 0.0)
+    full = capi.splice_jacobian(shared, idx, jac[:, idx], d.nnz)
+    assert np.array_equal(full, jac)
+    # bad arguments are refused
+    bad = idx.copy()
+    bad[0] = d.nnz
+    with pytest.raises(capi.EcudaError):
+        capi.splice_jacobian(shared, bad, jac[:, idx], d.nnz)
