@@ -210,6 +210,16 @@ __global__ void __launch_bounds__(256) k_gather_local(const double* __restrict__
         __stcs(dst + i, __ldcs(src + __ldg(idx + i)));
 }
 
+// Pulls the inputs of a batch (decision vectors, instance records) into L2 before the evaluation kernel starts
+// writing: a CTA's first loads then hit L2 instead of queueing in HBM behind the kernel's own write stream.
+__global__ void __launch_bounds__(256) k_prefetch_inputs(const char* a, size_t abytes, const char* b, size_t bbytes) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 128;
+    for (size_t o = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 128; o < abytes; o += stride)
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a + o));
+    for (size_t o = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 128; o < bbytes; o += stride)
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(b + o));
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -249,6 +259,7 @@ struct ecuda_ctx {
     bool barrier_used = false;  // ecuda_peer_barrier has been issued: ecuda_sync also reports its sticky status
     int ipopt_jac_mode = ECUDA_JAC_EXACT;
     bool force_generic = false;  // ECUDA_FORCE_GENERIC=1 in the environment: always run the generic kernel
+    bool prefetch = false;    // ECUDA_PREFETCH=1: k_prefetch_inputs before the evaluation kernel
     bool persist = false;     // ECUDA_PERSIST=1: finite differences on the persistent kernel (k_rows_n_fd_persist)
     int exact_kernel = 0;     // ECUDA_EXACT_KERNEL: 0 k_eval_rows (default), 1 "ring" k_rows_n, 2 "stream" k_stream_exact
     DevBuf desc;              // exact-mode triplet descriptors
@@ -590,6 +601,13 @@ static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
         ++h->launches;
     }
     if (io.f || io.g || io.jac) {
+        if (h->prefetch) {
+            k_prefetch_inputs<<<h->num_sms * 2, 256, 0, st>>>(reinterpret_cast<const char*>(io.x),
+                                                            sizeof(double) * io.batch * h->pd.nvars,
+                                                            reinterpret_cast<const char*>(io.inst),
+                                                            sizeof(double) * io.batch * h->pd.inst_stride);
+            ++h->launches;
+        }
         int rc = h->rowsn_N > 0 ? launch_rows_n<M>(h, io, st, grid) : 1;
         if (rc <= 0) {
         } else if (h->fast_ok) {
@@ -897,6 +915,10 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     CU(cudaMemcpy(h->desc.p, hp.tdesc.data(), sizeof(uint64_t) * hp.tdesc.size(), cudaMemcpyHostToDevice));
     pd.desc = static_cast<const unsigned long long*>(h->desc.p);
     h->persist = std::getenv("ECUDA_PERSIST") != nullptr;
+    {
+        const char* pf = std::getenv("ECUDA_PREFETCH");
+        h->prefetch = pf && pf[0] == '1';
+    }
     h->exact_kernel = 0;
     if (const char* ek = std::getenv("ECUDA_EXACT_KERNEL"))
         h->exact_kernel = std::strcmp(ek, "ring") == 0 ? 1 : std::strcmp(ek, "stream") == 0 ? 2 : 0;
