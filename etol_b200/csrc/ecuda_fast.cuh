@@ -247,10 +247,11 @@ ECUDA_HD void fast_phase_b(const ProbDev& pb, const PhaseDev& ph, int p, const E
     if (g) {
         // path rows: one row per thread
         for (int it = nthr - 1 - tid; it < np * N; it += nthr) {
-            const int k = fast_div(it, ph.mnp), q = it - k * np;
+            int k, q;
+            path_item(ph, it, k, q);
             const double* x = m.z + nc * N + k * NS;
             const double t = pt.h * ECUDA_LDG(ph.tau + k) + pt.m;
-            const int r = ph.goff + NS * N + pb.ne + it;
+            const int r = ph.goff + NS * N + pb.ne + k * np + q;
             const double val = ECUDA_LDG(sg + r) * path_row<M>(pb, ph, m, q, x[0], x[1], t);
             ECUDA_STREAM_STORE(g + r, val);
             if (io.nranks > 0) rr.viol = fmax(rr.viol, row_violation(io, pb, ph, m, b, r, val, 1));
@@ -322,8 +323,9 @@ ECUDA_HD void fast_phase_c(const ProbDev& pb, const PhaseDev& ph, int p, const E
         const int nP = (NS >= 2) ? N * 2 * np : 0, nU = (nc + 2) * N;
         for (int it = nthr - 1 - tid; it < nP + nU; it += nthr) {
             if (it < nP) {
-                const int k = fast_div(it, ph.m2np), rem = it - k * 2 * np;
-                const int j = rem >= np ? 1 : 0, q = rem - j * np;
+                const int j = it & 1;  // neighbouring lanes: the same path row, state columns 0 and 1
+                int k, q;
+                path_item(ph, it >> 1, k, q);
                 if (FD)
                     xcol_path_fd<M>(pb, ph, m, j, k, q, jac);
                 else

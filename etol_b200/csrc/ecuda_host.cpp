@@ -373,6 +373,8 @@ void fill_probdev(const HostProblem& hp, ProbDev* out) {
         ph.mN = fast_div_magic(ph.N);
         ph.mnp = fast_div_magic(ph.npath);
         ph.m2np = fast_div_magic(2 * ph.npath);
+        ph.mns = fast_div_magic(ph.nstat);
+        ph.mnt = fast_div_magic(ph.npath - ph.nstat);
     }
 }
 

@@ -42,11 +42,27 @@ struct PhaseDev {
     int nvars;      // (ns+nc)*N + 2
     int inst_off;   // offset (doubles) of this phase's static records inside the instance block
     unsigned mN, mnp, m2np;  // multiply-high reciprocals of N, npath, 2*npath (fast_div; 0 = divisor <= 1)
+    unsigned mns, mnt;       // ... of nstat and of npath - nstat (the track rows per node): path_item
     const double* D;    // [N][N] row-major
     const double* Dt;   // [N][N] transposed (Dt[l*N+k] = D[k][l]) : coalesced over rows k
     const double* tau;  // [N]
     const double* w;    // [N]
 };
+
+// Path rows as work items: item `it` of the phase's N * npath path rows -> (node k, row q of the node). The static
+// rows of all nodes come first, then the track rows, so that the lanes of a warp evaluate the same kind of row
+// (a moving-obstacle row costs two divisions and a waypoint search; in node-major order every warp paid for both).
+ECUDA_HD void path_item(const PhaseDev& ph, int it, int& k, int& q) {
+    const int nS = ph.nstat * ph.N;
+    if (it < nS) {
+        k = fast_div(it, ph.mns);
+        q = it - k * ph.nstat;
+    } else {
+        const int i2 = it - nS;
+        k = fast_div(i2, ph.mnt);
+        q = ph.nstat + (i2 - k * (ph.npath - ph.nstat));
+    }
+}
 
 struct ProbDev {
     int model, ns, nc, ne, nphases;

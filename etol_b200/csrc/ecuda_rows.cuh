@@ -270,12 +270,13 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     }
     it -= 1;
     if (it < np * N) {  // ---- path row (k,q)                       [phase_b path rows, xcol_path_*, node_item tracks]
-        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        int k, q;
+        path_item(ph, it, k, q);
         const double tau = ECUDA_LDG(ph.tau + k);
         const double t = pt.h * tau + pt.m;
         const int lcol0 = nc * N + k * NS;
         const double x0 = m.z[lcol0], x1 = m.z[lcol0 + 1];
-        const int r = ph.goff + NS * N + pb.ne + it;
+        const int r = ph.goff + NS * N + pb.ne + k * np + q;
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * path_row<M>(pb, ph, m, q, x0, x1, t);

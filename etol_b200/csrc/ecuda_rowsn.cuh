@@ -749,11 +749,12 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
     }
     it -= 1;
     if (it < np * N) {  // ---- path row (k,q)
-        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        int k, q;
+        path_item(ph, it, k, q);
         const double tau = m.tau[k];
         const double t = h * tau + mid;
         const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
-        const int r = ph.goff + NS * N + pb.ne + it;
+        const int r = ph.goff + NS * N + pb.ne + k * np + q;
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
@@ -1034,11 +1035,12 @@ ECUDA_HD void rn_item_exact(const ProbDev& pb, const PhaseDev& ph, int p, const 
     }
     it -= 1;
     if (it < np * N) {  // ---- path row (k,q)
-        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        int k, q;
+        path_item(ph, it, k, q);
         const double tau = ECUDA_LDG(ph.tau + k);
         const double t = h * tau + mid;
         const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
-        const int r = ph.goff + NS * N + pb.ne + it;
+        const int r = ph.goff + NS * N + pb.ne + k * np + q;
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);

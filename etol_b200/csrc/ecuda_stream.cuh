@@ -178,11 +178,12 @@ ECUDA_HD void st_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
     }
     it -= 1;
     if (it < np * N) {  // ---- path row (k,q): value, partials
-        const int k = fast_div(it, ph.mnp), q = it - k * np;
+        int k, q;
+        path_item(ph, it, k, q);
         const double tau = ECUDA_LDG(ph.tau + k);
         const double t = h * tau + mid;
         const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
-        const int lr = NS * N + pb.ne + it, r = ph.goff + lr;
+        const int lr = NS * N + pb.ne + k * np + q, r = ph.goff + lr;
         if (io.g) {
             const double val = ECUDA_LDG(sg + r) * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
             m.gbuf[lr] = val;
@@ -194,7 +195,7 @@ ECUDA_HD void st_item(const ProbDev& pb, const PhaseDev& ph, int p, const EvalIO
             Model<M>::static_row_dxy(cm.inst + ph.inst_off + q * Model<M>::REC, x0, x1, &ddx, &ddy);
         else
             track_row_partials(cm.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x0, x1, t, &ddx, &ddy, &ddt);
-        double* e = m.tab + desc_path_off(NS, nc, N) + it * 4;
+        double* e = m.tab + desc_path_off(NS, nc, N) + (k * np + q) * 4;
         e[0] = ddx;
         e[1] = ddy;
         if (TRK) {
