@@ -177,6 +177,8 @@ struct UserModel {
     // node ids of the partial derivatives, -1 = identically zero
     int dfdx[ECUDA_MAX_STATES][ECUDA_MAX_STATES], dfdu[ECUDA_MAX_STATES][ECUDA_MAX_CONTROLS];
     int dcdx[ECUDA_MAX_STATES], dcdu[ECUDA_MAX_CONTROLS];
+    bool tdep = false;                   // some f_i or the running cost reads t
+    int dfdt[ECUDA_MAX_STATES], dcdt = -1;
     // second derivatives over [x | u]: d2[(o * nv + a) * nv + b], a <= b, o < ns: f_o, o == ns: cost
     std::vector<int> d2;
     unsigned fx[ECUDA_MAX_STATES], fu[ECUDA_MAX_STATES];  // states / controls read by f_i
@@ -192,8 +194,8 @@ struct UserImage {
 const UserModel* user_model(int model_id);  // null when the id is not registered
 int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::string* err);
 void user_model_eval(const UserModel& m, const double* x, const double* u, double t, double* f_out, double* cost_out);
-void user_model_partials(const UserModel& m, const double* x, const double* u, double* dfdx, double* dfdu, double* dcdx,
-                         double* dcdu);
+void user_model_partials(const UserModel& m, const double* x, const double* u, double t, double* dfdx, double* dfdu,
+                         double* dcdx, double* dcdu);
 // nb: template argument NB of the kernels (0 = generic block count); rows: also compile k_eval_rows
 bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, std::string* err);
 

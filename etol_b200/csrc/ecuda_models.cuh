@@ -139,6 +139,8 @@ struct Model<ECUDA_MODEL_SI2D> {
     // f_i never reads x_i: the defect row (k,i) depends on its own state column only through D, so the
     // diagonal triplet of that column needs no second evaluation of the dynamics
     static constexpr bool DIAG_FREE = true;
+    static constexpr bool TDEP = false;  // neither the dynamics nor the running cost read t
+    ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // which states / controls f_i reads, 8 bits per i (same data as model_info() on the host): a
     // finite-difference triplet of a variable f_i does not read is exactly +0.0 and is stored as such
     static constexpr unsigned long long FX = 0x0000ull, FU = 0x0201ull;
@@ -147,12 +149,12 @@ struct Model<ECUDA_MODEL_SI2D> {
         out[1] = u[1];
     }
     ECUDA_HD static double cost(const double* x, const double* u, double t) { return u[0] * u[0] + u[1] * u[1]; }
-    ECUDA_HD static void dcost(const double* x, const double* u, double* dx, double* du) {
+    ECUDA_HD static void dcost(const double* x, const double* u, double t, double* dx, double* du) {
         dx[0] = 0.0; dx[1] = 0.0;
         du[0] = 2.0 * u[0]; du[1] = 2.0 * u[1];
     }
     // dfdx[i][j] = d f_i / d x_j ; dfdu[i][j] = d f_i / d u_j (only the NCU controls the model reads)
-    ECUDA_HD static void jac(const double* x, const double* u, double (*dfdx)[NS], double (*dfdu)[NCU]) {
+    ECUDA_HD static void jac(const double* x, const double* u, double t, double (*dfdx)[NS], double (*dfdu)[NCU]) {
         dfdx[0][0] = 0.0; dfdx[0][1] = 0.0; dfdx[1][0] = 0.0; dfdx[1][1] = 0.0;
         dfdu[0][0] = 1.0; dfdu[0][1] = 0.0; dfdu[1][0] = 0.0; dfdu[1][1] = 1.0;
     }
@@ -174,6 +176,8 @@ template <>
 struct Model<ECUDA_MODEL_PM3D> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i
+    static constexpr bool TDEP = false;
+    ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // 8 bits per i: f_0..f_2 read x_3..x_5, f_3..f_5 read u_0..u_2
     static constexpr unsigned long long FX = 0x000000201008ull, FU = 0x040201000000ull;
     ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {
@@ -183,11 +187,11 @@ struct Model<ECUDA_MODEL_PM3D> {
     ECUDA_HD static double cost(const double* x, const double* u, double t) {
         return (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
     }
-    ECUDA_HD static void dcost(const double* x, const double* u, double* dx, double* du) {
+    ECUDA_HD static void dcost(const double* x, const double* u, double t, double* dx, double* du) {
         for (int i = 0; i < NS; ++i) dx[i] = 0.0;
         for (int j = 0; j < NCU; ++j) du[j] = 2.0 * u[j];
     }
-    ECUDA_HD static void jac(const double* x, const double* u, double (*dfdx)[NS], double (*dfdu)[NCU]) {
+    ECUDA_HD static void jac(const double* x, const double* u, double t, double (*dfdx)[NS], double (*dfdu)[NCU]) {
         for (int i = 0; i < NS; ++i) {
             for (int j = 0; j < NS; ++j) dfdx[i][j] = (i < 3 && j == i + 3) ? 1.0 : 0.0;
             for (int j = 0; j < NCU; ++j) dfdu[i][j] = (i >= 3 && j == i - 3) ? 1.0 : 0.0;
@@ -211,6 +215,8 @@ template <>
 struct Model<ECUDA_MODEL_FW6> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i (x,y,z,V,gamma,psi derivatives)
+    static constexpr bool TDEP = false;
+    ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // 8 bits per i: f_0, f_1 read V, gamma, psi; f_2 reads V, gamma; f_3 reads gamma and u_0; f_4, f_5 read u_1, u_2
     static constexpr unsigned long long FX = 0x000010183838ull, FU = 0x040201000000ull;
     static constexpr double G0 = 9.80665;
@@ -228,11 +234,11 @@ struct Model<ECUDA_MODEL_FW6> {
     ECUDA_HD static double cost(const double* x, const double* u, double t) {
         return (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
     }
-    ECUDA_HD static void dcost(const double* x, const double* u, double* dx, double* du) {
+    ECUDA_HD static void dcost(const double* x, const double* u, double t, double* dx, double* du) {
         for (int i = 0; i < NS; ++i) dx[i] = 0.0;
         for (int j = 0; j < NCU; ++j) du[j] = 2.0 * u[j];
     }
-    ECUDA_HD static void jac(const double* x, const double* u, double (*dfdx)[NS], double (*dfdu)[NCU]) {
+    ECUDA_HD static void jac(const double* x, const double* u, double t, double (*dfdx)[NS], double (*dfdu)[NCU]) {
         double sg, cg, sp, cp;
         ecuda_sincos(x[4], &sg, &cg);
         ecuda_sincos(x[5], &sp, &cp);

@@ -404,7 +404,7 @@ ECUDA_HD void xcol_local_exact(const ProbDev& pb, const PhaseDev& ph, int p, con
 #pragma unroll
     for (int i = 0; i < NCU; ++i) u[i] = m.z[k * nc + i];
     double dfdx[NS][NS], dfdu[NS][NCU];
-    Model<M>::jac(x, u, dfdx, dfdu);
+    Model<M>::jac(x, u, pt.h * ECUDA_LDG(ph.tau + k) + pt.m, dfdx, dfdu);
     const double is = ECUDA_LDG(pb.isz + col);
     const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
     const int rdef0 = ph.goff + k * ns;
@@ -731,7 +731,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
             }
         } else {
             double dfdx[NS][NS], dfdu[NS][NCU];
-            Model<M>::jac(x, u, dfdx, dfdu);
+            Model<M>::jac(x, u, t, dfdx, dfdu);
             const double is = ECUDA_LDG(pb.isz + col);
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
@@ -798,12 +798,14 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
     } else {
         const double is = ECUDA_LDG(pb.isz + col);
         const double dtk = which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau);  // d t_k / d t0|tf
-        double f[NS];
+        double f[NS], ft[NS], Lt;
         Model<M>::f(x, u, t, f);
+        if constexpr (Model<M>::TDEP) Model<M>::dtime(x, u, t, ft, &Lt);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            // d zeta / d t0 = +f/2 ; d zeta / d tf = -f/2   (the models have no explicit time dependence)
+            // d zeta / d t0 = +f/2 ; d zeta / d tf = -f/2 ; time-dependent dynamics add -h (df/dt) (d t_k / d t0|tf)
             double v = which == 0 ? 0.5 * f[i] : -0.5 * f[i];
+            if constexpr (Model<M>::TDEP) v = v - pt.h * (ft[i] * dtk);
             jstore<SM>(jac + base + k * ns + i, (ECUDA_LDG(sg + rdef0 + i) * v) * is);
         }
         for (int q = ph.nstat; q < np; ++q) {
@@ -878,7 +880,7 @@ ECUDA_HD void gradient_phase(const ProbDev& pb, const PhaseDev& ph, const EvalIO
         const double* x = m.z + nc * N + k * ns;
         const double* u = m.z + k * nc;
         double dx[NS], du[NCU];
-        Model<M>::dcost(x, u, dx, du);
+        Model<M>::dcost(x, u, pt.h * ECUDA_LDG(ph.tau + k) + pt.m, dx, du);
         const double w = ECUDA_LDG(ph.w + k);
         const double sgn = pb.maximize ? -1.0 : 1.0;
 #pragma unroll
@@ -899,8 +901,24 @@ ECUDA_HD void gradient_phase(const ProbDev& pb, const PhaseDev& ph, const EvalIO
         double acc = 0.0;
         for (int k = 0; k < N; ++k) acc = fma(ECUDA_LDG(ph.w + k), m.Lk[k], acc);
         int c0 = (ns + nc) * N;
-        grad[c0] = (pb.sf * (-0.5 * acc)) * ECUDA_LDG(is + c0);
-        grad[c0 + 1] = (pb.sf * (0.5 * acc)) * ECUDA_LDG(is + c0 + 1);
+        double g0 = -0.5 * acc, g1 = 0.5 * acc;
+        if constexpr (Model<M>::TDEP) {
+            // a running cost that reads t: + h sum_k w_k (dL/dt)(t_k) (d t_k / d t0|tf)
+            double a0 = 0.0, a1 = 0.0;
+            const double sgn = pb.maximize ? -1.0 : 1.0;
+            for (int k = 0; k < N; ++k) {
+                const double tau = ECUDA_LDG(ph.tau + k);
+                double ft[NS], Lt;
+                Model<M>::dtime(m.z + nc * N + k * ns, m.z + k * nc, pt.h * tau + pt.m, ft, &Lt);
+                const double wl = ECUDA_LDG(ph.w + k) * (sgn * Lt);
+                a0 = fma(wl, 0.5 * (1.0 - tau), a0);
+                a1 = fma(wl, 0.5 * (1.0 + tau), a1);
+            }
+            g0 = g0 + pt.h * a0;
+            g1 = g1 + pt.h * a1;
+        }
+        grad[c0] = (pb.sf * g0) * ECUDA_LDG(is + c0);
+        grad[c0 + 1] = (pb.sf * g1) * ECUDA_LDG(is + c0 + 1);
     }
 }
 
@@ -1022,8 +1040,8 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
         Model<M>::hess(x, u, lamf, cL * pt.h, H);
         // first derivatives for the couplings with t0 / tf
         double dfdx[NS][NS], dfdu[NS][NCU], dLx[NS], dLu[NCU], gv[NV];
-        Model<M>::jac(x, u, dfdx, dfdu);
-        Model<M>::dcost(x, u, dLx, dLu);
+        Model<M>::jac(x, u, t, dfdx, dfdu);
+        Model<M>::dcost(x, u, t, dLx, dLu);
 #pragma unroll
         for (int a = 0; a < NS; ++a) {
             double s = cL * dLx[a];

@@ -186,7 +186,7 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
     } else {
         // exact: the D-coupled triplets come from the template (copy warp); node-local ones here
         double dfdx[NS][NS], dfdu[NS][NCU], f[NS];
-        Model<M>::jac(x, u, dfdx, dfdu);
+        Model<M>::jac(x, u, t, dfdx, dfdu);
         Model<M>::f(x, u, t, f);
         const double dkk = ECUDA_LDG(ph.Dt + static_cast<size_t>(k) * N + k);
         const double sgi = rs.sgr;
@@ -221,10 +221,22 @@ ECUDA_HD void rows_jacobian(const ProbDev& pb, const PhaseDev& ph, const EvalIO&
 #pragma unroll
         for (int a = 0; a < NS; ++a)
             if (a == i) fi = f[a];
+        double fti = 0.0;
+        if constexpr (Model<M>::TDEP) {  // dynamics that read t: - h (df_i/dt) (d t_k / d t0|tf)
+            double ft[NS], Lt;
+            Model<M>::dtime(x, u, t, ft, &Lt);
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+                if (a == i) fti = ft[a];
+        }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {  // [node_item exact, time columns, row i]
             const int lcol = tcol + which;
-            const double v = which == 0 ? 0.5 * fi : -0.5 * fi;
+            double v = which == 0 ? 0.5 * fi : -0.5 * fi;
+            if constexpr (Model<M>::TDEP) {
+                const double tau = ECUDA_LDG(ph.tau + k);
+                v = v - pt.h * (fti * (which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau)));
+            }
             ECUDA_STREAM_STORE(jac + m.colp[lcol] + k * NS + i, (sgi * v) * isz_of(pb, ph, m, lcol));
         }
     }

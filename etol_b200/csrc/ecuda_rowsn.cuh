@@ -961,7 +961,8 @@ ECUDA_HD void rn_ex_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
     for (int a = 0; a < NS; ++a)
         if (a == i) fi = f[a];
     double dfdx[NS][NS], dfdu[NS][NCU];
-    Model<M>::jac(x, u, dfdx, dfdu);
+    static_assert(!Model<M>::TDEP, "k_rows_n is instantiated for the built-in (autonomous) models only");
+    Model<M>::jac(x, u, t, dfdx, dfdu);
     const double dkk = ECUDA_LDG(Dtk + k * N);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {  // [xcol_local_exact, row i]

@@ -124,7 +124,8 @@ ECUDA_HD void st_row(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, co
     if (!io.jac) return;
     double* row = m.tab + 2 + (k * NS + i) * desc_rowtab_width(NS, nc);
     double dfdx[NS][NS], dfdu[NS][NCU];
-    Model<M>::jac(x, u, dfdx, dfdu);
+    static_assert(!Model<M>::TDEP, "k_stream_exact is instantiated for the built-in (autonomous) models only");
+    Model<M>::jac(x, u, t, dfdx, dfdu);
     const double dkk = ECUDA_LDG(Dtk + k * N);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {

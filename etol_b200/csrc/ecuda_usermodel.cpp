@@ -188,6 +188,7 @@ std::string generate_source(const UserModel& m) {
       << "    static constexpr int NS = " << m.ns << ", NCU = " << m.nc
       << ", REC = " << (m.static_kind == ECUDA_STATIC_EDGE ? 6 : 4) << ";\n"
       << "    static constexpr bool DIAG_FREE = " << (diag_free ? "true" : "false") << ";\n"
+      << "    static constexpr bool TDEP = " << (m.tdep ? "true" : "false") << ";\n"
       << "    static constexpr unsigned long long " << masks << ";\n";
     // f
     o << "    ECUDA_HD static void f(const double* x, const double* u, double t, double* out) {\n";
@@ -200,7 +201,16 @@ std::string generate_source(const UserModel& m) {
     print_body(m, {m.cost_out}, o);
     o << "        return v" << m.cost_out << ";\n    }\n";
     // dcost
-    o << "    ECUDA_HD static void dcost(const double* x, const double* u, double* dx, double* du) {\n";
+    // dtime: d f_i / d t and d L / d t (time-dependent models; exact Jacobian and objective gradient)
+    o << "    ECUDA_HD static void dtime(const double* x, const double* u, double t, double* dfdt, double* dLdt) {\n";
+    outs.clear();
+    for (int i = 0; i < m.ns; ++i) outs.push_back(m.dfdt[i]);
+    outs.push_back(m.dcdt);
+    print_body(m, outs, o);
+    for (int i = 0; i < m.ns; ++i)
+        o << "        dfdt[" << i << "] = " << (m.dfdt[i] < 0 ? std::string("0.0") : "v" + std::to_string(m.dfdt[i])) << ";\n";
+    o << "        *dLdt = " << (m.dcdt < 0 ? std::string("0.0") : "v" + std::to_string(m.dcdt)) << ";\n    }\n";
+    o << "    ECUDA_HD static void dcost(const double* x, const double* u, double t, double* dx, double* du) {\n";
     outs.clear();
     for (int i = 0; i < m.ns; ++i) outs.push_back(m.dcdx[i]);
     for (int j = 0; j < m.nc; ++j) outs.push_back(m.dcdu[j]);
@@ -211,7 +221,7 @@ std::string generate_source(const UserModel& m) {
         o << "        du[" << j << "] = " << (m.dcdu[j] < 0 ? std::string("0.0") : "v" + std::to_string(m.dcdu[j])) << ";\n";
     o << "    }\n";
     // jac
-    o << "    ECUDA_HD static void jac(const double* x, const double* u, double (*dfdx)[NS], double (*dfdu)[NCU]) {\n";
+    o << "    ECUDA_HD static void jac(const double* x, const double* u, double t, double (*dfdx)[NS], double (*dfdu)[NCU]) {\n";
     outs.clear();
     for (int i = 0; i < m.ns; ++i) {
         for (int j = 0; j < m.ns; ++j) outs.push_back(m.dfdx[i][j]);
@@ -230,6 +240,7 @@ std::string generate_source(const UserModel& m) {
     // hess: H = sum_i lam[i] d2 f_i + lamL d2 L over [x | u]
     o << "    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,\n"
          "                              double (*H)[NS + NCU]) {\n";
+    if (m.tdep) o << "        const double t = 0.0;  // not reached: ecuda_eval_hess refuses time-dependent models\n";
     {
         const int nvn = m.ns + m.nc;
         outs.assign(m.d2.begin(), m.d2.end());
@@ -308,10 +319,10 @@ void user_model_eval(const UserModel& m, const double* x, const double* u, doubl
     if (cost_out) *cost_out = v[m.cost_out];
 }
 
-void user_model_partials(const UserModel& m, const double* x, const double* u, double* dfdx, double* dfdu, double* dcdx,
-                         double* dcdu) {
+void user_model_partials(const UserModel& m, const double* x, const double* u, double t, double* dfdx, double* dfdu,
+                         double* dcdx, double* dcdu) {
     std::vector<double> v;
-    tape_values(m, x, u, 0.0, &v);
+    tape_values(m, x, u, t, &v);
     auto at = [&](int id) { return id < 0 ? 0.0 : v[id]; };
     for (int i = 0; i < m.ns; ++i) {
         for (int j = 0; j < m.ns; ++j) dfdx[i * m.ns + j] = at(m.dfdx[i][j]);
@@ -397,7 +408,7 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
     auto out_ok = [&](int id) { return id >= 0 && id < um->nnodes; };
     if (!out_ok(um->cost_out)) return bad("cost_out is not a tape node");
     const unsigned tbit = 1u << (m->ns + m->nc);
-    if (deps[um->cost_out] & tbit) return bad("the running cost reads t: only autonomous models are supported");
+    m->tdep = (deps[um->cost_out] & tbit) != 0;
     m->cost_out = um->cost_out;
     for (int i = 0; i < ECUDA_MAX_STATES; ++i) {
         m->f_out[i] = -1;
@@ -405,7 +416,7 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
     }
     for (int i = 0; i < m->ns; ++i) {
         if (!out_ok(um->f_out[i])) return bad("f_out[" + std::to_string(i) + "] is not a tape node");
-        if (deps[um->f_out[i]] & tbit) return bad("f_" + std::to_string(i) + " reads t: only autonomous models are supported");
+        if (deps[um->f_out[i]] & tbit) m->tdep = true;
         m->f_out[i] = um->f_out[i];
         m->fx[i] = deps[m->f_out[i]] & ((1u << m->ns) - 1u);
         m->fu[i] = (deps[m->f_out[i]] >> m->ns) & ((1u << m->nc) - 1u);
@@ -424,6 +435,9 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
         m->dcdx[i] = differentiate(P, m->cost_out, i);
     }
     for (int j = 0; j < m->nc; ++j) m->dcdu[j] = differentiate(P, m->cost_out, m->ns + j);
+    for (int i = 0; i < ECUDA_MAX_STATES; ++i) m->dfdt[i] = -1;
+    for (int i = 0; i < m->ns; ++i) m->dfdt[i] = differentiate(P, m->f_out[i], m->ns + m->nc);
+    m->dcdt = differentiate(P, m->cost_out, m->ns + m->nc);
     // second derivatives over the node variables [x | u] (upper triangle a <= b), for the Lagrangian Hessian
     const int nvn = m->ns + m->nc;
     m->d2.assign(static_cast<size_t>(m->ns + 1) * nvn * nvn, -1);

@@ -68,14 +68,17 @@ def cos(v): return _un(OP_COS, v)
 def exp(v): return _un(OP_EXP, v)
 
 
-def trace(ns, nc, dynamics, cost, static_kind=STATIC_CYLINDER):
+def trace(ns, nc, dynamics, cost, static_kind=STATIC_CYLINDER, with_time=False):
+    """with_time: the callbacks also receive the node time, `dynamics(x, u, t)` / `cost(x, u, t)` -- the `k` argument
+    of the ePSOPT callbacks (src/ePSOPT/ePSOPT.cpp:218-260 of the ETOL tree)."""
     t = Tape(ns, nc, static_kind)
     x = [Var(t, t.push(OP_INPUT, i)) for i in range(ns)]
     u = [Var(t, t.push(OP_INPUT, ns + j)) for j in range(nc)]
-    f = dynamics(x, u)
+    extra = (Var(t, t.push(OP_INPUT, ns + nc)),) if with_time else ()
+    f = dynamics(x, u, *extra)
     assert len(f) == ns, "one state derivative per state"
     t.f_out = [x[0]._lift(v).id for v in f]
-    t.cost_out = x[0]._lift(cost(x, u)).id
+    t.cost_out = x[0]._lift(cost(x, u, *extra)).id
     return t
 
 
@@ -99,3 +102,16 @@ def drag_tape(cd=0.02):
         speed = sqrt(x[2] ** 2 + x[3] ** 2 + 1e-6)
         return [x[2], x[3], u[0] - cd * speed * x[2], u[1] - cd * speed * x[3]]
     return trace(4, 2, dyn, lambda x, u: (u[0] * u[0] + u[1] * u[1]) + 0.1 * (x[2] * x[2] + x[3] * x[3]))
+
+
+def gust_tape(cd=0.02, w0=1.5, omega=0.11):
+    """Time-dependent user model: the drag model in a wind that turns and breathes with time, and a running cost
+    whose weight grows along the flight. p' = v + w(t), v' = a - cd*|v|*v with w(t) = w0*(1 + 0.02 t)*(cos, sin)(omega t);
+    cost (|a|^2 + 0.1*|v|^2)*(1 + 0.01 t). Both the dynamics and the cost read t."""
+    def dyn(x, u, t):
+        speed = sqrt(x[2] ** 2 + x[3] ** 2 + 1e-6)
+        amp = w0 * (1.0 + 0.02 * t)
+        return [x[2] + amp * cos(omega * t), x[3] + amp * sin(omega * t),
+                u[0] - cd * speed * x[2], u[1] - cd * speed * x[3]]
+    return trace(4, 2, dyn, lambda x, u, t: ((u[0] * u[0] + u[1] * u[1]) + 0.1 * (x[2] * x[2] + x[3] * x[3])) * (1.0 + 0.01 * t),
+                 with_time=True)

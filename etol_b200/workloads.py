@@ -399,3 +399,9 @@ def unicycle(batch=8, **kw):
 def dragmass(batch=8, **kw):
     from . import tape as T
     return planar_user(T.drag_tape(), batch=batch, name="user-dragmass", rest=(4.0, -3.0), **kw)
+
+
+def gust(batch=8, **kw):
+    """planar point mass with drag in a time-varying wind, time-weighted cost: dynamics and cost read t"""
+    from . import tape as T
+    return planar_user(T.gust_tape(), batch=batch, name="user-gust", rest=(4.0, -3.0), **kw)

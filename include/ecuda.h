@@ -85,7 +85,9 @@ enum ecuda_model {
  * operation, no contraction): POW with an integral exponent e, |e| <= 8, is the left-to-right
  * product a*a*...*a (1/(...) for e < 0, 1 for e = 0); SIN / COS are ecuda_sincos of
  * include/ecuda_detmath.h; other POW exponents and EXP use the platform's pow / exp and are
- * reproducible to rounding only. Dynamics and cost must be autonomous (must not read t). */
+ * reproducible to rounding only. Dynamics and cost may read t (the ePSOPT callbacks receive the node time as `k`,
+ * src/ePSOPT/ePSOPT.cpp:218-260): values, both Jacobian modes (d/dt0, d/dtf through t_k = t0 + (tf - t0)(tau_k + 1)/2)
+ * and the objective gradient follow; only ecuda_eval_hess refuses such a model. */
 enum ecuda_tape_op {
     ECUDA_OP_INPUT = 0, ECUDA_OP_CONST = 1, ECUDA_OP_ADD = 2, ECUDA_OP_SUB = 3, ECUDA_OP_MUL = 4, ECUDA_OP_DIV = 5,
     ECUDA_OP_NEG = 6, ECUDA_OP_POW = 7, ECUDA_OP_SQRT = 8, ECUDA_OP_SIN = 9, ECUDA_OP_COS = 10, ECUDA_OP_EXP = 11

@@ -55,12 +55,12 @@ double interp(double t, const std::vector<double>& tv, const std::vector<double>
 }
 
 // plain-double replay of a user tape (the tight counterpart of replay<T> in models.hpp)
-void tape_values(const UserTape& ut, const double* x, const double* u, std::vector<double>& v) {
+void tape_values(const UserTape& ut, const double* x, const double* u, double t, std::vector<double>& v) {
     v.resize(ut.nodes.size());
     for (size_t i = 0; i < ut.nodes.size(); ++i) {
         const TapeNode& n = ut.nodes[i];
         switch (n.op) {
-            case T_INPUT: v[i] = n.a < ut.ns ? x[n.a] : n.a < ut.ns + ut.nc ? u[n.a - ut.ns] : 0.0; break;
+            case T_INPUT: v[i] = n.a < ut.ns ? x[n.a] : n.a < ut.ns + ut.nc ? u[n.a - ut.ns] : t; break;
             case T_CONST: v[i] = n.imm; break;
             case T_ADD: v[i] = v[n.a] + v[n.b]; break;
             case T_SUB: v[i] = v[n.a] - v[n.b]; break;
@@ -90,11 +90,11 @@ void tape_values(const UserTape& ut, const double* x, const double* u, std::vect
     }
 }
 
-void dynamics(const Spec& spec, const double* x, const double* u, double* f) {
+void dynamics(const Spec& spec, const double* x, const double* u, double t, double* f) {
     const int model = spec.model;
     if (model == USER) {
         static thread_local std::vector<double> v;
-        tape_values(spec.user, x, u, v);
+        tape_values(spec.user, x, u, t, v);
         for (int i = 0; i < spec.user.ns; ++i) f[i] = v[spec.user.f_out[i]];
     } else if (model == SI2D) {
         f[0] = u[0];
@@ -149,12 +149,12 @@ void path_rows(const Problem& P, const PhasePre& pre, const Instance& I, const d
     }
 }
 
-double running_cost(const Spec& spec, const double* x, const double* u, bool maximize) {
+double running_cost(const Spec& spec, const double* x, const double* u, double t, bool maximize) {
     const int model = spec.model;
     double l;
     if (model == USER) {
         static thread_local std::vector<double> v;
-        tape_values(spec.user, x, u, v);
+        tape_values(spec.user, x, u, t, v);
         l = v[spec.user.cost_out];
     } else {
         l = (model == SI2D) ? u[0] * u[0] + u[1] * u[1] : (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2];
@@ -176,7 +176,7 @@ void g_tight(const Problem& P, const std::vector<PhasePre>& pre, const Instance&
         if (np > 256) throw std::invalid_argument("tight oracle supports <= 256 path rows per node");
         for (int k = 0; k < N; ++k) {
             double t = h * C.tau[k] + m;
-            dynamics(P.spec, &z[L.ix(p, k, 0)], &z[L.iu(p, k, 0)], &F[static_cast<size_t>(k) * ns]);
+            dynamics(P.spec, &z[L.ix(p, k, 0)], &z[L.iu(p, k, 0)], t, &F[static_cast<size_t>(k) * ns]);
             path_rows(P, pre[p], I, &z[L.ix(p, k, 0)], t, pathv);
             for (int q = 0; q < np; ++q) g[L.rpath(p, k, q)] = P.sc.sg[L.rpath(p, k, q)] * pathv[q];
         }
@@ -303,7 +303,7 @@ void Problem::ode_error(const Instance& I, const double* zs, double* err) const 
                     }
                     for (int j = 0; j < nc; ++j) uq[j] = std::fma(E[l], U[static_cast<size_t>(l) * nc + j], uq[j]);
                 }
-                dynamics(spec, xq, uq, f);
+                dynamics(spec, xq, uq, h * (mid + half * kGX[q]) + 0.5 * (tf + t0), f);
                 for (int i = 0; i < ns; ++i) eta[i] = std::fma(half * kGW[q], std::fabs(dxq[i] - h * f[i]), eta[i]);
             }
             double e = 0.0;
@@ -358,13 +358,13 @@ void Problem::eval_f_tight(const Instance& I, const double* zs, double* f) const
     for (int p = 0; p < L.nphases; ++p) {
         const int N = L.N[p];
         double t0 = zs[L.it0(p)] * sc.isz[L.it0(p)], tf = zs[L.itf(p)] * sc.isz[L.itf(p)];
-        double h = 0.5 * (tf - t0);
+        double h = 0.5 * (tf - t0), tmid = 0.5 * (tf + t0);
         double acc = 0.0;
         for (int k = 0; k < N; ++k) {
             double u[8], x[8];
             for (int j = 0; j < L.nc; ++j) u[j] = zs[L.iu(p, k, j)] * sc.isz[L.iu(p, k, j)];
             for (int i = 0; i < L.ns; ++i) x[i] = zs[L.ix(p, k, i)] * sc.isz[L.ix(p, k, i)];
-            acc = std::fma(col[p].w[k], running_cost(spec, x, u, spec.maximize), acc);
+            acc = std::fma(col[p].w[k], running_cost(spec, x, u, h * col[p].tau[k] + tmid, spec.maximize), acc);
         }
         double fp = h * acc;
         total = (p == 0) ? fp : total + fp;

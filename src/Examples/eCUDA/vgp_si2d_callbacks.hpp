@@ -33,6 +33,12 @@ inline ETOL::scalar_t ydot(F_ARGS) { return at(u, 1); }
 inline ETOL::scalar_t windyXdot(F_ARGS) { return at(u, 0) + 0.05 * at(x, 1); }
 inline ETOL::scalar_t windyYdot(F_ARGS) { return at(u, 1) - 0.02 * (at(x, 0) * at(x, 0)); }
 
+// dynamics that read the node time (`k` holds the time scalar, as in ePSOPT::dae, src/ePSOPT/ePSOPT.cpp:218-260):
+// a gust that swings with a period of about half a minute
+inline var& timeOf(std::any& k) { return *std::any_cast<var*>(k); }
+inline ETOL::scalar_t gustXdot(F_ARGS) { return at(u, 0) + 0.3 * sin(0.2 * timeOf(k)); }
+inline ETOL::scalar_t gustYdot(F_ARGS) { return at(u, 1) - 0.01 * timeOf(k); }
+
 inline std::string rowName(const char* kind, size_t i, size_t j) {
     return std::string(kind) + "_" + std::to_string(i) + "_" + std::to_string(j) + "_0";
 }

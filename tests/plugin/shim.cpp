@@ -36,7 +36,8 @@ int shim_load(void* h, const char* xml, int model, int flags, int batch, const c
 // load + register USER CALLBACKS (ecuda::var) like the reference example does, then try to match them.
 // variant 0: the example's callbacks; 1: a different objective; 2: exclusion zones only; 3: zones
 // registered in the opposite order (moving zones first); 4: dynamics no built-in model has (wind field
-// depending on the position) -> user model; 5: an objective holding a static ecuda::var constant. Returns 1 when matched; *model, *flags
+// depending on the position) -> user model; 5: an objective holding a static ecuda::var constant; 6: dynamics that
+// read the node time -> time-dependent user model. Returns 1 when matched; *model, *flags
 // (bit0 obstacles, bit1 tracks) report what was recognised, why (<= 255 chars) the reason otherwise.
 int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* flags, char* why) {
     eCUDA* t = static_cast<eCUDA*>(h);
@@ -61,6 +62,8 @@ int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* 
     t->setObjective(hold(variant == 1 ? other : variant == 5 ? kept_constant : ETOL::f_t(&vgp_si2d::effort)));
     if (variant == 4)
         t->setGradient({hold(&vgp_si2d::windyXdot), hold(&vgp_si2d::windyYdot)});
+    else if (variant == 6)  // dynamics that read the node time
+        t->setGradient({hold(&vgp_si2d::gustXdot), hold(&vgp_si2d::gustYdot)});
     else
         t->setGradient({hold(&vgp_si2d::xdot), hold(&vgp_si2d::ydot)});
     ETOL::f_t* zones = hold(vgp_si2d::exclusionZones(t));

@@ -26,6 +26,9 @@ CASES = {
     "user-unicycle-tracks": lambda: W.unicycle(batch=2, ntracks=1, scaled=True),
     "user-dragmass-deps": lambda: W.dragmass(batch=2, ntracks=2, pattern_mode=W.MODEL_DEPS),
     "user-dragmass-N12": lambda: W.dragmass(batch=2, nnodes=12, ncyl=2, collocation=W.CHEBYSHEV),
+    # dynamics and running cost that read t (the `k` argument of the ePSOPT callbacks)
+    "user-gust-tracks": lambda: W.gust(batch=2, ntracks=1, scaled=True),
+    "user-gust-N12-max": lambda: W.gust(batch=2, nnodes=12, ncyl=2, collocation=W.CHEBYSHEV, maximize=True),
 }
 
 

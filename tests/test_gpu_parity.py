@@ -42,6 +42,10 @@ CASES = {
     "user-dragmass": lambda: W.dragmass(batch=5, ntracks=1, scaled=True),
     "user-dragmass-N12-generic": lambda: W.dragmass(batch=3, nnodes=12, ncyl=2),
     "user-dragmass-N70-generic": lambda: W.dragmass(batch=2, nnodes=70, ncyl=3, maximize=True),
+    # user models whose dynamics and running cost read t (VERDICT r1 missing item 3)
+    "user-gust": lambda: W.gust(batch=5, ntracks=1, scaled=True),
+    "user-gust-cheb-deps": lambda: W.gust(batch=3, nnodes=40, collocation=W.CHEBYSHEV, pattern_mode=W.MODEL_DEPS),
+    "user-gust-N70-generic": lambda: W.gust(batch=2, nnodes=70, ncyl=3, maximize=True),
 }
 
 
@@ -89,7 +93,7 @@ def test_values_match_oracle(evaluators, name, mode):
 
 MESH_CASES = ["C0-ocp", "C0-ocp-cheb-max", "C2-pm3d-scaled-deps", "C3-fw6", "C3-fw6-small-scaled", "C4-multiphase",
               "C4-multiphase-ragged", "pm3d-N2", "pm3d-N65", "user-unicycle-tracks", "user-dragmass",
-              "user-dragmass-N70-generic"]
+              "user-dragmass-N70-generic", "user-gust", "user-gust-N70-generic"]
 
 
 @pytest.mark.parametrize("name", MESH_CASES)
@@ -329,6 +333,14 @@ def test_compact_exact_jacobian_splices_to_the_full_one(evaluators, name):
     ev.eval_compact_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jl.data_ptr(), capi.MEM_DEVICE, None)
     ev.sync()
     assert np.array_equal(jl.cpu().numpy(), out["jac_local"]) and np.array_equal(g.cpu().numpy(), full["g"])
+
+
+def test_hessian_refuses_time_dependent_user_models_loudly(evaluators):
+    """values, both Jacobian modes and the gradient support dynamics that read t; the exact Hessian does not yet, and
+    says so instead of returning second derivatives without the time couplings"""
+    ev, orc, wl = _get(evaluators, "user-gust")
+    with pytest.raises(RuntimeError, match="read t"):
+        ev.hess_host(wl.x, np.ones(wl.batch), np.zeros((wl.batch, ev.ncons)))
 
 
 def test_full_size_batch_properties():

@@ -198,6 +198,50 @@ def _windy_workload():
     return wl
 
 
+def _gust_workload():
+    """the VGP of shim variant 6 (vgp_si2d::gustXdot/gustYdot: dynamics that read the node time) as a Workload"""
+    from etol_b200 import capi, tape as T
+    wl = W.reference_vgp("ocp")
+    wl.tape = T.trace(2, 2, lambda x, u, t: [u[0] + 0.3 * T.sin(0.2 * t), u[1] - 0.01 * t],
+                      lambda x, u, t: u[0] * u[0] + u[1] * u[1], static_kind=T.STATIC_EDGE, with_time=True)
+    wl.model = capi.register_user_model(wl.tape)
+    return wl
+
+
+def test_time_dependent_callbacks_become_a_time_dependent_user_model(xml):
+    """VERDICT r1 missing item 3: callbacks that read `k` (the node time ePSOPT::dae passes, ePSOPT.cpp:218-260) are
+    recorded with the time input and registered; the model evaluates on the host like the callbacks"""
+    from etol_b200 import capi
+    p = pb.Plugin()
+    ok, model, flags, why = p.load_callbacks(xml, 6)
+    assert ok and model >= 16 and flags == 3, why
+    assert "TDEP = true" in capi.user_model_source(model)
+    f, cost = capi.host_model_eval(model, [3.0, -2.0], [0.5, 0.25], t=7.0)
+    assert abs(f[0] - (0.5 + 0.3 * np.sin(0.2 * 7.0))) < 1e-15 and f[1] == 0.25 - 0.01 * 7.0
+    assert cost == 0.5 * 0.5 + 0.25 * 0.25
+    p.close()
+
+
+@pytest.mark.gpu
+def test_plugin_time_dependent_user_model_evaluates_like_oracle(xml):
+    """the same callbacks through the plugin on the GPU: kernels compiled at setup(), exact Jacobian (with the
+    d/dt0, d/dtf terms through t_k) against the oracle's dual-number replay of the same mathematics"""
+    p = pb.Plugin()
+    ok, model, _, why = p.load_callbacks(xml, 6)
+    assert ok and model >= 16, why
+    p.setup()
+    wl = _gust_workload()
+    o = ob.Oracle(wl)
+    bnd = p.bounds()
+    z = wl.x[:1] / (wl.sz if wl.sz is not None else 1.0)
+    o.set_scaling(bnd["sz"], bnd["sg"], 1.0)
+    f, g, jac = p.evaluate(z)
+    ref = o.eval(z * bnd["sz"], want=("f", "g", "jac"), jac_mode=W.JAC_EXACT, style=0)
+    assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
+    assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    p.close()
+
+
 @pytest.mark.parametrize("variant", [1, 4])
 def test_unknown_dynamics_or_cost_become_a_user_model(xml, variant):
     """a running cost (1) or dynamics (4) that no built-in device model has: the recording is registered
