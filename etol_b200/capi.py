@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "ecuda_host_dims", "ecuda_host_structure", "ecuda_host_compact_structure", "ecuda_host_collocation", "ecuda_host_model_eval",
     "ecuda_host_path_eval", "ecuda_get_hess_structure", "ecuda_eval_hess", "ecuda_ipopt_eval_h", "ecuda_host_hess_structure",
     "ecuda_ode_error", "ecuda_resample", "ecuda_host_error_mesh", "ecuda_host_resample_matrix",
-    "ecuda_register_user_model", "ecuda_user_model_source", "ecuda_user_model_compile_check",
+    "ecuda_register_user_model", "ecuda_register_user_model_rows", "ecuda_user_model_source", "ecuda_user_model_compile_check",
 ]
 
 _lib = None
@@ -123,6 +123,7 @@ def lib():
     L.ecuda_resample.argtypes = [C.c_void_p, C.c_void_p, _ip, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ecuda_host_error_mesh.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
     L.ecuda_host_resample_matrix.argtypes = [C.c_int, C.c_int, C.c_int, _dp]
+    L.ecuda_register_user_model_rows.argtypes = [C.POINTER(UserModel), C.c_int32, _ip, _ip, C.c_char_p, C.c_size_t]
     L.ecuda_register_user_model.argtypes = [C.POINTER(UserModel), _ip, C.c_char_p, C.c_size_t]
     L.ecuda_user_model_source.argtypes = [C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.ecuda_user_model_compile_check.argtypes = [C.c_int32, C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
@@ -153,7 +154,13 @@ def register_user_model(tape):
     um.cost_out = tape.cost_out
     mid = C.c_int32(-1)
     err = C.create_string_buffer(512)
-    if lib().ecuda_register_user_model(C.byref(um), C.byref(mid), err, len(err)) != 0:
+    rows = np.array(getattr(tape, "row_out", []), dtype=np.int32)
+    if rows.size:  # traced path rows
+        rc = lib().ecuda_register_user_model_rows(C.byref(um), int(rows.size), rows.ctypes.data_as(_ip), C.byref(mid), err,
+                                                  len(err))
+    else:
+        rc = lib().ecuda_register_user_model(C.byref(um), C.byref(mid), err, len(err))
+    if rc != 0:
         raise EcudaError("ecuda_register_user_model: " + err.value.decode())
     _registered[key] = mid.value
     return mid.value
@@ -265,6 +272,18 @@ def edge_records(corners_xy):
     if lib().ecuda_si2d_edge_records(_p(c), c.shape[0], _p(out)) != 0:
         raise EcudaError("ecuda_si2d_edge_records failed")
     return out
+
+
+def host_path_eval(wl, inst_row, x, y, t):
+    """path rows of phase 0 of one instance block at position (x, y), time t (static, moving-zone, traced rows)"""
+    d = make_desc(wl)
+    inst_row = np.ascontiguousarray(inst_row, dtype=np.float64)
+    rows = np.zeros(wl.npath[0])
+    L = lib()
+    L.ecuda_host_path_eval.argtypes = [C.POINTER(ProblemDesc), _dp, C.c_double, C.c_double, C.c_double, _dp]
+    if L.ecuda_host_path_eval(C.byref(d), _p(inst_row), float(x), float(y), float(t), _p(rows)) != 0:
+        raise EcudaError("ecuda_host_path_eval failed")
+    return rows
 
 
 def pack_instances(wl, dims=None):

@@ -1393,9 +1393,10 @@ int ecuda_eval_hess(ecuda_handle h, const double* x, const double* sigma, double
     if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
     if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
     if (!x || !lambda || !vals) return fail(h, ECUDA_ERR_ARG, "x, lambda and vals are required");
-    if (h->um && h->um->tdep)
+    if (h->um && (h->um->tdep || !h->um->row_out.empty()))
         return fail(h, ECUDA_ERR_ARG, "the exact Hessian is not available for user models whose dynamics or cost read t "
-                                      "(values, both Jacobian modes and the objective gradient are)");
+                                      "or that have traced path rows (values, both Jacobian modes and the objective "
+                                      "gradient are)");
     if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
@@ -1688,6 +1689,8 @@ int ecuda_host_path_eval(const ecuda_problem_desc* desc, const double* inst, dou
     }
     for (int i = 0; i < desc->ntracks; ++i)
         rows[nstat + i] = track_row(inst + hp.track_off + i * hp.dims.track_size, desc->nwaypoints, x, y, t);
+    if (const UserModel* um = desc->model >= ECUDA_MODEL_USER_BASE ? user_model(desc->model) : nullptr)
+        user_model_rows(*um, x, y, t, rows + nstat + desc->ntracks);  // traced path rows
     return ECUDA_OK;
 }
 

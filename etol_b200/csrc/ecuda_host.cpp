@@ -185,11 +185,13 @@ bool build_layout(const ecuda_problem_desc& d, HostProblem* hp, std::string* err
     hp->N.clear(); hp->npath.clear(); hp->nstat.clear(); hp->zoff.clear(); hp->goff.clear();
     hp->nvars_p.clear(); hp->inst_off.clear();
     int z = 0, g = 0, io = 0;
+    const UserModel* um = d.model >= ECUDA_MODEL_USER_BASE ? user_model(d.model) : nullptr;
+    const int nuser = um ? static_cast<int>(um->row_out.size()) : 0;  // traced path rows of a user model
     for (int p = 0; p < d.nphases; ++p) {
         const int N = d.nnodes[p];
         if (N < 2) return fail("a phase needs at least 2 collocation nodes");
         if (d.nstatic[p] < 0) return fail("negative obstacle count");
-        const int np = d.nstatic[p] + d.ntracks;
+        const int np = d.nstatic[p] + d.ntracks + nuser;
         hp->N.push_back(N);
         hp->nstat.push_back(d.nstatic[p]);
         hp->npath.push_back(np);

@@ -177,6 +177,8 @@ struct UserModel {
     // node ids of the partial derivatives, -1 = identically zero
     int dfdx[ECUDA_MAX_STATES][ECUDA_MAX_STATES], dfdu[ECUDA_MAX_STATES][ECUDA_MAX_CONTROLS];
     int dcdx[ECUDA_MAX_STATES], dcdu[ECUDA_MAX_CONTROLS];
+    // traced path rows (may read states 0, 1 and t): output nodes and their partials (-1 = identically zero)
+    std::vector<int> row_out, drdx, drdy, drdt;
     bool tdep = false;                   // some f_i or the running cost reads t
     int dfdt[ECUDA_MAX_STATES], dcdt = -1;
     // second derivatives over [x | u]: d2[(o * nv + a) * nv + b], a <= b, o < ns: f_o, o == ns: cost
@@ -192,7 +194,9 @@ struct UserImage {
     std::string log;
 };
 const UserModel* user_model(int model_id);  // null when the id is not registered
-int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::string* err);
+int register_user_model(const ecuda_user_model* um, int nrows, const int32_t* row_out, int32_t* model_id, std::string* err);
+// values of the traced path rows of a user model at one point (host)
+void user_model_rows(const UserModel& m, double x0, double x1, double t, double* rows);
 void user_model_eval(const UserModel& m, const double* x, const double* u, double t, double* f_out, double* cost_out);
 void user_model_partials(const UserModel& m, const double* x, const double* u, double t, double* dfdx, double* dfdu,
                          double* dcdx, double* dcdu);

@@ -140,6 +140,7 @@ struct Model<ECUDA_MODEL_SI2D> {
     // diagonal triplet of that column needs no second evaluation of the dynamics
     static constexpr bool DIAG_FREE = true;
     static constexpr bool TDEP = false;  // neither the dynamics nor the running cost read t
+    static constexpr int NUSER = 0;  // traced path rows exist for user models only
     ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // which states / controls f_i reads, 8 bits per i (same data as model_info() on the host): a
     // finite-difference triplet of a variable f_i does not read is exactly +0.0 and is stored as such
@@ -177,6 +178,7 @@ struct Model<ECUDA_MODEL_PM3D> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i
     static constexpr bool TDEP = false;
+    static constexpr int NUSER = 0;  // traced path rows exist for user models only
     ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // 8 bits per i: f_0..f_2 read x_3..x_5, f_3..f_5 read u_0..u_2
     static constexpr unsigned long long FX = 0x000000201008ull, FU = 0x040201000000ull;
@@ -216,6 +218,7 @@ struct Model<ECUDA_MODEL_FW6> {
     static constexpr int NS = 6, NCU = 3, REC = 4;
     static constexpr bool DIAG_FREE = true;  // f_i never reads x_i (x,y,z,V,gamma,psi derivatives)
     static constexpr bool TDEP = false;
+    static constexpr int NUSER = 0;  // traced path rows exist for user models only
     ECUDA_HD static void dtime(const double*, const double*, double, double*, double* dLdt) { *dLdt = 0.0; }
     // 8 bits per i: f_0, f_1 read V, gamma, psi; f_2 reads V, gamma; f_3 reads gamma and u_0; f_4, f_5 read u_1, u_2
     static constexpr unsigned long long FX = 0x000010183838ull, FU = 0x040201000000ull;

@@ -183,7 +183,22 @@ template <int M>
 ECUDA_HD double path_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int q, double x, double y,
                          double t) {
     if (q < ph.nstat) return Model<M>::static_row(m.inst + ph.inst_off + q * Model<M>::REC, x, y);
+    if constexpr (Model<M>::NUSER > 0) {  // traced path rows of a user model follow the moving-zone rows
+        if (q - ph.nstat >= pb.ntracks) return Model<M>::user_row(q - ph.nstat - pb.ntracks, x, y, t);
+    }
     return track_row(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x, y, t);
+}
+// partials of path row q >= nstat (a moving zone, or a traced row of a user model) in x_0, x_1 and t
+template <int M>
+ECUDA_HD void moving_row_partials(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int q, double x, double y,
+                                  double t, double* ddx, double* ddy, double* ddt) {
+    if constexpr (Model<M>::NUSER > 0) {
+        if (q - ph.nstat >= pb.ntracks) {
+            Model<M>::user_row_partials(q - ph.nstat - pb.ntracks, x, y, t, ddx, ddy, ddt);
+            return;
+        }
+    }
+    track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x, y, t, ddx, ddy, ddt);
 }
 
 // canonical blocked dot of row k of D with state j of X: blocks of ECUDA_DOT_BLOCK nodes, each a
@@ -450,7 +465,7 @@ ECUDA_HD void xcol_path_exact(const ProbDev& pb, const PhaseDev& ph, const CtaMe
     if (q < ph.nstat)
         Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x0, x1, &ddx, &ddy);
     else
-        track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x0, x1, t, &ddx, &ddy, &ddt);
+        moving_row_partials<M>(pb, ph, m, q, x0, x1, t, &ddx, &ddy, &ddt);
     const double v = (j == 0) ? ddx : ddy;
     const int r = ph.goff + ns * N + pb.ne + k * np + q;
     const int pos = N - 1 + pb.xcnt[j] + ((k == 0 || k == N - 1) ? 1 : 0) + q;
@@ -810,8 +825,7 @@ ECUDA_HD void node_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eval
         }
         for (int q = ph.nstat; q < np; ++q) {
             double ddx, ddy, ddt;
-            track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x[0], x[1], t, &ddx,
-                               &ddy, &ddt);
+            moving_row_partials<M>(pb, ph, m, q, x[0], x[1], t, &ddx, &ddy, &ddt);
             jstore<SM>(jac + base + ns * N + k * ntr + (q - ph.nstat),
                                (ECUDA_LDG(sg + rpath0 + q) * (ddt * dtk)) * is);
         }

@@ -325,8 +325,7 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             if (q < ph.nstat)
                 Model<M>::static_row_dxy(m.inst + ph.inst_off + q * Model<M>::REC, x0, x1, &ddx, &ddy);
             else
-                track_row_partials(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x0, x1, t, &ddx, &ddy,
-                                   &ddt);
+                moving_row_partials<M>(pb, ph, m, q, x0, x1, t, &ddx, &ddy, &ddt);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int lcol = lcol0 + j;

@@ -260,6 +260,28 @@ std::string generate_source(const UserModel& m) {
             }
     }
     o << "    }\n";
+    // traced path rows
+    o << "    static constexpr int NUSER = " << m.row_out.size() << ";\n"
+      << "    ECUDA_HD static double user_row(int r, double x0, double x1, double t) {\n"
+         "        const double x[2] = {x0, x1};\n        const double* u = nullptr;\n        (void)x; (void)u; (void)t;\n";
+    for (size_t r = 0; r < m.row_out.size(); ++r) {
+        o << "        if (r == " << r << ") {\n";
+        print_body(m, {m.row_out[r]}, o);
+        o << "        return v" << m.row_out[r] << ";\n        }\n";
+    }
+    o << "        return 0.0;\n    }\n"
+      << "    ECUDA_HD static void user_row_partials(int r, double x0, double x1, double t, double* ddx, double* ddy, double* ddt) {\n"
+         "        const double x[2] = {x0, x1};\n        const double* u = nullptr;\n        (void)x; (void)u; (void)t;\n"
+         "        *ddx = 0.0; *ddy = 0.0; *ddt = 0.0;\n";
+    for (size_t r = 0; r < m.row_out.size(); ++r) {
+        o << "        if (r == " << r << ") {\n";
+        print_body(m, {m.drdx[r], m.drdy[r], m.drdt[r]}, o);
+        if (m.drdx[r] >= 0) o << "        *ddx = v" << m.drdx[r] << ";\n";
+        if (m.drdy[r] >= 0) o << "        *ddy = v" << m.drdy[r] << ";\n";
+        if (m.drdt[r] >= 0) o << "        *ddt = v" << m.drdt[r] << ";\n";
+        o << "        }\n";
+    }
+    o << "    }\n";
     const char* row = m.static_kind == ECUDA_STATIC_EDGE ? "edge_row" : "cylinder_row";
     o << "    ECUDA_HD static double static_row(const double* rec, double x, double y) { return " << row
       << "(rec, x, y); }\n"
@@ -319,6 +341,13 @@ void user_model_eval(const UserModel& m, const double* x, const double* u, doubl
     if (cost_out) *cost_out = v[m.cost_out];
 }
 
+void user_model_rows(const UserModel& m, double x0, double x1, double t, double* rows) {
+    std::vector<double> v;
+    const double x[ECUDA_MAX_STATES] = {x0, x1}, u[ECUDA_MAX_CONTROLS] = {0};
+    tape_values(m, x, u, t, &v);
+    for (size_t r = 0; r < m.row_out.size(); ++r) rows[r] = v[m.row_out[r]];
+}
+
 void user_model_partials(const UserModel& m, const double* x, const double* u, double t, double* dfdx, double* dfdu,
                          double* dcdx, double* dcdu) {
     std::vector<double> v;
@@ -339,7 +368,7 @@ const UserModel* user_model(int model_id) {
     return g_models[idx].get();
 }
 
-int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::string* err) {
+int register_user_model(const ecuda_user_model* um, int nrows, const int32_t* row_out, int32_t* model_id, std::string* err) {
     auto bad = [&](const std::string& msg) {
         *err = msg;
         return ECUDA_ERR_ARG;
@@ -349,13 +378,15 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
     if (um->ncontrols < 1 || um->ncontrols > ECUDA_MAX_CONTROLS) return bad("ncontrols must be 1..8");
     if (um->static_kind != ECUDA_STATIC_CYLINDER && um->static_kind != ECUDA_STATIC_EDGE) return bad("bad static_kind");
     if (um->nnodes < 1 || um->nnodes > (1 << 16)) return bad("tape length must be 1..65536");
+    if (nrows < 0 || nrows > ECUDA_MAX_USER_ROWS || (nrows > 0 && !row_out)) return bad("traced path rows: 0..16 per node");
     {  // the same model registered again (e.g. a plugin re-transcribing on a refined mesh): the same id
         std::lock_guard<std::mutex> lock(g_mu);
         for (const auto& e : g_models) {
             if (e->ns != um->nstates || e->nc != um->ncontrols || e->static_kind != um->static_kind ||
-                e->nregistered != um->nnodes || e->cost_out != um->cost_out)
+                e->nregistered != um->nnodes || e->cost_out != um->cost_out || static_cast<int>(e->row_out.size()) != nrows)
                 continue;
             bool same = true;
+            for (int r = 0; r < nrows && same; ++r) same = e->row_out[r] == row_out[r];
             for (int i = 0; i < um->nstates && same; ++i) same = e->f_out[i] == um->f_out[i];
             for (int k = 0; k < um->nnodes && same; ++k) {
                 const ecuda_tape_node &a = e->nodes[k], &b = um->nodes[k];
@@ -421,6 +452,13 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
         m->fx[i] = deps[m->f_out[i]] & ((1u << m->ns) - 1u);
         m->fu[i] = (deps[m->f_out[i]] >> m->ns) & ((1u << m->nc) - 1u);
     }
+    for (int r = 0; r < nrows; ++r) {
+        if (!out_ok(row_out[r])) return bad("row_out[" + std::to_string(r) + "] is not a tape node");
+        if (deps[row_out[r]] & ~(3u | tbit))
+            return bad("traced path row " + std::to_string(r) + " reads more than states 0, 1 and t (the read set of a "
+                       "moving-zone row, whose sparsity traced rows share)");
+        m->row_out.push_back(row_out[r]);
+    }
     // derivatives, appended to the same node list
     Pool P{m->nodes, deps};
     for (int i = 0; i < ECUDA_MAX_STATES; ++i) {
@@ -435,6 +473,11 @@ int register_user_model(const ecuda_user_model* um, int32_t* model_id, std::stri
         m->dcdx[i] = differentiate(P, m->cost_out, i);
     }
     for (int j = 0; j < m->nc; ++j) m->dcdu[j] = differentiate(P, m->cost_out, m->ns + j);
+    for (int id : m->row_out) {
+        m->drdx.push_back(differentiate(P, id, 0));
+        m->drdy.push_back(differentiate(P, id, 1));
+        m->drdt.push_back(differentiate(P, id, m->ns + m->nc));
+    }
     for (int i = 0; i < ECUDA_MAX_STATES; ++i) m->dfdt[i] = -1;
     for (int i = 0; i < m->ns; ++i) m->dfdt[i] = differentiate(P, m->f_out[i], m->ns + m->nc);
     m->dcdt = differentiate(P, m->cost_out, m->ns + m->nc);
@@ -632,7 +675,15 @@ extern "C" {
 
 int ecuda_register_user_model(const ecuda_user_model* m, int32_t* model_id, char* err, size_t errlen) {
     std::string e;
-    const int rc = ecuda::register_user_model(m, model_id, &e);
+    const int rc = ecuda::register_user_model(m, 0, nullptr, model_id, &e);
+    if (rc && err && errlen) std::snprintf(err, errlen, "%s", e.c_str());
+    return rc;
+}
+
+int ecuda_register_user_model_rows(const ecuda_user_model* m, int32_t nrows, const int32_t* row_out, int32_t* model_id,
+                                   char* err, size_t errlen) {
+    std::string e;
+    const int rc = ecuda::register_user_model(m, nrows, row_out, model_id, &e);
     if (rc && err && errlen) std::snprintf(err, errlen, "%s", e.c_str());
     return rc;
 }

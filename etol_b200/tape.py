@@ -21,13 +21,14 @@ class Tape:
     nodes: List[Tuple[int, int, int, float]] = field(default_factory=list)  # (op, a, b, imm)
     f_out: List[int] = field(default_factory=list)
     cost_out: int = -1
+    row_out: List[int] = field(default_factory=list)  # traced path rows (may read states 0, 1 and t)
 
     def push(self, op, a=-1, b=-1, imm=0.0):
         self.nodes.append((op, a, b, float(imm)))
         return len(self.nodes) - 1
 
     def key(self):
-        return (self.ns, self.nc, self.static_kind, tuple(self.nodes), tuple(self.f_out), self.cost_out)
+        return (self.ns, self.nc, self.static_kind, tuple(self.nodes), tuple(self.f_out), self.cost_out, tuple(self.row_out))
 
 
 class Var:
@@ -68,7 +69,7 @@ def cos(v): return _un(OP_COS, v)
 def exp(v): return _un(OP_EXP, v)
 
 
-def trace(ns, nc, dynamics, cost, static_kind=STATIC_CYLINDER, with_time=False):
+def trace(ns, nc, dynamics, cost, static_kind=STATIC_CYLINDER, with_time=False, rows=None):
     """with_time: the callbacks also receive the node time, `dynamics(x, u, t)` / `cost(x, u, t)` -- the `k` argument
     of the ePSOPT callbacks (src/ePSOPT/ePSOPT.cpp:218-260 of the ETOL tree)."""
     t = Tape(ns, nc, static_kind)
@@ -79,6 +80,11 @@ def trace(ns, nc, dynamics, cost, static_kind=STATIC_CYLINDER, with_time=False):
     assert len(f) == ns, "one state derivative per state"
     t.f_out = [x[0]._lift(v).id for v in f]
     t.cost_out = x[0]._lift(cost(x, u, *extra)).id
+    if rows is not None:
+        # traced path constraints: `rows(x0, x1, t) -> [values]`, evaluated at every node after the built-in zone rows
+        # (what ePSOPT does with every entry of _constraints, src/ePSOPT/ePSOPT.cpp:262-270)
+        tv = extra[0] if with_time else Var(t, t.push(OP_INPUT, ns + nc))
+        t.row_out = [x[0]._lift(v).id for v in rows(x[0], x[1], tv)]
     return t
 
 
@@ -115,3 +121,33 @@ def gust_tape(cd=0.02, w0=1.5, omega=0.11):
                 u[0] - cd * speed * x[2], u[1] - cd * speed * x[3]]
     return trace(4, 2, dyn, lambda x, u, t: ((u[0] * u[0] + u[1] * u[1]) + 0.1 * (x[2] * x[2] + x[3] * x[3])) * (1.0 + 0.01 * t),
                  with_time=True)
+
+
+def zone_rows(x0, x1, t):
+    """Path constraints none of the built-in zone rows can express, written as callbacks: a keep-out disc that grows
+    with time, an ellipse whose centre drifts with time, and a wall that only reads the first position state."""
+    grow = 40.0 + 0.8 * t
+    disc = grow * grow - ((x0 - 500.0) ** 2 + (x1 - 500.0) ** 2)
+    cx, cy = 200.0 + 4.0 * t, 700.0 - 3.0 * t
+    ell = 1.0 - (((x0 - cx) / 60.0) ** 2 + ((x1 - cy) / 30.0) ** 2)
+    wall = (x0 - 990.0) * 0.5
+    return [disc, ell, wall]
+
+
+def zone_tape(cd=0.02):
+    """the drag model with three traced path rows (zone_rows)"""
+    def dyn(x, u):
+        speed = sqrt(x[2] ** 2 + x[3] ** 2 + 1e-6)
+        return [x[2], x[3], u[0] - cd * speed * x[2], u[1] - cd * speed * x[3]]
+    return trace(4, 2, dyn, lambda x, u: (u[0] * u[0] + u[1] * u[1]) + 0.1 * (x[2] * x[2] + x[3] * x[3]), rows=zone_rows)
+
+
+def gust_zone_tape():
+    """time-dependent dynamics and cost (gust_tape) together with the traced path rows"""
+    g = gust_tape()
+    def dyn(x, u, t):
+        speed = sqrt(x[2] ** 2 + x[3] ** 2 + 1e-6)
+        amp = 1.5 * (1.0 + 0.02 * t)
+        return [x[2] + amp * cos(0.11 * t), x[3] + amp * sin(0.11 * t), u[0] - 0.02 * speed * x[2], u[1] - 0.02 * speed * x[3]]
+    return trace(4, 2, dyn, lambda x, u, t: ((u[0] * u[0] + u[1] * u[1]) + 0.1 * (x[2] * x[2] + x[3] * x[3])) * (1.0 + 0.01 * t),
+                 with_time=True, rows=zone_rows)

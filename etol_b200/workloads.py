@@ -69,7 +69,8 @@ class Workload:
 
     @property
     def npath(self):
-        return [s + self.ntracks for s in self.nstatic]
+        nuser = len(getattr(self.tape, "row_out", [])) if getattr(self, "tape", None) is not None else 0
+        return [s + self.ntracks + nuser for s in self.nstatic]
 
     @property
     def nvars(self):
@@ -405,3 +406,10 @@ def gust(batch=8, **kw):
     """planar point mass with drag in a time-varying wind, time-weighted cost: dynamics and cost read t"""
     from . import tape as T
     return planar_user(T.gust_tape(), batch=batch, name="user-gust", rest=(4.0, -3.0), **kw)
+
+
+def zone(batch=8, timedep=False, **kw):
+    """drag model (optionally in the time-varying wind) with three traced path constraints: a growing disc, a
+    drifting ellipse and a wall -- none of them a built-in zone row"""
+    from . import tape as T
+    return planar_user(T.gust_zone_tape() if timedep else T.zone_tape(), batch=batch, name="user-zone", rest=(4.0, -3.0), **kw)

@@ -62,6 +62,8 @@ class eCUDA : public TrajectoryOptimizer {
     // VGP data. False (with a reason) when nothing matches; setup() then fails like ePSOPT does on a
     // bad callback. Called by transcribe() when callbacks are registered.
     bool matchCallbacks(std::string* why = nullptr);
+    bool registerTape(const ecuda::Tape& tape, const std::vector<int>& f_ids, int cost_id, const std::vector<int>& row_ids,
+                      int32_t* id, std::string* msg);
     // true when setup() turned the callbacks into a user model (kernels compiled for them at run time)
     bool isUserModel() const;
 
@@ -115,6 +117,7 @@ class eCUDA : public TrajectoryOptimizer {
     int _model;
     bool _model_set, _obstacles_on, _tracks_on, _is_setup;
     bool _user_edges;  // user model: static path rows are edge ellipses (no explicit cylinders registered)
+    int _nuser_rows = 0;  // constraint rows that are none of the built-in zone rows: traced path rows of the user model
     size_t _batch;
     int _nodes;  // collocation nodes of the current mesh (0: nsteps + 1, the first mesh)
     std::vector<std::array<double, 3>> _cylinders;

@@ -77,6 +77,7 @@ enum ecuda_model {
 };
 #define ECUDA_MODEL_USER_BASE 16
 #define ECUDA_MAX_USER_MODELS 64
+#define ECUDA_MAX_USER_ROWS 16 /* traced path rows per node (ecuda_register_user_model_rows) */
 
 /* ---- user models: dynamics and running cost recorded from callbacks -------------------------------
  * What ePSOPT gets by running the VGP callbacks on ADOL-C adoubles (src/ePSOPT/ePSOPT.cpp:186-276),
@@ -304,6 +305,13 @@ int ecuda_host_resample_matrix(int kind, int nnodes_from, int nnodes_to, double*
  * with NVRTC (libnvrtc.so.12 must be loadable) at the first ecuda_set_problem that uses the id.
  * No GPU is needed to register. err (may be NULL) receives a message on failure. */
 int ecuda_register_user_model(const ecuda_user_model* m, int32_t* model_id, char* err, size_t errlen);
+/* as ecuda_register_user_model, with traced path constraints: row_out[nrows] are tape nodes, each one a path row that
+ * is evaluated at every node after the static and the moving-zone rows of the problem (npath = nstatic + ntracks +
+ * nrows) -- what ePSOPT does with every entry of _constraints (src/ePSOPT/ePSOPT.cpp:262-270) when it is none of the
+ * built-in zone rows. A traced row may read states 0, 1 and t: the read set of a moving-zone row, whose sparsity
+ * (columns x_0, x_1 of the node, t0, tf) it shares. Values, both Jacobian modes; ecuda_eval_hess refuses. */
+int ecuda_register_user_model_rows(const ecuda_user_model* m, int32_t nrows, const int32_t* row_out, int32_t* model_id,
+                                   char* err, size_t errlen);
 /* the generated CUDA source of a registered model (NUL-terminated; *needed = bytes incl. NUL; buf may be NULL) */
 int ecuda_user_model_source(int32_t model_id, char* buf, size_t buflen, size_t* needed);
 /* compiles the kernels of a registered model for `nnodes` collocation nodes without a device and returns the

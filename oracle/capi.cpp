@@ -46,6 +46,9 @@ void oracle_stage_user_tape(int ns, int nc, int edges, int n, const int32_t* op,
     g_staged = t;
 }
 
+// traced path rows of the staged tape (call after oracle_stage_user_tape)
+void oracle_stage_user_rows(int n, const int32_t* row_out) { g_staged.row_out.assign(row_out, row_out + n); }
+
 void* oracle_create(const oracle_desc* d) {
     try {
         Spec s;

@@ -231,6 +231,13 @@ Callbacks<T> make_callbacks(int model, const PhaseData* pd, const std::vector<Tr
         cb.constraints.push_back(path.constraints.at(0));       // ellipses per edge, or cylinders
         if (ut->edges) cb.constraints.push_back(path.constraints.at(1));  // moving circles
         else if (!tracks->empty()) cb.constraints.push_back(make_callbacks<T>(SI2D, pd, tracks).constraints.at(1));
+        if (!ut->row_out.empty())  // traced path rows: a third constraint callback, replayed like the dynamics
+            cb.constraints.push_back([ut](vector_t x, vector_t u, vector_t, std::vector<std::string>, std::any k,
+                                          std::any) -> scalar_t {
+                std::vector<T> fout;
+                for (int id : ut->row_out) fout.push_back(replay<T>(*ut, x, u, k, id));
+                return fout;
+            });
         return cb;
     }
     if (model == SI2D) {

@@ -48,6 +48,9 @@ struct UserTape {
     std::vector<TapeNode> nodes;
     std::vector<int> f_out;
     int cost_out = -1;
+    // traced path rows: one row per entry, evaluated at every node after the static and the moving-zone rows; may
+    // read states 0, 1 and t (the read set of a moving-zone row, whose sparsity they share)
+    std::vector<int> row_out;
 };
 enum CollocationKind { LEGENDRE = 0, CHEBYSHEV = 1 };
 enum PatternMode { DENSE_NODE = 0, MODEL_DEPS = 1 };

@@ -93,7 +93,7 @@ Layout make_layout(const Spec& s) {
     for (int p = 0; p < s.nphases; ++p) {
         int N = s.nnodes[p];
         if (N < 2) throw std::invalid_argument("need >= 2 nodes per phase");
-        int np = s.nstatic[p] + s.ntracks;
+        int np = s.nstatic[p] + s.ntracks + (s.model == USER ? static_cast<int>(s.user.row_out.size()) : 0);
         L.N.push_back(N);
         L.npath.push_back(np);
         L.zoff.push_back(zo);

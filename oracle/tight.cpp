@@ -141,6 +141,12 @@ void path_rows(const Problem& P, const PhasePre& pre, const Instance& I, const d
             double dist = dx * dx + dy * dy;
             out[q++] = dist * (-1.) + tr.radius * tr.radius;
         }
+        if (user && !P.spec.user.row_out.empty()) {  // traced rows read states 0, 1 and t only
+            static thread_local std::vector<double> v;
+            const double xs[8] = {x[0], x[1], 0, 0, 0, 0, 0, 0}, us[8] = {0};
+            tape_values(P.spec.user, xs, us, t, v);
+            for (int id : P.spec.user.row_out) out[q++] = v[id];
+        }
     } else {
         for (size_t c = 0; c < pre.cyl.size(); c += 3) {
             double dx = x[0] - pre.cyl[c], dy = x[1] - pre.cyl[c + 1];

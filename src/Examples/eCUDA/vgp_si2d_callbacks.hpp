@@ -115,5 +115,21 @@ inline ETOL::f_t movingZones(ETOL::TrajectoryOptimizer* t) {
     };
 }
 
+// a path constraint that is none of the VGP's zone constraints: a keep-out disc around (cx, cy) whose radius grows
+// with time, r(t) = r0 + rate * t. eCUDA records it and evaluates it on the GPU as a traced path row (it may read the
+// two position states and the time, like the moving zones above). Registers its parameter (bounds -1e6 .. 0).
+inline ETOL::f_t growingDisc(ETOL::TrajectoryOptimizer* t, double cx, double cy, double r0, double rate) {
+    const double horizon = t->getDt() * t->getNSteps();
+    t->addParams({ETOL::param_t(rowName("disc", 0, 0), {ETOL::var_t::CONTINUOUS, -1.e6, 0., 0., horizon})});
+    return [cx, cy, r0, rate](F_ARGS) -> ETOL::scalar_t {
+        var px = at(x, 0), py = at(x, 1);
+        var r = r0 + rate * *std::any_cast<var*>(k);
+        var dx = px - cx, dy = py - cy;
+        ETOL::fout_ecuda_t rows;
+        rows.push_back(r * r - (dx * dx + dy * dy));
+        return rows;
+    };
+}
+
 }  // namespace vgp_si2d
 #endif  // SRC_EXAMPLES_ECUDA_VGP_SI2D_CALLBACKS_HPP_

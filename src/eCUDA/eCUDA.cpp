@@ -147,6 +147,40 @@ bool agree(double a, double b) {
 }
 }  // namespace
 
+// the recording of the objective, the state derivatives and (optionally) constraint rows -> a user model of the library
+bool eCUDA::registerTape(const ecuda::Tape& tape, const std::vector<int>& f_ids, int cost_id, const std::vector<int>& row_ids,
+                         int32_t* id, std::string* msg) {
+    const size_t ns = getNStates(), nc = getNControls();
+    int last = cost_id;
+    for (int v : f_ids) last = std::max(last, v);
+    for (int v : row_ids) last = std::max(last, v);
+    std::vector<ecuda_tape_node> nodes(static_cast<size_t>(last) + 1);
+    for (int k = 0; k <= last; ++k) {
+        const ecuda::Node& n = tape.nodes[k];
+        nodes[k] = ecuda_tape_node{static_cast<int32_t>(n.op), n.a, n.b, 0, n.imm};
+    }
+    ecuda_user_model um{};
+    um.nstates = static_cast<int32_t>(ns);
+    um.ncontrols = static_cast<int32_t>(nc);
+    _user_edges = _cylinders.empty();
+    um.static_kind = _user_edges ? ECUDA_STATIC_EDGE : ECUDA_STATIC_CYLINDER;
+    um.nnodes = static_cast<int32_t>(nodes.size());
+    um.nodes = nodes.data();
+    for (size_t i = 0; i < ns && i < ECUDA_MAX_STATES; ++i) um.f_out[i] = f_ids[i];
+    um.cost_out = cost_id;
+    if (ns > ECUDA_MAX_STATES) {
+        *msg = "too many states";
+        return false;
+    }
+    char buf[256] = {0};
+    std::vector<int32_t> rows(row_ids.begin(), row_ids.end());
+    const int rc = rows.empty() ? ecuda_register_user_model(&um, id, buf, sizeof buf)
+                                : ecuda_register_user_model_rows(&um, static_cast<int32_t>(rows.size()), rows.data(), id, buf,
+                                                                 sizeof buf);
+    if (rc != ECUDA_OK) *msg = buf;
+    return rc == ECUDA_OK;
+}
+
 bool eCUDA::matchCallbacks(std::string* why) {
     auto no = [&](const std::string& msg) {
         if (why) *why = msg;
@@ -230,34 +264,20 @@ bool eCUDA::matchCallbacks(std::string* why) {
         // library, which differentiates it and compiles the kernels for it at setup().
         if (_model_set && _model < ECUDA_MODEL_USER_BASE)
             return no("objective / state derivatives do not agree with the device model selected by setModel()");
-        int last = cost_id;
-        for (int id : f_ids) last = std::max(last, id);
-        std::vector<ecuda_tape_node> nodes(static_cast<size_t>(last) + 1);
-        for (int k = 0; k <= last; ++k) {
-            const ecuda::Node& n = tape.nodes[k];
-            nodes[k] = ecuda_tape_node{static_cast<int32_t>(n.op), n.a, n.b, 0, n.imm};
-        }
-        ecuda_user_model um{};
-        um.nstates = static_cast<int32_t>(ns);
-        um.ncontrols = static_cast<int32_t>(nc);
-        _user_edges = _cylinders.empty();
-        um.static_kind = _user_edges ? ECUDA_STATIC_EDGE : ECUDA_STATIC_CYLINDER;
-        um.nnodes = static_cast<int32_t>(nodes.size());
-        um.nodes = nodes.data();
-        for (size_t i = 0; i < ns && i < ECUDA_MAX_STATES; ++i) um.f_out[i] = f_ids[i];
-        um.cost_out = cost_id;
         int32_t id = -1;
-        char msg[256] = {0};
-        if (ns > ECUDA_MAX_STATES || ecuda_register_user_model(&um, &id, msg, sizeof msg) != ECUDA_OK)
-            return no(std::string("the callbacks match no built-in device model and cannot become a user model: ") +
-                      (ns > ECUDA_MAX_STATES ? "too many states" : msg));
+        std::string msg;
+        if (!registerTape(tape, f_ids, cost_id, {}, &id, &msg))
+            return no("the callbacks match no built-in device model and cannot become a user model: " + msg);
         found = id;
     }
 
-    // ---- constraint rows against the path constraints the VGP data generates (static rows, then tracks)
+    // ---- constraint rows against the path constraints the VGP data generates (static rows, then tracks). Rows
+    // that follow the recognised ones and are none of them become TRACED path rows of a user model: the reference
+    // evaluates whatever _constraints holds at every node (ePSOPT.cpp:262-270).
     bool matched = row_ids.empty();
     bool use_obs = false, use_trk = false;
-    for (int combo = 3; combo >= 1 && !matched; --combo) {
+    size_t nbuiltin = 0;
+    for (int combo = 3; combo >= 0 && !matched; --combo) {
         const bool obs = combo & 1, trk = combo & 2;
         if (trk && found != ECUDA_MODEL_SI2D && found < ECUDA_MODEL_USER_BASE) continue;
         if ((obs && getObstacles_Raw()->empty() && _cylinders.empty()) || (trk && getTracks()->empty())) continue;
@@ -266,23 +286,36 @@ bool eCUDA::matchCallbacks(std::string* why) {
         d.batch = 1;
         ecuda_dims dims{};
         if (ecuda_host_dims(&d, &dims) != ECUDA_OK) continue;
-        if (static_cast<size_t>(d.nstatic[0] + d.ntracks) != row_ids.size()) continue;
-        std::vector<double> inst, rows(row_ids.size());
+        const size_t nb = static_cast<size_t>(d.nstatic[0] + d.ntracks);
+        if (nb > row_ids.size() || (combo == 0 && nb != 0)) continue;
+        std::vector<double> inst, rows(nb + 1);
         buildInstanceFor(&inst, found, obs, trk, d, dims.inst_stride);
         bool ok = true;
-        for (int p = 0; p < npts && ok; ++p) {
+        for (int p = 0; p < npts && ok && nb > 0; ++p) {
             ecuda_host_path_eval(&d, inst.data(), pts[p][0], pts[p][1], pts[p][ns + nc], rows.data());
-            for (size_t q = 0; q < rows.size() && ok; ++q) ok = agree(vals[p][row_ids[q]], rows[q]);
+            for (size_t q = 0; q < nb && ok; ++q) ok = agree(vals[p][row_ids[q]], rows[q]);
         }
         if (ok) {
             matched = true;
             use_obs = obs;
             use_trk = trk;
+            nbuiltin = nb;
         }
     }
     if (!matched)
         return no("the " + std::to_string(row_ids.size()) +
                   " constraint rows are not the exclusion-zone / moving-zone constraints of the loaded VGP");
+    _nuser_rows = static_cast<int>(row_ids.size() - nbuiltin);
+    if (_nuser_rows > 0) {
+        // the model (built-in or recorded) is registered again together with the traced rows
+        std::vector<int> extra(row_ids.begin() + static_cast<long>(nbuiltin), row_ids.end());
+        int32_t id = -1;
+        std::string msg;
+        if (!registerTape(tape, f_ids, cost_id, extra, &id, &msg))
+            return no(std::to_string(_nuser_rows) + " constraint rows are none of the zone constraints of the loaded VGP "
+                      "and cannot become traced path rows: " + msg);
+        found = id;
+    }
     _model = found;
     _model_set = true;
     _obstacles_on = use_obs;
@@ -339,7 +372,7 @@ void eCUDA::transcribe() {
         fail("device model expects " + std::to_string(_problem.dims.nstates) + " states, the VGP has " +
              std::to_string(ns));
     // npath = #parameters (ePSOPT.cpp:58): every path row must have its parameter
-    const size_t npath = nstatic + static_cast<size_t>(d.ntracks);
+    const size_t npath = nstatic + static_cast<size_t>(d.ntracks) + static_cast<size_t>(_nuser_rows);
     if (npath != getParams()->size())
         fail("path rows (" + std::to_string(npath) + ") and registered parameters (" +
              std::to_string(getParams()->size()) + ") differ");
@@ -433,6 +466,16 @@ void eCUDA::buildBounds() {
     if (!usesEdges(_model))
         for (size_t c = 0; c < _cylinders.size(); ++c) _problem.path_names.push_back(paramName("cyl", c, 0, 0));
     for (int i = 0; i < _problem.desc.ntracks; ++i) _problem.path_names.push_back(paramName("ball", i, 0, 0));
+    if (_nuser_rows > 0) {
+        // traced rows: the parameters no zone row was registered under, in the std::map order ePSOPT::addBounds
+        // walks (ePSOPT.cpp:147-150)
+        std::vector<std::string> rest;
+        for (const auto& kv : *getParams())
+            if (std::find(_problem.path_names.begin(), _problem.path_names.end(), kv.first) == _problem.path_names.end())
+                rest.push_back(kv.first);
+        for (int r = 0; r < _nuser_rows; ++r)
+            _problem.path_names.push_back(r < static_cast<int>(rest.size()) ? rest[r] : paramName("row", r, 0, 0));
+    }
     const size_t np = _problem.path_names.size();
     const size_t p0 = e0 + 2 * ns;
     for (int k = 0; k < N; ++k)

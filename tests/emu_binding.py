@@ -63,7 +63,13 @@ def user_lib(tape):
         um.f_out[i] = v
     um.cost_out = tape.cost_out
     mid = C.c_int32(-1)
-    assert L.ecuda_register_user_model(C.byref(um), C.byref(mid), None, 0) == 0
+    rows = np.array(getattr(tape, "row_out", []), dtype=np.int32)
+    if rows.size:
+        L.ecuda_register_user_model_rows.argtypes = capi.lib().ecuda_register_user_model_rows.argtypes
+        assert L.ecuda_register_user_model_rows(C.byref(um), int(rows.size), rows.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                C.byref(mid), None, 0) == 0
+    else:
+        assert L.ecuda_register_user_model(C.byref(um), C.byref(mid), None, 0) == 0
     _user_libs[key] = (L, mid.value)
     return _user_libs[key]
 

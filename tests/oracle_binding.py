@@ -51,6 +51,7 @@ def lib():
         L.oracle_eval_batch.restype = C.c_double
         L.oracle_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                         C.c_int, C.c_int]
+        L.oracle_stage_user_rows.argtypes = [C.c_int, _ip]
         L.oracle_stage_user_tape.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, C.c_int]
         L.oracle_hess_structure.argtypes = [C.c_void_p, _ip, _ip]
         L.oracle_eval_hess.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
@@ -98,6 +99,8 @@ class Oracle:
             lib().oracle_stage_user_tape(t.ns, t.nc, int(t.static_kind == 1), len(t.nodes), ops.ctypes.data_as(_ip),
                                          aa.ctypes.data_as(_ip), bb.ctypes.data_as(_ip), _p(imm),
                                          fo.ctypes.data_as(_ip), t.cost_out)
+            ro = np.array(getattr(t, "row_out", []), dtype=np.int32)
+            lib().oracle_stage_user_rows(len(ro), ro.ctypes.data_as(_ip))
             d.model = 3
         for p in range(wl.nphases):
             d.nnodes[p] = wl.nnodes[p]

@@ -37,7 +37,9 @@ int shim_load(void* h, const char* xml, int model, int flags, int batch, const c
 // variant 0: the example's callbacks; 1: a different objective; 2: exclusion zones only; 3: zones
 // registered in the opposite order (moving zones first); 4: dynamics no built-in model has (wind field
 // depending on the position) -> user model; 5: an objective holding a static ecuda::var constant; 6: dynamics that
-// read the node time -> time-dependent user model. Returns 1 when matched; *model, *flags
+// read the node time -> time-dependent user model; 7: a third constraint callback that is none of the zone
+// constraints (a disc that grows with time) -> traced path row of a user model; 8: a constraint row that reads a
+// control -> refused. Returns 1 when matched; *model, *flags
 // (bit0 obstacles, bit1 tracks) report what was recognised, why (<= 255 chars) the reason otherwise.
 int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* flags, char* why) {
     eCUDA* t = static_cast<eCUDA*>(h);
@@ -73,6 +75,13 @@ int shim_load_callbacks(void* h, const char* xml, int variant, int* model, int* 
         ETOL::f_t* movers = hold(vgp_si2d::movingZones(t));
         if (variant == 3)
             t->setConstraints({movers, zones});
+        else if (variant == 8) {  // a constraint row that reads a control: cannot be a traced path row
+            t->addParams({ETOL::param_t("ctl_0_0_0", {ETOL::var_t::CONTINUOUS, -1., 1., 0., t->getDt() * t->getNSteps()})});
+            t->setConstraints({zones, movers, hold([](F_ARGS) -> ETOL::scalar_t {
+                                   return ETOL::fout_ecuda_t{vgp_si2d::at(u, 0) * vgp_si2d::at(x, 0)};
+                               })});
+        } else if (variant == 7)  // one more constraint that is none of the VGP's zones: a traced path row
+            t->setConstraints({zones, movers, hold(vgp_si2d::growingDisc(t, 3.0, 3.5, 0.2, 0.01))});
         else
             t->setConstraints({zones, movers});
     }

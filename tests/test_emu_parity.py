@@ -29,6 +29,9 @@ CASES = {
     # dynamics and running cost that read t (the `k` argument of the ePSOPT callbacks)
     "user-gust-tracks": lambda: W.gust(batch=2, ntracks=1, scaled=True),
     "user-gust-N12-max": lambda: W.gust(batch=2, nnodes=12, ncyl=2, collocation=W.CHEBYSHEV, maximize=True),
+    # traced path constraints (rows that are none of the built-in zone rows), with and without moving zones
+    "user-zone-tracks": lambda: W.zone(batch=2, ntracks=2, scaled=True),
+    "user-zone-gust-N12": lambda: W.zone(batch=2, timedep=True, nnodes=12, ncyl=0, pattern_mode=W.MODEL_DEPS),
 }
 
 
