@@ -17,10 +17,12 @@ _lib = None
 def build(out=LIB, user_header=None):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     extra = [] if user_header is None else ['-DECUDA_USER_MODEL_HEADER="%s"' % user_header]
+    tmp = "%s.%d.tmp" % (out, os.getpid())  # atomic: parallel test workers may build the same library
     subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas"] + extra +
-                   ["-shared", "-o", out, os.path.join(EMU_DIR, "emu.cpp"),
+                   ["-shared", "-o", tmp, os.path.join(EMU_DIR, "emu.cpp"),
                     os.path.join(ROOT, "etol_b200", "csrc", "ecuda_host.cpp"),
                     os.path.join(ROOT, "etol_b200", "csrc", "ecuda_usermodel.cpp"), "-ldl"], check=True)
+    os.replace(tmp, out)
 
 
 def _sources():
