@@ -282,6 +282,7 @@ struct ecuda_ctx {
     DevBuf serr, resmat, sxnew, ssznew;
     // compact exact output (ecuda_eval_compact): indices of the per-instance triplets, built on first use
     std::vector<int32_t> local_index;
+    std::vector<int32_t> hess_ir, hess_jc;  // Hessian structure, built on first request
     DevBuf lidx, sjl;
     // HOST-buffer calls are pipelined over instance chunks (eval_host): copy streams and their events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -341,7 +342,7 @@ static int upload_scaling(ecuda_ctx* h) {
     std::vector<double> isz(nv);
     for (int c = 0; c < nv; ++c) isz[c] = 1.0 / h->h_sz[c];  // reciprocal rounded once, on the host
     int rc;
-    if ((rc = ensure(h, h->isz, sizeof(double) * nv))) return rc;
+    if ((rc = ensure(h, h->isz, sizeof(double) * nv + 16))) return rc;
     if ((rc = ensure(h, h->sg, sizeof(double) * ng))) return rc;
     CU(cudaMemcpy(h->isz.p, isz.data(), sizeof(double) * nv, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->sg.p, h->h_sg.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
@@ -476,7 +477,7 @@ static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
 // BASELINE configurations; other shapes take the kernels above
 template <int M, int N, bool FD, bool TRK, bool SUM>
 static int launch_rows_n_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
-    constexpr bool RING = !FD;  // see k_rows_n
+    constexpr bool RING = !FD || ECUDA_RN_FD_RING;  // see k_rows_n
     static std::mutex mu;
     static size_t configured[64] = {0};
     size_t ring = 0;  // the store ring: three buffers of the largest node group of any phase
@@ -836,6 +837,8 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
         if (!build_collocation(desc->collocation, hp.N[p], &hp.col[p], &err)) return fail(h, ECUDA_ERR_ARG, err);
     h->hp = hp;
     h->local_index.clear();
+    h->hess_ir.clear();
+    h->hess_jc.clear();
     h->have_problem = false;
     h->have_inst = false;
     h->have_bounds = false;
@@ -908,7 +911,7 @@ int ecuda_set_problem(ecuda_handle h, const ecuda_problem_desc* desc) {
     } else {
         unload_user_kernels(h);
     }
-    if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1)))) return rc;
+    if ((rc = ensure(h, h->colptr, sizeof(int32_t) * (pd.nvars + 1) + 16))) return rc;  // + 16: bulk copies read whole 16-byte units
     CU(cudaMemcpy(h->colptr.p, hp.colptr.data(), sizeof(int32_t) * (pd.nvars + 1), cudaMemcpyHostToDevice));
     pd.colptr = static_cast<const int*>(h->colptr.p);
     if ((rc = ensure(h, h->desc, sizeof(uint64_t) * std::max<size_t>(1, hp.tdesc.size())))) return rc;
@@ -1376,8 +1379,8 @@ int ecuda_ode_error(ecuda_handle h, const double* x, double* err, int memkind, v
 int ecuda_get_hess_structure(ecuda_handle h, int32_t* nnz_h, int32_t* iRow, int32_t* jCol) {
     if (!h) return ECUDA_ERR_ARG;
     if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
-    std::vector<int32_t> ir, jc;
-    build_hess_structure(h->hp, &ir, &jc);
+    if (h->hess_ir.empty()) build_hess_structure(h->hp, &h->hess_ir, &h->hess_jc);  // once per problem (IPOPT asks every iteration)
+    const std::vector<int32_t>&ir = h->hess_ir, &jc = h->hess_jc;
     if (nnz_h) *nnz_h = static_cast<int32_t>(ir.size());
     const int base = h->hp.desc.index_base;
     for (size_t e = 0; e < ir.size(); ++e) {

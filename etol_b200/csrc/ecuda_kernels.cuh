@@ -418,6 +418,16 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes = static_cast<uint32_t>(pb.inst_stride) * 8u;
+#if ECUDA_RN_TMAZ
+        if (FD) {  // decision vector, 1/sz and column pointers ride on the same barrier (launcher checked the alignment)
+            const int nv = rn_nv<M>(pb, N);
+            const uint32_t zb = static_cast<uint32_t>(nv + (nv & 1)) * 8u, cb = rn_cp_bytes(nv);
+            mbar_expect_tx(&bar, bytes + 2u * zb + cb);
+            bulk_g2s(m.rawz, io.x + static_cast<size_t>(b) * pb.nvars + ph.zoff, zb, &bar);
+            bulk_g2s(m.rawis, pb.isz + ph.zoff, zb, &bar);
+            bulk_g2s(m.rawcp, pb.colptr + ph.zoff, cb, &bar);
+        } else
+#endif
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(m.inst, io.inst + static_cast<size_t>(b) * pb.inst_stride, bytes, &bar);
     }
@@ -432,8 +442,9 @@ __global__ void __launch_bounds__(kThreads, FD ? ECUDA_MIN_CTAS_ROWSN_FD : ECUDA
         cm.bl = bnd;
         cm.bu = bnd + nbnd;
     }
+    if (FD && ECUDA_RN_TMAZ) mbar_wait(&bar, 0);  // the stage reads the bulk-copied raw vectors
     rn_stage<M, N, FD>(pb, ph, io, m, b, tid, nthr);
-    mbar_wait(&bar, 0);
+    if (!(FD && ECUDA_RN_TMAZ)) mbar_wait(&bar, 0);
     __syncthreads();
     RnRow<N> st;
     double viol, fval;

@@ -104,7 +104,13 @@ struct RnMem {
     const double* dt;   // [N*N] D^T (dt[l*N + k] = D[k][l]); exact mode: the global array
     const double* tau;  // [N]
     const double* w;    // [N]
+    // ECUDA_RN_TMAZ: raw copies of x[b], 1/sz and the column pointers (bulk copies; 16-byte aligned, padded)
+    double* rawz;
+    double* rawis;
+    int* rawcp;
 };
+// bytes of the column-pointer bulk copy (multiple of 16)
+ECUDA_HD unsigned rn_cp_bytes(int nv) { return (static_cast<unsigned>(nv) * 4u + 15u) & ~15u; }
 
 template <int M>
 ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N + 2; }
@@ -112,6 +118,30 @@ ECUDA_HD int rn_nv(const ProbDev& pb, int N) { return (Model<M>::NS + pb.nc) * N
 // ECUDA_RN_DSMEM: the one-shot FD kernel copies D^T, tau and w into shared memory per CTA. Measured on C2: 0.165 ms
 // with the copy, 0.159 ms reading them through L1 (the copy costs more than the shorter load latency saves), so it is
 // off; the persistent kernel, which copies once per CTA lifetime, always has them in shared memory.
+// ECUDA_RN_TMAZ: the one-shot FD kernel fetches the decision vector, 1/sz and the column pointers with TMA bulk copies
+// (the mbarrier that already brings the instance records) instead of per-thread loads, and stages from shared memory.
+#ifndef ECUDA_RN_TMAZ
+#define ECUDA_RN_TMAZ 0
+#endif
+// ECUDA_RN_NOSCATTER (experiment, WRONG RESULTS): the finite-difference kernel computes the node-local triplets, the
+// g values and the item rows but does not store them -- an upper bound for what removing the scattered 8-byte stores
+// can buy (scripts/wroof2.cu: under that store pattern an L2 hit costs 3300 cycles instead of 800).
+#ifndef ECUDA_RN_NOSCATTER
+#define ECUDA_RN_NOSCATTER 0
+#endif
+#if ECUDA_RN_NOSCATTER && defined(__CUDA_ARCH__)
+#define RN_LOCAL_STORE(p, v)                         \
+    do {                                             \
+        const double v_ = (v);                       \
+        if (v_ == 1.2345678e-300) __stcs((p), v_);   \
+    } while (0)
+#else
+#define RN_LOCAL_STORE(p, v) ECUDA_STREAM_STORE(p, v)
+#endif
+// ECUDA_RN_FD_RING: finite differences through the shared-memory store ring as well (measured slower, see k_rows_n)
+#ifndef ECUDA_RN_FD_RING
+#define ECUDA_RN_FD_RING 0
+#endif
 #ifndef ECUDA_RN_DSMEM
 #define ECUDA_RN_DSMEM 0
 #endif
@@ -144,6 +174,7 @@ ECUDA_HD size_t rn_doubles(const ProbDev& pb, int N, bool fd) {
     size_t n = static_cast<size_t>(pb.inst_stride) + nve;
     n += fd ? 4 * nv : 2 * nv;
     if (fd && ECUDA_RN_DSMEM) n += static_cast<size_t>(N) * N + 2 * static_cast<size_t>(N + (N & 1));
+    if (fd && ECUDA_RN_TMAZ) n += 2 * nve + rn_cp_bytes(static_cast<int>(nv)) / 8;
     return n + (n & 1);
 }
 
@@ -160,6 +191,14 @@ ECUDA_HD void rn_carve(RnMem& m, double* base, const ProbDev& pb, int N, bool fd
     if (fd) {
         m.rec = reinterpret_cast<FdRec*>(base);
         base += 4 * nv;
+        if (ECUDA_RN_TMAZ) {
+            m.rawz = base;
+            base += nve;
+            m.rawis = base;
+            base += nve;
+            m.rawcp = reinterpret_cast<int*>(base);
+            base += rn_cp_bytes(static_cast<int>(nv)) / 8;
+        }
         m.dt = base;
         base += static_cast<size_t>(N) * N;
         m.tau = base;
@@ -185,9 +224,15 @@ ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
     for (int u = 0; u < 2; ++u) {
         const int c = tid + u * nthr;
         if (c < nv) {
-            zt[u] = ECUDA_LDG(xs + c);
-            s[u] = ECUDA_LDG(is + c);
-            cp[u] = ECUDA_LDG(cpg + c);
+            if (FD && ECUDA_RN_TMAZ) {
+                zt[u] = m.rawz[c];
+                s[u] = m.rawis[c];
+                cp[u] = m.rawcp[c];
+            } else {
+                zt[u] = ECUDA_LDG(xs + c);
+                s[u] = ECUDA_LDG(is + c);
+                cp[u] = ECUDA_LDG(cpg + c);
+            }
         }
     }
     constexpr bool DSM = FD && ECUDA_RN_DSMEM;
@@ -212,9 +257,15 @@ ECUDA_HD void rn_stage(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, 
             for (int u = 0; u < 2; ++u) {
                 const int c = c0 + u * nthr;
                 if (c < nv) {
-                    zt[u] = ECUDA_LDG(xs + c);
-                    s[u] = ECUDA_LDG(is + c);
-                    cp[u] = ECUDA_LDG(cpg + c);
+                    if (FD && ECUDA_RN_TMAZ) {
+                        zt[u] = m.rawz[c];
+                        s[u] = m.rawis[c];
+                        cp[u] = m.rawcp[c];
+                    } else {
+                        zt[u] = ECUDA_LDG(xs + c);
+                        s[u] = ECUDA_LDG(is + c);
+                        cp[u] = ECUDA_LDG(cpg + c);
+                    }
                 }
             }
         }
@@ -366,7 +417,7 @@ ECUDA_HD void rn_fd_begin(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
     const double dv = rn_dot<NS, N>(m.dt + k, zx + i, st.P);
     if (io.g) {
         const double val = st.sgr * (dv - st.hfv);
-        ECUDA_STREAM_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
+        RN_LOCAL_STORE(io.g + static_cast<size_t>(b) * pb.ncons + r, val);
         if (SUM) viol = fmax(viol, row_violation(io, pb, ph, cm, b, r, val, 0));
     }
 }
@@ -466,7 +517,7 @@ ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalI
         if (rk < 0 || (DS && j == i)) continue;
         const FdRec& rc = rx[k * NS + j];
         if (j != i && !reads_state<M>(i, j)) {  // f_i does not read x_j: g+ == g- bit for bit
-            ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), 0.0);
+            RN_LOCAL_STORE(jac + (rc.cp + k + rk), 0.0);
             continue;
         }
         double xq[NS], xr[NS], fp[NS], fm[NS];
@@ -486,7 +537,7 @@ ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalI
             }
         const double gp = sgr * (((i == j) ? dpk : dv) - h * fpi);
         const double gm = sgr * (((i == j) ? dmk : dv) - h * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
     }
     // the node's control columns U(k,c)                                 [node_item, c < nc, row i]
     for (int c = 0; c < nc; ++c) {
@@ -494,7 +545,7 @@ ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalI
         if (rk < 0) continue;
         const FdRec& rc = m.rec[k * nc + c];
         if (c >= NCU || !reads_control<M>(i, c)) {  // unused or unread control: exactly +0.0
-            ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+            RN_LOCAL_STORE(jac + (rc.cp + rk), 0.0);
             continue;
         }
         double up[NCU], um[NCU], fp[NS], fm[NS];
@@ -514,7 +565,7 @@ ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalI
             }
         const double gp = sgr * (dv - h * fpi);
         const double gm = sgr * (dv - h * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
     }
     // t0 / tf columns                                                    [node_item, time columns, row i]
 #pragma unroll
@@ -537,7 +588,7 @@ ECUDA_HD void rn_fd_local_all(const ProbDev& pb, const PhaseDev& ph, const EvalI
             }
         const double gp = sgr * (dv - hp * fpi);
         const double gm = sgr * (dv - hm * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
     }
 }
 
@@ -583,7 +634,7 @@ ECUDA_HD void rn_fd_piece(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
         if (rk < 0 || (DS && j == i)) return;
         const FdRec& rc = m.rec[nc * N + k * NS + j];
         if (j != i && !reads_state<M>(i, j)) {  // f_i does not read x_j: g+ == g- bit for bit
-            ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), 0.0);
+            RN_LOCAL_STORE(jac + (rc.cp + k + rk), 0.0);
             return;
         }
         double dpk = 0.0, dmk = 0.0;
@@ -605,17 +656,17 @@ ECUDA_HD void rn_fd_piece(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
             }
         const double gp = sgr * (((i == j) ? dpk : dv) - h * fpi);
         const double gm = sgr * (((i == j) ? dmk : dv) - h * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + k + rk), (gp - gm) * rc.ri);
     } else if (IS_U) {  // the node's control column U(k,c)                 [node_item, c < nc, row i]
         constexpr int c = IS_U ? P - ECUDA_MAX_STATES : 0;
         const int rk = pb.urank[c][i];
         if (rk < 0) return;
         const FdRec& rc = m.rec[k * nc + c];
         if constexpr (c >= NCU) {  // a control the model does not use: exactly +0.0
-            ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+            RN_LOCAL_STORE(jac + (rc.cp + rk), 0.0);
         } else {
             if (!reads_control<M>(i, c)) {  // unread control: exactly +0.0
-                ECUDA_STREAM_STORE(jac + (rc.cp + rk), 0.0);
+                RN_LOCAL_STORE(jac + (rc.cp + rk), 0.0);
                 return;
             }
             double up[NCU], um[NCU], fp[NS], fm[NS];
@@ -635,7 +686,7 @@ ECUDA_HD void rn_fd_piece(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
                 }
             const double gp = sgr * (dv - h * fpi);
             const double gm = sgr * (dv - h * fmi);
-            ECUDA_STREAM_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
+            RN_LOCAL_STORE(jac + (rc.cp + rk), (gp - gm) * rc.ri);
         }
     } else {  // t0 / tf column                                            [node_item, time columns, row i]
         constexpr int which = IS_T ? P - ECUDA_MAX_STATES - ECUDA_MAX_CONTROLS : 0;
@@ -657,7 +708,7 @@ ECUDA_HD void rn_fd_piece(const ProbDev& pb, const PhaseDev& ph, const EvalIO& i
             }
         const double gp = sgr * (dv - hp * fpi);
         const double gm = sgr * (dv - hm * fmi);
-        ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + k * NS + i), (gp - gm) * rc.ri);
     }
 }
 // the pieces that run after node group G: P = G, G + ngroups, ...
@@ -758,7 +809,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
-            ECUDA_STREAM_STORE(g + r, val);
+            RN_LOCAL_STORE(g + r, val);
             note(r, val, 1);
         }
         if (!jac) return;
@@ -768,7 +819,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             const FdRec& rc = rx[k * NS + j];
             const double vp = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xp : x0, j == 1 ? rc.xp : x1, t);
             const double vm = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xm : x0, j == 1 ? rc.xm : x1, t);
-            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[j] + ev + q), (s * vp - s * vm) * rc.ri);
+            RN_LOCAL_STORE(jac + (rc.cp + N - 1 + pb.xcnt[j] + ev + q), (s * vp - s * vm) * rc.ri);
         }
         if (TRK && q >= ph.nstat) {
 #pragma unroll
@@ -781,7 +832,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
                 const double tp = hp * tau + mp, tm = hm * tau + mm;
                 const double vp = rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, tp);
                 const double vm = rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, tm);
-                ECUDA_STREAM_STORE(jac + (rc.cp + NS * N + k * ntr + (q - ph.nstat)), (s * vp - s * vm) * rc.ri);
+                RN_LOCAL_STORE(jac + (rc.cp + NS * N + k * ntr + (q - ph.nstat)), (s * vp - s * vm) * rc.ri);
             }
         }
         return;
@@ -795,12 +846,12 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * zx[lx];
-            ECUDA_STREAM_STORE(g + r, val);
+            RN_LOCAL_STORE(g + r, val);
             note(r, val, 2);
         }
         if (jac) {
             const FdRec& rc = rx[lx];
-            ECUDA_STREAM_STORE(jac + (rc.cp + N - 1 + pb.xcnt[i]), (s * rc.xp - s * rc.xm) * rc.ri);
+            RN_LOCAL_STORE(jac + (rc.cp + N - 1 + pb.xcnt[i]), (s * rc.xp - s * rc.xm) * rc.ri);
         }
         return;
     }
@@ -810,13 +861,13 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double s = ECUDA_LDG(sg + r);
         if (g) {
             const double val = s * (tf - t0);
-            ECUDA_STREAM_STORE(g + r, val);
+            RN_LOCAL_STORE(g + r, val);
             note(r, val, 3);
             if (p + 1 < pb.nphases) {  // time continuity with the next phase
                 const PhaseDev& nx = pb.ph[p + 1];
                 const int rl = pb.linkoff + p * (NS + 1) + NS;
                 const double other = other_phase_value(pb, io, b, nx.zoff + (NS + nc) * nx.N);
-                ECUDA_STREAM_STORE(g + rl, ECUDA_LDG(sg + rl) * (tf - other));
+                RN_LOCAL_STORE(g + rl, ECUDA_LDG(sg + rl) * (tf - other));
             }
         }
         if (!jac) return;
@@ -827,20 +878,20 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             const double ri = rc.ri;
             const double t0p = which == 0 ? rc.xp : t0, tfp = which == 1 ? rc.xp : tf;
             const double t0m = which == 0 ? rc.xm : t0, tfm = which == 1 ? rc.xm : tf;
-            ECUDA_STREAM_STORE(jac + at, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
+            RN_LOCAL_STORE(jac + at, (s * (tfp - t0p) - s * (tfm - t0m)) * ri);
             if (which == 0 && p > 0) {
                 const PhaseDev& pv = pb.ph[p - 1];
                 const int rl = pb.linkoff + (p - 1) * (NS + 1) + NS;
                 const double sl = ECUDA_LDG(sg + rl);
                 const double o = other_phase_value(pb, io, b, pv.zoff + (NS + nc) * pv.N + 1);
-                ECUDA_STREAM_STORE(jac + at + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
+                RN_LOCAL_STORE(jac + at + 1, (sl * (o - t0p) - sl * (o - t0m)) * ri);
             }
             if (which == 1 && p + 1 < pb.nphases) {
                 const PhaseDev& nx = pb.ph[p + 1];
                 const int rl = pb.linkoff + p * (NS + 1) + NS;
                 const double sl = ECUDA_LDG(sg + rl);
                 const double o = other_phase_value(pb, io, b, nx.zoff + (NS + nc) * nx.N);
-                ECUDA_STREAM_STORE(jac + at + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
+                RN_LOCAL_STORE(jac + at + 1, (sl * (tfp - o) - sl * (tfm - o)) * ri);
             }
         }
         return;
@@ -859,10 +910,10 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const int r = pb.linkoff + p * (NS + 1) + i;
         const double s = ECUDA_LDG(sg + r);
         const double o = other_phase_value(pb, io, b, nx.zoff + nc * nx.N + i);
-        if (g) ECUDA_STREAM_STORE(g + r, s * (zx[lx] - o));
+        if (g) RN_LOCAL_STORE(g + r, s * (zx[lx] - o));
         if (jac) {
             const FdRec& rc = rx[lx];
-            ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * (rc.xp - o) - s * (rc.xm - o)) * rc.ri);
+            RN_LOCAL_STORE(jac + (rc.cp + pos), (s * (rc.xp - o) - s * (rc.xm - o)) * rc.ri);
         }
     } else if (jac) {
         const PhaseDev& pv = pb.ph[p - 1];
@@ -870,7 +921,7 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double s = ECUDA_LDG(sg + r);
         const double o = other_phase_value(pb, io, b, pv.zoff + nc * pv.N + (pv.N - 1) * NS + i);
         const FdRec& rc = rx[lx];
-        ECUDA_STREAM_STORE(jac + (rc.cp + pos), (s * (o - rc.xp) - s * (o - rc.xm)) * rc.ri);
+        RN_LOCAL_STORE(jac + (rc.cp + pos), (s * (o - rc.xp) - s * (o - rc.xm)) * rc.ri);
     }
 }
 

@@ -84,8 +84,18 @@ class eCUDA : public TrajectoryOptimizer {
     void setBatch(size_t nInstances);
     size_t getBatch() const;
     // raw instance-data block of instance b (layout: ecuda_upload_instances); valid after setup()
+    // per-instance data block (layout of ecuda_upload_instances). Edits survive the mesh refinement of solve();
+    // setup() starts again from the loaded VGP. Edits of getProblem()'s node-dependent arrays (zl, zu, gl, gu, sz,
+    // guess) apply to the current mesh only: per-state / per-control bounds belong in the VGP (setXlower, ...).
     std::vector<double>& instanceData(size_t b);
     void uploadInstances();  // push edited instance data to the device
+    // test hooks: transcription as solve() re-runs it on a mesh of `nodes` nodes (from_setup: as setup() does)
+    void retranscribeForTest(int nodes, bool from_setup) {
+        if (from_setup) _inst_user = false;
+        _nodes = nodes;
+        transcribe();
+    }
+    const std::vector<std::vector<double>>& instanceBlocksForTest() const { return _inst; }
 
     // next node count of the automatic mesh refinement, from the (nodes, error) history of the solves so far
     static int nextMeshSize(const std::vector<std::pair<int, double>>& history, const ecuda_alg_t& alg);
@@ -122,6 +132,7 @@ class eCUDA : public TrajectoryOptimizer {
     int _nodes;  // collocation nodes of the current mesh (0: nsteps + 1, the first mesh)
     std::vector<std::array<double, 3>> _cylinders;
     std::vector<std::vector<double>> _inst;  // per-instance data blocks
+    bool _inst_user = false;                 // handed out through instanceData(): kept across re-meshing in solve()
     std::vector<double> _zscaled;            // scratch: z * sz
 };
 

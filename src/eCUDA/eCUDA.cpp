@@ -326,6 +326,7 @@ bool eCUDA::matchCallbacks(std::string* why) {
 // ---- setup ------------------------------------------------------------------------------------------------
 void eCUDA::setup() {
     _nodes = 0;  // the first mesh: nsteps + 1 nodes (ePSOPT.cpp:44)
+    _inst_user = false;  // instance data starts from the loaded VGP again
     transcribe();
     deviceSetup();
 }
@@ -412,10 +413,15 @@ void eCUDA::transcribe() {
     }
     for (int c = 0; c < nv; ++c) _problem.guess[c] = std::min(std::max(_problem.guess[c], _problem.zl[c]), _problem.zu[c]);
 
-    // per-instance data: every instance starts as a copy of the loaded VGP
-    _inst.assign(_batch, std::vector<double>());
-    buildInstance(&_inst[0]);
-    for (size_t b = 1; b < _batch; ++b) _inst[b] = _inst[0];
+    // per-instance data: every instance starts as a copy of the loaded VGP. The block does not depend on the mesh:
+    // when solve() re-transcribes on a refined mesh, data edited through instanceData() is kept (setup() resets it).
+    std::vector<double> fresh;
+    buildInstance(&fresh);
+    const bool keep = _inst_user && _inst.size() == _batch && !_inst.empty() && _inst[0].size() == fresh.size();
+    if (!keep) {
+        _inst.assign(_batch, fresh);
+        _inst_user = false;
+    }
 
 }
 
@@ -572,7 +578,10 @@ void eCUDA::buildInstanceFor(std::vector<double>* out, int model, bool obstacles
         }
 }
 
-std::vector<double>& eCUDA::instanceData(size_t b) { return _inst.at(b); }
+std::vector<double>& eCUDA::instanceData(size_t b) {
+    _inst_user = true;  // the caller may edit it: keep it when solve() re-meshes
+    return _inst.at(b);
+}
 
 void eCUDA::uploadInstances() {
     if (!_is_setup) fail("uploadInstances() before setup()");
@@ -705,30 +714,46 @@ int eCUDA::solveOnce() {
         if (grad && ecuda_eval_grad_f(h, zs, grad, ECUDA_MEM_HOST, nullptr) != ECUDA_OK) return false;
         return true;
     };
-    std::vector<int32_t> hrow, hcol;
-    if (_algorithm.hessian == "exact") {
-        int32_t hn = 0;
-        if (ecuda_get_hess_structure(h, &hn, nullptr, nullptr) != ECUDA_OK) fail("ecuda_get_hess_structure");
-        hrow.resize(hn);
-        hcol.resize(hn);
-        ecuda_get_hess_structure(h, nullptr, hrow.data(), hcol.data());
-        P.hnnz = hn;
-        P.hrow = hrow.data();
-        P.hcol = hcol.data();
-        P.eval_h = [h](const double* zs, double sigma, const double* lambda, double* hv) -> bool {
-            return ecuda_eval_hess(h, zs, nullptr, sigma, lambda, hv, ECUDA_MEM_HOST, nullptr) == ECUDA_OK;
-        };
-    }
     ecuda_nlp::Options opt;
     opt.max_iter = _algorithm.nlp_iter_max;
     opt.tol = _algorithm.nlp_tolerance;
     opt.print_level = _algorithm.print_level;
     std::vector<double> z(nv);
     for (int c = 0; c < nv; ++c) z[c] = _problem.guess[c] * _problem.sz[c];
-    ecuda_nlp::Result R;
     const bool want_ipopt = _algorithm.nlp_method == "IPOPT";
+    const bool use_ipopt = want_ipopt && ecuda_nlp::have_ipopt();
+    std::vector<int32_t> hrow, hcol;
+    if (_algorithm.hessian == "exact") {
+        // The exact Lagrangian Hessian (ecuda_eval_hess) is what IPOPT gets through eval_h. The built-in driver does
+        // not use it (it keeps a damped-BFGS model): say so instead of silently ignoring the setting. User models
+        // that read t or carry traced path rows have no device Hessian yet: IPOPT then runs with its limited-memory
+        // approximation.
+        int32_t hn = 0;
+        if (ecuda_get_hess_structure(h, &hn, nullptr, nullptr) != ECUDA_OK) fail("ecuda_get_hess_structure");
+        std::vector<double> probe(static_cast<size_t>(hn)), lam0(static_cast<size_t>(ng), 0.0);
+        const bool available = ecuda_eval_hess(h, z.data(), nullptr, 1.0, lam0.data(), probe.data(), ECUDA_MEM_HOST, nullptr) == ECUDA_OK;
+        if (!use_ipopt) {
+            if (_algorithm.print_level > 0)
+                std::cout << "eCUDA: hessian = \"exact\" is used by the IPOPT adapter only; the built-in NLP driver keeps its "
+                             "quasi-Newton model" << std::endl;
+        } else if (!available) {
+            std::cout << "eCUDA: no exact Hessian for this model (" << ecuda_last_error(h)
+                      << "); IPOPT runs with hessian_approximation = limited-memory" << std::endl;
+        } else {
+            hrow.resize(hn);
+            hcol.resize(hn);
+            ecuda_get_hess_structure(h, nullptr, hrow.data(), hcol.data());
+            P.hnnz = hn;
+            P.hrow = hrow.data();
+            P.hcol = hcol.data();
+            P.eval_h = [h](const double* zs, double sigma, const double* lambda, double* hv) -> bool {
+                return ecuda_eval_hess(h, zs, nullptr, sigma, lambda, hv, ECUDA_MEM_HOST, nullptr) == ECUDA_OK;
+            };
+        }
+    }
+    ecuda_nlp::Result R;
     int rc;
-    if (want_ipopt && ecuda_nlp::have_ipopt())
+    if (use_ipopt)
         rc = ecuda_nlp::solve_ipopt(P, opt, &z, &R);
     else
         rc = ecuda_nlp::solve_builtin(P, opt, &z, &R);

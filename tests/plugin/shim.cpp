@@ -118,6 +118,19 @@ void shim_instance(void* h, int b, double* out) {
     std::vector<double>& v = static_cast<eCUDA*>(h)->instanceData(b);
     std::memcpy(out, v.data(), sizeof(double) * v.size());
 }
+// edit one value of instance b's data block through instanceData(), then transcribe again the way
+// solve() does when it refines the mesh (more nodes); returns the value found afterwards. again_setup != 0 re-runs
+// transcription the way setup() does instead (starts from the loaded VGP again).
+double shim_edit_instance_and_remesh(void* h, int b, int index, double value, int more_nodes, int as_setup) {
+    eCUDA* t = static_cast<eCUDA*>(h);
+    t->instanceData(static_cast<size_t>(b)).at(static_cast<size_t>(index)) = value;
+    if (as_setup)
+        t->retranscribeForTest(0, true);
+    else
+        t->retranscribeForTest(t->getProblem()->desc.nnodes[0] + more_nodes, false);
+    const std::vector<std::vector<double>>& inst = t->instanceBlocksForTest();
+    return inst.at(static_cast<size_t>(b)).at(static_cast<size_t>(index));
+}
 void shim_structure(void* h, int32_t* irow, int32_t* jcol, int32_t* grp) {
     ETOL::ecuda_prob_t* p = static_cast<eCUDA*>(h)->getProblem();
     std::memcpy(irow, p->iRow.data(), sizeof(int32_t) * p->iRow.size());

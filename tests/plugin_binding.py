@@ -31,6 +31,8 @@ def lib():
         L.shim_bounds.argtypes = [C.c_void_p] + [_dp] * 7
         L.shim_instance.argtypes = [C.c_void_p, C.c_int, _dp]
         L.shim_structure.argtypes = [C.c_void_p, _ip, _ip, _ip]
+        L.shim_edit_instance_and_remesh.restype = C.c_double
+        L.shim_edit_instance_and_remesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
         L.shim_save_xml.argtypes = [C.c_void_p, C.c_char_p]
         L.shim_save_csv.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.shim_interp.restype = C.c_double
@@ -122,6 +124,9 @@ class Plugin:
         out = np.zeros(self.dims.inst_stride)
         self.L.shim_instance(self.h, b, out.ctypes.data_as(_dp))
         return out
+
+    def edit_instance_and_remesh(self, b, index, value, more_nodes=8, as_setup=False):
+        return float(self.L.shim_edit_instance_and_remesh(self.h, b, index, value, more_nodes, int(as_setup)))
 
     def structure(self):
         d = self.dims

@@ -451,3 +451,14 @@ def test_delayed_states_fail_loudly(tmp_path):
             assert r.returncode == 0 and "loaded" in r.stdout, r.stderr
         else:
             assert r.returncode != 0 and "delayed states / controls" in r.stderr and "loaded" not in r.stdout
+
+
+def test_edited_instance_data_survives_remeshing_but_not_setup(xml):
+    """solve() transcribes again on every refined mesh; data edited through instanceData() used to be
+    rebuilt from the loaded VGP from the second mesh on. The instance block does not depend on the mesh: it is kept."""
+    p = pb.Plugin().load(xml)
+    orig = p.instance(0)[0]
+    assert p.edit_instance_and_remesh(0, 0, orig + 0.125, more_nodes=8) == orig + 0.125
+    assert p.dims is not None
+    assert p.edit_instance_and_remesh(0, 0, orig + 0.25, as_setup=True) == orig
+    p.close()
