@@ -19,4 +19,4 @@ except Exception as e:
 PY
 echo "== reference arm at N=$N"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null | tail -c 600
-echo; ./build/tools/lat
+
