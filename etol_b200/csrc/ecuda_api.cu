@@ -269,8 +269,8 @@ struct ecuda_ctx {
     // user model (ecuda_register_user_model): kernels compiled with NVRTC, loaded per handle
     const UserModel* um = nullptr;
     cudaLibrary_t ulib = nullptr;
-    cudaKernel_t ukern[UserImage::NKERNELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ukern_smem[UserImage::NKERNELS] = {0, 0, 0, 0, 0, 0};
+    cudaKernel_t ukern[UserImage::NKERNELS] = {};
+    size_t ukern_smem[UserImage::NKERNELS] = {};
     DevBuf slam, ssig, shess;  // staging for ecuda_eval_hess with host buffers
     DevBuf bcls;               // flag word of k_bounds_classify
     DevBuf bev;                // compact bounds for the fused summary (see EvalIO::bev); valid when bounds_compact
@@ -653,17 +653,23 @@ static int unload_user_kernels(ecuda_ctx* h) {
 static int load_user_kernels(ecuda_ctx* h) {
     // one compilation per (model, block count, kernel set) and process
     static std::mutex mu;
-    static std::map<std::tuple<int, int, bool>, std::shared_ptr<UserImage>> cache;
+    static std::map<std::tuple<int, int, bool, int, bool>, std::shared_ptr<UserImage>> cache;
     const int nb = (h->nb_uniform >= 3 && h->nb_uniform <= 5) ? h->nb_uniform : 0;
+    // the N-specialised finite-difference kernel (k_rows_n) under the rule of launch_rows_n_mn: every phase has N
+    // nodes, one defect row per thread, and the row owners are at least half of the CTA
+    const int ns = h->pd.ns, rn = h->rowsn_N;
+    const int rowsn = (h->fast_ok && rn > 0 && 2 * ns * rn >= kThreads && ns * rn <= kThreads) ? rn : 0;
+    bool trk = false;
+    for (int p = 0; p < h->pd.nphases; ++p) trk = trk || h->pd.ph[p].npath > h->pd.ph[p].nstat;
     std::shared_ptr<UserImage> img;
     {
         std::lock_guard<std::mutex> lock(mu);
-        auto key = std::make_tuple(h->um->id, nb, h->fast_ok);
+        auto key = std::make_tuple(h->um->id, nb, h->fast_ok, rowsn, trk);
         auto it = cache.find(key);
         if (it == cache.end()) {
             std::shared_ptr<UserImage> fresh(new UserImage);
             std::string err;
-            if (!user_model_compile(*h->um, nb, h->fast_ok, fresh.get(), &err)) return fail(h, ECUDA_ERR_CUDA, err);
+            if (!user_model_compile(*h->um, nb, h->fast_ok, rowsn, trk, fresh.get(), &err)) return fail(h, ECUDA_ERR_CUDA, err);
             it = cache.emplace(key, fresh).first;
         }
         img = it->second;
@@ -702,6 +708,13 @@ static int launch_eval_user(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
                              : h->smem_fast_exact + h->smem_isz +
                                    (copy_warp ? (kCopySlots * kCopyChunk + 2) * sizeof(double) : 0);
             if (io.nranks > 0) smem += 2 * static_cast<size_t>(phase_ncons(h->pd, h->pd.ph[0]) + 2) * sizeof(double);
+            if (fd && io.nranks == 0 && h->ukern[UserImage::ROWSN_FD]) {
+                // k_rows_n<USER, N, FD>: shared memory as rn_doubles (instance records, z, one FdRec per variable)
+                const size_t nv = static_cast<size_t>(h->pd.ns + h->pd.nc) * h->rowsn_N + 2, nve = nv + (nv & 1);
+                size_t n = static_cast<size_t>(h->pd.inst_stride) + nve + 4 * nv;
+                n += n & 1;
+                rc = launch_user(h, UserImage::ROWSN_FD, dim3(grid), kThreads, n * sizeof(double), io, st);
+            } else
             rc = launch_user(h, fd ? UserImage::ROWS_FD : UserImage::ROWS_EXACT, dim3(grid),
                              kThreads + (copy_warp ? kCopyWarpThreads : 0), smem, io, st);
         } else {

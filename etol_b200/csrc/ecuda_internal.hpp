@@ -188,7 +188,7 @@ struct UserModel {
 };
 // compiled kernels of one user model for one dot-block count
 struct UserImage {
-    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, ODE_ERROR = 4, HESS = 5, NKERNELS = 6 };
+    enum { GENERIC = 0, GRAD = 1, ROWS_FD = 2, ROWS_EXACT = 3, ODE_ERROR = 4, HESS = 5, ROWSN_FD = 6, NKERNELS = 7 };
     std::vector<char> cubin;
     std::string name[NKERNELS];  // lowered kernel names ("" = not compiled)
     std::string log;
@@ -200,8 +200,10 @@ void user_model_rows(const UserModel& m, double x0, double x1, double t, double*
 void user_model_eval(const UserModel& m, const double* x, const double* u, double t, double* f_out, double* cost_out);
 void user_model_partials(const UserModel& m, const double* x, const double* u, double t, double* dfdx, double* dfdu,
                          double* dcdx, double* dcdu);
-// nb: template argument NB of the kernels (0 = generic block count); rows: also compile k_eval_rows
-bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, std::string* err);
+// nb: template argument NB of the kernels (0 = generic block count); rows: also compile k_eval_rows; rowsn_N > 0: also
+// the N-specialised finite-difference kernel k_rows_n<USER, rowsn_N, FD, trk> (trk: the problem has path rows beyond the
+// static records)
+bool user_model_compile(const UserModel& m, int nb, bool rows, int rowsn_N, bool trk, UserImage* out, std::string* err);
 
 struct Collocation {
     int N = 0;

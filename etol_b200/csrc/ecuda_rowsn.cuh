@@ -1012,8 +1012,15 @@ ECUDA_HD void rn_ex_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
     for (int a = 0; a < NS; ++a)
         if (a == i) fi = f[a];
     double dfdx[NS][NS], dfdu[NS][NCU];
-    static_assert(!Model<M>::TDEP, "k_rows_n is instantiated for the built-in (autonomous) models only");
     Model<M>::jac(x, u, t, dfdx, dfdu);
+    double fti = 0.0;
+    if constexpr (Model<M>::TDEP) {  // dynamics that read t: - h (df_i/dt) (d t_k / d t0|tf) in the time columns
+        double ft[NS], Lt;
+        Model<M>::dtime(x, u, t, ft, &Lt);
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+            if (a == i) fti = ft[a];
+    }
     const double dkk = ECUDA_LDG(Dtk + k * N);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {  // [xcol_local_exact, row i]
@@ -1043,7 +1050,11 @@ ECUDA_HD void rn_ex_end(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io,
 #pragma unroll
     for (int which = 0; which < 2; ++which) {  // [node_item exact, time columns, row i]
         const ExVals rc = rn_load(m.erec + (NS + nc) * N + which);
-        const double v = which == 0 ? 0.5 * fi : -0.5 * fi;
+        double v = which == 0 ? 0.5 * fi : -0.5 * fi;
+        if constexpr (Model<M>::TDEP) {
+            const double tau = ECUDA_LDG(ph.tau + k);
+            v = v - h * (fti * (which == 0 ? 0.5 * (1.0 - tau) : 0.5 * (1.0 + tau)));
+        }
         ECUDA_STREAM_STORE(jac + (rc.cp + k * NS + i), (sgr * v) * rc.isz);
     }
 }

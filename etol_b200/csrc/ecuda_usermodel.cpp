@@ -600,7 +600,7 @@ bool load_kernel_sources(std::vector<std::string>* texts, std::string* err) {
 
 }  // namespace
 
-bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, std::string* err) {
+bool user_model_compile(const UserModel& m, int nb, bool rows, int rowsn_N, bool trk, UserImage* out, std::string* err) {
     Nvrtc nv;
     if (!load_nvrtc(&nv, err)) return false;
     std::vector<std::string> texts;
@@ -631,6 +631,9 @@ bool user_model_compile(const UserModel& m, int nb, bool rows, UserImage* out, s
     if (rows) {
         exprs[UserImage::ROWS_FD] = "ecuda::k_eval_rows<" + M + ", " + NB + ", true>";
         exprs[UserImage::ROWS_EXACT] = "ecuda::k_eval_rows<" + M + ", " + NB + ", false>";
+        if (rowsn_N > 0)  // <M, N, FD, TRK, SUM, RING>
+            exprs[UserImage::ROWSN_FD] = "ecuda::k_rows_n<" + M + ", " + std::to_string(rowsn_N) + ", true, " +
+                                         (trk ? "true" : "false") + ", false, false>";
     }
     for (const std::string& e : exprs)
         if (!e.empty() && (rc = nv.AddNameExpression(prog, e.c_str()))) {
@@ -704,7 +707,9 @@ int ecuda_user_model_compile_check(int32_t model_id, int nnodes, size_t* image_b
     const bool rows = nb >= 3 && nb <= 5;
     ecuda::UserImage img;
     std::string err;
-    const bool ok = ecuda::user_model_compile(*m, rows ? nb : 0, rows, &img, &err);
+    // the N-specialised kernel under the same rule as the handle applies (ecuda_api.cu: user_rowsn_N)
+    const int rn = rows && 2 * m->ns * nnodes >= 256 && m->ns * nnodes <= 256 ? nnodes : 0;
+    const bool ok = ecuda::user_model_compile(*m, rows ? nb : 0, rows, rn, true, &img, &err);
     if (log && loglen) std::snprintf(log, loglen, "%s", ok ? img.log.c_str() : err.c_str());
     if (!ok) return ECUDA_ERR_CUDA;
     if (image_bytes) *image_bytes = img.cubin.size();
