@@ -36,8 +36,12 @@ class TrajectoryOptimizer {
     void loadConfigs(const char* filepath);   // ETOL XML: <etol><states><controls><exzones><mexzones>
     void saveConfigs(const char* filepath);
     void addParams(std::list<param_t> params);
-    void addExclZone(border_t* border);
+    void addExclZone(border_t* border);  // keeps the raw border and its convex partition (getObstacles)
     void addAdjTrack(track_t* track);
+    // convex partition of a simple polygon: per piece a lower and an upper chain, both sorted left to right
+    // (reference TrajectoryOptimizer.hpp:118-128); slopes and lengths of the chain edges for the MIP formulations
+    static region_t genRegion(border_t* border);
+    static void calcSlopes(const region_t& region, std::vector<seg_t>* lowers, std::vector<seg_t>* uppers);
 
     // trajectory -> CSV. Never overwrites: bumps the trailing integer of the stem until the name is free.
     static std::string save(traj_t* traj, std::string fp = "traj.csv");
@@ -156,7 +160,7 @@ class TrajectoryOptimizer {
     size_t _rhorizon;
     paramset_t _parameters;
     std::vector<border_t> _obstacles_raw;
-    std::list<region_t> _obstacles;  // convex partitions: only MIP eSolvers use them; left empty here
+    std::list<region_t> _obstacles;  // convex partitions (genRegion): what the MIP eSolvers of the reference consume
     std::list<track_t> _tracks;
     std::vector<f_t*> _constraints;
     std::vector<f_t*> _eq;

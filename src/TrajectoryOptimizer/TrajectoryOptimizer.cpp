@@ -12,14 +12,19 @@
 //     so exponents ("1e-3") are accepted where XPath 1.0 numbers would give NaN;
 //   * resetConfigs() also clears _xlower/_xupper/_parameters/_nSteps, so loading twice into one
 //     object replaces the VGP instead of appending to it;
-//   * addExclZone keeps the raw border only: the CGAL convex partition feeds the MIP eSolvers and
-//     plotting, neither of which is part of this tree.
+//   * addExclZone partitions the border into convex pieces like the reference (:84-159), but without CGAL: ear
+//     clipping followed by a Hertel-Mehlhorn merge instead of CGAL::optimal_convex_partition_2 -- a valid convex
+//     partition with lower / upper chains per piece, not necessarily the minimum number of pieces. Only the MIP
+//     eSolvers and plotting consume it; neither is part of this tree.
 #include <ETOL/TrajectoryOptimizer.hpp>
 
 #include <expat.h>
 #include <sys/stat.h>
 
+#include <algorithm>
+#include <array>
 #include <cassert>
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -372,7 +377,150 @@ void TrajectoryOptimizer::printConfigs() {
 void TrajectoryOptimizer::addParams(std::list<param_t> params) {
     for (const param_t& p : params) _parameters.insert(p);  // std::map: first insertion of a name wins
 }
-void TrajectoryOptimizer::addExclZone(border_t* border) { _obstacles_raw.push_back(*border); }
+// ---- convex partition of an exclusion zone (reference :84-159 genRegion, :161-207 calcSlopes) ------------------
+namespace {
+struct P2 {
+    double x, y;
+};
+double cross(const P2& o, const P2& a, const P2& b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); }
+bool inside_tri(const P2& p, const P2& a, const P2& b, const P2& c) {
+    return cross(a, b, p) >= 0.0 && cross(b, c, p) >= 0.0 && cross(c, a, p) >= 0.0;
+}
+// counter-clockwise simple polygon -> triangles (vertex indices), ear clipping
+std::vector<std::array<int, 3>> ear_clip(const std::vector<P2>& v) {
+    std::vector<int> idx(v.size());
+    for (size_t i = 0; i < v.size(); ++i) idx[i] = static_cast<int>(i);
+    std::vector<std::array<int, 3>> tris;
+    size_t guard = 0;
+    while (idx.size() > 3 && guard++ < 4 * v.size() * v.size()) {
+        bool clipped = false;
+        for (size_t i = 0; i < idx.size(); ++i) {
+            const int a = idx[(i + idx.size() - 1) % idx.size()], b = idx[i], c = idx[(i + 1) % idx.size()];
+            if (cross(v[a], v[b], v[c]) <= 0.0) continue;  // reflex or degenerate corner
+            bool ear = true;
+            for (int q : idx)
+                if (q != a && q != b && q != c && inside_tri(v[q], v[a], v[b], v[c])) {
+                    ear = false;
+                    break;
+                }
+            if (!ear) continue;
+            tris.push_back({a, b, c});
+            idx.erase(idx.begin() + static_cast<long>(i));
+            clipped = true;
+            break;
+        }
+        if (!clipped) {  // collinear leftovers: drop a degenerate corner and go on
+            bool dropped = false;
+            for (size_t i = 0; i < idx.size() && !dropped; ++i) {
+                const int a = idx[(i + idx.size() - 1) % idx.size()], b = idx[i], c = idx[(i + 1) % idx.size()];
+                if (cross(v[a], v[b], v[c]) == 0.0) {
+                    idx.erase(idx.begin() + static_cast<long>(i));
+                    dropped = true;
+                }
+            }
+            if (!dropped) break;
+        }
+    }
+    if (idx.size() == 3 && cross(v[idx[0]], v[idx[1]], v[idx[2]]) > 0.0) tris.push_back({idx[0], idx[1], idx[2]});
+    return tris;
+}
+bool convex_ccw(const std::vector<int>& poly, const std::vector<P2>& v) {
+    const size_t n = poly.size();
+    for (size_t i = 0; i < n; ++i)
+        if (cross(v[poly[i]], v[poly[(i + 1) % n]], v[poly[(i + 2) % n]]) < 0.0) return false;
+    return true;
+}
+// Hertel-Mehlhorn: remove a diagonal whenever the union of the two pieces it separates is still convex
+std::vector<std::vector<int>> merge_convex(const std::vector<std::array<int, 3>>& tris, const std::vector<P2>& v) {
+    std::vector<std::vector<int>> polys;
+    for (const auto& t : tris) polys.push_back({t[0], t[1], t[2]});
+    bool merged = true;
+    while (merged) {
+        merged = false;
+        for (size_t a = 0; a < polys.size() && !merged; ++a)
+            for (size_t b = a + 1; b < polys.size() && !merged; ++b) {
+                const std::vector<int>&A = polys[a], &B = polys[b];
+                for (size_t i = 0; i < A.size() && !merged; ++i) {
+                    const int p = A[i], q = A[(i + 1) % A.size()];  // edge p -> q of A; B must hold q -> p
+                    for (size_t j = 0; j < B.size() && !merged; ++j) {
+                        if (B[j] != q || B[(j + 1) % B.size()] != p) continue;
+                        std::vector<int> u;  // A from q round to p, then B from p round to q (both without the shared edge)
+                        for (size_t s = 0; s < A.size(); ++s) u.push_back(A[(i + 1 + s) % A.size()]);
+                        for (size_t s = 2; s < B.size(); ++s) u.push_back(B[(j + s) % B.size()]);
+                        if (!convex_ccw(u, v)) continue;
+                        polys[a] = u;
+                        polys.erase(polys.begin() + static_cast<long>(b));
+                        merged = true;
+                    }
+                }
+            }
+    }
+    return polys;
+}
+}  // namespace
+
+region_t TrajectoryOptimizer::genRegion(border_t* border) {
+    region_t region;
+    if (border == nullptr || border->size() < 3) return region;
+    std::vector<P2> v;
+    for (const corner_t& c : *border) {
+        if (!v.empty() && v.back().x == c.at(0) && v.back().y == c.at(1)) continue;  // repeated corner
+        v.push_back({c.at(0), c.at(1)});
+    }
+    if (v.size() > 1 && v.front().x == v.back().x && v.front().y == v.back().y) v.pop_back();  // explicitly closed
+    if (v.size() < 3) return region;
+    double area2 = 0.0;
+    for (size_t i = 0; i < v.size(); ++i) area2 += v[i].x * v[(i + 1) % v.size()].y - v[(i + 1) % v.size()].x * v[i].y;
+    if (area2 == 0.0) return region;
+    if (area2 < 0.0) std::reverse(v.begin(), v.end());  // work counter-clockwise
+    for (const std::vector<int>& poly : merge_convex(ear_clip(v), v)) {
+        // lower chain: counter-clockwise from the leftmost to the rightmost vertex; upper chain: the other way round,
+        // stored left to right as well (the reference sorts both segments from left to right, :81-83)
+        size_t il = 0, ir = 0;
+        for (size_t i = 1; i < poly.size(); ++i) {
+            const P2 &p = v[poly[i]], &l = v[poly[il]], &r = v[poly[ir]];
+            if (p.x < l.x || (p.x == l.x && p.y < l.y)) il = i;
+            if (p.x > r.x || (p.x == r.x && p.y > r.y)) ir = i;
+        }
+        boundary_t bd;
+        for (size_t i = il;; i = (i + 1) % poly.size()) {
+            bd.lower.push_back({v[poly[i]].x, v[poly[i]].y, 0.});
+            if (i == ir) break;
+        }
+        for (size_t i = ir;; i = (i + 1) % poly.size()) {
+            bd.upper.push_front({v[poly[i]].x, v[poly[i]].y, 0.});
+            if (i == il) break;
+        }
+        region.push_back(bd);
+    }
+    return region;
+}
+
+void TrajectoryOptimizer::calcSlopes(const region_t& region, std::vector<seg_t>* lowers, std::vector<seg_t>* uppers) {
+    lowers->clear();
+    uppers->clear();
+    auto chain = [](const border_t& b) {
+        seg_t seg;
+        for (auto it = b.begin(); it != b.end() && std::next(it) != b.end(); ++it) {
+            const double dely = std::next(it)->at(1) - it->at(1), delx = std::next(it)->at(0) - it->at(0);
+            edge_prop_t prop;
+            prop.slope = delx == 0. ? DBL_MAX : dely / delx;  // vertical edge: DBL_MAX as in the reference (:173-176)
+            prop.length = std::sqrt(delx * delx + dely * dely);
+            seg.push_back(edge_t(*it, prop));
+        }
+        return seg;
+    };
+    for (const boundary_t& bd : region) {
+        lowers->push_back(chain(bd.lower));
+        uppers->push_back(chain(bd.upper));
+    }
+}
+
+void TrajectoryOptimizer::addExclZone(border_t* border) {
+    _obstacles_raw.push_back(*border);
+    region_t obstacle = genRegion(border);
+    if (!obstacle.empty()) _obstacles.push_back(obstacle);
+}
 void TrajectoryOptimizer::addAdjTrack(track_t* track) { _tracks.push_back(*track); }
 
 void TrajectoryOptimizer::errorHandler() {

@@ -131,6 +131,32 @@ double shim_edit_instance_and_remesh(void* h, int b, int index, double value, in
     const std::vector<std::vector<double>>& inst = t->instanceBlocksForTest();
     return inst.at(static_cast<size_t>(b)).at(static_cast<size_t>(index));
 }
+// convex partition of a polygon (TrajectoryOptimizer::genRegion + calcSlopes): returns the number of pieces; out holds,
+// per piece, [nlower, nupper, lower xy..., upper xy..., lower slopes (nlower-1), upper slopes (nupper-1)]
+int shim_gen_region(const double* xy, int n, double* out, int cap) {
+    ETOL::border_t border;
+    for (int i = 0; i < n; ++i) border.push_back({xy[2 * i], xy[2 * i + 1], 0.});
+    ETOL::region_t region = ETOL::TrajectoryOptimizer::genRegion(&border);
+    std::vector<ETOL::seg_t> lowers, uppers;
+    ETOL::TrajectoryOptimizer::calcSlopes(region, &lowers, &uppers);
+    int w = 0, piece = 0;
+    auto put = [&](double v) {
+        if (w < cap) out[w] = v;
+        ++w;
+    };
+    for (const ETOL::boundary_t& bd : region) {
+        put(static_cast<double>(bd.lower.size()));
+        put(static_cast<double>(bd.upper.size()));
+        for (const ETOL::corner_t& c : bd.lower) { put(c[0]); put(c[1]); }
+        for (const ETOL::corner_t& c : bd.upper) { put(c[0]); put(c[1]); }
+        for (const ETOL::edge_t& e : lowers[piece]) put(e.second.slope);
+        for (const ETOL::edge_t& e : uppers[piece]) put(e.second.slope);
+        ++piece;
+    }
+    return w <= cap ? piece : -w;
+}
+// number of partitioned exclusion zones the loaded VGP holds (addExclZone fills them while loading)
+int shim_num_partitioned_zones(void* h) { return static_cast<int>(static_cast<eCUDA*>(h)->getObstacles()->size()); }
 void shim_structure(void* h, int32_t* irow, int32_t* jcol, int32_t* grp) {
     ETOL::ecuda_prob_t* p = static_cast<eCUDA*>(h)->getProblem();
     std::memcpy(irow, p->iRow.data(), sizeof(int32_t) * p->iRow.size());

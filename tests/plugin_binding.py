@@ -31,6 +31,8 @@ def lib():
         L.shim_bounds.argtypes = [C.c_void_p] + [_dp] * 7
         L.shim_instance.argtypes = [C.c_void_p, C.c_int, _dp]
         L.shim_structure.argtypes = [C.c_void_p, _ip, _ip, _ip]
+        L.shim_gen_region.argtypes = [_dp, C.c_int, _dp, C.c_int]
+        L.shim_num_partitioned_zones.argtypes = [C.c_void_p]
         L.shim_edit_instance_and_remesh.restype = C.c_double
         L.shim_edit_instance_and_remesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
         L.shim_save_xml.argtypes = [C.c_void_p, C.c_char_p]
@@ -222,3 +224,21 @@ def nlp_solve(n, m, zl, zu, gl, gu, irow, jcol, evalfn, z0, max_iter=300, tol=1e
                               jcol.ctypes.data_as(_ip), EVAL_CB(cb), max_iter, tol, print_level,
                               z.ctypes.data_as(_dp), res.ctypes.data_as(_dp))
     return rc, z, dict(iterations=int(res[0]), objective=res[1], max_violation=res[2])
+
+
+def gen_region(xy):
+    """convex partition of a polygon -> list of (lower [n][2], upper [m][2], lower slopes, upper slopes)"""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    out = np.zeros(64 * len(xy) + 64)
+    n = lib().shim_gen_region(xy.ctypes.data_as(_dp), len(xy), out.ctypes.data_as(_dp), len(out))
+    assert n >= 0
+    pieces, w = [], 0
+    for _ in range(n):
+        nl, nu = int(out[w]), int(out[w + 1])
+        w += 2
+        lo = out[w:w + 2 * nl].reshape(nl, 2).copy(); w += 2 * nl
+        up = out[w:w + 2 * nu].reshape(nu, 2).copy(); w += 2 * nu
+        sl = out[w:w + nl - 1].copy(); w += nl - 1
+        su = out[w:w + nu - 1].copy(); w += nu - 1
+        pieces.append((lo, up, sl, su))
+    return pieces

