@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(kThreads, NB > 0 ? ECUDA_MIN_CTAS : 1) k_eval(
 // kCopySlots buffers of kCopyChunk doubles; one lane drives it. Used when nnz is even, so that the
 // template element e and its destination b*nnz + e always agree modulo 16 bytes.
 constexpr int kCopyWarpThreads = 32;
+#ifndef ECUDA_EXACT_NOWAIT
+#define ECUDA_EXACT_NOWAIT 0
+#endif
 #ifndef ECUDA_COPY_SLOTS
 #define ECUDA_COPY_SLOTS 4
 #endif
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         double* ring = bnd + 2 * nbnd;
         ring += (reinterpret_cast<uintptr_t>(ring) & 8) ? 1 : 0;
         if (io.jac) copy_warp_template(pb, ph, io, b, ring, copy_bars, tid - kThreads);
+#if !ECUDA_EXACT_NOWAIT
         __syncthreads();
+#endif
         return;
     }
     if (tid == 0) {
@@ -325,7 +330,11 @@ __global__ void __launch_bounds__(FD ? kThreads : kThreads + kCopyWarpThreads,
         // (storing the control / time-column triplets, which lie outside the template's range, before this
         // barrier was measured: 0.158 vs 0.148 ms -- the second evaluation of the model costs more than the
         // shorter wait saves)
+#if ECUDA_EXACT_NOWAIT  // experiment (RACE, wrong results): what the wait for the template copy costs
+        if (copy_warp) named_barrier(1, kThreads); else __syncthreads();
+#else
         __syncthreads();  // all threads: the template has landed before the node-local triplets overwrite it
+#endif
         rows_jacobian<M, NB, FD>(pb, ph, io, m, b, tid, rs);
         rows_other<M, NB, FD>(pb, ph, p, io, m, b, tid, nthr, rs, false, true);
     }
