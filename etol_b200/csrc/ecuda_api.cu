@@ -1202,6 +1202,7 @@ int ecuda_eval_compact(ecuda_handle h, const double* x, double* f, double* g, do
     if (!h) return ECUDA_ERR_ARG;
     if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
     if (!jac_local) return fail(h, ECUDA_ERR_ARG, "jac_local is required (use ecuda_eval for values only)");
+    if (h->hp.desc.batch > 65535) return fail(h, ECUDA_ERR_ARG, "ecuda_eval_compact: batch > 65535");
     if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
     CU(cudaSetDevice(h->device));
     int rc;
@@ -1212,7 +1213,6 @@ int ecuda_eval_compact(ecuda_handle h, const double* x, double* f, double* g, do
     if ((rc = ensure(h, h->sjac, sizeof(double) * B * nz))) return rc;
     double* full = static_cast<double*>(h->sjac.p);
     const dim3 grid(static_cast<unsigned>((nl + 255) / 256), static_cast<unsigned>(B));
-    if (B > 65535) return fail(h, ECUDA_ERR_ARG, "ecuda_eval_compact: batch > 65535");
     if (memkind == ECUDA_MEM_DEVICE) {
         if ((rc = eval_common(h, x, f, g, full, nullptr, ECUDA_JAC_EXACT, ECUDA_MEM_DEVICE, stream))) return rc;
         k_gather_local<<<grid, 256, 0, st>>>(full, static_cast<const int32_t*>(h->lidx.p), jac_local, (int)nz, (int)nl);
