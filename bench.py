@@ -581,7 +581,8 @@ def run_ecuda(args):
         e2e = {"value": world * B * nsteps / (float(te.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(8 * B * nv), "d2h_bytes_per_step": int(8 * B * (1 + ng + nz)),
                "steps": nsteps, "what": "ecuda_eval with pinned HOST x/f/g/J buffers: H2D of x, kernel, D2H of "
-                                        "f, g and all Jacobian values, every step"}
+                                        "f, g and all Jacobian values, every step (the library pipelines the call over "
+                                        "instance chunks on three streams)"}
 
     # ---- exact mode end to end: the full triplet array against the compact form (ecuda_eval_compact: only the
     # per-instance triplets cross PCIe; the D-coupled ones are the same for every instance). Same pinned buffers.
