@@ -1409,10 +1409,6 @@ int ecuda_eval_hess(ecuda_handle h, const double* x, const double* sigma, double
     if (!h->have_problem) return fail(h, ECUDA_ERR_STATE, "set_problem has not succeeded");
     if (!h->have_inst) return fail(h, ECUDA_ERR_STATE, "upload_instances has not been called");
     if (!x || !lambda || !vals) return fail(h, ECUDA_ERR_ARG, "x, lambda and vals are required");
-    if (h->um && (h->um->tdep || !h->um->row_out.empty()))
-        return fail(h, ECUDA_ERR_ARG, "the exact Hessian is not available for user models whose dynamics or cost read t "
-                                      "or that have traced path rows (values, both Jacobian modes and the objective "
-                                      "gradient are)");
     if (memkind != ECUDA_MEM_HOST && memkind != ECUDA_MEM_DEVICE) return fail(h, ECUDA_ERR_ARG, "bad memkind");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;

@@ -179,6 +179,9 @@ struct UserModel {
     int dcdx[ECUDA_MAX_STATES], dcdu[ECUDA_MAX_CONTROLS];
     // traced path rows (may read states 0, 1 and t): output nodes and their partials (-1 = identically zero)
     std::vector<int> row_out, drdx, drdy, drdt;
+    std::vector<int> rhess;              // per traced row: d2/dx2, dxdy, dy2, dxdt, dydt, dt2
+    // time part of the second derivatives (o < ns: f_o, o == ns: cost): d2/dv dt over [x | u], d2/dt2
+    std::vector<int> dvt, dtt;
     bool tdep = false;                   // some f_i or the running cost reads t
     int dfdt[ECUDA_MAX_STATES], dcdt = -1;
     // second derivatives over [x | u]: d2[(o * nv + a) * nv + b], a <= b, o < ns: f_o, o == ns: cost

@@ -159,7 +159,7 @@ struct Model<ECUDA_MODEL_SI2D> {
         dfdx[0][0] = 0.0; dfdx[0][1] = 0.0; dfdx[1][0] = 0.0; dfdx[1][1] = 0.0;
         dfdu[0][0] = 1.0; dfdu[0][1] = 0.0; dfdu[1][0] = 0.0; dfdu[1][1] = 1.0;
     }
-    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+    ECUDA_HD static void hess(const double* x, const double* u, double t, const double* lam, double lamL,
                               double (*H)[NS + NCU]) {
         for (int a = 0; a < NS + NCU; ++a)
             for (int b = 0; b < NS + NCU; ++b) H[a][b] = (a == b && a >= NS) ? 2.0 * lamL : 0.0;
@@ -199,7 +199,7 @@ struct Model<ECUDA_MODEL_PM3D> {
             for (int j = 0; j < NCU; ++j) dfdu[i][j] = (i >= 3 && j == i - 3) ? 1.0 : 0.0;
         }
     }
-    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+    ECUDA_HD static void hess(const double* x, const double* u, double t, const double* lam, double lamL,
                               double (*H)[NS + NCU]) {
         for (int a = 0; a < NS + NCU; ++a)
             for (int b = 0; b < NS + NCU; ++b) H[a][b] = (a == b && a >= NS) ? 2.0 * lamL : 0.0;
@@ -255,7 +255,7 @@ struct Model<ECUDA_MODEL_FW6> {
         dfdx[2][3] = sg;       dfdx[2][4] = V * cg;
         dfdx[3][4] = -G0 * cg;
     }
-    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,
+    ECUDA_HD static void hess(const double* x, const double* u, double t, const double* lam, double lamL,
                               double (*H)[NS + NCU]) {
         double sg, cg, sp, cp;
         ecuda_sincos(x[4], &sg, &cg);

@@ -1051,7 +1051,7 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
         for (int j = 0; j < NCU; ++j) u[j] = m.z[k * nc + j];
         const double cL = sig * ECUDA_LDG(ph.w + k);
         double H[NV][NV];
-        Model<M>::hess(x, u, lamf, cL * pt.h, H);
+        Model<M>::hess(x, u, t, lamf, cL * pt.h, H);
         // first derivatives for the couplings with t0 / tf
         double dfdx[NS][NS], dfdu[NS][NCU], dLx[NS], dLu[NCU], gv[NV];
         Model<M>::jac(x, u, t, dfdx, dfdu);
@@ -1070,6 +1070,19 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
             for (int i = 0; i < NS; ++i) s = fma(cdef[i], dfdu[i][a], s);
             gv[NS + a] = s;
         }
+        // dynamics / cost that read t (user models): d2/dv dt, d/dt and d2/dt2 of h (sum_i c_i f_i + c_L L)
+        double gt[NV], tt0 = 0.0, tt1 = 0.0, tt2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < NV; ++a) gt[a] = 0.0;
+        if constexpr (Model<M>::TDEP) {
+            double sth, stth, st1, stt1, g1[NV];
+            Model<M>::tdir(x, u, t, lamf, cL * pt.h, gt, &sth, &stth);   // weights carry h: h G_vt, h G_t, h G_tt
+            Model<M>::tdir(x, u, t, cdef, cL, g1, &st1, &stt1);          // G_t without h (from d h / d t0|tf = -+ 1/2)
+            (void)sth; (void)stt1; (void)g1;
+            tt0 = -(st1 * ta) + (stth * ta) * ta;
+            tt1 = 0.5 * (st1 * (ta - tb)) + (stth * ta) * tb;
+            tt2 = st1 * tb + (stth * tb) * tb;
+        }
         // path rows: static obstacles (position block), moving circles (position block, time couplings)
         double xt[2] = {0.0, 0.0}, tt = 0.0;
         const int rp0 = ph.goff + NS * N + pb.ne + k * np;
@@ -1082,6 +1095,16 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
                 H[0][1] = fma(c, hxy, H[0][1]);
                 H[1][0] = fma(c, hxy, H[1][0]);
                 H[1][1] = fma(c, hyy, H[1][1]);
+            } else if (Model<M>::NUSER > 0 && q - nstat >= pb.ntracks) {  // traced path row of a user model
+                double h6[6];
+                if constexpr (Model<M>::NUSER > 0) Model<M>::user_row_hess(q - nstat - pb.ntracks, x[0], x[1], t, h6);
+                H[0][0] = fma(c, h6[0], H[0][0]);
+                H[0][1] = fma(c, h6[1], H[0][1]);
+                H[1][0] = fma(c, h6[1], H[1][0]);
+                H[1][1] = fma(c, h6[2], H[1][1]);
+                xt[0] = fma(c, h6[3], xt[0]);
+                xt[1] = fma(c, h6[4], xt[1]);
+                tt = fma(c, h6[5], tt);
             } else {
                 double hxt, hyt, htt;
                 track_row_hess(m.inst + pb.track_off + (q - nstat) * pb.track_size, pb.nway, t, &hxt, &hyt, &htt);
@@ -1092,9 +1115,9 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
                 tt = fma(c, htt, tt);
             }
         }
-        m.hf[3 * k] = (tt * ta) * ta;
-        m.hf[3 * k + 1] = (tt * ta) * tb;
-        m.hf[3 * k + 2] = (tt * tb) * tb;
+        m.hf[3 * k] = (tt * ta) * ta + tt0;
+        m.hf[3 * k + 1] = (tt * ta) * tb + tt1;
+        m.hf[3 * k + 2] = (tt * tb) * tb + tt2;
         // control columns of the node
         for (int j = 0; j < nc; ++j) {
             double* col = out + k * Cu + j * (nc + NS + 2) - j * (j - 1) / 2;
@@ -1120,8 +1143,12 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
                     if (a == j) v = H[i][NS + a];
                 col[(nc - j) + i] = (v * sj) * ECUDA_LDG(isz + nc * N + k * NS + i);
             }
-            col[(nc - j) + NS] = ((-0.5 * gj) * sj) * iszt0;
-            col[(nc - j) + NS + 1] = ((0.5 * gj) * sj) * iszt1;
+            double gtj = 0.0;
+#pragma unroll
+            for (int a = 0; a < NCU; ++a)
+                if (a == j) gtj = gt[NS + a];
+            col[(nc - j) + NS] = ((-0.5 * gj + gtj * ta) * sj) * iszt0;
+            col[(nc - j) + NS + 1] = ((0.5 * gj + gtj * tb) * sj) * iszt1;
         }
         // state columns of the node
 #pragma unroll
@@ -1130,7 +1157,7 @@ ECUDA_HD void hess_nodes(const ProbDev& pb, const PhaseDev& ph, int p, const Hes
             const double si = ECUDA_LDG(isz + nc * N + k * NS + i);
 #pragma unroll
             for (int i2 = i; i2 < NS; ++i2) col[i2 - i] = (H[i][i2] * si) * ECUDA_LDG(isz + nc * N + k * NS + i2);
-            const double xti = i < 2 ? xt[i] : 0.0;
+            const double xti = (i < 2 ? xt[i] : 0.0) + gt[i];
             col[NS - i] = ((-0.5 * gv[i] + xti * ta) * si) * iszt0;
             col[NS - i + 1] = ((0.5 * gv[i] + xti * tb) * si) * iszt1;
         }

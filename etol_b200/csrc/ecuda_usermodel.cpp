@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -238,9 +239,9 @@ std::string generate_source(const UserModel& m) {
     }
     o << "    }\n";
     // hess: H = sum_i lam[i] d2 f_i + lamL d2 L over [x | u]
-    o << "    ECUDA_HD static void hess(const double* x, const double* u, const double* lam, double lamL,\n"
-         "                              double (*H)[NS + NCU]) {\n";
-    if (m.tdep) o << "        const double t = 0.0;  // not reached: ecuda_eval_hess refuses time-dependent models\n";
+    o << "    ECUDA_HD static void hess(const double* x, const double* u, double t, const double* lam, double lamL,\n"
+         "                              double (*H)[NS + NCU]) {\n"
+         "        (void)t;\n";
     {
         const int nvn = m.ns + m.nc;
         outs.assign(m.d2.begin(), m.d2.end());
@@ -258,6 +259,47 @@ std::string generate_source(const UserModel& m) {
                 o << "        H[" << a << "][" << b << "] = " << (sum.empty() ? std::string("0.0") : sum) << ";\n";
                 if (b != a) o << "        H[" << b << "][" << a << "] = H[" << a << "][" << b << "];\n";
             }
+    }
+    o << "    }\n";
+    // tdir: time part of the weighted second derivatives, gt[v] = sum_i lam[i] d2f_i/dv dt + lamL d2L/dv dt,
+    // st = sum_i lam[i] df_i/dt + lamL dL/dt, stt = sum_i lam[i] d2f_i/dt2 + lamL d2L/dt2
+    o << "    ECUDA_HD static void tdir(const double* x, const double* u, double t, const double* lam, double lamL,\n"
+         "                              double* gt, double* st, double* stt) {\n"
+         "        (void)x; (void)u; (void)t;\n";
+    {
+        const int nvn = m.ns + m.nc;
+        outs.assign(m.dvt.begin(), m.dvt.end());
+        outs.insert(outs.end(), m.dtt.begin(), m.dtt.end());
+        for (int i = 0; i < m.ns; ++i) outs.push_back(m.dfdt[i]);
+        outs.push_back(m.dcdt);
+        print_body(m, outs, o);
+        auto wsum = [&](const std::function<int(int)>& id) {
+            std::string sum;
+            for (int k = 0; k <= m.ns; ++k) {
+                const int n = id(k);
+                if (n < 0) continue;
+                const std::string term =
+                    (k < m.ns ? "lam[" + std::to_string(k) + "]" : std::string("lamL")) + " * v" + std::to_string(n);
+                sum = sum.empty() ? term : "(" + sum + ") + " + term;
+            }
+            return sum.empty() ? std::string("0.0") : sum;
+        };
+        for (int a = 0; a < nvn; ++a)
+            o << "        gt[" << a << "] = " << wsum([&](int k) { return m.dvt[static_cast<size_t>(k) * nvn + a]; }) << ";\n";
+        o << "        *st = " << wsum([&](int k) { return k < m.ns ? m.dfdt[k] : m.dcdt; }) << ";\n";
+        o << "        *stt = " << wsum([&](int k) { return m.dtt[k]; }) << ";\n    }\n";
+    }
+    // second derivatives of the traced path rows in (x_0, x_1, t)
+    o << "    ECUDA_HD static void user_row_hess(int r, double x0, double x1, double t, double* h) {\n"
+         "        const double x[2] = {x0, x1};\n        const double* u = nullptr;\n        (void)x; (void)u; (void)t;\n"
+         "        for (int e = 0; e < 6; ++e) h[e] = 0.0;\n";
+    for (size_t r = 0; r < m.row_out.size(); ++r) {
+        o << "        if (r == " << r << ") {\n";
+        std::vector<int> six(m.rhess.begin() + static_cast<long>(6 * r), m.rhess.begin() + static_cast<long>(6 * r + 6));
+        print_body(m, six, o);
+        for (int e = 0; e < 6; ++e)
+            if (six[e] >= 0) o << "        h[" << e << "] = v" << six[e] << ";\n";
+        o << "        }\n";
     }
     o << "    }\n";
     // traced path rows
@@ -491,6 +533,27 @@ int register_user_model(const ecuda_user_model* um, int nrows, const int32_t* ro
             for (int b = a; b < nvn; ++b)
                 m->d2[(static_cast<size_t>(o) * nvn + a) * nvn + b] = differentiate(P, first, b);
         }
+    {  // time part of the second derivatives, and the second derivatives of the traced rows
+        const int tslot = m->ns + m->nc;
+        m->dvt.assign(static_cast<size_t>(m->ns + 1) * nvn, -1);
+        m->dtt.assign(static_cast<size_t>(m->ns + 1), -1);
+        for (int o = 0; o <= m->ns; ++o) {
+            for (int a = 0; a < nvn; ++a) {
+                const int first = o < m->ns ? (a < m->ns ? m->dfdx[o][a] : m->dfdu[o][a - m->ns])
+                                            : (a < m->ns ? m->dcdx[a] : m->dcdu[a - m->ns]);
+                m->dvt[static_cast<size_t>(o) * nvn + a] = differentiate(P, first, tslot);
+            }
+            m->dtt[o] = differentiate(P, o < m->ns ? m->dfdt[o] : m->dcdt, tslot);
+        }
+        for (size_t r = 0; r < m->row_out.size(); ++r) {
+            m->rhess.push_back(differentiate(P, m->drdx[r], 0));
+            m->rhess.push_back(differentiate(P, m->drdx[r], 1));
+            m->rhess.push_back(differentiate(P, m->drdy[r], 1));
+            m->rhess.push_back(differentiate(P, m->drdx[r], tslot));
+            m->rhess.push_back(differentiate(P, m->drdy[r], tslot));
+            m->rhess.push_back(differentiate(P, m->drdt[r], tslot));
+        }
+    }
     m->source = generate_source(*m);
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_models.size() >= ECUDA_MAX_USER_MODELS) return bad("too many user models (64 per process)");

@@ -88,7 +88,7 @@ enum ecuda_model {
  * include/ecuda_detmath.h; other POW exponents and EXP use the platform's pow / exp and are
  * reproducible to rounding only. Dynamics and cost may read t (the ePSOPT callbacks receive the node time as `k`,
  * src/ePSOPT/ePSOPT.cpp:218-260): values, both Jacobian modes (d/dt0, d/dtf through t_k = t0 + (tf - t0)(tau_k + 1)/2)
- * and the objective gradient follow; only ecuda_eval_hess refuses such a model. */
+ * the objective gradient and the Lagrangian Hessian (d2/dv dt, d2/dt2 of f and L) follow. */
 enum ecuda_tape_op {
     ECUDA_OP_INPUT = 0, ECUDA_OP_CONST = 1, ECUDA_OP_ADD = 2, ECUDA_OP_SUB = 3, ECUDA_OP_MUL = 4, ECUDA_OP_DIV = 5,
     ECUDA_OP_NEG = 6, ECUDA_OP_POW = 7, ECUDA_OP_SQRT = 8, ECUDA_OP_SIN = 9, ECUDA_OP_COS = 10, ECUDA_OP_EXP = 11
@@ -309,7 +309,7 @@ int ecuda_register_user_model(const ecuda_user_model* m, int32_t* model_id, char
  * is evaluated at every node after the static and the moving-zone rows of the problem (npath = nstatic + ntracks +
  * nrows) -- what ePSOPT does with every entry of _constraints (src/ePSOPT/ePSOPT.cpp:262-270) when it is none of the
  * built-in zone rows. A traced row may read states 0, 1 and t: the read set of a moving-zone row, whose sparsity
- * (columns x_0, x_1 of the node, t0, tf) it shares. Values, both Jacobian modes; ecuda_eval_hess refuses. */
+ * (columns x_0, x_1 of the node, t0, tf) it shares. Values, both Jacobian modes and the Lagrangian Hessian. */
 int ecuda_register_user_model_rows(const ecuda_user_model* m, int32_t nrows, const int32_t* row_out, int32_t* model_id,
                                    char* err, size_t errlen);
 /* the generated CUDA source of a registered model (NUL-terminated; *needed = bytes incl. NUL; buf may be NULL) */

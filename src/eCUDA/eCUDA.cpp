@@ -725,9 +725,8 @@ int eCUDA::solveOnce() {
     std::vector<int32_t> hrow, hcol;
     if (_algorithm.hessian == "exact") {
         // The exact Lagrangian Hessian (ecuda_eval_hess) is what IPOPT gets through eval_h. The built-in driver does
-        // not use it (it keeps a damped-BFGS model): say so instead of silently ignoring the setting. User models
-        // that read t or carry traced path rows have no device Hessian yet: IPOPT then runs with its limited-memory
-        // approximation.
+        // not use it (it keeps a damped-BFGS model): say so instead of silently ignoring the setting. Should the
+        // device Hessian be unavailable for a model, IPOPT runs with its limited-memory approximation.
         int32_t hn = 0;
         if (ecuda_get_hess_structure(h, &hn, nullptr, nullptr) != ECUDA_OK) fail("ecuda_get_hess_structure");
         std::vector<double> probe(static_cast<size_t>(hn)), lam0(static_cast<size_t>(ng), 0.0);

@@ -126,7 +126,8 @@ def test_resample_matches_oracle(evaluators, name):
 
 HESS_CASES = ["C0-ocp", "C0-mip", "C0-ocp-cheb-max", "C0-ocp-deps-base1", "C2-pm3d-64", "C2-pm3d-scaled-deps", "C3-fw6",
               "C3-fw6-small-scaled", "C4-multiphase", "C4-multiphase-ragged", "pm3d-N2", "pm3d-no-obstacles",
-              "user-pm3d", "user-unicycle-tracks", "user-unicycle-cheb-deps", "user-dragmass", "user-dragmass-N70-generic"]
+              "user-pm3d", "user-unicycle-tracks", "user-unicycle-cheb-deps", "user-dragmass", "user-dragmass-N70-generic",
+              "user-gust", "user-gust-cheb-deps", "user-zone", "user-zone-gust-cheb", "user-zone-N70-generic"]
 
 
 @pytest.mark.parametrize("name", HESS_CASES)
@@ -339,13 +340,33 @@ def test_compact_exact_jacobian_splices_to_the_full_one(evaluators, name):
     assert np.array_equal(jl.cpu().numpy(), out["jac_local"]) and np.array_equal(g.cpu().numpy(), full["g"])
 
 
-def test_hessian_refuses_time_dependent_user_models_loudly(evaluators):
-    """values, both Jacobian modes and the gradient support dynamics that read t; the exact Hessian does not yet, and
-    says so instead of returning second derivatives without the time couplings"""
-    for name in ("user-gust", "user-zone"):
-        ev, orc, wl = _get(evaluators, name)
-        with pytest.raises(RuntimeError, match="read t"):
-            ev.hess_host(wl.x, np.ones(wl.batch), np.zeros((wl.batch, ev.ncons)))
+@pytest.mark.parametrize("chunks", ["1", "3", "8"])
+def test_chunked_host_path_gives_the_same_bits(evaluators, chunks):
+    """HOST-buffer calls run in instance chunks on three streams (eval_host); any chunk count -- more chunks than
+    instances included -- must return what the device-pointer path returns, for every output and both modes."""
+    import torch
+    for name in ("C2-pm3d-scaled-deps", "C4-multiphase", "user-zone"):
+        wl = CASES[name]()
+        os.environ["ECUDA_HOST_CHUNKS"] = chunks  # read by ecuda_create
+        try:
+            ev = capi.Evaluator(wl, device=0)
+        finally:
+            os.environ.pop("ECUDA_HOST_CHUNKS", None)
+        dev = torch.device("cuda:0")
+        x = torch.from_numpy(wl.x).to(dev)
+        for mode in (W.JAC_FD, W.JAC_EXACT):
+            got = ev.eval_host(wl.x, want=("f", "g", "jac", "grad"), jac_mode=mode)
+            f = torch.empty(wl.batch, dtype=torch.float64, device=dev)
+            g = torch.empty((wl.batch, ev.ncons), dtype=torch.float64, device=dev)
+            jac = torch.empty((wl.batch, ev.nnz), dtype=torch.float64, device=dev)
+            ev.eval_ptr(x.data_ptr(), f.data_ptr(), g.data_ptr(), jac.data_ptr(), mode, capi.MEM_DEVICE, None)
+            ev.sync()
+            assert np.array_equal(got["f"], f.cpu().numpy()) and np.array_equal(got["g"], g.cpu().numpy())
+            assert np.array_equal(got["jac"], jac.cpu().numpy()), (name, mode, chunks)
+            assert np.isfinite(got["grad"]).all()
+        only_g = ev.eval_host(wl.x, want=("g",), jac_mode=W.JAC_FD)
+        assert only_g["f"] is None and only_g["jac"] is None and np.array_equal(only_g["g"], got["g"])
+        ev.close()
 
 
 def test_full_size_batch_properties():

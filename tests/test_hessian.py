@@ -16,6 +16,9 @@ CASES = {
     "multiphase": lambda: W.pm3d_multiphase(batch=1, nphases=2, nnodes=6, ncyl=1),
     "user-unicycle-tracks": lambda: W.unicycle(batch=1, nnodes=8, ncyl=2, ntracks=1),
     "user-dragmass": lambda: W.dragmass(batch=1, nnodes=8, ncyl=1, scaled=True),
+    # round 2: dynamics / cost that read t, and traced path rows
+    "user-gust": lambda: W.gust(batch=1, nnodes=8, ncyl=1, ntracks=1),
+    "user-zone-gust": lambda: W.zone(batch=1, timedep=True, nnodes=7, ncyl=1, scaled=True),
 }
 
 
