@@ -1019,7 +1019,10 @@ ECUDA_HD void ode_error_intervals(const ProbDev& pb, const PhaseDev& ph, int p, 
 //   for its path rows;  node block  h (sum_i c_i d2 f_i + c_L d2 L) + sum_q c_q d2 p_q;
 //   (v, t0 | tf) = (-+1/2) (sum_i c_i df_i/dv + c_L dL/dv) + c_q d2p_q/dvdt (a | b)   [moving circles only];
 //   (t0 | tf, t0 | tf) = sum over nodes and moving circles of c_q d2p_q/dt2 (a a | a b | b b).
-// Dynamics and cost are autonomous, so they add nothing to the time-time block. Entries are multiplied by
+// Built-in dynamics and cost are autonomous and add nothing to the time-time block; user models that read t add, with
+// G = sum_i c_i f_i + c_L L:  (v, t0 | tf) += h G_vt (a | b);  (t0,t0) += -G_t a + h G_tt a a;  (t0,tf) += G_t (a - b)/2 +
+// h G_tt a b;  (tf,tf) += G_t b + h G_tt b b  (Model::tdir). Traced path rows bring all six second derivatives in
+// (x_0, x_1, t) (Model::user_row_hess). Entries are multiplied by
 // 1/sz of both variables (the solver's variables are z sz). Thread k owns node k; the 3 time-time partial
 // sums per node go through shared memory (m.hf, 3 per node) and thread 0 adds them in node order.
 template <int M>
