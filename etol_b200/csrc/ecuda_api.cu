@@ -542,10 +542,9 @@ static int launch_rows_n_mn(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int
     if (!TRK && h->pd.ntracks > 0) return 1;
     const bool fd = io.jac && io.jac_mode == ECUDA_JAC_FD_INDEXSET;
     if (fd) {
-        // the row-owner layout gives the D-coupled work to the threads that own a defect row: it pays when those are
-        // at least half of the CTA (C2 240 and C4 180 of 256: 0.158 vs 0.179 ms, 0.089 vs 0.116 ms); a phase with few
-        // rows (C0: 66) is faster on the column-owner kernel, which spreads that work over all threads (0.164 vs 0.207)
-        if (2 * Model<M>::NS * N < kThreads && !std::getenv("ECUDA_ROWS_ALWAYS")) return 1;
+        // Round 1 / early round 2 kept phases with few defect rows (C0: 66 of 256 threads) on the column-owner kernel
+        // (0.164 vs 0.207 ms). Since the path-row work items are grouped by kind (path_item) the N-specialised kernel
+        // wins there too: C0 0.133 vs 0.147 ms, the 17-node variant 0.098 vs 0.120 ms. ECUDA_NO_ROWSN=1 switches back.
         if (h->persist && io.nranks == 0 && h->pd.nphases == 1 && (h->pd.nvars & 1) == 0 && (h->pd.inst_stride & 1) == 0 &&
             (reinterpret_cast<uintptr_t>(io.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(io.inst) & 15) == 0)
             return launch_rows_n_persist<M, N, TRK>(h, io, st);
@@ -656,9 +655,9 @@ static int load_user_kernels(ecuda_ctx* h) {
     static std::map<std::tuple<int, int, bool, int, bool>, std::shared_ptr<UserImage>> cache;
     const int nb = (h->nb_uniform >= 3 && h->nb_uniform <= 5) ? h->nb_uniform : 0;
     // the N-specialised finite-difference kernel (k_rows_n) under the rule of launch_rows_n_mn: every phase has N
-    // nodes, one defect row per thread, and the row owners are at least half of the CTA
+    // nodes and one defect row per thread
     const int ns = h->pd.ns, rn = h->rowsn_N;
-    const int rowsn = (h->fast_ok && rn > 0 && 2 * ns * rn >= kThreads && ns * rn <= kThreads) ? rn : 0;
+    const int rowsn = (h->fast_ok && rn > 0 && ns * rn <= kThreads) ? rn : 0;
     bool trk = false;
     for (int p = 0; p < h->pd.nphases; ++p) trk = trk || h->pd.ph[p].npath > h->pd.ph[p].nstat;
     std::shared_ptr<UserImage> img;

@@ -771,7 +771,7 @@ int ecuda_user_model_compile_check(int32_t model_id, int nnodes, size_t* image_b
     ecuda::UserImage img;
     std::string err;
     // the N-specialised kernel under the same rule as the handle applies (ecuda_api.cu: user_rowsn_N)
-    const int rn = rows && 2 * m->ns * nnodes >= 256 && m->ns * nnodes <= 256 ? nnodes : 0;
+    const int rn = rows && m->ns * nnodes <= 256 ? nnodes : 0;
     const bool ok = ecuda::user_model_compile(*m, rows ? nb : 0, rows, rn, true, &img, &err);
     if (log && loglen) std::snprintf(log, loglen, "%s", ok ? img.log.c_str() : err.c_str());
     if (!ok) return ECUDA_ERR_CUDA;

@@ -6,7 +6,7 @@ from etol_b200 import capi, workloads as W
 dev = torch.device("cuda", 0)
 B = 4096
 which = os.environ.get("CASE", "c0")
-wl = W.reference_vgp("ocp", batch=B, jitter=0.02) if which == "c0" else W.fw6(batch=int(os.environ.get("BATCH", "64"))) if which == "c3" else W.pm3d_multiphase(batch=1024)
+wl = W.reference_vgp("ocp", batch=B, jitter=0.02) if which == "c0" else W.reference_vgp("mip", batch=B, jitter=0.02) if which == "c0mip" else W.fw6(batch=int(os.environ.get("BATCH", "64"))) if which == "c3" else W.pm3d_multiphase(batch=1024)
 B = wl.batch
 ev = capi.Evaluator(wl, device=0)
 x = torch.from_numpy(wl.x).to(dev)
