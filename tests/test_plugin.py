@@ -302,6 +302,14 @@ def test_plugin_traced_path_row_evaluates_like_oracle(xml):
     ref = o.eval(z * bnd["sz"], want=("f", "g", "jac"), jac_mode=W.JAC_EXACT, style=0)
     assert rel_err(f, ref["f"]) <= TOL_VALUE and rel_err(g, ref["g"]) <= TOL_VALUE
     assert rel_err(jac, ref["jac"]) <= TOL_JAC
+    # and the NLP is solved with the traced row in it: the trajectory stays outside the growing disc at every node
+    p.set_mesh("manual")
+    rc, score, iters, viol = p.solve(max_iter=400)
+    assert rc == 0 and viol <= 1e-8, (rc, viol, iters)
+    X = p.traj(0, 2, 33)
+    r = 0.2 + 0.01 * X[:, 0]
+    assert np.all((X[:, 1] - 3.0) ** 2 + (X[:, 2] - 3.5) ** 2 >= r * r - 1e-8)
+    assert np.allclose(X[0, 1:], [1.0, 2.0], atol=1e-6) and np.allclose(X[-1, 1:], [5.0, 4.0], atol=0.0101)
     p.close()
 
 
