@@ -46,13 +46,25 @@ def cuda_sources():
 
 
 def build_libecuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("ecuda_api.cu", "ecuda_host.cpp", "ecuda_usermodel.cpp", "ecuda_mesh.cpp")]
+    """nvcc sm_100a. ecuda_api.cu is compiled as two translation units (the second one, ecuda_api_rowsn.cu, holds the
+    instantiations of the N-specialised kernel family) next to the three host files, all in parallel, then linked."""
+    srcs = [os.path.join(CSRC, f) for f in ("ecuda_api.cu", "ecuda_api_rowsn.cu", "ecuda_host.cpp", "ecuda_usermodel.cpp",
+                                            "ecuda_mesh.cpp")]
     if not force and not _stale(LIBECUDA, cuda_sources()):
         return LIBECUDA
-    env = dict(os.environ)
-    cmd = [_nvcc(), "-ccbin", _cxx()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-shared", "-o", LIBECUDA] + srcs + ["-ldl"]
-    subprocess.run(cmd, check=True, env=env)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(ROOT, "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    base = [_nvcc(), "-ccbin", _cxx()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        subprocess.run(base + ["-c", "-o", obj, src], check=True)
+        return obj
+
+    with ThreadPoolExecutor(len(srcs)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    subprocess.run(base + ["-shared", "-o", LIBECUDA] + objs + ["-ldl"], check=True)
     return LIBECUDA
 
 

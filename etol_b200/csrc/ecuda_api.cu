@@ -25,6 +25,17 @@
 
 #include "ecuda_kernels.cuh"
 
+// This file is compiled as two translation units so that the build takes half the time: the main one, and (with
+// ECUDA_TU_ROWSN defined, through ecuda_api_rowsn.cu) one that holds only the launchers -- and therefore the
+// instantiations -- of the N-specialised kernel family (k_rows_n, k_rows_n_fd_persist, k_stream_exact).
+namespace ecuda {
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+}  // namespace ecuda
+
+#ifndef ECUDA_TU_ROWSN
 namespace ecuda {
 
 // multi-phase objective: f = sf * (((f_0 + f_1) + f_2) + ...)
@@ -220,12 +231,8 @@ __global__ void __launch_bounds__(256) k_prefetch_inputs(const char* a, size_t a
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(b + o));
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
-
 }  // namespace ecuda
+#endif  // !ECUDA_TU_ROWSN
 
 using namespace ecuda;
 
@@ -323,6 +330,7 @@ static void release(DevBuf& b) {
     b.bytes = 0;
 }
 
+#ifndef ECUDA_TU_ROWSN
 // exact-mode template of the instance-independent triplets; depends on the scaling and on D
 static int upload_template(ecuda_ctx* h) {
     if (h->hp.col.empty()) return ECUDA_OK;  // collocation data not built yet
@@ -473,6 +481,13 @@ static int launch_keval_image(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
     return ECUDA_OK;
 }
 
+#endif  // !ECUDA_TU_ROWSN
+
+// defined in the ECUDA_TU_ROWSN translation unit: the N-specialised kernels for the handle's model and node count;
+// returns 1 when no instantiation matches (the caller falls back)
+int ecuda_launch_rows_n(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid);
+
+#ifdef ECUDA_TU_ROWSN
 // N-specialised row-owner kernels (ecuda_rowsn.cuh): instantiated ahead of time for the node counts of the
 // BASELINE configurations; other shapes take the kernels above
 template <int M, int N, bool FD, bool TRK, bool SUM>
@@ -575,6 +590,14 @@ static int launch_rows_n(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int gr
     }
     return 1;
 }
+int ecuda_launch_rows_n(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
+    switch (h->pd.model) {
+        case ECUDA_MODEL_SI2D: return launch_rows_n<ECUDA_MODEL_SI2D>(h, io, st, grid);
+        case ECUDA_MODEL_PM3D: return launch_rows_n<ECUDA_MODEL_PM3D>(h, io, st, grid);
+        default: return 1;
+    }
+}
+#else  // main translation unit from here on
 
 template <int M, int NB>
 static int launch_keval_fast_mode(ecuda_ctx* h, const EvalIO& io, cudaStream_t st, int grid) {
@@ -608,7 +631,7 @@ static int launch_eval_t(ecuda_ctx* h, const EvalIO& io, cudaStream_t st) {
                                                             sizeof(double) * io.batch * h->pd.inst_stride);
             ++h->launches;
         }
-        int rc = h->rowsn_N > 0 ? launch_rows_n<M>(h, io, st, grid) : 1;
+        int rc = h->rowsn_N > 0 ? ecuda_launch_rows_n(h, io, st, grid) : 1;
         if (rc <= 0) {
         } else if (h->fast_ok) {
             rc = ECUDA_OK;
@@ -1792,3 +1815,4 @@ int ecuda_ipopt_eval_jac_g(ecuda_handle h, int n, const double* x, int new_x, in
 }
 
 }  // extern "C"
+#endif  // ECUDA_TU_ROWSN

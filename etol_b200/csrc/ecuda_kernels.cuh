@@ -148,7 +148,7 @@ constexpr int kCopyWarpThreads = 32;
 constexpr int kCopySlots = ECUDA_COPY_SLOTS;
 constexpr int kCopyChunk = ECUDA_COPY_CHUNK;  // doubles (1024 = 8 KB)
 
-__device__ void copy_warp_template(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, int b, double* ring,
+static __device__ void copy_warp_template(const ProbDev& pb, const PhaseDev& ph, const EvalIO& io, int b, double* ring,
                                    uint64_t* bars, int lane) {
     const int e0 = __ldg(pb.colptr + ph.zoff + pb.nc * ph.N);             // first state column of the phase
     const int e1 = __ldg(pb.colptr + ph.zoff + (pb.nc + pb.ns) * ph.N);   // its t0 column
