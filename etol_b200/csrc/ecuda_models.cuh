@@ -90,16 +90,26 @@ ECUDA_HD int track_interval(const double* trk, int nway, double t) {
     }
     return j;
 }
-ECUDA_HD double track_row(const double* trk, int nway, double x, double y, double t) {
+// centre of the moving zone at time t (the two divisions and the waypoint search of a track row), and the row value
+// for a given centre: track_row is their composition, so callers that evaluate one row at several positions and one
+// time (value and the x / y finite differences) may compute the centre once and get the same bits
+ECUDA_HD void track_center(const double* trk, int nway, double t, double* xc, double* yc) {
     int j = track_interval(trk, nway, t);
     const double* a = trk + 1 + 3 * j;
     const double* b = a + 3;
-    double xc = (t - a[0]) * (b[1] - a[1]) / (b[0] - a[0]) + a[1];
-    double yc = (t - a[0]) * (b[2] - a[2]) / (b[0] - a[0]) + a[2];
+    *xc = (t - a[0]) * (b[1] - a[1]) / (b[0] - a[0]) + a[1];
+    *yc = (t - a[0]) * (b[2] - a[2]) / (b[0] - a[0]) + a[2];
+}
+ECUDA_HD double track_row_at(const double* trk, double xc, double yc, double x, double y) {
     double dx = x - xc;
     double dy = y - yc;
     double dist = dx * dx + dy * dy;
     return dist * (-1.) + trk[0] * trk[0];
+}
+ECUDA_HD double track_row(const double* trk, int nway, double x, double y, double t) {
+    double xc, yc;
+    track_center(trk, nway, t, &xc, &yc);
+    return track_row_at(trk, xc, yc, x, y);
 }
 ECUDA_HD void track_row_partials(const double* trk, int nway, double x, double y, double t, double* ddx,
                                  double* ddy, double* ddt) {
@@ -108,8 +118,10 @@ ECUDA_HD void track_row_partials(const double* trk, int nway, double x, double y
     const double* b = a + 3;
     double sx = (b[1] - a[1]) / (b[0] - a[0]);
     double sy = (b[2] - a[2]) / (b[0] - a[0]);
-    double xc = (t - a[0]) * (b[1] - a[1]) / (b[0] - a[0]) + a[1];
-    double yc = (t - a[0]) * (b[2] - a[2]) / (b[0] - a[0]) + a[2];
+    // the centre from the slopes (two divisions instead of four; the value row keeps the reference's formula, the
+    // analytic partials are compared to 1e-9 and differ from it in the last bit at most)
+    double xc = (t - a[0]) * sx + a[1];
+    double yc = (t - a[0]) * sy + a[2];
     double dx = x - xc;
     double dy = y - yc;
     *ddx = -2.0 * dx;

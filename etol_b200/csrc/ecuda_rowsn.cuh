@@ -807,8 +807,17 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double x0 = zx[k * NS], x1 = zx[k * NS + 1];
         const int r = ph.goff + NS * N + pb.ne + k * np + q;
         const double s = ECUDA_LDG(sg + r);
+        // a moving-zone row at the node time: the zone's centre (two divisions, a waypoint search) is computed once for
+        // the value and the four position perturbations -- the same operations, hence the same bits, as track_row
+        const bool trk_row = TRK && q >= ph.nstat && q - ph.nstat < pb.ntracks;
+        const double* trk = cm.inst + pb.track_off + (trk_row ? q - ph.nstat : 0) * pb.track_size;
+        double xc = 0.0, yc = 0.0;
+        if (trk_row) track_center(trk, pb.nway, t, &xc, &yc);
+        auto row_at = [&](double xa, double ya) {
+            return trk_row ? track_row_at(trk, xc, yc, xa, ya) : rn_path_row<M, TRK>(pb, ph, cm, q, xa, ya, t);
+        };
         if (g) {
-            const double val = s * rn_path_row<M, TRK>(pb, ph, cm, q, x0, x1, t);
+            const double val = s * row_at(x0, x1);
             RN_LOCAL_STORE(g + r, val);
             note(r, val, 1);
         }
@@ -817,8 +826,8 @@ ECUDA_HD void rn_item_fd(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const FdRec& rc = rx[k * NS + j];
-            const double vp = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xp : x0, j == 1 ? rc.xp : x1, t);
-            const double vm = rn_path_row<M, TRK>(pb, ph, cm, q, j == 0 ? rc.xm : x0, j == 1 ? rc.xm : x1, t);
+            const double vp = row_at(j == 0 ? rc.xp : x0, j == 1 ? rc.xp : x1);
+            const double vm = row_at(j == 0 ? rc.xm : x0, j == 1 ? rc.xm : x1);
             RN_LOCAL_STORE(jac + (rc.cp + N - 1 + pb.xcnt[j] + ev + q), (s * vp - s * vm) * rc.ri);
         }
         if (TRK && q >= ph.nstat) {
