@@ -188,6 +188,27 @@ ECUDA_HD double path_row(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m,
     }
     return track_row(m.inst + pb.track_off + (q - ph.nstat) * pb.track_size, pb.nway, x, y, t);
 }
+// path row q at ONE time and several positions (value and the x / y finite differences of a row): a moving-zone row
+// computes its centre -- two divisions and a waypoint search -- once; same operations as path_row, hence the same bits
+template <int M>
+struct PathRowAt {
+    const ProbDev& pb;
+    const PhaseDev& ph;
+    const CtaMem& m;
+    int q;
+    double t, xc, yc;
+    bool trk;
+    const double* rec;
+    ECUDA_HD PathRowAt(const ProbDev& pb_, const PhaseDev& ph_, const CtaMem& m_, int q_, double t_)
+        : pb(pb_), ph(ph_), m(m_), q(q_), t(t_), xc(0.0), yc(0.0) {
+        trk = q >= ph.nstat && q - ph.nstat < pb.ntracks;
+        rec = m.inst + pb.track_off + (trk ? q - ph.nstat : 0) * pb.track_size;
+        if (trk) track_center(rec, pb.nway, t, &xc, &yc);
+    }
+    ECUDA_HD double operator()(double x, double y) const {
+        return trk ? track_row_at(rec, xc, yc, x, y) : path_row<M>(pb, ph, m, q, x, y, t);
+    }
+};
 // partials of path row q >= nstat (a moving zone, or a traced row of a user model) in x_0, x_1 and t
 template <int M>
 ECUDA_HD void moving_row_partials(const ProbDev& pb, const PhaseDev& ph, const CtaMem& m, int q, double x, double y,
@@ -397,8 +418,9 @@ ECUDA_HD void xcol_path_fd(const ProbDev& pb, const PhaseDev& ph, const CtaMem& 
     const double x0 = m.z[nc * N + k * ns], x1 = m.z[nc * N + k * ns + 1];
     const int r = ph.goff + ns * N + pb.ne + k * np + q;
     const double s = ECUDA_LDG(pb.sg + r);
-    double vp = path_row<M>(pb, ph, m, q, j == 0 ? xpv : x0, j == 1 ? xpv : x1, t);
-    double vm = path_row<M>(pb, ph, m, q, j == 0 ? xmv : x0, j == 1 ? xmv : x1, t);
+    const PathRowAt<M> row(pb, ph, m, q, t);
+    double vp = row(j == 0 ? xpv : x0, j == 1 ? xpv : x1);
+    double vm = row(j == 0 ? xmv : x0, j == 1 ? xmv : x1);
     const int pos = N - 1 + pb.xcnt[j] + ((k == 0 || k == N - 1) ? 1 : 0) + q;
     ECUDA_STREAM_STORE(jac + m.colp[lcol] + pos, (s * vp - s * vm) * ri);
 }

@@ -290,8 +290,9 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
         const double x0 = m.z[lcol0], x1 = m.z[lcol0 + 1];
         const int r = ph.goff + NS * N + pb.ne + k * np + q;
         const double s = ECUDA_LDG(sg + r);
+        const PathRowAt<M> row(pb, ph, m, q, t);  // value and position perturbations share a moving zone's centre
         if (g) {
-            const double val = s * path_row<M>(pb, ph, m, q, x0, x1, t);
+            const double val = s * row(x0, x1);
             ECUDA_STREAM_STORE(g + r, val);
             note(r, val, 1);
         }
@@ -302,8 +303,8 @@ ECUDA_HD void other_item(const ProbDev& pb, const PhaseDev& ph, int p, const Eva
             for (int j = 0; j < 2; ++j) {
                 const int lcol = lcol0 + j;
                 const double xpv = m.xp[lcol], xmv = m.xm[lcol];
-                const double vp = path_row<M>(pb, ph, m, q, j == 0 ? xpv : x0, j == 1 ? xpv : x1, t);
-                const double vm = path_row<M>(pb, ph, m, q, j == 0 ? xmv : x0, j == 1 ? xmv : x1, t);
+                const double vp = row(j == 0 ? xpv : x0, j == 1 ? xpv : x1);
+                const double vm = row(j == 0 ? xmv : x0, j == 1 ? xmv : x1);
                 ECUDA_STREAM_STORE(jac + m.colp[lcol] + N - 1 + pb.xcnt[j] + ev + q, (s * vp - s * vm) * m.rinv[lcol]);
             }
             if (q >= ph.nstat) {
