@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 TAG=${1:-c0}; W=${2:-c0}
 if [ $W = c0 ]; then
 CASE=c0 timeout 300 python scripts/c0_time.py 2>&1 | tail -1
-CASE=c0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval -s 4 -c 1 -o gpurun_out/prof_${TAG}_c0fd -f python scripts/c0_time.py > gpurun_out/ncu_${TAG}_c0.log 2>&1
+CASE=c0 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_eval|k_rows_n" -s 4 -c 1 -o gpurun_out/prof_${TAG}_c0fd -f python scripts/c0_time.py > gpurun_out/ncu_${TAG}_c0.log 2>&1
 echo "ncu c0 rc=$?"
 else
 BATCH=64 JAC=fd timeout 300 python scripts/c3_once.py | tail -1
