@@ -680,7 +680,11 @@ static int load_user_kernels(ecuda_ctx* h) {
     // the N-specialised finite-difference kernel (k_rows_n) under the rule of launch_rows_n_mn: every phase has N
     // nodes and one defect row per thread
     const int ns = h->pd.ns, rn = h->rowsn_N;
-    const int rowsn = (h->fast_ok && rn > 0 && ns * rn <= kThreads) ? rn : 0;
+    int rowsn = (h->fast_ok && rn > 0 && ns * rn <= kThreads) ? rn : 0;
+    if (rowsn) {  // its shared memory (launch_eval_user) must fit one CTA, else the round-1 kernels run
+        const size_t nv = static_cast<size_t>(ns + h->pd.nc) * rn + 2;
+        if ((static_cast<size_t>(h->pd.inst_stride) + nv + 1 + 4 * nv + 1) * sizeof(double) > 227 * 1024 - 1024) rowsn = 0;
+    }
     bool trk = false;
     for (int p = 0; p < h->pd.nphases; ++p) trk = trk || h->pd.ph[p].npath > h->pd.ph[p].nstat;
     std::shared_ptr<UserImage> img;
